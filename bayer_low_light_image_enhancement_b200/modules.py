@@ -1,0 +1,490 @@
+"""Host-side mirror of the reference's ``nn.Module`` surface for the RawFormer inference hot path.
+
+Every class keeps the reference's constructor signature, parameter/buffer names and shapes, so a reference
+``state_dict`` loads with ``strict=True``; every ``forward`` is one call through the C ABI
+(``include/rawformer_b200.h``) into hand-written sm_100a kernels.  The ``torch.nn`` layers created below are
+*parameter containers only* (names, shapes, default initialisation); their own ``forward`` is never used.
+
+Reference: ``FrequencyawareLumaChromaAttentionRAWFormer.py`` (FLCA_RF).  Inference only (no autograd).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import BlockWeights, ModelWeights, check, f32c, ptr, stream_ptr
+
+_DEFAULT_PRECISION = os.environ.get("RAWFORMER_B200_PRECISION", "fp32")
+MODEL_SIZES = {"S": 32, "B": 48, "L": 64}  # reference test.py:85
+
+
+def set_default_precision(p: str):
+    """'fp32' (parity mode, max-abs <= 1e-4 vs the reference) or 'bf16' (tensor-core mode)."""
+    global _DEFAULT_PRECISION
+    _lib.dtype_code(p)
+    _DEFAULT_PRECISION = p
+
+
+def get_default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+def _conv(ci, co, k, bias=True, groups=1):
+    return nn.Conv2d(ci, co, kernel_size=k, stride=1, padding=k // 2, groups=groups, bias=bias)
+
+
+class _Op(nn.Module):
+    """Shared plumbing: precision selection, weight marshalling, workspace."""
+
+    precision = None  # None -> package default
+
+    def _dtype(self):
+        return _lib.dtype_code(self.precision or _DEFAULT_PRECISION)
+
+    @staticmethod
+    def _prep(x, name="input", channels=None):
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError(f"{name} must be a 4-d tensor [B,C,H,W]")
+        _lib.init_device(x.device)
+        x = f32c(x.detach())
+        if channels is not None and x.shape[1] != channels:
+            raise ValueError(f"{name} has {x.shape[1]} channels, expected {channels}")
+        return x
+
+
+def _fill(bw: BlockWeights, keep: list, **tensors):
+    for k, t in tensors.items():
+        t = f32c(t.detach())
+        keep.append(t)
+        setattr(bw, k, t.data_ptr())
+
+
+def downshuffle(var, r):
+    """Pixel-unshuffle, out channel = c*r*r + r*i + j.  Reference: FLCA_RF.py:18-33."""
+    x = _Op._prep(var)
+    b, c, h, w = x.shape
+    out = torch.empty(b, c * r * r, h // r, w // r, dtype=torch.float32, device=x.device)
+    if out.numel():
+        check(_lib.load().rf_downshuffle(ptr(x), ptr(out), b, c, h, w, r, stream_ptr(x.device)), "rf_downshuffle")
+    return out
+
+
+class PixelShuffle(_Op):
+    """nn.PixelShuffle(r).  Reference: FLCA_RF.py:328,369."""
+
+    def __init__(self, upscale_factor=2):
+        super().__init__()
+        self.upscale_factor = upscale_factor
+
+    def forward(self, x):
+        x = self._prep(x)
+        r = self.upscale_factor
+        b, c, h, w = x.shape
+        if c % (r * r):
+            raise ValueError("channels must be divisible by r*r")
+        out = torch.empty(b, c // (r * r), h * r, w * r, dtype=torch.float32, device=x.device)
+        if out.numel():
+            check(_lib.load().rf_pixelshuffle(ptr(x), ptr(out), b, c // (r * r), h, w, r, stream_ptr(x.device)),
+                  "rf_pixelshuffle")
+        return out
+
+
+class HaarDWT(_Op):
+    """2x2 stride-2 Haar analysis; returns LL, (LH, HL, HH).  Reference: FLCA_RF.py:39-73.
+
+    The filter buffer is built exactly like the reference (fp32 outer products of 1/sqrt(2) vectors), so the
+    coefficient is 0x1.fffffep-2, not 0.5."""
+
+    def __init__(self):
+        super().__init__()
+        lo = torch.tensor([1.0, 1.0]) / math.sqrt(2.0)
+        hi = torch.tensor([1.0, -1.0]) / math.sqrt(2.0)
+        bank = [torch.outer(a, b) for a in (lo, hi) for b in (lo, hi)]  # LL, LH, HL, HH
+        self.register_buffer("filt", torch.stack(bank, 0).unsqueeze(1))
+
+    def forward(self, x):
+        x = self._prep(x)
+        b, c, h, w = x.shape
+        h2, w2 = (h + 1) // 2, (w + 1) // 2
+        outs = [torch.empty(b, c, h2, w2, dtype=torch.float32, device=x.device) for _ in range(4)]
+        filt = f32c(self.filt.to(x.device))
+        check(_lib.load().rf_haar_dwt(ptr(x), ptr(filt), *(ptr(o) for o in outs), b, c, h, w, stream_ptr(x.device)),
+              "rf_haar_dwt")
+        return outs[0], (outs[1], outs[2], outs[3])
+
+
+class BayerLumaChroma(_Op):
+    """Luma / chroma guidance from packed RGGB planes.  Reference: FLCA_RF.py:79-97."""
+
+    def __init__(self, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+        for n, v in (("r_w", 0.299), ("g_w", 0.587), ("b_w", 0.114)):
+            self.register_buffer(n, torch.tensor(v, dtype=torch.float32))
+
+    def rgb_weights(self):
+        return [float(self.r_w), float(self.g_w), float(self.b_w)]
+
+    def forward(self, x):
+        x = self._prep(x, "x", 4)
+        b, _, h, w = x.shape
+        y, cr, cb = (torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device) for _ in range(3))
+        ws = _lib.shared_workspace(256 * b + 256, x.device)
+        wts = (C.c_float * 3)(*self.rgb_weights())
+        check(_lib.load().rf_luma_chroma(ptr(x), ptr(y), ptr(cr), ptr(cb), wts, float(self.eps), b, h, w, ptr(ws),
+                                         ws.numel(), stream_ptr(x.device)), "rf_luma_chroma")
+        return y, cr, cb
+
+
+class LayerNorm(_Op):
+    """Per-pixel nn.LayerNorm over channels of an NCHW tensor.  Reference: FLCA_RF.py:180-187."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.body = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        x = self._prep(x, "x", self.body.normalized_shape[0])
+        b, c, h, w = x.shape
+        out = torch.empty_like(x)
+        wt, bs = f32c(self.body.weight.detach()), f32c(self.body.bias.detach())
+        check(_lib.load().rf_layernorm(ptr(x), ptr(wt), ptr(bs), ptr(out), float(self.body.eps), 0, b, c, h, w,
+                                       stream_ptr(x.device)), "rf_layernorm")
+        return out
+
+
+class _BlockPart(_Op):
+    """A piece of a Conv_Transformer that runs through one rf_*_forward entry point."""
+
+    def _weights(self, bw, keep):
+        raise NotImplementedError
+
+    def _run(self, fn_name, C_, x, extra_in=(), hy_wy=None, variant=None):
+        lib = _lib.load()
+        b, _, h, w = x.shape
+        hy, wy = hy_wy if hy_wy is not None else (h, w)
+        bw, keep = BlockWeights(), []
+        self._weights(bw, keep)
+        dt = self._dtype()
+        nbytes = lib.rf_block_workspace_bytes(C_, dt, b, h, w, hy, wy)
+        ws = _lib.shared_workspace(nbytes, x.device)
+        out = torch.empty_like(x)
+        args = [C.byref(bw), C_, dt]
+        if variant is not None:
+            args.append(variant)
+        args += [ptr(x), *(ptr(t) for t in extra_in), ptr(out), b, h, w]
+        if hy_wy is not None:
+            args += [hy, wy]
+        args += [ptr(ws), ws.numel(), stream_ptr(x.device)]
+        check(getattr(lib, fn_name)(*args), fn_name)
+        return out
+
+
+class FLCA(_BlockPart):
+    """Frequency-aware luma-chroma attention.  Reference: FLCA_RF.py:103-162."""
+
+    variant = _lib.RF_VARIANT_FLCA
+
+    def __init__(self, channels, r_ratio=8, eps=1e-8):
+        super().__init__()
+        self.channels = channels
+        self.eps = eps
+        self.dwt = HaarDWT()
+        self.low_attn = nn.Sequential(_conv(1, channels, 3, bias=False), nn.Sigmoid())
+        self.high_attn = nn.Sequential(_conv(1, channels, 3, bias=False), nn.Tanh())
+        self.chroma_attn = nn.Sequential(_conv(2, channels, 3, bias=False), nn.Sigmoid())
+        hidden = max(8, channels // r_ratio)
+        self.se = nn.Sequential(nn.AdaptiveAvgPool2d(1), _conv(channels, hidden, 1), nn.ReLU(inplace=True),
+                                _conv(hidden, channels, 1), nn.Sigmoid())
+        self.alpha = nn.Parameter(torch.tensor(1.0))
+        self.beta = nn.Parameter(torch.tensor(1.0))
+        self.gamma = nn.Parameter(torch.tensor(1.0))
+        if abs(eps - 1e-8) > 1e-20:
+            raise NotImplementedError("FLCA eps is fixed to the reference default 1e-8 in the kernels")
+
+    def _weights(self, bw, keep):
+        _fill(bw, keep, flca_low_w=self.low_attn[0].weight, flca_high_w=self.high_attn[0].weight,
+              flca_chroma_w=self.chroma_attn[0].weight, flca_se_w1=self.se[1].weight, flca_se_b1=self.se[1].bias,
+              flca_se_w2=self.se[3].weight, flca_se_b2=self.se[3].bias, flca_alpha=self.alpha, flca_beta=self.beta,
+              flca_gamma=self.gamma, flca_filt=self.dwt.filt)
+
+    def forward(self, feat, y, cr, cb):
+        feat = self._prep(feat, "feat", self.channels)
+        y, cr, cb = (self._prep(t, n, 1) for t, n in ((y, "y"), (cr, "cr"), (cb, "cb")))
+        return self._run("rf_flca_forward", self.channels, feat, (y, cr, cb), tuple(y.shape[-2:]), self.variant)
+
+
+class Downsample(_Op):
+    """Bias-free 3x3 C->C/2 then pixel-unshuffle: [B,C,H,W] -> [B,2C,H/2,W/2].  Reference: FLCA_RF.py:168-177."""
+
+    def __init__(self, n_feat):
+        super().__init__()
+        self.n_feat = n_feat
+        self.body = nn.Sequential(_conv(n_feat, n_feat // 2, 3, bias=False))
+
+    def forward(self, x):
+        return _downsample_call(self, self.body[0].weight, self.n_feat, x)
+
+
+def _downsample_call(op, weight, n_feat, x):
+    x = op._prep(x, "x", n_feat)
+    b, c, h, w = x.shape
+    lib = _lib.load()
+    dt = op._dtype()
+    ws = _lib.shared_workspace(lib.rf_block_workspace_bytes(c, dt, b, h, w, h, w), x.device)
+    out = torch.empty(b, 2 * c, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    wt = f32c(weight.detach())
+    check(lib.rf_downsample_forward(ptr(wt), c, dt, ptr(x), ptr(out), b, h, w, ptr(ws), ws.numel(),
+                                    stream_ptr(x.device)), "rf_downsample_forward")
+    return out
+
+
+class conv_ffn(_BlockPart):
+    """1x1 -> depthwise 3x3 -> GELU(erf) -> 1x1.  Reference: FLCA_RF.py:190-209."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU or out_features != in_features or hidden_features != 2 * in_features:
+            raise NotImplementedError("kernels implement the reference configuration: hidden = 2*dim, GELU, out = dim")
+        self.in_features = in_features
+        self.pointwise1 = _conv(in_features, hidden_features, 1)
+        self.depthwise = _conv(hidden_features, hidden_features, 3, groups=hidden_features)
+        self.pointwise2 = _conv(hidden_features, out_features, 1)
+        self.act_layer = act_layer()
+
+    def _weights(self, bw, keep):
+        _fill(bw, keep, pw1_w=self.pointwise1.weight, pw1_b=self.pointwise1.bias, ffn_dw_w=self.depthwise.weight,
+              ffn_dw_b=self.depthwise.bias, pw2_w=self.pointwise2.weight, pw2_b=self.pointwise2.bias)
+
+    def forward(self, x):
+        x = self._prep(x, "x", self.in_features)
+        return self._run("rf_conv_ffn_forward", self.in_features, x)
+
+
+class Attention(_BlockPart):
+    """Transposed (channel) attention with 8 heads.  Reference: FLCA_RF.py:212-235."""
+
+    def __init__(self, dim, num_heads, bias):
+        super().__init__()
+        if num_heads != 8 or not bias or dim % 8:
+            raise NotImplementedError("kernels implement the reference configuration: 8 heads, bias=True, dim % 8 == 0")
+        self.dim = dim
+        self.num_heads = num_heads
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.qkv = _conv(dim, dim * 3, 1, bias=bias)
+        self.qkv_dwconv = _conv(dim * 3, dim * 3, 3, bias=bias, groups=dim * 3)
+        self.project_out = _conv(dim, dim, 1, bias=bias)
+
+    def _weights(self, bw, keep):
+        _fill(bw, keep, temperature=self.temperature, qkv_w=self.qkv.weight, qkv_b=self.qkv.bias,
+              qkv_dw_w=self.qkv_dwconv.weight, qkv_dw_b=self.qkv_dwconv.bias, proj_w=self.project_out.weight,
+              proj_b=self.project_out.bias)
+
+    def forward(self, x):
+        x = self._prep(x, "x", self.dim)
+        return self._run("rf_attention_forward", self.dim, x)
+
+
+class TransformerBlock(_BlockPart):
+    """x += attn(LN(x)); x += ffn(LN(x)).  Reference: FLCA_RF.py:238-254."""
+
+    def __init__(self, dim, num_heads, ffn_expansion_factor, bias):
+        super().__init__()
+        self.dim = dim
+        self.norm1 = LayerNorm(dim)
+        self.attn = Attention(dim, num_heads, bias)
+        self.norm2 = LayerNorm(dim)
+        self.ffn = conv_ffn(dim, dim * ffn_expansion_factor, dim)
+
+    def _weights(self, bw, keep):
+        self.attn._weights(bw, keep)
+        self.ffn._weights(bw, keep)
+        _fill(bw, keep, norm1_w=self.norm1.body.weight, norm1_b=self.norm1.body.bias, norm2_w=self.norm2.body.weight,
+              norm2_b=self.norm2.body.bias)
+
+    def forward(self, x):
+        x = self._prep(x, "x", self.dim)
+        return self._run("rf_transformer_block_forward", self.dim, x)
+
+
+class Conv_Transformer(_BlockPart):
+    """FLCA branch || transformer branch -> 1x1 reduce -> 3x3 -> LeakyReLU(0.2).  Reference: FLCA_RF.py:257-278.
+    This is the block the README calls "WaveTransformBlock"."""
+
+    variant = _lib.RF_VARIANT_FLCA
+
+    def __init__(self, in_channel, num_heads=8, ffn_expansion_factor=2):
+        super().__init__()
+        self.in_channel = in_channel
+        self.FLCA = self._make_flca(in_channel)
+        self.Transformer = TransformerBlock(dim=in_channel, num_heads=num_heads,
+                                            ffn_expansion_factor=ffn_expansion_factor, bias=True)
+        self.channel_reduce = _conv(in_channel * 2, in_channel, 1)
+        self.Conv_out = _conv(in_channel, in_channel, 3)
+        self.lrelu = nn.LeakyReLU(0.2, inplace=False)
+
+    def _make_flca(self, c):
+        return FLCA(c)
+
+    def _weights(self, bw, keep):
+        self.FLCA._weights(bw, keep)
+        self.Transformer._weights(bw, keep)
+        _fill(bw, keep, reduce_w=self.channel_reduce.weight, reduce_b=self.channel_reduce.bias,
+              convout_w=self.Conv_out.weight, convout_b=self.Conv_out.bias)
+
+    def forward(self, feat, y, cr, cb):
+        feat = self._prep(feat, "feat", self.in_channel)
+        y, cr, cb = (self._prep(t, n, 1) for t, n in ((y, "y"), (cr, "cr"), (cb, "cb")))
+        return self._run("rf_conv_transformer_forward", self.in_channel, feat, (y, cr, cb), tuple(y.shape[-2:]),
+                         self.variant)
+
+
+WaveTransformBlock = Conv_Transformer  # north-star / README name for the same block
+
+
+class RawFormer(_Op):
+    """RawFormer with FLCA: raw Bayer [B,1,H,W] -> RGB [B,3,H,W].  Reference: FLCA_RF.py:284-370.
+
+    Extra keywords (not in the reference): ``model_size`` in {'S','B','L'} -> dim 32/48/64 (reference
+    test.py:50,85) and ``precision`` in {'fp32','bf16'}.  H and W must be multiples of 16."""
+
+    variant = _lib.RF_VARIANT_FLCA
+
+    def __init__(self, inp_channels=1, out_channels=3, dim=48, num_heads=[8, 8, 8, 8], ffn_expansion_factor=2,
+                 model_size=None, precision=None):
+        super().__init__()
+        if model_size is not None:
+            dim = MODEL_SIZES[str(model_size).upper()]
+        if inp_channels != 1 or out_channels != 3 or list(num_heads) != [8, 8, 8, 8] or ffn_expansion_factor != 2:
+            raise NotImplementedError("kernels implement the reference configuration: 1 -> 3 channels, 8 heads, ffn x2")
+        if dim % 8:
+            raise ValueError("dim must be a multiple of 8 (8 heads)")
+        self.dim = dim
+        self.precision = precision
+        self.lrelu = nn.LeakyReLU(0.2, inplace=False)
+        self.luma_chroma = BayerLumaChroma()
+        self.embedding = _conv(inp_channels * 4, dim, 3)
+        widths = [dim, dim * 2, dim * 4, dim * 8]
+        self.conv_tran1 = self._block(widths[0])
+        self.down1 = self._down(widths[0])
+        self.conv_tran2 = self._block(widths[1])
+        self.down2 = self._down(widths[1])
+        self.conv_tran3 = self._block(widths[2])
+        self.down3 = self._down(widths[2])
+        self.conv_tran4 = self._block(widths[3])
+        for n, s in ((1, 2), (2, 1), (3, 0)):
+            setattr(self, f"up{n}", nn.ConvTranspose2d(widths[s + 1], widths[s], 2, stride=2))
+            setattr(self, f"channel_reduce{n}", _conv(widths[s + 1], widths[s], 1))
+            setattr(self, f"conv_tran{4 + n}", self._block(widths[s]))
+        self.conv_out = _conv(dim, out_channels * 4, 3)
+        self.pixelshuffle = PixelShuffle(2)
+        self._extra_init()
+        self._pack_cache = None
+
+    def _block(self, c):
+        return Conv_Transformer(c, 8, 2)
+
+    def _down(self, c):
+        return Downsample(c)
+
+    def _down_weight(self, n):
+        return getattr(self, f"down{n}").body[0].weight
+
+    def _extra_init(self):
+        pass
+
+    # -- weight marshalling ---------------------------------------------------------------------
+    def _model_weights(self):
+        mw, keep = ModelWeights(), []
+
+        def dp(t):
+            t = f32c(t.detach())
+            keep.append(t)
+            return t.data_ptr()
+
+        mw.embedding_w, mw.embedding_b = dp(self.embedding.weight), dp(self.embedding.bias)
+        for i in range(7):
+            getattr(self, f"conv_tran{i + 1}")._weights(mw.blocks[i], keep)
+        for n in range(3):
+            mw.down_w[n] = dp(self._down_weight(n + 1))
+            up = getattr(self, f"up{n + 1}")
+            mw.up_w[n], mw.up_b[n] = dp(up.weight), dp(up.bias)
+            cr = getattr(self, f"channel_reduce{n + 1}")
+            mw.reduce_w[n], mw.reduce_b[n] = dp(cr.weight), dp(cr.bias)
+        mw.conv_out_w, mw.conv_out_b = dp(self.conv_out.weight), dp(self.conv_out.bias)
+        for i, v in enumerate(self.luma_chroma.rgb_weights()):
+            mw.rgb_w_host[i] = v
+        return mw, keep
+
+    def _signature(self, device, dt):
+        sig = [str(device), dt]
+        for t in list(self.parameters()) + list(self.buffers()):
+            sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
+
+    def packed_weights(self, device, dt):
+        """Kernel-layout parameter blob (re-packed when any parameter changes)."""
+        sig = self._signature(device, dt)
+        if self._pack_cache is not None and self._pack_cache[0] == sig:
+            return self._pack_cache[1]
+        lib = _lib.load()
+        if next(self.parameters()).device != device:
+            raise RuntimeError("model parameters and input are on different devices")
+        nbytes = lib.rf_model_packed_bytes(self.dim, dt, self.variant)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        mw, keep = self._model_weights()
+        check(lib.rf_model_pack(C.byref(mw), self.dim, dt, self.variant, ptr(blob), nbytes, stream_ptr(device)),
+              "rf_model_pack")
+        torch.cuda.current_stream(device).synchronize()  # keep[] may be freed after this
+        self._pack_cache = (sig, blob)
+        return blob
+
+    def _check_input(self, x):
+        x = self._prep(x, "x", 1)
+        b, _, h, w = x.shape
+        if h % 16 or w % 16 or h == 0 or w == 0:
+            raise ValueError(f"raw frame {h}x{w}: H and W must be non-zero multiples of 16")
+        return x
+
+    def forward(self, x):
+        x = self._check_input(x)
+        b, _, h, w = x.shape
+        lib = _lib.load()
+        dt = self._dtype()
+        blob = self.packed_weights(x.device, dt)
+        ws = _lib.shared_workspace(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), x.device)
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
+        check(lib.rf_rawformer_forward(ptr(blob), self.dim, dt, self.variant, ptr(x), ptr(out), b, h, w, ptr(ws),
+                                       ws.numel(), stream_ptr(x.device)), "rf_rawformer_forward")
+        return out
+
+    def forward_profiled(self, x, cap=4096):
+        """Same forward with a CUDA-event pair around every launch (synchronises).  Returns (out, launches) where
+        launches is a list of dicts {name, ms, bytes, flops} in launch order."""
+        x = self._check_input(x)
+        b, _, h, w = x.shape
+        lib = _lib.load()
+        dt = self._dtype()
+        blob = self.packed_weights(x.device, dt)
+        ws = _lib.shared_workspace(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), x.device)
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
+        ms = (C.c_float * cap)()
+        ids = (C.c_int * cap)()
+        n = C.c_int(0)
+        check(lib.rf_rawformer_forward_profiled(ptr(blob), self.dim, dt, self.variant, ptr(x), ptr(out), b, h, w,
+                                                ptr(ws), ws.numel(), stream_ptr(x.device), ms, ids, cap, C.byref(n)),
+              "rf_rawformer_forward_profiled")
+        launches = []
+        by, fl = C.c_double(0), C.c_double(0)
+        for i in range(min(n.value, cap)):
+            lib.rf_profiled_launch_info(i, C.byref(by), C.byref(fl))
+            launches.append({"name": lib.rf_kernel_name(ids[i]).decode(), "ms": float(ms[i]), "bytes": by.value,
+                             "flops": fl.value})
+        return out, launches

@@ -1,0 +1,208 @@
+/*
+ * rawformer_b200.h — C ABI of the B200-native RawFormer inference hot path.
+ *
+ * The reference (Gaurav14cs17/Bayer_Low_light_Image_Enhancement) is pure PyTorch and has no FFI; the
+ * entry points below are what a binding for its hot path would call.  Each one cites the reference
+ * interface it replaces (file:line relative to the reference tree; FLCA_RF = Frequencyaware-
+ * LumaChromaAttentionRAWFormer.py, ML_RF = MultiLvlFrequencyawareLumaChromaAttentionRAWFormer.py,
+ * WFB = RawFomer_WFB_FFAB/).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless the parameter name ends in `_host`.
+ *  - Tensors at this boundary use the reference's own layout: contiguous NCHW float32.
+ *  - The caller owns every buffer, including the workspace; nothing is allocated or freed here.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are re-entrant and
+ *    stream-ordered, and may be captured into a CUDA graph.
+ *  - Return value: RF_OK (0) or a negative rf_status; nothing is thrown across the ABI.
+ *  - sm_100a only: rf_init() fails with RF_ERR_ARCH on any other device.  There is no CPU fallback.
+ *  - `dtype` selects the INTERNAL precision: RF_F32 (fp32 activations, fp32 FFMA; parity mode,
+ *    max-abs <= 1e-4 vs the reference) or RF_BF16 (bf16 activations and tensor-core operands, fp32
+ *    accumulation and statistics).
+ */
+#ifndef RAWFORMER_B200_H
+#define RAWFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rf_status {
+  RF_OK = 0,
+  RF_ERR_BAD_SHAPE = -1,   /* shape rule violated (H,W multiples of 16, dim % 8, even DWT sizes ...) */
+  RF_ERR_BAD_ARG = -2,     /* null / misaligned pointer, unknown enum */
+  RF_ERR_ARCH = -3,        /* device is not sm_100 */
+  RF_ERR_CUDA = -4,        /* a CUDA runtime call or launch failed (see rf_last_cuda_error) */
+  RF_ERR_WORKSPACE = -5,   /* workspace too small */
+  RF_ERR_UNSUPPORTED = -6  /* valid request this build does not implement */
+} rf_status;
+
+typedef enum rf_dtype { RF_F32 = 0, RF_BF16 = 1 } rf_dtype;
+
+/* Model variant: FLCA_RF.py::RawFormer or ML_RF.py::RawFormer (flca_levels = 2). */
+typedef enum rf_variant { RF_VARIANT_FLCA = 0, RF_VARIANT_ML = 1 } rf_variant;
+
+const char* rf_strerror(int status);
+int rf_version(void);
+/* Last CUDA error code observed by this library on the calling thread (0 if none). */
+int rf_last_cuda_error(void);
+/* Checks that `device` is an sm_100 part and caches its properties.  Must succeed before any other call. */
+int rf_init(int device);
+/* Number of kernels this library launched on the calling thread since the last rf_reset_launch_count(). */
+long long rf_launch_count(void);
+void rf_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Index / wavelet operators (bit-exact index work).  NCHW float32 in and out.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* downshuffle(var, r)  — FLCA_RF.py:18-33.  in [B,C,H,W] -> out [B,C*r*r,H/r,W/r], channel c*r*r+r*i+j. */
+int rf_downshuffle(const float* in, float* out, int B, int C, int H, int W, int r, void* stream);
+/* nn.PixelShuffle(r) — FLCA_RF.py:328,369.  in [B,C*r*r,H,W] -> out [B,C,H*r,W*r]. */
+int rf_pixelshuffle(const float* in, float* out, int B, int C_out, int H, int W, int r, void* stream);
+/* CustomDWT.forward — README.md:111-117.  k16_host = the 4x4 matrix (after the /2 of norm=True),
+ * row n = sub-band, column t = tap (a,b,c,d = TL,TR,BL,BR).  in [B,C,H,W] -> out [B,4C,H/2,W/2] (n*C+c). */
+int rf_custom_dwt(const float* in, float* out, const float* k16_host, int B, int C, int H, int W, void* stream);
+/* CustomIDWT.forward — README.md:139-144.  in [B,4C,H,W] -> out [B,C,2H,2W]. */
+int rf_custom_idwt(const float* in, float* out, const float* k16_host, int B, int C, int H, int W, void* stream);
+/* HaarDWT.forward — FLCA_RF.py:56-73.  filt = device [4,1,2,2] buffer (`dwt.filt`).  in [B,C,H,W];
+ * LL,LH,HL,HH each [B,C,ceil(H/2),ceil(W/2)] (reflect pad right/bottom for odd sizes). */
+int rf_haar_dwt(const float* in, const float* filt, float* LL, float* LH, float* HL, float* HH,
+                int B, int C, int H, int W, void* stream);
+/* dwt_init — WFB/blocks.py:102-115.  in [B,C,H,W] -> out [4B,C,H/2,W/2] (LL,HL,LH,HH on the batch axis). */
+int rf_dwt_init(const float* in, float* out, int B, int C, int H, int W, void* stream);
+/* iwt_init — WFB/blocks.py:119-136.  in [4B,C,H,W] -> out [B,C,2H,2W]. */
+int rf_iwt_init(const float* in, float* out, int B, int C, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Guidance and normalisation
+ * ---------------------------------------------------------------------------------------------- */
+
+/* BayerLumaChroma.forward — FLCA_RF.py:87-97.  x_ds [B,4,h,w] -> y,cr,cb [B,1,h,w].
+ * rgb_w_host = {r_w,g_w,b_w}.  workspace: 4*B bytes. */
+int rf_luma_chroma(const float* x_ds, float* y, float* cr, float* cb, const float* rgb_w_host, float eps,
+                   int B, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+/* LayerNorm.forward — FLCA_RF.py:185-187 (mode 0, nn.LayerNorm over C per pixel);
+ * WithBias_LayerNorm / BiasFree_LayerNorm — WFB/model.py:89-122 (mode 0 / mode 1: no mean subtraction, no bias). */
+int rf_layernorm(const float* in, const float* weight, const float* bias, float* out, float eps, int mode,
+                 int B, int C, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv_Transformer ("WaveTransformBlock") and its parts.
+ * Weights are passed in PyTorch's native layouts (float32, device); absent parts may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rf_block_weights {
+  /* FLCA — FLCA_RF.py:103-134 */
+  const float* flca_low_w;     /* low_attn.0.weight    [C,1,3,3] */
+  const float* flca_high_w;    /* high_attn.0.weight   [C,1,3,3] */
+  const float* flca_chroma_w;  /* chroma_attn.0.weight [C,2,3,3] */
+  const float* flca_se_w1;     /* se.1.weight [hid,C,1,1], hid = max(8, C/8) */
+  const float* flca_se_b1;     /* se.1.bias   [hid] */
+  const float* flca_se_w2;     /* se.3.weight [C,hid,1,1] */
+  const float* flca_se_b2;     /* se.3.bias   [C] */
+  const float* flca_alpha;     /* 0-d */
+  const float* flca_beta;      /* 0-d */
+  const float* flca_gamma;     /* 0-d */
+  const float* flca_filt;      /* dwt.filt [4,1,2,2] */
+  /* TransformerBlock — FLCA_RF.py:238-254 */
+  const float* norm1_w;        /* norm1.body.weight [C] */
+  const float* norm1_b;
+  const float* temperature;    /* attn.temperature [8,1,1] */
+  const float* qkv_w;          /* attn.qkv.weight [3C,C,1,1] */
+  const float* qkv_b;
+  const float* qkv_dw_w;       /* attn.qkv_dwconv.weight [3C,1,3,3] */
+  const float* qkv_dw_b;
+  const float* proj_w;         /* attn.project_out.weight [C,C,1,1] */
+  const float* proj_b;
+  const float* norm2_w;
+  const float* norm2_b;
+  const float* pw1_w;          /* ffn.pointwise1.weight [2C,C,1,1] */
+  const float* pw1_b;
+  const float* ffn_dw_w;       /* ffn.depthwise.weight [2C,1,3,3] */
+  const float* ffn_dw_b;
+  const float* pw2_w;          /* ffn.pointwise2.weight [C,2C,1,1] */
+  const float* pw2_b;
+  /* Conv_Transformer tail — FLCA_RF.py:268-277 */
+  const float* reduce_w;       /* channel_reduce.weight [C,2C,1,1] */
+  const float* reduce_b;
+  const float* convout_w;      /* Conv_out.weight [C,C,3,3] */
+  const float* convout_b;
+  /* FLCA_Pyramid extras — ML_RF.py:86-120 (NULL for RF_VARIANT_FLCA) */
+  const float* pyr_low_w[2];   /* low_attn.{l}.0.weight  [C,1,3,3] */
+  const float* pyr_high_w[2];  /* high_attn.{l}.0.weight [C,1,3,3] */
+  const float* pyr_gate_w[2];  /* freq_gate_head.{l}.weight [2,2,1,1] */
+  const float* pyr_gate_b[2];  /* freq_gate_head.{l}.bias [2] */
+  const float* pyr_cgate_w;    /* chroma_gate.weight [1,1,1,1] */
+  const float* pyr_cgate_b;    /* chroma_gate.bias [1] */
+  const float* pyr_res_w0;     /* res_proj.0.weight [C,C,1,1] */
+  const float* pyr_res_b0;
+  const float* pyr_res_w2;     /* res_proj.2.weight [C,C,1,1] */
+  const float* pyr_res_b2;
+} rf_block_weights;
+
+size_t rf_block_workspace_bytes(int C, int dtype, int B, int Hf, int Wf, int Hy, int Wy);
+
+/* FLCA.forward(feat, y, cr, cb) — FLCA_RF.py:136-162.  feat [B,C,Hf,Wf]; y,cr,cb [B,1,Hy,Wy]. */
+int rf_flca_forward(const rf_block_weights* w, int C, int dtype, const float* feat, const float* y, const float* cr,
+                    const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Attention.forward(x) — FLCA_RF.py:221-235 (num_heads = 8). */
+int rf_attention_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* conv_ffn.forward(x) — FLCA_RF.py:204-209 (hidden = 2C). */
+int rf_conv_ffn_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* TransformerBlock.forward(x) — FLCA_RF.py:251-254. */
+int rf_transformer_block_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H,
+                                 int W, void* workspace, size_t workspace_bytes, void* stream);
+/* Conv_Transformer.forward(feat, y, cr, cb) — FLCA_RF.py:272-278 (variant ML: ML_RF.py:252-258). */
+int rf_conv_transformer_forward(const rf_block_weights* w, int C, int dtype, int variant, const float* feat,
+                                const float* y, const float* cr, const float* cb, float* out, int B, int Hf, int Wf,
+                                int Hy, int Wy, void* workspace, size_t workspace_bytes, void* stream);
+/* Downsample.forward(x) — FLCA_RF.py:176-177.  conv_w = body.0.weight [C/2,C,3,3]; out [B,2C,H/2,W/2]. */
+int rf_downsample_forward(const float* conv_w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole model — RawFormer.forward, FLCA_RF.py:330-370 (variant ML: ML_RF.py:356-416)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rf_model_weights {
+  const float* embedding_w;        /* embedding.weight [d,4,3,3] */
+  const float* embedding_b;
+  rf_block_weights blocks[7];      /* conv_tran1..7 */
+  const float* down_w[3];          /* down{n}.body.0.weight (ML: down{n}.0.weight) [C/2,C,3,3] */
+  const float* up_w[3];            /* up{n}.weight [2C,C,2,2] (ConvTranspose2d layout: in,out,kh,kw) */
+  const float* up_b[3];
+  const float* reduce_w[3];        /* channel_reduce{n}.weight [C,2C,1,1] */
+  const float* reduce_b[3];
+  const float* conv_out_w;         /* conv_out.weight [12,d,3,3] */
+  const float* conv_out_b;
+  float rgb_w_host[3];             /* luma_chroma.{r_w,g_w,b_w} (host values) */
+} rf_model_weights;
+
+/* Bytes of the packed (kernel-layout) parameter blob for a model of base width `dim`. */
+size_t rf_model_packed_bytes(int dim, int dtype, int variant);
+/* Re-packs PyTorch-layout weights into the kernel layout (device-side, stream-ordered). */
+int rf_model_pack(const rf_model_weights* w, int dim, int dtype, int variant, void* packed, size_t packed_bytes,
+                  void* stream);
+/* Workspace needed by rf_rawformer_forward for raw frames [B,1,H,W]. */
+size_t rf_rawformer_workspace_bytes(int dim, int dtype, int variant, int B, int H, int W);
+/* raw [B,1,H,W] float32 -> out [B,3,H,W] float32.  H, W multiples of 16; dim % 8 == 0. */
+int rf_rawformer_forward(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int B,
+                         int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+/* Same forward with a cudaEvent pair around every launch; synchronises the stream.  Fills up to `cap` entries of
+ * kernel_ms_host / kernel_id_host (RF_K_* ids below) and returns the launch count in *n_host. */
+int rf_rawformer_forward_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out,
+                                  int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream,
+                                  float* kernel_ms_host, int* kernel_id_host, int cap, int* n_host);
+/* Human-readable name of a kernel id reported by rf_rawformer_forward_profiled. */
+const char* rf_kernel_name(int kernel_id);
+/* Algorithmic (compulsory) bytes and FLOPs the launch `index` of the last profiled forward moved/did. */
+int rf_profiled_launch_info(int index, double* bytes_host, double* flops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAWFORMER_B200_H */
