@@ -54,7 +54,7 @@ def _digest():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
-    stamp = os.path.join(BUILD_DIR, "digest.txt")
+    stamp = LIB_PATH + ".digest"  # travels with the .so (build/ does not)
     dig = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB_PATH

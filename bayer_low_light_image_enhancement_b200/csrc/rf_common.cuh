@@ -1,7 +1,14 @@
-// Shared device/host helpers for the RawFormer sm_100a kernels.
+// Shared host/device helpers for the RawFormer sm_100a kernels.
+//
+// Internal conventions:
+//   * activations are NHWC ("pixel rows"): [B, H, W, C] of T, T = float (parity mode) or bf16;
+//   * per-channel parameters, statistics and guidance maps are always fp32;
+//   * every launcher takes a Ctx (stream + bump arena over the caller's workspace); in `dry` mode the
+//     launchers do nothing, which is how the *_workspace_bytes queries size the arena.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/rawformer_b200.h"
@@ -9,6 +16,7 @@
 namespace rf {
 
 typedef __nv_bfloat16 bf16;
+typedef long long i64;
 
 // ---------------------------------------------------------------------------------------------
 // launch bookkeeping (per host thread): count, optional per-launch CUDA events for profiling
@@ -20,13 +28,16 @@ enum KernelId {
   RF_K_GUIDANCE,
   RF_K_FLCA_MOD,
   RF_K_SE_FINALIZE,
-  RF_K_LN_QKV,
+  RF_K_FOLD_REDUCE,
+  RF_K_LAYERNORM,
+  RF_K_GEMM_QKV,
   RF_K_DW_QKV_GRAM,
   RF_K_ATTN_FINALIZE,
-  RF_K_PROJ_RESID,
-  RF_K_LN_PW1,
-  RF_K_DW_GELU_PW2,
-  RF_K_CAT_REDUCE,
+  RF_K_GEMM_PROJ,
+  RF_K_GEMM_PW1,
+  RF_K_DW_GELU,
+  RF_K_GEMM_PW2,
+  RF_K_GEMM_CAT_REDUCE,
   RF_K_CONV3X3_OUT,
   RF_K_DOWN_CONV,
   RF_K_UP_CONVT,
@@ -36,12 +47,13 @@ enum KernelId {
   RF_K_LAYOUT,
   RF_K_WEIGHT_PACK,
   RF_K_MISC,
-  RF_K_PYR_GATES,
   RF_K_PYR_SPATIAL,
-  RF_K_PYR_RES1,
-  RF_K_PYR_RES2,
+  RF_K_GEMM_PYR_RES1,
+  RF_K_GEMM_PYR_RES2,
+  RF_K_CHANNEL_SUMS,
   RF_K_TAIL_STATS,
   RF_K_TAIL_APPLY,
+  RF_K_INDEX_OP,
   RF_K_COUNT
 };
 
@@ -56,10 +68,14 @@ struct LaunchRecorder {
   double* flops = nullptr;
   cudaStream_t stream = 0;
   int last_cuda_error = 0;
+  // info of the last profiled forward (kept after profiling ends)
+  int last_n = 0;
+  int* last_ids = nullptr;
+  double* last_bytes = nullptr;
+  double* last_flops = nullptr;
 };
 LaunchRecorder& recorder();
 
-// Call before / after a kernel launch.
 void launch_begin(int kernel_id, double algo_bytes, double algo_flops);
 void launch_end();
 
@@ -69,6 +85,7 @@ struct ScopedLaunch {
 };
 
 int check_cuda(cudaError_t e);
+int num_sms();
 
 #define RF_CUDA(x)                          \
   do {                                      \
@@ -82,32 +99,49 @@ int check_cuda(cudaError_t e);
   } while (0)
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline i64 cdivl(i64 a, i64 b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t esize(int dtype) { return dtype == RF_BF16 ? 2 : 4; }
+
+// Bump allocator over the caller-owned workspace.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  size_t peak = 0;
+  void* alloc(size_t bytes) {
+    off = align_up(off, 256);
+    char* p = base ? base + off : nullptr;
+    off += bytes;
+    if (off > peak) peak = off;
+    return p;
+  }
+  template <typename U>
+  U* get(size_t n) { return reinterpret_cast<U*>(alloc(n * sizeof(U))); }
+  void* elems(size_t n, int dtype) { return alloc(n * esize(dtype)); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Ctx {
+  cudaStream_t stream = 0;
+  Arena arena;
+  bool dry = false;   // size the arena only, launch nothing
+  int dtype = RF_F32;
+  bool fits() const { return dry || arena.peak <= arena.cap; }
+};
 
 // ---------------------------------------------------------------------------------------------
-// element conversion helpers
+// device helpers
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-struct Elem;
-template <>
-struct Elem<float> {
-  static constexpr int VEC = 4;  // elements per 16-byte vector
-  __device__ __forceinline__ static float to_f(float v) { return v; }
-  __device__ __forceinline__ static float from_f(float v) { return v; }
-};
-template <>
-struct Elem<bf16> {
-  static constexpr int VEC = 8;
-  __device__ __forceinline__ static float to_f(bf16 v) { return __bfloat162float(v); }
-  __device__ __forceinline__ static bf16 from_f(float v) { return __float2bfloat16_rn(v); }
-};
-
-// 16-byte vector load/store of T as floats
-__device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
-  float4 t = *reinterpret_cast<const float4*>(p);
-  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#ifdef __CUDACC__
+// 8 consecutive elements of T as floats (16 B for bf16, 32 B for float)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void load_vec(const bf16* p, float (&v)[8]) {
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   uint4 t = *reinterpret_cast<const uint4*>(p);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
@@ -116,30 +150,47 @@ __device__ __forceinline__ void load_vec(const bf16* p, float (&v)[8]) {
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void store_vec(bf16* p, const float (&v)[8]) {
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   uint4 t;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = t;
 }
-// pair store
-__device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-__device__ __forceinline__ void store_pair(bf16* p, float a, float b) {
-  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
-__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ float2 load_pair(const bf16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  uint2 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f(bf16& d, float v) { d = __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float lrelu_f(float x) { return x >= 0.f ? x : 0.2f * x; }
 
-// float max via integer atomics (handles negatives)
+// float max via integer atomics (handles negatives); *addr must be initialised to -inf
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f)
     atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -163,9 +214,10 @@ __device__ __forceinline__ void bilinear_taps(int dst, int n_in, int n_out, int&
   if (n_in == n_out) { i0 = dst; i1 = dst; lam = 0.f; return; }
   float scale = (float)n_in / (float)n_out;
   float src = fmaxf(((float)dst + 0.5f) * scale - 0.5f, 0.f);
-  i0 = min((int)floorf(src), n_in - 1);
+  i0 = min((int)src, n_in - 1);
   i1 = min(i0 + 1, n_in - 1);
   lam = src - (float)i0;
 }
+#endif  // __CUDACC__
 
 }  // namespace rf

@@ -1,0 +1,173 @@
+// Callers either side of the forward and the WFB gated-GELU FFN.
+#include "rf_kernels.cuh"
+
+namespace rf {
+
+// test.py:117-118 -- clamp(0,1) * 255 -> uint8 (C-style truncation, like numpy astype) -> HWC
+__global__ void __launch_bounds__(256) k_post_u8(const float* __restrict__ in, unsigned char* __restrict__ out, i64 hw) {
+  const i64 b = blockIdx.y;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (i64)gridDim.x * blockDim.x) {
+    unsigned char v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = in[(b * 3 + c) * hw + i];
+      x = fminf(fmaxf(x, 0.f), 1.f);           // torch.clamp (NaN propagates; cast of NaN is 0 here)
+      v[c] = (unsigned char)(int)__fmul_rn(x, 255.f);
+    }
+    unsigned char* o = out + (b * hw + i) * 3;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+  }
+}
+
+// WFB/load_dataset.py:88-89 and correctdataloader.py:103
+__global__ void __launch_bounds__(256)
+k_pre_u16(const unsigned short* __restrict__ raw, float* __restrict__ out, float black, float white, float denom, float ratio,
+          i64 n) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    float x = fminf(fmaxf((float)raw[i], black), white);
+    x = __fmul_rn(__fdiv_rn(__fsub_rn(x, black), denom), ratio);
+    out[i] = fminf(x, 1.0f);
+  }
+}
+
+// gated-GELU core: x1 = dwA(t)+bA, x2 = dwB(t)+bB, g = gelu(x2)*x1 + gelu(x1)*x2     (WFB/model.py:61-63)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gated_dw(const T* __restrict__ t, const float* __restrict__ wA, const float* __restrict__ bA, const float* __restrict__ wB,
+           const float* __restrict__ bB, T* __restrict__ out, int H, int W, int Cn) {
+  const i64 b = blockIdx.y;
+  const int cv = Cn >> 3;
+  const i64 total = (i64)H * W * cv;
+  const T* img = t + b * (i64)H * W * Cn;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    const i64 p = i / cv;
+    const int y = (int)(p / W), x = (int)(p % W);
+    float a1[8], a2[8];
+    load8(bA + c0, a1);
+    load8(bB + c0, a2);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        float v[8], ka[8], kb[8];
+        load8(img + ((i64)yy * W + xx) * Cn + c0, v);
+        load8(wA + ((dy + 1) * 3 + dx + 1) * Cn + c0, ka);
+        load8(wB + ((dy + 1) * 3 + dx + 1) * Cn + c0, kb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] = fmaf(v[j], ka[j], a1[j]);
+          a2[j] = fmaf(v[j], kb[j], a2[j]);
+        }
+      }
+    }
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = gelu_erf_f(a2[j]) * a1[j] + gelu_erf_f(a1[j]) * a2[j];
+    store8(out + (b * (i64)H * W + p) * Cn + c0, g);
+  }
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" {
+
+int rf_postprocess_u8(const float* in, unsigned char* out, int B, int H, int W, void* stream) {
+  if (!in || !out) return RF_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || W <= 0) return (B < 0 || H < 0 || W < 0) ? RF_ERR_BAD_SHAPE : RF_OK;
+  i64 hw = (i64)H * W;
+  unsigned gx = (unsigned)(cdivl(hw, 256) < 8 * num_sms() ? cdivl(hw, 256) : 8 * num_sms());
+  ScopedLaunch sl(RF_K_INDEX_OP, 15.0 * B * hw);
+  k_post_u8<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(in, out, hw);
+  return check_cuda(cudaGetLastError());
+}
+
+int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,
+                      void* stream) {
+  if (!raw || !out) return RF_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || W <= 0) return (B < 0 || H < 0 || W < 0) ? RF_ERR_BAD_SHAPE : RF_OK;
+  i64 n = (i64)B * H * W;
+  const float denom = (float)((double)white - (double)black + 1e-6);
+  unsigned gx = (unsigned)(cdivl(n, 256) < 8 * num_sms() ? cdivl(n, 256) : 8 * num_sms());
+  ScopedLaunch sl(RF_K_INDEX_OP, 6.0 * n);
+  k_pre_u16<<<gx, 256, 0, (cudaStream_t)stream>>>(raw, out, black, white, denom, ratio, n);
+  return check_cuda(cudaGetLastError());
+}
+
+int rf_feedforward_gated(const float* project_in_w, const float* project_in_b, const float* dwA_w, const float* dwA_b,
+                         const float* dwB_w, const float* dwB_b, const float* project_out_w, const float* project_out_b,
+                         int C, int hidden, int dtype, const float* x, float* out, int B, int H, int W, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!project_in_w || !dwA_w || !dwB_w || !project_out_w || !x || !out || !workspace) return RF_ERR_BAD_ARG;
+  if (dtype != RF_F32 && dtype != RF_BF16) return RF_ERR_BAD_ARG;
+  if (C <= 0 || C % 8 || hidden <= 0 || hidden % 8 || B <= 0 || H <= 0 || W <= 0) return RF_ERR_BAD_SHAPE;
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  ctx.dtype = dtype;
+  ctx.arena.base = (char*)workspace;
+  ctx.arena.cap = workspace_bytes;
+  if ((uintptr_t)workspace % 256) {
+    size_t adj = 256 - (uintptr_t)workspace % 256;
+    ctx.arena.base += adj;
+    ctx.arena.cap = workspace_bytes > adj ? workspace_bytes - adj : 0;
+  }
+  recorder().last_cuda_error = 0;
+  Arena& A = ctx.arena;
+  const i64 P = (i64)H * W;
+  void* w_in = A.elems((size_t)hidden * C, dtype);
+  void* w_out = A.elems((size_t)C * hidden, dtype);
+  float* b_in = A.get<float>(hidden);
+  float* b_out = A.get<float>(C);
+  float* wA = A.get<float>(9 * (size_t)hidden);
+  float* wB = A.get<float>(9 * (size_t)hidden);
+  float* bA = A.get<float>(hidden);
+  float* bB = A.get<float>(hidden);
+  void* xT = A.elems((size_t)B * P * C, dtype);
+  void* t = A.elems((size_t)B * P * hidden, dtype);
+  void* g = A.elems((size_t)B * P * hidden, dtype);
+  void* oT = A.elems((size_t)B * P * C, dtype);
+  if (!ctx.fits()) return RF_ERR_WORKSPACE;
+  launch_pack3(ctx, project_in_w, w_in, dtype, 1, 1, hidden * C, 0, 0, 1, 0, 0, 1, 0);
+  launch_pack3(ctx, project_out_w, w_out, dtype, 1, 1, hidden * C, 0, 0, 1, 0, 0, 1, 0);
+  launch_fill_f32(ctx, b_in, 0.f, hidden);
+  launch_fill_f32(ctx, b_out, 0.f, C);
+  launch_fill_f32(ctx, bA, 0.f, hidden);
+  launch_fill_f32(ctx, bB, 0.f, hidden);
+  if (project_in_b) launch_pack3(ctx, project_in_b, b_in, RF_F32, 1, 1, hidden, 0, 0, 1, 0, 0, 1, 0);
+  if (project_out_b) launch_pack3(ctx, project_out_b, b_out, RF_F32, 1, 1, C, 0, 0, 1, 0, 0, 1, 0);
+  if (dwA_b) launch_pack3(ctx, dwA_b, bA, RF_F32, 1, 1, hidden, 0, 0, 1, 0, 0, 1, 0);
+  if (dwB_b) launch_pack3(ctx, dwB_b, bB, RF_F32, 1, 1, hidden, 0, 0, 1, 0, 0, 1, 0);
+  launch_pack3(ctx, dwA_w, wA, RF_F32, 1, 9, hidden, 0, 1, 9, 0, hidden, 1, 0);
+  launch_pack3(ctx, dwB_w, wB, RF_F32, 1, 9, hidden, 0, 1, 9, 0, hidden, 1, 0);
+  launch_nchw_to_nhwc(ctx, x, xT, B, C, P);
+  GemmP g1;
+  g1.A1 = xT; g1.K1 = C; g1.lda1 = C; g1.Wt = w_in; g1.bias = b_in; g1.Y = t; g1.ldy = hidden;
+  g1.M = (int)P; g1.N = hidden; g1.B = B; g1.kernel_id = RF_K_GEMM_PW1;
+  launch_gemm(ctx, g1);
+  {
+    i64 total = P * (hidden / 8);
+    unsigned gx = (unsigned)(cdivl(total, 256) < 16 * num_sms() ? cdivl(total, 256) : 16 * num_sms());
+    ScopedLaunch sl(RF_K_DW_GELU, 2.0 * B * P * hidden * esize(dtype), 36.0 * B * P * hidden);
+    if (dtype == RF_BF16)
+      k_gated_dw<bf16><<<dim3(gx, B), 256, 0, ctx.stream>>>((const bf16*)t, wA, bA, wB, bB, (bf16*)g, H, W, hidden);
+    else
+      k_gated_dw<float><<<dim3(gx, B), 256, 0, ctx.stream>>>((const float*)t, wA, bA, wB, bB, (float*)g, H, W, hidden);
+  }
+  GemmP g2;
+  g2.A1 = g; g2.K1 = hidden; g2.lda1 = hidden; g2.Wt = w_out; g2.bias = b_out; g2.Y = oT; g2.ldy = C;
+  g2.R = xT; g2.ldr = C;
+  g2.M = (int)P; g2.N = C; g2.B = B; g2.kernel_id = RF_K_GEMM_PW2;
+  launch_gemm(ctx, g2);
+  launch_nhwc_to_nchw(ctx, oT, out, B, C, P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e);
+  return recorder().last_cuda_error ? RF_ERR_CUDA : RF_OK;
+}
+
+}  // extern "C"

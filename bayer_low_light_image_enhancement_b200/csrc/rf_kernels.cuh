@@ -1,0 +1,147 @@
+// Internal launcher interface between the kernel translation units and the orchestration (rf_model.cu).
+// All tensors are device pointers; activations are NHWC of the context's dtype unless stated otherwise.
+#pragma once
+#include "rf_common.cuh"
+
+namespace rf {
+
+// ---- kernel-layout parameters of one Conv_Transformer (pointers into the packed blob) -----------------
+struct PackedBlock {
+  int C = 0, hid = 0;
+  // FLCA (variant FLCA): [9 taps][4 maps: LL, |high|, cr, cb][C]; (variant ML): [9][6: LL1,hi1,LL2,hi2,cr,cb][C]
+  float* flca_w = nullptr;
+  float* abg = nullptr;        // alpha, beta, gamma (FLCA only)
+  float* se_w1 = nullptr;      // [hid][C]
+  float* se_b1 = nullptr;
+  float* se_w2 = nullptr;      // [C][hid]
+  float* se_b2 = nullptr;
+  float* ln1_g = nullptr; float* ln1_b = nullptr;
+  void* qkv_w = nullptr;       // T [3C][C]
+  float* qkv_b = nullptr;
+  float* qkv_dw_w = nullptr;   // [9][3C]
+  float* qkv_dw_b = nullptr;
+  float* temperature = nullptr;  // [8]
+  float* proj_w = nullptr;     // fp32 master [C][C]
+  float* proj_b = nullptr;
+  float* ln2_g = nullptr; float* ln2_b = nullptr;
+  void* pw1_w = nullptr;       // T [2C][C]
+  float* pw1_b = nullptr;
+  float* ffn_dw_w = nullptr;   // [9][2C]
+  float* ffn_dw_b = nullptr;
+  void* pw2_w = nullptr;       // T [C][2C]
+  float* pw2_b = nullptr;
+  float* red_w = nullptr;      // fp32 master [C][2C]
+  float* red_b = nullptr;
+  void* convout_w = nullptr;   // T [C][9][C]  (k = tap*C + ci)
+  float* convout_b = nullptr;
+  // ML extras
+  float* gate_w = nullptr;     // [2 levels][2][2]
+  float* gate_b = nullptr;     // [2][2]
+  float* cgate = nullptr;      // [2] = weight, bias
+  void* res_w0 = nullptr;      // T [C][C]
+  float* res_b0 = nullptr;
+  void* res_w2 = nullptr;      // T [C][C]
+  float* res_b2 = nullptr;
+};
+
+struct PackedModel {
+  int dim = 0;
+  float* rgb_w = nullptr;      // [3]
+  float* embed_w = nullptr;    // [9][4][d]
+  float* embed_b = nullptr;
+  PackedBlock blocks[7];
+  void* down_w[3] = {};        // T [C/2][9][C]
+  void* up_w[3] = {};          // T [4*Co][Ci], row = (2i+j)*Co + co
+  float* up_b[3] = {};         // [4*Co]
+  void* red_w[3] = {};         // T [C][2C]
+  float* red_b[3] = {};
+  float* head_w = nullptr;     // [9][d][12]
+  float* head_b = nullptr;     // [12]
+  float* haar = nullptr;       // [16] analysis filter (a,b,c,d taps of LL,LH,HL,HH)
+};
+
+// ---- generic "pixel-row" GEMM / implicit conv (rf_gemm.cu) ----------------------------------------------
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH_RES = 3 /* Y = R + 0.2*tanh(acc+bias) */ };
+enum { AMODE_ROWS = 0, AMODE_CONV3 = 1 };
+enum { OMODE_ROWS = 0, OMODE_CONVT = 1, OMODE_UNSHUFFLE = 2 };
+
+struct GemmP {
+  const void* A1 = nullptr; const void* A2 = nullptr;  // [B][M][K1], [B][M][K2] (A2 optional: concatenated K)
+  const void* Wt = nullptr;                             // [N][K1+K2] (K contiguous); per image if w_img != 0
+  const float* bias = nullptr;                          // [N]
+  const void* R = nullptr;                              // residual [B][M][N] (OMODE_ROWS only)
+  void* Y = nullptr;
+  i64 lda1 = 0, lda2 = 0, ldr = 0, ldy = 0;             // row pitches in elements
+  i64 w_img = 0;                                        // elements between per-image weights (0 = shared)
+  int M = 0, N = 0, K1 = 0, K2 = 0, B = 1;
+  int act = ACT_NONE, amode = AMODE_ROWS, omode = OMODE_ROWS;
+  int H = 0, W = 0;                                     // image size of the rows (m = y*W + x) for CONV3/CONVT/UNSHUFFLE
+  int kernel_id = RF_K_MISC;
+};
+void launch_gemm(Ctx& ctx, const GemmP& p);
+
+// ---- layout / index kernels (rf_index_ops.cu) --------------------------------------------------------------
+void launch_nchw_to_nhwc(Ctx& ctx, const float* in, void* out, int B, int C, i64 HW);   // fp32 NCHW -> T NHWC
+void launch_nhwc_to_nchw(Ctx& ctx, const void* in, float* out, int B, int C, i64 HW);   // T NHWC -> fp32 NCHW
+void launch_fill_f32(Ctx& ctx, float* p, float v, i64 n);
+// generic strided 3-d copy with conversion: dst[doff + a*da + b*db + c*dc] = src[a*sa + b*sb + c*sc]
+void launch_pack3(Ctx& ctx, const float* src, void* dst, int dst_dtype, int A, int Bn, int Cn, i64 sa, i64 sb, i64 sc,
+                  i64 da, i64 db, i64 dc, i64 doff);
+
+// ---- guidance (rf_guidance.cu) ---------------------------------------------------------------------------------
+// raw [B,1,H,W] -> x_ds [B,h,w,4] fp32, y_raw [B,h,w], ymax[B] (must be pre-filled with -inf)
+void launch_pack_luma(Ctx& ctx, const float* raw, float* x_ds, float* y_raw, float* ymax, const float* rgb_w, int B,
+                      int H, int W);
+// y = y_raw / max(ymax, eps); cr = r - y; cb = b - y     (planar [B,h,w] each)
+void launch_luma_finalize(Ctx& ctx, const float* x_ds, const float* y_raw, const float* ymax, float eps, float* y,
+                          float* cr, float* cb, int B, int h, int w);
+// Haar analysis of a 1-channel map + high-band magnitude: y [B,Hy,Wy] -> LL, yh [B,ceil(Hy/2),ceil(Wy/2)]
+void launch_dwt_high(Ctx& ctx, const float* y, const float* filt16, float* LL, float* yh, int B, int Hy, int Wy);
+// bilinear-resized guidance at one stage: G [B,Hf,Wf,NG]; NG = 4 (LL,yh,cr,cb) or 8 (LL1,yh1,LL2,yh2,cr,cb,chr_mag,0)
+// means (optional, ML): [B][8] sums of the NG maps over the stage (divide by Hf*Wf on use); must be zeroed.
+void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
+                           const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
+                           int NG, float* sums, int B, int Hf, int Wf);
+
+// ---- FLCA (rf_flca.cu) ---------------------------------------------------------------------------------------------
+int flca_num_partials(int C, int B, i64 P);
+// xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][nblk][C] channel sums
+void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
+                     float* partial, int nblk, int B, int Hf, int Wf, int C);
+// ML: xs = x * (ga * sig(conv(mapA)) + gb * tanh(conv(mapB)))  [mode 0, level l] or xs = x * gc*sig(conv(cr,cb)) [mode 1]
+void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,
+                        int level, int B, int Hf, int Wf, int C);
+// gates[b][0..5] = (alpha_0, beta_0, alpha_1, beta_1, gamma, 0) from the stage sums
+void launch_pyr_gates(Ctx& ctx, const float* sums, i64 P, const float* gate_w, const float* gate_b, const float* cgate,
+                      float* gates, int B);
+// per-channel sums of an NHWC tensor -> partial [B][nblk][C]
+void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int B, i64 P, int C);
+// s = sigmoid(W2 relu(W1 mean + b1) + b2)  -> scale [B][C]
+void launch_se_finalize(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1,
+                        const float* w2, const float* b2, float* scale, int B, int C, int hid);
+// wred[b][n][k] = red_w[n][k] * (k < C ? scale[b][k] : 1)   (T output)
+void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* wred, int B, int C);
+// out = x * scale[b][c]
+void launch_scale_channels(Ctx& ctx, const void* x, const float* scale, void* out, int B, i64 P, int C);
+
+// ---- transformer branch (rf_attn.cu) -----------------------------------------------------------------------------
+void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, void* out, float eps, int mode, i64 rows,
+                      int C);
+// depthwise 3x3 on qkv_pre [B,H,W,3C]; writes v [B,H,W,C]; accumulates stats[b] = {gram [8][c][c], qn2 [C], kn2 [C]}
+void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, float* stats, int B,
+                       int H, int W, int C);
+inline i64 attn_stats_floats(int C) { return (i64)C * (C / 8) + 2 * C; }
+// Mw[b] = proj_w * blockdiag(softmax(gram / (|q||k|) * temperature))   (T [B][C][C])
+void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
+                          int C);
+// depthwise 3x3 (+bias) with optional exact GELU: in/out [B,H,W,Cn]
+void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H,
+                   int W, int Cn, int kernel_id);
+// embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
+void launch_embed(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d);
+void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float* out, int B, int h, int w_, int d);
+// ML tail: out += 0.12*(mean(up(in_rgb)) - mean(out)); out += 0.03*(up8(LL2) - Y(out))
+void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_);
+void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_);
+
+}  // namespace rf

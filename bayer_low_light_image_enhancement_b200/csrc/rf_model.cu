@@ -1,0 +1,665 @@
+// Orchestration of the RawFormer forward (FLCA_RF.py:330-370, ML_RF.py:356-416) and of its sub-modules, plus the
+// C-ABI entry points that take PyTorch-layout weights / NCHW fp32 tensors (include/rawformer_b200.h).
+//
+// Everything here is host code that enqueues kernels on the caller's stream and bump-allocates from the caller's
+// workspace.  The same code runs in "dry" mode to answer the *_workspace_bytes queries.
+#include <string.h>
+
+#include "rf_kernels.cuh"
+
+namespace rf {
+
+int profile_begin(cudaStream_t stream, int cap);
+int profile_end(float* ms_host, int* ids_host, int cap_out, int* n_host);
+
+// ---------------------------------------------------------------------------------------------
+// packed-parameter layout (a pure function of dim/dtype/variant, so pack and forward agree)
+// ---------------------------------------------------------------------------------------------
+struct Layout {
+  char* base;
+  size_t off = 0;
+  explicit Layout(void* b) : base((char*)b) {}
+  void* take(size_t bytes) {
+    off = align_up(off, 256);
+    char* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  float* f32(size_t n) { return (float*)take(n * 4); }
+  void* elems(size_t n, int dtype) { return take(n * esize(dtype)); }
+};
+
+static PackedBlock layout_block(Layout& L, int C, int dtype, int variant) {
+  PackedBlock pb;
+  pb.C = C;
+  pb.hid = C / 8 > 8 ? C / 8 : 8;
+  const size_t c = C;
+  pb.flca_w = L.f32(9 * (variant == RF_VARIANT_ML ? 6 : 4) * c);
+  pb.abg = L.f32(4);
+  pb.se_w1 = L.f32(pb.hid * c); pb.se_b1 = L.f32(pb.hid);
+  pb.se_w2 = L.f32(c * pb.hid); pb.se_b2 = L.f32(c);
+  pb.ln1_g = L.f32(c); pb.ln1_b = L.f32(c);
+  pb.qkv_w = L.elems(3 * c * c, dtype); pb.qkv_b = L.f32(3 * c);
+  pb.qkv_dw_w = L.f32(27 * c); pb.qkv_dw_b = L.f32(3 * c);
+  pb.temperature = L.f32(8);
+  pb.proj_w = L.f32(c * c); pb.proj_b = L.f32(c);
+  pb.ln2_g = L.f32(c); pb.ln2_b = L.f32(c);
+  pb.pw1_w = L.elems(2 * c * c, dtype); pb.pw1_b = L.f32(2 * c);
+  pb.ffn_dw_w = L.f32(18 * c); pb.ffn_dw_b = L.f32(2 * c);
+  pb.pw2_w = L.elems(2 * c * c, dtype); pb.pw2_b = L.f32(c);
+  pb.red_w = L.f32(2 * c * c); pb.red_b = L.f32(c);
+  pb.convout_w = L.elems(9 * c * c, dtype); pb.convout_b = L.f32(c);
+  if (variant == RF_VARIANT_ML) {
+    pb.gate_w = L.f32(8); pb.gate_b = L.f32(4); pb.cgate = L.f32(2);
+    pb.res_w0 = L.elems(c * c, dtype); pb.res_b0 = L.f32(c);
+    pb.res_w2 = L.elems(c * c, dtype); pb.res_b2 = L.f32(c);
+  }
+  return pb;
+}
+
+static const int kBlockStage[7] = {0, 1, 2, 3, 2, 1, 0};
+
+static PackedModel layout_model(Layout& L, int dim, int dtype, int variant) {
+  PackedModel pm;
+  pm.dim = dim;
+  const size_t d = dim;
+  pm.rgb_w = L.f32(4);
+  pm.haar = L.f32(16);
+  pm.embed_w = L.f32(36 * d); pm.embed_b = L.f32(d);
+  for (int i = 0; i < 7; ++i) pm.blocks[i] = layout_block(L, dim << kBlockStage[i], dtype, variant);
+  for (int n = 0; n < 3; ++n) {
+    const size_t C = d << n;           // down{n+1}: C -> C/2 (then unshuffle -> 2C)
+    pm.down_w[n] = L.elems((C / 2) * 9 * C, dtype);
+    const size_t Co = d << (2 - n);    // up{n+1}: 2Co -> Co
+    pm.up_w[n] = L.elems(4 * Co * 2 * Co, dtype);
+    pm.up_b[n] = L.f32(4 * Co);
+    pm.red_w[n] = L.elems(Co * 2 * Co, dtype);
+    pm.red_b[n] = L.f32(Co);
+  }
+  pm.head_w = L.f32(9 * d * 12); pm.head_b = L.f32(12);
+  return pm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing from PyTorch layouts
+// ---------------------------------------------------------------------------------------------
+static void copy_f32(Ctx& ctx, const float* src, float* dst, i64 n) {
+  if (src) launch_pack3(ctx, src, dst, RF_F32, 1, 1, (int)n, 0, 0, 1, 0, 0, 1, 0);
+}
+static void copy_T(Ctx& ctx, const float* src, void* dst, i64 n) {
+  if (src) launch_pack3(ctx, src, dst, ctx.dtype, 1, 1, (int)n, 0, 0, 1, 0, 0, 1, 0);
+}
+// depthwise / 1-input-channel 3x3 [Cn,Cin,3,3] (input channel `ch`) -> dst[(t*NW + g)*Cn + c]
+static void pack_taps(Ctx& ctx, const float* src, int Cin, int ch, float* dst, int NW, int g, int Cn) {
+  if (src) launch_pack3(ctx, src + ch * 9, dst, RF_F32, 1, 9, Cn, 0, 1, (i64)Cin * 9, 0, (i64)NW * Cn, 1, (i64)g * Cn);
+}
+// dense 3x3 [N,Ci,3,3] -> T [N][9][Ci]
+static void pack_conv3(Ctx& ctx, const float* src, void* dst, int N, int Ci) {
+  if (src) launch_pack3(ctx, src, dst, ctx.dtype, N, 9, Ci, (i64)Ci * 9, 1, 9, (i64)9 * Ci, Ci, 1, 0);
+}
+
+static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& pb, int variant) {
+  const int C = pb.C, hid = pb.hid;
+  if (variant == RF_VARIANT_ML) {
+    for (int l = 0; l < 2; ++l) {
+      pack_taps(ctx, w.pyr_low_w[l], 1, 0, pb.flca_w, 6, 2 * l, C);
+      pack_taps(ctx, w.pyr_high_w[l], 1, 0, pb.flca_w, 6, 2 * l + 1, C);
+      copy_f32(ctx, w.pyr_gate_w[l], pb.gate_w + 4 * l, 4);
+      copy_f32(ctx, w.pyr_gate_b[l], pb.gate_b + 2 * l, 2);
+    }
+    pack_taps(ctx, w.flca_chroma_w, 2, 0, pb.flca_w, 6, 4, C);
+    pack_taps(ctx, w.flca_chroma_w, 2, 1, pb.flca_w, 6, 5, C);
+    copy_f32(ctx, w.pyr_cgate_w, pb.cgate, 1);
+    copy_f32(ctx, w.pyr_cgate_b, pb.cgate + 1, 1);
+    copy_T(ctx, w.pyr_res_w0, pb.res_w0, (i64)C * C);
+    copy_f32(ctx, w.pyr_res_b0, pb.res_b0, C);
+    copy_T(ctx, w.pyr_res_w2, pb.res_w2, (i64)C * C);
+    copy_f32(ctx, w.pyr_res_b2, pb.res_b2, C);
+  } else {
+    pack_taps(ctx, w.flca_low_w, 1, 0, pb.flca_w, 4, 0, C);
+    pack_taps(ctx, w.flca_high_w, 1, 0, pb.flca_w, 4, 1, C);
+    pack_taps(ctx, w.flca_chroma_w, 2, 0, pb.flca_w, 4, 2, C);
+    pack_taps(ctx, w.flca_chroma_w, 2, 1, pb.flca_w, 4, 3, C);
+    copy_f32(ctx, w.flca_alpha, pb.abg, 1);
+    copy_f32(ctx, w.flca_beta, pb.abg + 1, 1);
+    copy_f32(ctx, w.flca_gamma, pb.abg + 2, 1);
+  }
+  copy_f32(ctx, w.flca_se_w1, pb.se_w1, (i64)hid * C);
+  copy_f32(ctx, w.flca_se_b1, pb.se_b1, hid);
+  copy_f32(ctx, w.flca_se_w2, pb.se_w2, (i64)C * hid);
+  copy_f32(ctx, w.flca_se_b2, pb.se_b2, C);
+  copy_f32(ctx, w.norm1_w, pb.ln1_g, C);
+  copy_f32(ctx, w.norm1_b, pb.ln1_b, C);
+  copy_T(ctx, w.qkv_w, pb.qkv_w, (i64)3 * C * C);
+  copy_f32(ctx, w.qkv_b, pb.qkv_b, 3 * C);
+  pack_taps(ctx, w.qkv_dw_w, 1, 0, pb.qkv_dw_w, 1, 0, 3 * C);
+  copy_f32(ctx, w.qkv_dw_b, pb.qkv_dw_b, 3 * C);
+  copy_f32(ctx, w.temperature, pb.temperature, 8);
+  copy_f32(ctx, w.proj_w, pb.proj_w, (i64)C * C);
+  copy_f32(ctx, w.proj_b, pb.proj_b, C);
+  copy_f32(ctx, w.norm2_w, pb.ln2_g, C);
+  copy_f32(ctx, w.norm2_b, pb.ln2_b, C);
+  copy_T(ctx, w.pw1_w, pb.pw1_w, (i64)2 * C * C);
+  copy_f32(ctx, w.pw1_b, pb.pw1_b, 2 * C);
+  pack_taps(ctx, w.ffn_dw_w, 1, 0, pb.ffn_dw_w, 1, 0, 2 * C);
+  copy_f32(ctx, w.ffn_dw_b, pb.ffn_dw_b, 2 * C);
+  copy_T(ctx, w.pw2_w, pb.pw2_w, (i64)2 * C * C);
+  copy_f32(ctx, w.pw2_b, pb.pw2_b, C);
+  copy_f32(ctx, w.reduce_w, pb.red_w, (i64)2 * C * C);
+  copy_f32(ctx, w.reduce_b, pb.red_b, C);
+  pack_conv3(ctx, w.convout_w, pb.convout_w, C, C);
+  copy_f32(ctx, w.convout_b, pb.convout_b, C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// building blocks on NHWC activations
+// ---------------------------------------------------------------------------------------------
+struct Stage {           // guidance of one U-Net stage
+  int H = 0, W = 0;
+  float* G = nullptr;    // [B,H,W,NG]
+  float* sums = nullptr; // ML: [B][8] sums of the guidance maps
+};
+
+static GemmP gemm_rows(const void* A, int K, const void* Wt, const float* bias, void* Y, int N, int B, i64 M, int kid) {
+  GemmP p;
+  p.A1 = A; p.K1 = K; p.lda1 = K;
+  p.Wt = Wt; p.bias = bias; p.Y = Y; p.ldy = N;
+  p.M = (int)M; p.N = N; p.B = B; p.kernel_id = kid;
+  return p;
+}
+
+// FLCA branch: returns xmod (un-scaled) and the SE scale [B][C]
+static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void* feat, const Stage& sg, int B, void** xmod_out,
+                        float** scale_out) {
+  const int C = pb.C, H = sg.H, W = sg.W;
+  const i64 P = (i64)H * W;
+  Arena& A = ctx.arena;
+  const int nblk = flca_num_partials(C, B, P);
+  float* partial = A.get<float>((size_t)B * nblk * C);
+  float* scale = A.get<float>((size_t)B * C);
+  void* xmod = nullptr;
+  if (variant == RF_VARIANT_FLCA) {
+    xmod = A.elems((size_t)B * P * C, ctx.dtype);
+    launch_flca_mod(ctx, feat, sg.G, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
+  } else {
+    float* gates = A.get<float>((size_t)B * 6);
+    launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
+    void* xa = A.elems((size_t)B * P * C, ctx.dtype);
+    void* xb = A.elems((size_t)B * P * C, ctx.dtype);
+    const size_t mk = A.mark();
+    void* xs = A.elems((size_t)B * P * C, ctx.dtype);
+    void* t1 = A.elems((size_t)B * P * C, ctx.dtype);
+    const void* cur = feat;
+    void* nxt = xa;
+    for (int step = 0; step < 3; ++step) {
+      launch_pyr_spatial(ctx, cur, sg.G, pb.flca_w, gates, xs, step < 2 ? 0 : 1, step < 2 ? step : 0, B, H, W, C);
+      GemmP g1 = gemm_rows(xs, C, pb.res_w0, pb.res_b0, t1, C, B, P, RF_K_GEMM_PYR_RES1);
+      g1.act = ACT_RELU;
+      launch_gemm(ctx, g1);
+      GemmP g2 = gemm_rows(t1, C, pb.res_w2, pb.res_b2, nxt, C, B, P, RF_K_GEMM_PYR_RES2);
+      g2.act = ACT_TANH_RES;
+      g2.R = cur; g2.ldr = C;
+      launch_gemm(ctx, g2);
+      cur = nxt;
+      nxt = (nxt == xa) ? xb : xa;
+    }
+    A.release(mk);
+    xmod = const_cast<void*>(cur);  // == xa after three steps
+    launch_channel_sums(ctx, xmod, partial, nblk, B, P, C);
+  }
+  launch_se_finalize(ctx, partial, nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C, pb.hid);
+  *xmod_out = xmod;
+  *scale_out = scale;
+}
+
+// out = (resid ? resid : 0) + Attention(xin)   (xin is already normalised when called from the transformer block)
+static void attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W) {
+  const int C = pb.C;
+  const i64 P = (i64)H * W;
+  Arena& A = ctx.arena;
+  const size_t mk = A.mark();
+  void* qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
+  launch_gemm(ctx, gemm_rows(xin, C, pb.qkv_w, pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV));
+  void* v = A.elems((size_t)B * P * C, ctx.dtype);
+  const i64 nst = attn_stats_floats(C);
+  float* stats = A.get<float>((size_t)B * nst);
+  launch_fill_f32(ctx, stats, 0.f, B * nst);
+  launch_dwqkv_gram(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, v, stats, B, H, W, C);
+  void* Mw = A.elems((size_t)B * C * C, ctx.dtype);
+  launch_attn_finalize(ctx, stats, pb.temperature, pb.proj_w, Mw, B, C);
+  GemmP g = gemm_rows(v, C, Mw, pb.proj_b, out, C, B, P, RF_K_GEMM_PROJ);
+  g.w_img = (i64)C * C;
+  g.R = resid; g.ldr = C;
+  launch_gemm(ctx, g);
+  A.release(mk);
+}
+
+// out = (resid ? resid : 0) + conv_ffn(xin)
+static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W) {
+  const int C = pb.C;
+  const i64 P = (i64)H * W;
+  Arena& A = ctx.arena;
+  const size_t mk = A.mark();
+  void* hpre = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+  launch_gemm(ctx, gemm_rows(xin, C, pb.pw1_w, pb.pw1_b, hpre, 2 * C, B, P, RF_K_GEMM_PW1));
+  void* h = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+  launch_dwconv(ctx, hpre, pb.ffn_dw_w, pb.ffn_dw_b, h, 1, B, H, W, 2 * C, RF_K_DW_GELU);
+  GemmP g = gemm_rows(h, 2 * C, pb.pw2_w, pb.pw2_b, out, C, B, P, RF_K_GEMM_PW2);
+  g.R = resid; g.ldr = C;
+  launch_gemm(ctx, g);
+  A.release(mk);
+}
+
+static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void* out, int B, int H, int W) {
+  const int C = pb.C;
+  const i64 P = (i64)H * W;
+  Arena& A = ctx.arena;
+  const size_t mk = A.mark();
+  void* ln = A.elems((size_t)B * P * C, ctx.dtype);
+  void* x1 = A.elems((size_t)B * P * C, ctx.dtype);
+  launch_layernorm(ctx, feat, pb.ln1_g, pb.ln1_b, ln, 1e-5f, 0, B * P, C);
+  attention(ctx, pb, ln, feat, x1, B, H, W);
+  launch_layernorm(ctx, x1, pb.ln2_g, pb.ln2_b, ln, 1e-5f, 0, B * P, C);
+  ffn(ctx, pb, ln, x1, out, B, H, W);
+  A.release(mk);
+}
+
+static void conv3x3(Ctx& ctx, const void* in, const void* w, const float* bias, void* out, int Cin, int N, int act, int omode,
+                    int B, int H, int W, int kid) {
+  GemmP p;
+  p.A1 = in; p.K1 = 9 * Cin; p.lda1 = Cin; p.amode = AMODE_CONV3;
+  p.Wt = w; p.bias = bias; p.Y = out;
+  p.ldy = omode == OMODE_UNSHUFFLE ? 4 * N : N;
+  p.M = H * W; p.N = N; p.B = B; p.H = H; p.W = W; p.act = act; p.omode = omode; p.kernel_id = kid;
+  launch_gemm(ctx, p);
+}
+
+static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const void* feat, const Stage& sg, void* out,
+                             int B) {
+  const int C = pb.C, H = sg.H, W = sg.W;
+  const i64 P = (i64)H * W;
+  Arena& A = ctx.arena;
+  const size_t mk = A.mark();
+  void* xmod;
+  float* scale;
+  flca_branch(ctx, pb, variant, feat, sg, B, &xmod, &scale);
+  void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
+  launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
+  void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
+  transformer(ctx, pb, feat, x2, B, H, W);
+  void* xr = A.elems((size_t)B * P * C, ctx.dtype);
+  GemmP g = gemm_rows(xmod, C, wred, pb.red_b, xr, C, B, P, RF_K_GEMM_CAT_REDUCE);
+  g.A2 = x2; g.K2 = C; g.lda2 = C;
+  g.w_img = (i64)C * 2 * C;
+  launch_gemm(ctx, g);
+  conv3x3(ctx, xr, pb.convout_w, pb.convout_b, out, C, C, ACT_LRELU, OMODE_ROWS, B, H, W, RF_K_CONV3X3_OUT);
+  A.release(mk);
+}
+
+// guidance of one stage from planar y-derived maps
+static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const float* LL1, const float* yh1, int H1, int W1,
+                       const float* LL2, const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy,
+                       int B) {
+  const int NG = variant == RF_VARIANT_ML ? 8 : 4;
+  sg.H = Hf; sg.W = Wf;
+  sg.G = ctx.arena.get<float>((size_t)B * Hf * Wf * NG);
+  sg.sums = nullptr;
+  if (variant == RF_VARIANT_ML) {
+    sg.sums = ctx.arena.get<float>((size_t)B * 8);
+    launch_fill_f32(ctx, sg.sums, 0.f, (i64)B * 8);
+  }
+  launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf);
+}
+
+struct GuidanceMaps {
+  float *LL1 = nullptr, *yh1 = nullptr, *LL2 = nullptr, *yh2 = nullptr;
+  int H1 = 0, W1 = 0, H2 = 0, W2 = 0;
+};
+static GuidanceMaps make_pyramid(Ctx& ctx, int variant, const float* y, const float* filt, int B, int Hy, int Wy) {
+  GuidanceMaps g;
+  g.H1 = (Hy + 1) / 2; g.W1 = (Wy + 1) / 2;
+  g.LL1 = ctx.arena.get<float>((size_t)B * g.H1 * g.W1);
+  g.yh1 = ctx.arena.get<float>((size_t)B * g.H1 * g.W1);
+  launch_dwt_high(ctx, y, filt, g.LL1, g.yh1, B, Hy, Wy);
+  if (variant == RF_VARIANT_ML) {
+    g.H2 = (g.H1 + 1) / 2; g.W2 = (g.W1 + 1) / 2;
+    g.LL2 = ctx.arena.get<float>((size_t)B * g.H2 * g.W2);
+    g.yh2 = ctx.arena.get<float>((size_t)B * g.H2 * g.W2);
+    launch_dwt_high(ctx, g.LL1, filt, g.LL2, g.yh2, B, g.H1, g.W1);
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole model
+// ---------------------------------------------------------------------------------------------
+static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const float* raw, float* out, int B, int H, int W) {
+  const int d = pm.dim;
+  const int h = H / 2, w = W / 2;
+  Arena& A = ctx.arena;
+  const i64 P0 = (i64)h * w;
+  float* x_ds = A.get<float>((size_t)B * P0 * 4);
+  float* y_raw = A.get<float>((size_t)B * P0);
+  float* ymax = A.get<float>((size_t)B);
+  float* y = A.get<float>((size_t)B * P0);
+  float* cr = A.get<float>((size_t)B * P0);
+  float* cb = A.get<float>((size_t)B * P0);
+  launch_fill_f32(ctx, ymax, -INFINITY, B);
+  launch_pack_luma(ctx, raw, x_ds, y_raw, ymax, pm.rgb_w, B, H, W);
+  launch_luma_finalize(ctx, x_ds, y_raw, ymax, 1e-6f, y, cr, cb, B, h, w);
+  GuidanceMaps gm = make_pyramid(ctx, variant, y, pm.haar, B, h, w);
+  Stage st[4];
+  for (int s = 0; s < 4; ++s)
+    make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w,
+               B);
+  auto feat_buf = [&](int s) { return A.elems((size_t)B * (P0 >> (2 * s)) * ((size_t)d << s), ctx.dtype); };
+  void* x0 = feat_buf(0);
+  launch_embed(ctx, x_ds, pm.embed_w, pm.embed_b, x0, B, h, w, d);
+  void* enc[4];
+  void* cur = x0;
+  for (int s = 0; s < 4; ++s) {
+    enc[s] = feat_buf(s);
+    conv_transformer(ctx, pm.blocks[s], variant, cur, st[s], enc[s], B);
+    if (s < 3) {
+      void* pooled = feat_buf(s + 1);
+      const int C = d << s;
+      conv3x3(ctx, enc[s], pm.down_w[s], nullptr, pooled, C, C / 2, ACT_NONE, OMODE_UNSHUFFLE, B, h >> s, w >> s,
+              RF_K_DOWN_CONV);
+      cur = pooled;
+    }
+  }
+  cur = enc[3];
+  for (int n = 0; n < 3; ++n) {
+    const int s = 2 - n;               // output stage
+    const int Co = d << s, Ci = 2 * Co;
+    const int Hs = h >> s, Ws = w >> s;
+    const i64 Ps = (i64)Hs * Ws;
+    void* up = feat_buf(s);
+    GemmP g = gemm_rows(cur, Ci, pm.up_w[n], pm.up_b[n], up, 4 * Co, B, Ps / 4, RF_K_UP_CONVT);
+    g.omode = OMODE_CONVT; g.H = Hs / 2; g.W = Ws / 2; g.ldy = Co;
+    launch_gemm(ctx, g);
+    void* fused = feat_buf(s);
+    GemmP r = gemm_rows(up, Co, pm.red_w[n], pm.red_b[n], fused, Co, B, Ps, RF_K_SKIP_REDUCE);
+    r.A2 = enc[s]; r.K2 = Co; r.lda2 = Co;
+    launch_gemm(ctx, r);
+    void* dec = feat_buf(s);
+    conv_transformer(ctx, pm.blocks[4 + n], variant, fused, st[s], dec, B);
+    cur = dec;
+  }
+  launch_head(ctx, cur, pm.head_w, pm.head_b, out, B, h, w, d);
+  if (variant == RF_VARIANT_ML) {
+    float* sums = A.get<float>((size_t)B * 8);
+    launch_fill_f32(ctx, sums, 0.f, (i64)B * 8);
+    launch_tail_stats(ctx, out, x_ds, sums, B, h, w);
+    launch_tail_apply(ctx, out, sums, gm.LL2, gm.H2, gm.W2, B, h, w);
+  }
+  return RF_OK;
+}
+
+static int check_model_args(int dim, int dtype, int variant, int B, int H, int W) {
+  if (dtype != RF_F32 && dtype != RF_BF16) return RF_ERR_BAD_ARG;
+  if (variant != RF_VARIANT_FLCA && variant != RF_VARIANT_ML) return RF_ERR_BAD_ARG;
+  if (dim <= 0 || dim % 8) return RF_ERR_BAD_SHAPE;
+  if (dim > 64) return RF_ERR_UNSUPPORTED;  // C <= 512 (Gram register tiling, TMEM columns)
+  if (B <= 0 || H <= 0 || W <= 0 || H % 16 || W % 16) return RF_ERR_BAD_SHAPE;
+  return RF_OK;
+}
+
+static int check_block_args(int C, int dtype, int B, int H, int W) {
+  if (dtype != RF_F32 && dtype != RF_BF16) return RF_ERR_BAD_ARG;
+  if (C <= 0 || C % 8) return RF_ERR_BAD_SHAPE;
+  if (C > 512) return RF_ERR_UNSUPPORTED;
+  if (B <= 0 || H <= 0 || W <= 0) return RF_ERR_BAD_SHAPE;
+  return RF_OK;
+}
+
+static int finish(Ctx& ctx) {
+  if (!ctx.fits()) return RF_ERR_WORKSPACE;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e);
+  if (recorder().last_cuda_error != 0) return RF_ERR_CUDA;
+  return RF_OK;
+}
+
+static Ctx make_ctx(void* ws, size_t ws_bytes, void* stream, int dtype, bool dry) {
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  ctx.arena.base = dry ? nullptr : (char*)ws;
+  ctx.arena.cap = ws_bytes;
+  if (!dry && ws != nullptr && (uintptr_t)ws % 256) {  // keep every arena block 256-byte aligned
+    size_t adj = 256 - (uintptr_t)ws % 256;
+    ctx.arena.base += adj;
+    ctx.arena.cap = ws_bytes > adj ? ws_bytes - adj : 0;
+  }
+  ctx.dry = dry;
+  ctx.dtype = dtype;
+  if (!dry) recorder().last_cuda_error = 0;
+  return ctx;
+}
+
+// sub-module entry: pack the given weights into the arena, convert NCHW->NHWC, build the stage guidance
+struct BlockEnv {
+  PackedBlock pb;
+  Stage sg;
+  void* x = nullptr;     // NHWC input
+  void* outT = nullptr;  // NHWC output
+};
+
+template <typename F>
+static int run_block_entry(const rf_block_weights* w, int C, int dtype, int variant, const float* feat, const float* y,
+                           const float* cr, const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy, void* ws,
+                           size_t ws_bytes, void* stream, bool dry, size_t* peak, F body) {
+  Ctx ctx = make_ctx(ws, ws_bytes, stream, dtype, dry);
+  Arena& A = ctx.arena;
+  BlockEnv env;
+  {
+    Layout L(dry ? nullptr : A.base);
+    env.pb = layout_block(L, C, dtype, variant);
+    A.alloc(L.off);
+  }
+  const i64 P = (i64)Hf * Wf;
+  env.x = A.elems((size_t)B * P * C, dtype);
+  env.outT = A.elems((size_t)B * P * C, dtype);
+  if (!dry && !ctx.fits()) return RF_ERR_WORKSPACE;
+  if (!dry) {
+    // the workspace must hold the plan; re-check after the body via finish()
+    pack_block(ctx, *w, env.pb, variant);
+    launch_nchw_to_nhwc(ctx, feat, env.x, B, C, P);
+  }
+  if (y != nullptr || dry) {
+    if (Hy > 0 && Wy > 0) {
+      GuidanceMaps gm = make_pyramid(ctx, variant, y, w ? w->flca_filt : nullptr, B, Hy, Wy);
+      make_stage(ctx, variant, env.sg, Hf, Wf, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, Hy, Wy, B);
+    }
+  }
+  env.sg.H = Hf; env.sg.W = Wf;
+  if (!dry && !ctx.fits()) return RF_ERR_WORKSPACE;
+  body(ctx, env);
+  if (!dry && !ctx.fits()) return RF_ERR_WORKSPACE;
+  launch_nhwc_to_nchw(ctx, env.outT, out, B, C, P);
+  if (peak) *peak = A.peak;
+  return dry ? RF_OK : finish(ctx);
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" {
+
+size_t rf_block_workspace_bytes(int C, int dtype, int B, int Hf, int Wf, int Hy, int Wy) {
+  if (check_block_args(C, dtype, B, Hf, Wf) != RF_OK) return 0;
+  size_t best = 0;
+  for (int variant = 0; variant < 2; ++variant) {
+    size_t peak = 0;
+    run_block_entry(nullptr, C, dtype, variant, nullptr, nullptr, nullptr, nullptr, nullptr, B, Hf, Wf, Hy, Wy, nullptr, 0,
+                    nullptr, true, &peak, [&](Ctx& ctx, BlockEnv& env) {
+                      conv_transformer(ctx, env.pb, variant, env.x, env.sg, env.outT, B);
+                    });
+    if (peak > best) best = peak;
+  }
+  return best + 4096;
+}
+
+#define RF_BLOCK_PRECHECK(need_guidance)                                              \
+  if (!w || !out || !workspace) return RF_ERR_BAD_ARG;                                \
+  {                                                                                   \
+    int _s = check_block_args(C, dtype, B, H_, W_);                                   \
+    if (_s != RF_OK) return _s;                                                       \
+  }
+
+int rf_flca_forward(const rf_block_weights* w, int C, int dtype, int variant, const float* feat, const float* y,
+                    const float* cr, const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  const int H_ = Hf, W_ = Wf;
+  RF_BLOCK_PRECHECK(true)
+  if (!feat || !y || !cr || !cb || Hy <= 0 || Wy <= 0) return RF_ERR_BAD_ARG;
+  if (variant != RF_VARIANT_FLCA && variant != RF_VARIANT_ML) return RF_ERR_BAD_ARG;
+  if (!w->flca_filt) return RF_ERR_BAD_ARG;
+  return run_block_entry(w, C, dtype, variant, feat, y, cr, cb, out, B, Hf, Wf, Hy, Wy, workspace, workspace_bytes, stream,
+                         false, nullptr, [&](Ctx& ctx, BlockEnv& env) {
+                           void* xmod;
+                           float* scale;
+                           flca_branch(ctx, env.pb, variant, env.x, env.sg, B, &xmod, &scale);
+                           launch_scale_channels(ctx, xmod, scale, env.outT, B, (i64)Hf * Wf, C);
+                         });
+}
+
+int rf_attention_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  const int H_ = H, W_ = W;
+  RF_BLOCK_PRECHECK(false)
+  if (!x) return RF_ERR_BAD_ARG;
+  return run_block_entry(w, C, dtype, RF_VARIANT_FLCA, x, nullptr, nullptr, nullptr, out, B, H, W, 0, 0, workspace,
+                         workspace_bytes, stream, false, nullptr,
+                         [&](Ctx& ctx, BlockEnv& env) { attention(ctx, env.pb, env.x, nullptr, env.outT, B, H, W); });
+}
+
+int rf_conv_ffn_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  const int H_ = H, W_ = W;
+  RF_BLOCK_PRECHECK(false)
+  if (!x) return RF_ERR_BAD_ARG;
+  return run_block_entry(w, C, dtype, RF_VARIANT_FLCA, x, nullptr, nullptr, nullptr, out, B, H, W, 0, 0, workspace,
+                         workspace_bytes, stream, false, nullptr,
+                         [&](Ctx& ctx, BlockEnv& env) { ffn(ctx, env.pb, env.x, nullptr, env.outT, B, H, W); });
+}
+
+int rf_transformer_block_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H,
+                                 int W, void* workspace, size_t workspace_bytes, void* stream) {
+  const int H_ = H, W_ = W;
+  RF_BLOCK_PRECHECK(false)
+  if (!x) return RF_ERR_BAD_ARG;
+  return run_block_entry(w, C, dtype, RF_VARIANT_FLCA, x, nullptr, nullptr, nullptr, out, B, H, W, 0, 0, workspace,
+                         workspace_bytes, stream, false, nullptr,
+                         [&](Ctx& ctx, BlockEnv& env) { transformer(ctx, env.pb, env.x, env.outT, B, H, W); });
+}
+
+int rf_conv_transformer_forward(const rf_block_weights* w, int C, int dtype, int variant, const float* feat, const float* y,
+                                const float* cr, const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  const int H_ = Hf, W_ = Wf;
+  RF_BLOCK_PRECHECK(true)
+  if (!feat || !y || !cr || !cb || Hy <= 0 || Wy <= 0) return RF_ERR_BAD_ARG;
+  if (variant != RF_VARIANT_FLCA && variant != RF_VARIANT_ML) return RF_ERR_BAD_ARG;
+  if (!w->flca_filt) return RF_ERR_BAD_ARG;
+  return run_block_entry(w, C, dtype, variant, feat, y, cr, cb, out, B, Hf, Wf, Hy, Wy, workspace, workspace_bytes, stream,
+                         false, nullptr, [&](Ctx& ctx, BlockEnv& env) {
+                           conv_transformer(ctx, env.pb, variant, env.x, env.sg, env.outT, B);
+                         });
+}
+
+int rf_downsample_forward(const float* conv_w, int C, int dtype, const float* x, float* out, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!conv_w || !x || !out || !workspace) return RF_ERR_BAD_ARG;
+  RF_TRY(check_block_args(C, dtype, B, H, W));
+  if ((H & 1) || (W & 1) || (C % 16)) return RF_ERR_BAD_SHAPE;
+  Ctx ctx = make_ctx(workspace, workspace_bytes, stream, dtype, false);
+  Arena& A = ctx.arena;
+  const i64 P = (i64)H * W;
+  void* wT = A.elems((size_t)(C / 2) * 9 * C, dtype);
+  void* xT = A.elems((size_t)B * P * C, dtype);
+  void* oT = A.elems((size_t)B * (P / 4) * 2 * C, dtype);
+  if (!ctx.fits()) return RF_ERR_WORKSPACE;
+  pack_conv3(ctx, conv_w, wT, C / 2, C);
+  launch_nchw_to_nhwc(ctx, x, xT, B, C, P);
+  conv3x3(ctx, xT, wT, nullptr, oT, C, C / 2, ACT_NONE, OMODE_UNSHUFFLE, B, H, W, RF_K_DOWN_CONV);
+  launch_nhwc_to_nchw(ctx, oT, out, B, 2 * C, P / 4);
+  return finish(ctx);
+}
+
+// ---- whole model --------------------------------------------------------------------------------------
+
+size_t rf_model_packed_bytes(int dim, int dtype, int variant) {
+  if (dim <= 0 || dim % 8 || (dtype != RF_F32 && dtype != RF_BF16)) return 0;
+  Layout L(nullptr);
+  layout_model(L, dim, dtype, variant);
+  return L.off + 256;
+}
+
+int rf_model_pack(const rf_model_weights* w, int dim, int dtype, int variant, void* packed, size_t packed_bytes,
+                  void* stream) {
+  if (!w || !packed) return RF_ERR_BAD_ARG;
+  RF_TRY(check_model_args(dim, dtype, variant, 1, 16, 16));
+  if (packed_bytes < rf_model_packed_bytes(dim, dtype, variant)) return RF_ERR_WORKSPACE;
+  if ((uintptr_t)packed % 256) return RF_ERR_BAD_ARG;
+  Ctx ctx = make_ctx(nullptr, 0, stream, dtype, false);
+  Layout L(packed);
+  PackedModel pm = layout_model(L, dim, dtype, variant);
+  RF_CUDA(cudaMemcpyAsync(pm.rgb_w, w->rgb_w_host, 3 * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+  const float* filt = variant == RF_VARIANT_ML ? w->blocks[0].flca_filt : w->blocks[0].flca_filt;
+  if (!filt) return RF_ERR_BAD_ARG;
+  copy_f32(ctx, filt, pm.haar, 16);
+  if (!w->embedding_w || !w->embedding_b || !w->conv_out_w || !w->conv_out_b) return RF_ERR_BAD_ARG;
+  launch_pack3(ctx, w->embedding_w, pm.embed_w, RF_F32, 9, 4, dim, 1, 9, 36, (i64)4 * dim, dim, 1, 0);
+  copy_f32(ctx, w->embedding_b, pm.embed_b, dim);
+  for (int i = 0; i < 7; ++i) pack_block(ctx, w->blocks[i], pm.blocks[i], variant);
+  for (int n = 0; n < 3; ++n) {
+    const int C = dim << n;
+    if (!w->down_w[n] || !w->up_w[n] || !w->up_b[n] || !w->reduce_w[n] || !w->reduce_b[n]) return RF_ERR_BAD_ARG;
+    pack_conv3(ctx, w->down_w[n], pm.down_w[n], C / 2, C);
+    const int Co = dim << (2 - n), Ci = 2 * Co;
+    // ConvTranspose2d weight [Ci,Co,2,2] -> T [(2i+j)][Co][Ci]
+    launch_pack3(ctx, w->up_w[n], pm.up_w[n], dtype, 4, Co, Ci, 1, 4, (i64)Co * 4, (i64)Co * Ci, Ci, 1, 0);
+    launch_pack3(ctx, w->up_b[n], pm.up_b[n], RF_F32, 4, 1, Co, 0, 0, 1, Co, 0, 1, 0);
+    copy_T(ctx, w->reduce_w[n], pm.red_w[n], (i64)Co * 2 * Co);
+    copy_f32(ctx, w->reduce_b[n], pm.red_b[n], Co);
+  }
+  launch_pack3(ctx, w->conv_out_w, pm.head_w, RF_F32, 9, dim, 12, 1, 9, (i64)dim * 9, (i64)dim * 12, 12, 1, 0);
+  copy_f32(ctx, w->conv_out_b, pm.head_b, 12);
+  return finish(ctx);
+}
+
+size_t rf_rawformer_workspace_bytes(int dim, int dtype, int variant, int B, int H, int W) {
+  if (check_model_args(dim, dtype, variant, B, H, W) != RF_OK) return 0;
+  Ctx ctx = make_ctx(nullptr, 0, nullptr, dtype, true);
+  Layout L(nullptr);
+  PackedModel pm = layout_model(L, dim, dtype, variant);
+  model_forward(ctx, pm, variant, nullptr, nullptr, B, H, W);
+  return ctx.arena.peak + 4096;
+}
+
+int rf_rawformer_forward(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int B, int H,
+                         int W, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!packed || !raw || !out || !workspace) return RF_ERR_BAD_ARG;
+  RF_TRY(check_model_args(dim, dtype, variant, B, H, W));
+  if ((uintptr_t)packed % 256 || (uintptr_t)raw % 16 || (uintptr_t)out % 16) return RF_ERR_BAD_ARG;
+  if (workspace_bytes < rf_rawformer_workspace_bytes(dim, dtype, variant, B, H, W) - 4096) return RF_ERR_WORKSPACE;
+  Ctx ctx = make_ctx(workspace, workspace_bytes, stream, dtype, false);
+  Layout L(const_cast<void*>(packed));
+  PackedModel pm = layout_model(L, dim, dtype, variant);
+  RF_TRY(model_forward(ctx, pm, variant, raw, out, B, H, W));
+  return finish(ctx);
+}
+
+int rf_rawformer_forward_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int B,
+                                  int H, int W, void* workspace, size_t workspace_bytes, void* stream, float* kernel_ms_host,
+                                  int* kernel_id_host, int cap, int* n_host) {
+  if (cap <= 0) return RF_ERR_BAD_ARG;
+  RF_TRY(profile_begin((cudaStream_t)stream, cap));
+  int st = rf_rawformer_forward(packed, dim, dtype, variant, raw, out, B, H, W, workspace, workspace_bytes, stream);
+  int st2 = profile_end(kernel_ms_host, kernel_id_host, cap, n_host);
+  return st != RF_OK ? st : st2;
+}
+
+}  // extern "C"

@@ -144,9 +144,10 @@ typedef struct rf_block_weights {
 
 size_t rf_block_workspace_bytes(int C, int dtype, int B, int Hf, int Wf, int Hy, int Wy);
 
-/* FLCA.forward(feat, y, cr, cb) — FLCA_RF.py:136-162.  feat [B,C,Hf,Wf]; y,cr,cb [B,1,Hy,Wy]. */
-int rf_flca_forward(const rf_block_weights* w, int C, int dtype, const float* feat, const float* y, const float* cr,
-                    const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy, void* workspace,
+/* FLCA.forward(feat, y, cr, cb) — FLCA_RF.py:136-162 (variant ML: FLCA_Pyramid.forward, ML_RF.py:132-183, levels = 2).
+ * feat [B,C,Hf,Wf]; y,cr,cb [B,1,Hy,Wy]. */
+int rf_flca_forward(const rf_block_weights* w, int C, int dtype, int variant, const float* feat, const float* y,
+                    const float* cr, const float* cb, float* out, int B, int Hf, int Wf, int Hy, int Wy, void* workspace,
                     size_t workspace_bytes, void* stream);
 /* Attention.forward(x) — FLCA_RF.py:221-235 (num_heads = 8). */
 int rf_attention_forward(const rf_block_weights* w, int C, int dtype, const float* x, float* out, int B, int H, int W,
@@ -164,6 +165,26 @@ int rf_conv_transformer_forward(const rf_block_weights* w, int C, int dtype, int
 /* Downsample.forward(x) — FLCA_RF.py:176-177.  conv_w = body.0.weight [C/2,C,3,3]; out [B,2C,H/2,W/2]. */
 int rf_downsample_forward(const float* conv_w, int C, int dtype, const float* x, float* out, int B, int H, int W,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* FeedForward.forward(x) — WFB/model.py:42-65 (gated-GELU FFN) with the two eval-mode Conv2d_BN branches and the
+ * identity already folded into ONE depthwise 3x3 + bias (the reference's own fuse(), WFB/model.py:67-87):
+ *   t = project_in(x); x1 = dwA(t); x2 = dwB(t); y = project_out(gelu(x2)*x1 + gelu(x1)*x2) + x.
+ * project_in_w [hidden,C,1,1], dwA_w/dwB_w [hidden,1,3,3], project_out_w [C,hidden,1,1]; biases may be NULL.
+ * hidden % 8 == 0 is required by the 16-byte vector kernels (pad int(2.66*C) up on the host with zero weights). */
+int rf_feedforward_gated(const float* project_in_w, const float* project_in_b, const float* dwA_w, const float* dwA_b,
+                         const float* dwB_w, const float* dwB_b, const float* project_out_w, const float* project_out_b,
+                         int C, int hidden, int dtype, const float* x, float* out, int B, int H, int W, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Callers either side of the forward
+ * ---------------------------------------------------------------------------------------------- */
+/* test.py:117-118: clamp(pred,0,1) -> *255 -> uint8 (truncation) -> HWC.  in [B,3,H,W] f32 -> out [B,H,W,3] u8. */
+int rf_postprocess_u8(const float* in, unsigned char* out, int B, int H, int W, void* stream);
+/* WFB/load_dataset.py:88-89: clip(raw,black,white) -> (x-black)/(white-black+1e-6)*ratio, then min(.,1)
+ * (correctdataloader.py:103).  raw [B,H,W] u16 -> out [B,1,H,W] f32. */
+int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole model — RawFormer.forward, FLCA_RF.py:330-370 (variant ML: ML_RF.py:356-416)
