@@ -45,10 +45,10 @@ def _digest():
         [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_ROOT, "include", "rawformer_b200.h")]
     )
     for p in files:
-        h.update(p.encode())
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith("/")).encode())
     return h.hexdigest()
 
 

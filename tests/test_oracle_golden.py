@@ -151,3 +151,18 @@ def test_ml_tail_and_bilinear():
     g = T.gen_input("rand", (1, 1, 12, 20), 32)
     for tag, size in (("x2", (24, 40)), ("d2", (6, 10)), ("d4", (3, 5)), ("odd", (9, 14)), ("same", (12, 20))):
         assert np.abs(O.bilinear_resize(g, size) - OPS[f"bilinear_{tag}"]).max() <= 1e-6, tag
+
+
+@pytest.mark.parametrize("case", T.MODEL_CASES, ids=[c[0] for c in T.MODEL_CASES])
+def test_torch_port(case):
+    """The functional-PyTorch CPU port used as bench.py's cpu_baseline / reference arm, against the same goldens."""
+    import torch
+
+    from oracle import rawformer_torch as P
+
+    name, variant, dim, H, W, kind, seed, scale, b = case
+    sd = T.make_state_dict(T.build_model(variant, dim), 1234 + seed, scale)
+    x = torch.from_numpy(T.gen_input(kind, (b, 1, H, W), seed))
+    out = P.rawformer_forward(sd, x, variant).numpy()
+    ref = T.load_golden(name)["out"]
+    assert np.abs(out - ref).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
