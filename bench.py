@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the RawFormer inference hot path on B200 (BASELINE.json metric: MP/s of RAW input).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S|B|L] [--variant flca|ml]
+
+A "step" = one forward over one synthetic SID-Sony-shaped frame (raw 2848x4256 -> packed 1424x2128x4) per GPU.
+N = 1 workload = BASELINE configs[1]: RawFormer-S, full frame, bf16.  N > 1 (torchrun) is image-parallel: every rank
+runs its own frames, no data-path collective ("weak" scaling); timing = max over ranks of CUDA-event time.
+
+Prints ONE JSON line (see the driver contract): value = device-resident throughput, e2e = same metric through the
+public nn.Module call with pinned HOST buffers (H2D + forward + D2H inside the timed region), roofline = the
+dominant kernel of the step (per-launch CUDA events on the launching stream), cpu_baseline = the functional-PyTorch
+CPU port of the reference timed on this box's host cores on a bounded sample.
+`--impl reference` times that CPU port alone (rank 0 only) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H_RAW, W_RAW = 2848, 4256  # SID Sony frame
+MP_FRAME = H_RAW * W_RAW / 1e6
+METRIC = "megapixels/sec of RAW input (SID Sony full frame)"
+SIZES = {"S": 32, "B": 48, "L": 64}
+TENSOR_KERNELS = ("gemm_", "conv3x3_out", "down_conv3x3", "up_convT", "skip_reduce")
+
+
+def workload_name(args, world):
+    return (f"RawFormer-{args.size} ({args.variant}) forward, full SID Sony frame raw {H_RAW}x{W_RAW} "
+            f"(packed 1424x2128x4), {args.frames} frame(s) per GPU per step, random-init weights")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_burst": d["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_burst": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_port_setup(size, variant, h, w, seed=0):
+    import torch
+
+    import rf_testlib as T
+    from oracle import rawformer_torch as P
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    dim = SIZES[size]
+    sd = T.make_state_dict(T.build_model(variant, dim), seed=1234, scale=1.0)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(1, 1, h, w, generator=g)
+    return (lambda: P.rawformer_forward(sd, x, variant)), torch.get_num_threads()
+
+
+def time_cpu_port(size, variant, budget_s=25.0):
+    """Bounded CPU sample: 1024x1024 raw crop first; the full frame once if the budget allows."""
+    fn, threads = cpu_port_setup(size, variant, 1024, 1024)
+    fn()  # warm-up
+    t0 = time.perf_counter()
+    fn()
+    dt = time.perf_counter() - t0
+    mp = 1024 * 1024 / 1e6
+    best = {"value": mp / dt, "sample": f"RawFormer-{size} ({variant}) fp32, 1 frame raw 1024x1024 (1.05 MP), 1 warm-up + 1 timed"}
+    est_full = dt * (MP_FRAME / mp) * 2.2  # the reference is ~2x slower per MP at full frame
+    if est_full < budget_s:
+        fn_full, _ = cpu_port_setup(size, variant, H_RAW, W_RAW)
+        t0 = time.perf_counter()
+        fn_full()
+        dt = time.perf_counter() - t0
+        best = {"value": MP_FRAME / dt, "sample": f"RawFormer-{size} ({variant}) fp32, 1 full frame raw {H_RAW}x{W_RAW} (12.12 MP), 1 timed run"}
+    best.update(unit="MP/s", cores=threads, kind="port")
+    return best
+
+
+def run_reference(args):
+    """Reference arm: the CPU port of the reference forward on this box's host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h = w = 1024
+    fn, threads = cpu_port_setup(args.size, args.variant, h, w)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    mp = h * w / 1e6
+    val = args.steps * mp / dt
+    sample = (f"CPU port of the reference forward (oracle/rawformer_torch.py, fp32, {threads} threads); each step = "
+              f"one raw {h}x{w} crop (1.05 MP) of the frame")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, args.gpus), "cpu_sample": f"raw {h}x{w} crop per step"},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rf_testlib as T
+
+    import bayer_low_light_image_enhancement_b200 as rf
+    from bayer_low_light_image_enhancement_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    dim = SIZES[args.size]
+    cls = rf.RawFormer if args.variant == "flca" else rf.multilevel.RawFormer
+    model = cls(dim=dim, precision=args.precision)
+    model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)  # random-init weights
+    model = model.to(dev).eval()
+    B = args.frames
+    gen = torch.Generator().manual_seed(rank)
+    x_host = torch.rand(B, 1, H_RAW, W_RAW, generator=gen).pin_memory()
+    out_host = torch.empty(B, 3, H_RAW, W_RAW).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    with torch.no_grad():
+        # ---- device-resident throughput ----
+        for _ in range(args.warmup):
+            model(x_dev)
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        lib.rf_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = model(x_dev)
+        e1.record()
+        barrier()
+        launches = lib.rf_launch_count()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end through the public call with host buffers ----
+        for _ in range(2):
+            out_host.copy_(model(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)
+            out_host.copy_(model(xd), non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+
+        # ---- per-kernel times (CUDA events around every launch, on the launching stream) ----
+        agg = {}
+        n_prof = 3
+        for _ in range(n_prof):
+            _, launches_prof = model.forward_profiled(x_dev)
+            for l in launches_prof:
+                a = agg.setdefault(l["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
+                a["ms"] += l["ms"]
+                a["bytes"] += l["bytes"]
+                a["flops"] += l["flops"]
+                a["n"] += 1
+        barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total_prof_ms = sum(a["ms"] for a in agg.values())
+    top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    is_tensor = top_name.startswith(TENSOR_KERNELS)
+    if is_tensor:
+        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"]}
+    else:
+        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
+    roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
+                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=None)
+    breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])[:8]
+
+    frames_total = args.steps * B * world
+    value = frames_total * MP_FRAME / (ms_total * 1e-3)
+    e2e_val = frames_total * MP_FRAME / (ms_e2e * 1e-3)
+    cpu = time_cpu_port(args.size, args.variant) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "precision": args.precision,
+                   "parallelism": f"image-parallel x{world}" if world > 1 else "single GPU",
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush"},
+        "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in breakdown},
+        "model_roofline": {"flops_per_frame": 320.5 * dim * dim * 3030272 + 875.0 * dim * 3030272,
+                           "achieved_tflops": (320.5 * dim * dim + 875.0 * dim) * 3030272 * frames_total / (ms_total * 1e-3) / 1e12},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="S", choices=list(SIZES))
+    ap.add_argument("--variant", default="flca", choices=["flca", "ml"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
