@@ -67,6 +67,7 @@ _SIGS = {
     "rf_version": (_i, []),
     "rf_last_cuda_error": (_i, []),
     "rf_init": (_i, [_i]),
+    "rf_set_tcgen05": (_i, [_i]),
     "rf_launch_count": (C.c_longlong, []),
     "rf_reset_launch_count": (None, []),
     "rf_downshuffle": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _fp]),

@@ -7,6 +7,9 @@
 
 namespace rf {
 
+void set_tcgen05_enabled(bool on);
+bool tcgen05_enabled();
+
 static thread_local LaunchRecorder g_rec;
 LaunchRecorder& recorder() { return g_rec; }
 
@@ -86,6 +89,12 @@ int rf_init(int device) {
   RF_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return RF_ERR_ARCH;
   return RF_OK;
+}
+
+int rf_set_tcgen05(int enable) {
+  int prev = rf::tcgen05_enabled() ? 1 : 0;
+  if (enable >= 0) rf::set_tcgen05_enabled(enable != 0);
+  return prev;
 }
 
 long long rf_launch_count(void) { return g_rec.count; }

@@ -1,11 +1,474 @@
-// tcgen05 / TMEM / TMA contraction kernels (bf16 operands, fp32 accumulation in tensor memory).
+// tcgen05 / TMEM / TMA contraction kernel for the bf16 mode (sm_100a only).
+//
+//   D[128 pixels x BN] (fp32, tensor memory) += A[128 x 64] (smem, TMA, 128B swizzle) * W[BN x 64]^T (smem, TMA)
+//
+// One CTA = one 128-row pixel tile x one BN-column slice.  Warp roles (192 threads):
+//   warp 0   : TMA producer  (one elected lane; full/empty mbarrier ring of `stages` k-blocks)
+//   warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16)
+//   warps 2-5: epilogue  (tcgen05.ld 32x32b -> bias / activation / residual -> bf16 -> global)
+// A operand forms:
+//   rows  : 3-d tensor map [K, M, B]; k-blocks run over A1 then A2 (K-concatenation = the cat fusions)
+//   conv3 : 4-d tensor map [C, W, H, B]; the M tile is a th x tw pixel patch and every 3x3 tap is the same box
+//           shifted by (dx,dy) -- out-of-bounds rows/columns are zero-filled by TMA = the conv's zero padding.
+// K tails (K % 64 != 0) are zero-filled by TMA on both operands; the MMA loop skips all-zero 16-wide slices.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "rf_kernels.cuh"
 
 namespace rf {
 
-bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& p) {
-  (void)ctx; (void)p;
-  return false;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 4;
+
+struct TcParams {
+  const float* bias;
+  const bf16* R;
+  bf16* Y;
+  i64 ldr, ldy;
+  int M, N, B;         // rows per image, total output columns, images
+  int BN;              // columns per CTA (multiple of 16, <= 256)
+  int act, amode, omode;
+  int H, W;            // image size of the rows (conv / convT / unshuffle addressing)
+  int tw, th;          // conv patch (tw*th == 128)
+  int tiles_x;         // conv: patches per image row
+  int kb1, kb2;        // k-blocks from A1 (per tap for conv) and A2
+  int K1, K2;          // K of A1 (per tap for conv: Cin) and A2
+  int taps;            // 1 or 9
+  int stages;
+  int w_per_image;     // 1: weight tensor map coordinate 2 = image index
+  int tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B stacked with SBO = 1024 B.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+          const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A tile 16 KB][stages x W tile BN*128 B][barriers]
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)p.BN * 128;
+  const uint32_t sA = base, sW = base + p.stages * a_bytes;
+  const uint32_t bars = sW + p.stages * w_bytes;          // 8-byte aligned (multiples of 128)
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * TC_MAX_STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.taps * p.kb1 + p.kb2;
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.y * p.BN;
+  // tile origin
+  int m0 = 0, px0 = 0, py0 = 0;
+  if (p.amode == AMODE_CONV3) {
+    px0 = (blockIdx.x % p.tiles_x) * p.tw;
+    py0 = (blockIdx.x / p.tiles_x) * p.th;
+  } else {
+    m0 = blockIdx.x * TC_BM;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA1);
+    if (p.kb2) tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t tx = a_bytes + w_bytes;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages, it = i / p.stages;
+        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        mbar_expect_tx(full_bar(s), tx);
+        const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
+        if (p.amode == AMODE_CONV3) {
+          const int tap = i / p.kb1, cb = i - tap * p.kb1;
+          tma_load_4d(dstA, &mapA1, full_bar(s), cb * TC_BK, px0 + tap % 3 - 1, py0 + tap / 3 - 1, b);
+          tma_load_3d(dstW, &mapW, full_bar(s), cb * TC_BK, tap, n0);
+        } else if (i < p.kb1) {
+          tma_load_3d(dstA, &mapA1, full_bar(s), i * TC_BK, m0, b);
+          tma_load_3d(dstW, &mapW, full_bar(s), i * TC_BK, n0, p.w_per_image ? b : 0);
+        } else {
+          const int j = i - p.kb1;
+          tma_load_3d(dstA, &mapA2, full_bar(s), j * TC_BK, m0, b);
+          tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * TC_BK, n0, p.w_per_image ? b : 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages, it = i / p.stages;
+        mbar_wait(full_bar(s), it & 1);
+        tc_fence_after();
+        // valid K in this block (zero-filled beyond): skip all-zero 16-wide slices
+        int kvalid;
+        if (p.amode == AMODE_CONV3) {
+          const int cb = i % p.kb1;
+          kvalid = min(TC_BK, p.K1 - cb * TC_BK);
+        } else if (i < p.kb1) {
+          kvalid = min(TC_BK, p.K1 - i * TC_BK);
+        } else {
+          kvalid = min(TC_BK, p.K2 - (i - p.kb1) * TC_BK);
+        }
+        const int ksteps = (kvalid + 15) >> 4;
+        const uint64_t adesc = make_sw128_desc(sA + s * a_bytes);
+        const uint64_t bdesc = make_sw128_desc(sW + s * w_bytes);
+        for (int k = 0; k < ksteps; ++k) {
+          // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);               // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;         // row of the tile
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    // output row
+    bool row_ok;
+    i64 orow = 0;        // OMODE_ROWS: row index into R/Y
+    int oy = 0, ox = 0;  // pixel coordinates (conv / scatter modes)
+    if (p.amode == AMODE_CONV3) {
+      oy = py0 + r / p.tw;
+      ox = px0 + r % p.tw;
+      row_ok = oy < p.H && ox < p.W;
+      orow = (i64)b * p.M + (i64)oy * p.W + ox;
+    } else {
+      const int m = m0 + r;
+      row_ok = m < p.M;
+      orow = (i64)b * p.M + m;
+      if (p.omode != OMODE_ROWS) { oy = m / p.W; ox = m - oy * p.W; }
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int n = n0 + c;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
+          f[j] += bq.x; f[j + 1] += bq.y; f[j + 2] += bq.z; f[j + 3] += bq.w;
+        }
+      }
+      if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = lrelu_f(f[j]);
+      } else if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act == ACT_TANH_RES) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.2f * tanhf(f[j]);
+      }
+      if (p.omode == OMODE_ROWS) {
+        if (p.R) {
+          float r8[8];
+          load8(p.R + orow * p.ldr + n, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += r8[j];
+          load8(p.R + orow * p.ldr + n + 8, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
+        }
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = f[j];
+        store8(p.Y + orow * p.ldy + n, o8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
+        store8(p.Y + orow * p.ldy + n + 8, o8);
+      } else if (p.omode == OMODE_CONVT) {
+        const int Co = p.N >> 2;
+        const int ij = n / Co, co = n - ij * Co;   // 16-wide chunk never straddles ij (Co % 16 == 0)
+        const i64 dst = (((i64)b * 2 * p.H + 2 * oy + (ij >> 1)) * (2 * p.W) + 2 * ox + (ij & 1)) * p.ldy + co;
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = f[j];
+        store8(p.Y + dst, o8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
+        store8(p.Y + dst + 8, o8);
+      } else {
+        const i64 dst = (((i64)b * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1)) * p.ldy + 2 * (oy & 1) + (ox & 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p.Y[dst + (i64)(n + j) * 4] = __float2bfloat16_rn(f[j]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// bf16 tensor, dims[0] contiguous; strides in elements for dims 1..rank-1; box = elements per dim
+static bool make_map(CUtensorMap* m, const void* base, int rank, const i64* dims, const i64* strides_elems, const int* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * 2;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int pick_bn(int N) {
+  if (N % 16) return 0;
+  if (N <= 256) return N;
+  for (int parts = 2; parts <= 64; ++parts) {
+    if (N % parts) continue;
+    int bn = N / parts;
+    if (bn <= 256 && bn % 16 == 0) return bn;
+  }
+  return 0;
+}
+
+static bool g_tc_enabled = true;
+static bool g_tc_checked = false;
+void set_tcgen05_enabled(bool on) { g_tc_enabled = on; g_tc_checked = true; }
+bool tcgen05_enabled() { return g_tc_enabled; }
+
+bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
+  if (!g_tc_checked) {
+    g_tc_checked = true;
+    const char* e = getenv("RAWFORMER_B200_NO_TCGEN05");
+    if (e && e[0] == '1') g_tc_enabled = false;
+  }
+  if (!g_tc_enabled || ctx.dtype != RF_BF16) return false;
+  const int BN = pick_bn(g.N);
+  if (BN == 0) return false;
+  if (g.K1 % 8 || g.K2 % 8) return false;
+  if (g.omode == OMODE_CONVT && ((g.N / 4) % 16)) return false;
+  if (g.amode == AMODE_CONV3 && g.A2) return false;
+  if (g.amode != AMODE_CONV3 && (g.lda1 != g.K1 || (g.A2 && g.lda2 != g.K2))) return false;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = g.bias; p.R = (const bf16*)g.R; p.Y = (bf16*)g.Y; p.ldr = g.ldr; p.ldy = g.ldy;
+  p.M = g.M; p.N = g.N; p.B = g.B; p.BN = BN; p.act = g.act; p.amode = g.amode; p.omode = g.omode; p.H = g.H; p.W = g.W;
+  p.w_per_image = g.w_img != 0;
+  CUtensorMap mA1, mA2, mW;
+  int grid_x;
+  if (g.amode == AMODE_CONV3) {
+    const int Cin = g.K1 / 9;
+    p.taps = 9; p.K1 = Cin; p.K2 = 0; p.kb1 = cdiv(Cin, TC_BK); p.kb2 = 0;
+    // patch shape: minimise padded area
+    int best_tw = 16;
+    i64 best = -1;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+      const int th = 128 / tw;
+      const i64 area = (i64)cdiv(g.W, tw) * tw * cdiv(g.H, th) * th;
+      if (best < 0 || area < best) { best = area; best_tw = tw; }
+    }
+    p.tw = best_tw; p.th = 128 / best_tw;
+    p.tiles_x = cdiv(g.W, p.tw);
+    grid_x = p.tiles_x * cdiv(g.H, p.th);
+    const i64 dA[4] = {Cin, g.W, g.H, g.B};
+    const i64 sA[4] = {1, g.lda1, g.lda1 * g.W, g.lda1 * g.W * g.H};
+    const int bA[4] = {TC_BK, p.tw, p.th, 1};
+    if (!make_map(&mA1, g.A1, 4, dA, sA, bA)) return false;
+    mA2 = mA1;
+    const i64 dW[3] = {Cin, 9, g.N};
+    const i64 sW[3] = {1, Cin, (i64)9 * Cin};
+    const int bW[3] = {TC_BK, 1, BN};
+    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return false;
+  } else {
+    p.taps = 1; p.K1 = g.K1; p.K2 = g.A2 ? g.K2 : 0;
+    p.kb1 = cdiv(g.K1, TC_BK); p.kb2 = g.A2 ? cdiv(g.K2, TC_BK) : 0;
+    p.tw = 128; p.th = 1; p.tiles_x = 1;
+    grid_x = cdiv(g.M, TC_BM);
+    const i64 dA[3] = {g.K1, g.M, g.B};
+    const i64 sA[3] = {1, g.lda1, g.lda1 * g.M};
+    const int bA[3] = {TC_BK, TC_BM, 1};
+    if (!make_map(&mA1, g.A1, 3, dA, sA, bA)) return false;
+    if (g.A2) {
+      const i64 dA2[3] = {g.K2, g.M, g.B};
+      const i64 sA2[3] = {1, g.lda2, g.lda2 * g.M};
+      if (!make_map(&mA2, g.A2, 3, dA2, sA2, bA)) return false;
+    } else {
+      mA2 = mA1;
+    }
+    const i64 K = g.K1 + (g.A2 ? g.K2 : 0);
+    const i64 dW[3] = {K, g.N, g.w_img ? g.B : 1};
+    const i64 sW[3] = {1, K, g.w_img ? g.w_img : K * g.N};
+    const int bW[3] = {TC_BK, BN, 1};
+    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return false;
+  }
+  const int nkb = p.taps * p.kb1 + p.kb2;
+  p.stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
+  int cols = 32;
+  while (cols < BN) cols *= 2;
+  p.tmem_cols = cols;
+  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * 128 + (size_t)BN * 128) + 8 * (2 * TC_MAX_STAGES + 2);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+    smem_set = 227 * 1024;
+  }
+  const int K = g.K1 + g.K2;
+  const double es = 2.0, rows = (double)g.B * g.M;
+  const double abytes = rows * (g.amode == AMODE_CONV3 ? g.K1 / 9 : K) * es;
+  const double bytes = abytes + rows * g.N * es * (g.R ? 2.0 : 1.0) + (double)g.N * K * es * (g.w_img ? g.B : 1);
+  ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
+  dim3 grid(grid_x, g.N / BN, g.B);
+  k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, p);
+  return true;
 }
 
 }  // namespace rf

@@ -51,6 +51,9 @@ int rf_last_cuda_error(void);
 /* Checks that `device` is an sm_100 part and caches its properties.  Must succeed before any other call. */
 int rf_init(int device);
 /* Number of kernels this library launched on the calling thread since the last rf_reset_launch_count(). */
+/* bf16 mode: 1 (default) = contractions run on the tcgen05/TMEM/TMA kernels, 0 = on the CUDA-core FFMA kernels
+ * (A/B testing of the two device paths; both are CUDA).  enable < 0 only queries.  Returns the previous setting. */
+int rf_set_tcgen05(int enable);
 long long rf_launch_count(void);
 void rf_reset_launch_count(void);
 
