@@ -122,46 +122,11 @@ __device__ __forceinline__ void dw3x3_at(const T* __restrict__ img, const float*
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_dwconv(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int gelu,
-         int H, int W, int Cn) {
-  const i64 b = blockIdx.y;
-  const int cv = Cn >> 3;
-  const i64 total = (i64)H * W * cv;
-  const T* img = in + b * (i64)H * W * Cn;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * 8;
-    const i64 p = i / cv;
-    const int y = (int)(p / W), x = (int)(p % W);
-    float acc[8];
-    dw3x3_at(img, w, bias, H, W, Cn, y, x, c0, acc);
-    if (gelu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = gelu_erf_f(acc[j]);
-    }
-    store8(out + (b * (i64)H * W + p) * Cn + c0, acc);
-  }
-}
-
-void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H, int W,
-                   int Cn, int kernel_id) {
-  if (ctx.dry) return;
-  i64 total = (i64)H * W * (Cn / 8);
-  unsigned gx = (unsigned)(cdivl(total, 256) < 16 * num_sms() ? cdivl(total, 256) : 16 * num_sms());
-  double px = (double)B * H * W;
-  ScopedLaunch sl(kernel_id, 2.0 * px * Cn * esize(ctx.dtype), 18.0 * px * Cn);
-  if (ctx.dtype == RF_BF16)
-    k_dwconv<bf16><<<dim3(gx, B), 256, 0, ctx.stream>>>((const bf16*)in, dw_w, dw_b, (bf16*)out, gelu, H, W, Cn);
-  else
-    k_dwconv<float><<<dim3(gx, B), 256, 0, ctx.stream>>>((const float*)in, dw_w, dw_b, (float*)out, gelu, H, W, Cn);
-}
-
 // ---------------------------------------------------------------------------------------------
 // pass B of the attention: depthwise 3x3 on qkv_pre, store v, accumulate Gram + squared norms.
 // Persistent blocks loop over tiles of TP pixels; q,k of a tile are staged in smem (fp32) and the per-head c x c
 // Gram patches are accumulated in registers across all tiles of the block; one atomicAdd per entry at the end.
-// stats[b] = { gram[8][c][c], qn2[C], kn2[C] }.
+// stats[b] = { G[C][C] (row = q channel, col = k channel; only the per-head diagonal blocks are written), qn2[C], kn2[C] }.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int PT, int NP>  // PT x PT register patch, NP patches per thread
 __global__ void __launch_bounds__(256)
@@ -257,7 +222,7 @@ k_dwqkv_gram(const T* __restrict__ qkv, const float* __restrict__ w, const float
     }
     __syncthreads();
   }
-  float* st = stats + b * ((i64)C * c + 2 * C);
+  float* st = stats + b * ((i64)C * C + 2 * C);
 #pragma unroll
   for (int a = 0; a < NP; ++a) {
     const int pe = tid + a * nthr;
@@ -267,13 +232,13 @@ k_dwqkv_gram(const T* __restrict__ qkv, const float* __restrict__ w, const float
 #pragma unroll
       for (int i = 0; i < PT; ++i)
 #pragma unroll
-        for (int j = 0; j < PT; ++j) atomicAdd(st + ((i64)h * c + i0 + i) * c + j0 + j, acc[a][i][j]);
+        for (int j = 0; j < PT; ++j) atomicAdd(st + ((i64)h * c + i0 + i) * C + h * c + j0 + j, acc[a][i][j]);
     }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int ch = tid + r * nthr;
-    if (ch < 2 * C) atomicAdd(st + (i64)C * c + ch, n2[r]);
+    if (ch < 2 * C) atomicAdd(st + (i64)C * C + ch, n2[r]);
   }
 }
 
@@ -348,10 +313,10 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
   float* nk = nq + c;
   const int h = blockIdx.x;
   const i64 b = blockIdx.y;
-  const float* st = stats + b * ((i64)C * c + 2 * C);
-  const float* gram = st + (i64)h * c * c;
-  const float* qn2 = st + (i64)C * c + h * c;
-  const float* kn2 = st + (i64)C * c + C + h * c;
+  const float* st = stats + b * ((i64)C * C + 2 * C);
+  const float* gram = st + ((i64)h * c) * C + h * c;   // diagonal block of head h, row pitch C
+  const float* qn2 = st + (i64)C * C + h * c;
+  const float* kn2 = st + (i64)C * C + C + h * c;
   const int tid = threadIdx.x;
   for (int i = tid; i < c; i += blockDim.x) {
     nq[i] = fmaxf(sqrtf(qn2[i]), 1e-12f);
@@ -361,7 +326,7 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
   const float temp = temperature[h];
   for (int e = tid; e < c * c; e += blockDim.x) {
     const int i = e / c, j = e - i * c;
-    attn[i * (c + 1) + j] = gram[e] / (nq[i] * nk[j]) * temp;
+    attn[i * (c + 1) + j] = gram[(i64)i * C + j] / (nq[i] * nk[j]) * temp;
   }
   __syncthreads();
   for (int i = tid; i < c; i += blockDim.x) {  // row softmax (c <= 64: one thread per row is fine)

@@ -54,6 +54,7 @@ enum KernelId {
   RF_K_TAIL_STATS,
   RF_K_TAIL_APPLY,
   RF_K_INDEX_OP,
+  RF_K_GEMM_GRAM,
   RF_K_COUNT
 };
 

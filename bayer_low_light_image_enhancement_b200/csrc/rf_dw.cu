@@ -1,0 +1,157 @@
+// Strip-mined depthwise 3x3 on NHWC activations.
+//
+// One thread owns 4 channels of a strip of L horizontally adjacent pixels and slides a 3-column window along the
+// strip: every input column (3 rows x 4 channels) is loaded once and feeds the three outputs it touches, the 36 tap
+// weights stay in registers.  That is 3(L+2)/L vector loads per output instead of 9 + weights, which is what moves
+// these kernels from L1-bound to HBM-bound.
+//   MODE 0: out = [gelu](dw(in) + bias), NHWC                       (conv_ffn.depthwise + GELU, FLCA_RF.py:206-207)
+//   MODE 1: in = qkv_pre [.,3C]: v -> NHWC [.,C]; q,k -> channel-major planes qk[b][2C][Ppad] (so the Gram
+//           q k^T over pixels is a K-major tensor-core GEMM) and their squared norms -> sumsq[b][2C]
+//           (Attention.qkv_dwconv + F.normalize statistics, FLCA_RF.py:223-229)
+#include "rf_kernels.cuh"
+
+namespace rf {
+
+template <typename T, int MODE, int L>
+__global__ void __launch_bounds__(256)
+k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+           T* __restrict__ qk, float* __restrict__ sumsq, int gelu, int H, int W, int Cn, int C, i64 Ppad, i64 total) {
+  __shared__ float s_sq[MODE == 1 ? 1024 : 1];
+  const int tid = threadIdx.x;
+  const i64 b = blockIdx.y;
+  if (MODE == 1) {
+    for (int i = tid; i < 2 * C; i += blockDim.x) s_sq[i] = 0.f;
+    __syncthreads();
+  }
+  const i64 idx = (i64)blockIdx.x * blockDim.x + tid;
+  if (idx < total) {
+    const int V4 = Cn >> 2, SW = (W + L - 1) / L;
+    const int c0 = (int)(idx % V4) * 4;
+    const i64 strip = idx / V4;
+    const int x0 = (int)(strip % SW) * L, y = (int)(strip / SW);
+    const i64 P = (i64)H * W;
+    const T* img = in + b * P * Cn;
+    float wv[9][4], bs[4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) load4(w + t * Cn + c0, wv[t]);
+    load4(bias + c0, bs);
+    float a[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[s][k] = 0.f;
+    float sq[4] = {0.f, 0.f, 0.f, 0.f};
+    __align__(16) T buf[4][L];
+    const bool is_qk = MODE == 1 && c0 < 2 * C;
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) {
+      const int xc = x0 - 1 + j;
+      float v[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        if (yy >= 0 && yy < H && xc >= 0 && xc < W) {
+          load4(img + ((i64)yy * W + xc) * Cn + c0, v[r]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[r][k] = 0.f;
+        }
+      }
+      float* aN = a[(j + 2) % 3];  // output q = j      (this column is its left neighbour, kx = 0)
+      float* aC = a[(j + 1) % 3];  // output q = j - 1  (kx = 1)
+      float* aD = a[j % 3];        // output q = j - 2  (kx = 2) -> complete after this column
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        aN[k] = fmaf(wv[6][k], v[2][k], fmaf(wv[3][k], v[1][k], fmaf(wv[0][k], v[0][k], bs[k])));
+        aC[k] = fmaf(wv[7][k], v[2][k], fmaf(wv[4][k], v[1][k], fmaf(wv[1][k], v[0][k], aC[k])));
+        aD[k] = fmaf(wv[8][k], v[2][k], fmaf(wv[5][k], v[1][k], fmaf(wv[2][k], v[0][k], aD[k])));
+      }
+      const int q = j - 2;
+      if (q >= 0 && x0 + q < W) {
+        float o[4] = {aD[0], aD[1], aD[2], aD[3]};
+        if (MODE == 0) {
+          if (gelu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = gelu_erf_f(o[k]);
+          }
+          store4(out + (b * P + (i64)y * W + x0 + q) * Cn + c0, o);
+        } else if (is_qk) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            from_f(buf[k][q], o[k]);
+            const float r = to_f(buf[k][q]);  // statistics of the values the Gram GEMM will actually read
+            sq[k] = fmaf(r, r, sq[k]);
+          }
+        } else {
+          store4(out + (b * P + (i64)y * W + x0 + q) * C + (c0 - 2 * C), o);
+        }
+      }
+    }
+    if (is_qk) {
+      const i64 pix = (i64)y * W + x0;
+      const int nv = min(L, W - x0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        T* dst = qk + (b * 2 * C + c0 + k) * Ppad + pix;
+        if (nv == L && (((uintptr_t)dst) & 15) == 0) {
+#pragma unroll
+          for (int q = 0; q < L; q += 16 / (int)sizeof(T))
+            *reinterpret_cast<uint4*>(dst + q) = *reinterpret_cast<const uint4*>(&buf[k][q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < L; ++q)
+            if (q < nv) dst[q] = buf[k][q];
+        }
+        atomicAdd(&s_sq[c0 + k], sq[k]);
+      }
+    }
+  }
+  if (MODE == 1) {
+    __syncthreads();
+    for (int i = tid; i < 2 * C; i += blockDim.x) {
+      const float v = s_sq[i];
+      if (v != 0.f) atomicAdd(sumsq + b * 2 * C + i, v);
+    }
+  }
+}
+
+template <typename T, int MODE>
+static void run_dw_strip(Ctx& ctx, const void* in, const float* w, const float* bias, void* out, void* qk, float* sumsq,
+                         int gelu, int B, int H, int W, int Cn, int C, i64 Ppad) {
+  constexpr int L = 8;
+  const i64 total = (i64)H * cdiv(W, L) * (Cn / 4);
+  dim3 grid((unsigned)cdivl(total, 256), B);
+  k_dw_strip<T, MODE, L><<<grid, 256, 0, ctx.stream>>>((const T*)in, w, bias, (T*)out, (T*)qk, sumsq, gelu, H, W, Cn, C, Ppad,
+                                                      total);
+}
+
+void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H, int W,
+                   int Cn, int kernel_id) {
+  if (ctx.dry) return;
+  double px = (double)B * H * W;
+  ScopedLaunch sl(kernel_id, 2.0 * px * Cn * esize(ctx.dtype), 18.0 * px * Cn);
+  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
+  else run_dw_strip<float, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
+}
+
+void launch_dwqkv_planes(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, void* qk, float* sumsq,
+                         int B, int H, int W, int C, i64 Ppad) {
+  if (ctx.dry) return;
+  double px = (double)B * H * W;
+  ScopedLaunch sl(RF_K_DW_QKV_GRAM, 6.0 * px * C * esize(ctx.dtype), 54.0 * px * C);
+  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, v, qk, sumsq, 0, B, H, W, 3 * C, C, Ppad);
+  else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, v, qk, sumsq, 0, B, H, W, 3 * C, C, Ppad);
+}
+
+__global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict__ stats, int C) {
+  const i64 b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * C) stats[b * ((i64)C * C + 2 * C) + (i64)C * C + i] = sumsq[b * 2 * C + i];
+}
+void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C) {
+  if (ctx.dry) return;
+  ScopedLaunch sl(RF_K_MISC);
+  k_copy_norms<<<dim3(cdiv(2 * C, 256), B), 256, 0, ctx.stream>>>(sumsq, stats, C);
+}
+
+}  // namespace rf

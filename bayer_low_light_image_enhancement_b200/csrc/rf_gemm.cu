@@ -178,6 +178,10 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& p);
 void launch_gemm(Ctx& ctx, const GemmP& p) {
   if (ctx.dry || p.M <= 0 || p.N <= 0 || p.B <= 0) return;
   if (ctx.dtype == RF_BF16 && launch_gemm_tcgen05(ctx, p)) return;
+  if (p.omode == OMODE_ATOMIC_F32) {  // only the tcgen05 kernel implements the split-K atomic epilogue
+    recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   launch_gemm_cuda_core(ctx, p);
 }
 

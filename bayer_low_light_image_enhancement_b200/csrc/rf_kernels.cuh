@@ -63,7 +63,7 @@ struct PackedModel {
 // ---- generic "pixel-row" GEMM / implicit conv (rf_gemm.cu) ----------------------------------------------
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH_RES = 3 /* Y = R + 0.2*tanh(acc+bias) */ };
 enum { AMODE_ROWS = 0, AMODE_CONV3 = 1 };
-enum { OMODE_ROWS = 0, OMODE_CONVT = 1, OMODE_UNSHUFFLE = 2 };
+enum { OMODE_ROWS = 0, OMODE_CONVT = 1, OMODE_UNSHUFFLE = 2, OMODE_ATOMIC_F32 = 3 /* split-K: atomicAdd into fp32 Y */ };
 
 struct GemmP {
   const void* A1 = nullptr; const void* A2 = nullptr;  // [B][M][K1], [B][M][K2] (A2 optional: concatenated K)
@@ -73,6 +73,9 @@ struct GemmP {
   void* Y = nullptr;
   i64 lda1 = 0, lda2 = 0, ldr = 0, ldy = 0;             // row pitches in elements
   i64 w_img = 0;                                        // elements between per-image weights (0 = shared)
+  i64 a1_img = 0;                                       // elements between images of A1 (0 = lda1*M)
+  i64 ldw = 0;                                          // row pitch of Wt in elements (0 = K1+K2)
+  int ksplit = 1;                                       // split-K factor (OMODE_ATOMIC_F32 only)
   int M = 0, N = 0, K1 = 0, K2 = 0, B = 1;
   int act = ACT_NONE, amode = AMODE_ROWS, omode = OMODE_ROWS;
   int H = 0, W = 0;                                     // image size of the rows (m = y*W + x) for CONV3/CONVT/UNSHUFFLE
@@ -130,7 +133,13 @@ void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, v
 // depthwise 3x3 on qkv_pre [B,H,W,3C]; writes v [B,H,W,C]; accumulates stats[b] = {gram [8][c][c], qn2 [C], kn2 [C]}
 void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, float* stats, int B,
                        int H, int W, int C);
-inline i64 attn_stats_floats(int C) { return (i64)C * (C / 8) + 2 * C; }
+inline i64 attn_stats_floats(int C) { return (i64)C * C + 2 * C; }
+// strip-mined variant for the tensor-core Gram: v NHWC, q/k as channel-major planes qk[b][2C][Ppad], sumsq[b][2C]
+void launch_dwqkv_planes(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, void* qk,
+                         float* sumsq, int B, int H, int W, int C, i64 Ppad);
+bool tcgen05_enabled();
+// stats[b][C*C + i] = sumsq[b][i], i < 2C
+void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C);
 // Mw[b] = proj_w * blockdiag(softmax(gram / (|q||k|) * temperature))   (T [B][C][C])
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
                           int C);

@@ -30,9 +30,14 @@ int check_cuda(cudaError_t e) {
   return RF_ERR_CUDA;
 }
 
+static int g_debug_sync = -1;
+static int g_cur_kernel = -1;
+const char* kernel_name_of(int id);
+
 void launch_begin(int kernel_id, double algo_bytes, double algo_flops) {
   LaunchRecorder& r = g_rec;
   r.count++;
+  g_cur_kernel = kernel_id;
   if (r.profiling && r.n < r.cap) {
     r.ids[r.n] = kernel_id;
     r.bytes[r.n] = algo_bytes;
@@ -41,8 +46,19 @@ void launch_begin(int kernel_id, double algo_bytes, double algo_flops) {
   }
 }
 
+
 void launch_end() {
   LaunchRecorder& r = g_rec;
+  if (g_debug_sync < 0) {
+    const char* e = getenv("RAWFORMER_B200_DEBUG");
+    g_debug_sync = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_debug_sync) {  // debugging aid: synchronise after every launch and name the first failing kernel
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess && r.last_cuda_error == 0)
+      fprintf(stderr, "[rawformer_b200] kernel '%s' (launch #%lld) failed: %s\n", kernel_name_of(g_cur_kernel), r.count,
+              cudaGetErrorString(e));
+  }
   if (r.profiling) {
     if (r.n < r.cap) cudaEventRecord(r.ev[2 * r.n + 1], r.stream);
     r.n++;
@@ -56,7 +72,9 @@ static const char* const kKernelNames[RF_K_COUNT] = {
     "gemm_qkv", "dw_qkv_gram", "attn_finalize", "gemm_proj_resid", "gemm_pw1", "dw_gelu", "gemm_pw2_resid",
     "gemm_cat_reduce", "conv3x3_out", "down_conv3x3", "up_convT", "skip_reduce", "embed", "head", "layout",
     "weight_pack", "misc", "pyr_spatial", "gemm_pyr_res1", "gemm_pyr_res2", "channel_sums", "tail_stats",
-    "tail_apply", "index_op"};
+    "tail_apply", "index_op", "gemm_gram"};
+
+const char* kernel_name_of(int id) { return (id >= 0 && id < RF_K_COUNT) ? kKernelNames[id] : "?"; }
 
 }  // namespace rf
 

@@ -40,6 +40,7 @@ struct TcParams {
   int taps;            // 1 or 9
   int stages;
   int w_per_image;     // 1: weight tensor map coordinate 2 = image index
+  int ksplit;          // split-K factor: blockIdx.z = b*ksplit + split (OMODE_ATOMIC_F32)
   int tmem_cols;
 };
 
@@ -156,8 +157,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.taps * p.kb1 + p.kb2;
-  const int b = blockIdx.z;
+  const int nkb_all = p.taps * p.kb1 + p.kb2;
+  const int b = blockIdx.z / p.ksplit, split = blockIdx.z - b * p.ksplit;
+  const int kb_per = (nkb_all + p.ksplit - 1) / p.ksplit;
+  const int kb_begin = split * kb_per;
+  const int nkb = min(nkb_all, kb_begin + kb_per) - kb_begin;   // k-blocks of this CTA
+  if (nkb <= 0) return;                                         // uniform for the whole CTA
   const int n0 = blockIdx.y * p.BN;
   // tile origin
   int m0 = 0, px0 = 0, py0 = 0;
@@ -189,8 +194,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t tx = a_bytes + w_bytes;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages, it = i / p.stages;
+      for (int il = 0; il < nkb; ++il) {
+        const int i = kb_begin + il;
+        const int s = il % p.stages, it = il / p.stages;
         if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
         mbar_expect_tx(full_bar(s), tx);
         const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
@@ -212,8 +218,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages, it = i / p.stages;
+      for (int il = 0; il < nkb; ++il) {
+        const int i = kb_begin + il;
+        const int s = il % p.stages, it = il / p.stages;
         mbar_wait(full_bar(s), it & 1);
         tc_fence_after();
         // valid K in this block (zero-filled beyond): skip all-zero 16-wide slices
@@ -231,7 +238,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         const uint64_t bdesc = make_sw128_desc(sW + s * w_bytes);
         for (int k = 0; k < ksteps; ++k) {
           // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (i | k) ? 1u : 0u);
+          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (il | k) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
       }
@@ -285,7 +292,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = 0.2f * tanhf(f[j]);
       }
-      if (p.omode == OMODE_ROWS) {
+      if (p.omode == OMODE_ATOMIC_F32) {
+        float* yf = reinterpret_cast<float*>(p.Y) + orow * p.ldy + n;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < p.N) atomicAdd(yf + j, f[j]);
+      } else if (p.omode == OMODE_ROWS) {
         if (p.R) {
           float r8[8];
           load8(p.R + orow * p.ldr + n, r8);
@@ -393,10 +405,12 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   if (!g_tc_enabled || ctx.dtype != RF_BF16) return false;
   const int BN = pick_bn(g.N);
   if (BN == 0) return false;
-  if (g.K1 % 8 || g.K2 % 8) return false;
+  if (g.omode != OMODE_ATOMIC_F32 && (g.K1 % 8 || g.K2 % 8)) return false;  // (Gram: pitch is padded, TMA zero-fills the K tail)
+  if (g.lda1 % 8 || (g.A2 && g.lda2 % 8) || (g.ldw % 8)) return false;
   if (g.omode == OMODE_CONVT && ((g.N / 4) % 16)) return false;
   if (g.amode == AMODE_CONV3 && g.A2) return false;
-  if (g.amode != AMODE_CONV3 && (g.lda1 != g.K1 || (g.A2 && g.lda2 != g.K2))) return false;
+  if (g.amode != AMODE_CONV3 && g.omode != OMODE_ATOMIC_F32 && (g.lda1 != g.K1 || (g.A2 && g.lda2 != g.K2))) return false;
+  if (g.omode == OMODE_ATOMIC_F32 && (g.amode != AMODE_ROWS || g.A2 || g.bias || g.R || g.act != ACT_NONE)) return false;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -434,7 +448,7 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     p.tw = 128; p.th = 1; p.tiles_x = 1;
     grid_x = cdiv(g.M, TC_BM);
     const i64 dA[3] = {g.K1, g.M, g.B};
-    const i64 sA[3] = {1, g.lda1, g.lda1 * g.M};
+    const i64 sA[3] = {1, g.lda1, g.a1_img ? g.a1_img : g.lda1 * g.M};
     const int bA[3] = {TC_BK, TC_BM, 1};
     if (!make_map(&mA1, g.A1, 3, dA, sA, bA)) return false;
     if (g.A2) {
@@ -445,12 +459,15 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       mA2 = mA1;
     }
     const i64 K = g.K1 + (g.A2 ? g.K2 : 0);
+    const i64 ldw = g.ldw ? g.ldw : K;
     const i64 dW[3] = {K, g.N, g.w_img ? g.B : 1};
-    const i64 sW[3] = {1, K, g.w_img ? g.w_img : K * g.N};
+    const i64 sW[3] = {1, ldw, g.w_img ? g.w_img : ldw * g.N};
     const int bW[3] = {TC_BK, BN, 1};
     if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return false;
   }
-  const int nkb = p.taps * p.kb1 + p.kb2;
+  const int nkb_all = p.taps * p.kb1 + p.kb2;
+  p.ksplit = (g.omode == OMODE_ATOMIC_F32 && g.ksplit > 1) ? (g.ksplit < nkb_all ? g.ksplit : nkb_all) : 1;
+  const int nkb = cdiv(nkb_all, p.ksplit);
   p.stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
   int cols = 32;
   while (cols < BN) cols *= 2;
@@ -466,7 +483,7 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   const double abytes = rows * (g.amode == AMODE_CONV3 ? g.K1 / 9 : K) * es;
   const double bytes = abytes + rows * g.N * es * (g.R ? 2.0 : 1.0) + (double)g.N * K * es * (g.w_img ? g.B : 1);
   ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
-  dim3 grid(grid_x, g.N / BN, g.B);
+  dim3 grid(grid_x, g.N / BN, g.B * p.ksplit);
   k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, p);
   return true;
 }
