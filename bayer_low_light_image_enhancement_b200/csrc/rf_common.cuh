@@ -190,6 +190,27 @@ __device__ __forceinline__ void from_f(bf16& d, float v) { d = __float2bfloat16_
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float lrelu_f(float x) { return x >= 0.f ? x : 0.2f * x; }
+// bf16-mode transcendental forms (errors far below bf16 resolution): MUFU-based sigmoid / tanh, and the exact-erf
+// GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) instead of the branchy libdevice erff.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * __expf(-z * z);       // erfc(|x|/sqrt2)
+  const float cdf = x >= 0.f ? 1.0f - 0.5f * erfc_z : 0.5f * erfc_z;
+  return x * cdf;
+}
+template <typename T> struct FastMath { static constexpr bool value = false; };
+template <> struct FastMath<__nv_bfloat16> { static constexpr bool value = true; };
 
 // float max via integer atomics (handles negatives); *addr must be initialised to -inf
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {

@@ -12,22 +12,38 @@
 
 namespace rf {
 
+template <typename T> struct RawVec;
+template <> struct RawVec<bf16> {
+  typedef uint2 type;
+  __device__ static __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
+  __device__ static __forceinline__ void unpack(const uint2& t, float (&v)[4]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
+template <> struct RawVec<float> {
+  typedef float4 type;
+  __device__ static __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static __forceinline__ void unpack(const float4& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+};
+
 template <typename T, int MODE, int L>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384, 2)
 k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
            T* __restrict__ qk, float* __restrict__ sumsq, int gelu, int H, int W, int Cn, int C, i64 Ppad, i64 total) {
-  __shared__ float s_sq[MODE == 1 ? 1024 : 1];
-  const int tid = threadIdx.x;
+  // block = (Cn/4 channel groups, SY strips); total = strips per image
+  __shared__ float s_sq[MODE == 1 ? 1024 : 1];  // [SY][2C] partial squared norms (SY*2C <= 1024)
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
   const i64 b = blockIdx.y;
+  const i64 strip = (i64)blockIdx.x * blockDim.y + threadIdx.y;
+  const int c0 = threadIdx.x * 4;
   if (MODE == 1) {
-    for (int i = tid; i < 2 * C; i += blockDim.x) s_sq[i] = 0.f;
+    for (int i = tid; i < (int)blockDim.y * 2 * C; i += nthr) s_sq[i] = 0.f;
     __syncthreads();
   }
-  const i64 idx = (i64)blockIdx.x * blockDim.x + tid;
-  if (idx < total) {
-    const int V4 = Cn >> 2, SW = (W + L - 1) / L;
-    const int c0 = (int)(idx % V4) * 4;
-    const i64 strip = idx / V4;
+  if (strip < total) {
+    const int SW = (W + L - 1) / L;
     const int x0 = (int)(strip % SW) * L, y = (int)(strip / SW);
     const i64 P = (i64)H * W;
     const T* img = in + b * P * Cn;
@@ -35,6 +51,7 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
 #pragma unroll
     for (int t = 0; t < 9; ++t) load4(w + t * Cn + c0, wv[t]);
     load4(bias + c0, bs);
+    typedef typename RawVec<T>::type raw_t;
     float a[3][4];
 #pragma unroll
     for (int s = 0; s < 3; ++s)
@@ -50,12 +67,9 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int yy = y + r - 1;
-        if (yy >= 0 && yy < H && xc >= 0 && xc < W) {
-          load4(img + ((i64)yy * W + xc) * Cn + c0, v[r]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[r][k] = 0.f;
-        }
+        raw_t rv = RawVec<T>::zero();
+        if (yy >= 0 && yy < H && xc >= 0 && xc < W) rv = *reinterpret_cast<const raw_t*>(img + ((i64)yy * W + xc) * Cn + c0);
+        RawVec<T>::unpack(rv, v[r]);
       }
       float* aN = a[(j + 2) % 3];  // output q = j      (this column is its left neighbour, kx = 0)
       float* aC = a[(j + 1) % 3];  // output q = j - 1  (kx = 1)
@@ -72,7 +86,7 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
         if (MODE == 0) {
           if (gelu) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = gelu_erf_f(o[k]);
+            for (int k = 0; k < 4; ++k) o[k] = FastMath<T>::value ? gelu_erf_fast(o[k]) : gelu_erf_f(o[k]);
           }
           store4(out + (b * P + (i64)y * W + x0 + q) * Cn + c0, o);
         } else if (is_qk) {
@@ -102,14 +116,15 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
           for (int q = 0; q < L; ++q)
             if (q < nv) dst[q] = buf[k][q];
         }
-        atomicAdd(&s_sq[c0 + k], sq[k]);
+        s_sq[threadIdx.y * 2 * C + c0 + k] = sq[k];
       }
     }
   }
   if (MODE == 1) {
     __syncthreads();
-    for (int i = tid; i < 2 * C; i += blockDim.x) {
-      const float v = s_sq[i];
+    for (int i = tid; i < 2 * C; i += nthr) {
+      float v = 0.f;
+      for (int sy = 0; sy < (int)blockDim.y; ++sy) v += s_sq[sy * 2 * C + i];
       if (v != 0.f) atomicAdd(sumsq + b * 2 * C + i, v);
     }
   }
@@ -119,9 +134,11 @@ template <typename T, int MODE>
 static void run_dw_strip(Ctx& ctx, const void* in, const float* w, const float* bias, void* out, void* qk, float* sumsq,
                          int gelu, int B, int H, int W, int Cn, int C, i64 Ppad) {
   constexpr int L = 8;
-  const i64 total = (i64)H * cdiv(W, L) * (Cn / 4);
-  dim3 grid((unsigned)cdivl(total, 256), B);
-  k_dw_strip<T, MODE, L><<<grid, 256, 0, ctx.stream>>>((const T*)in, w, bias, (T*)out, (T*)qk, sumsq, gelu, H, W, Cn, C, Ppad,
+  const i64 total = (i64)H * cdiv(W, L);   // strips per image
+  const int V4 = Cn / 4;
+  const int SY = V4 >= 256 ? 1 : 256 / V4;
+  dim3 grid((unsigned)cdivl(total, SY), B), block(V4, SY);
+  k_dw_strip<T, MODE, L><<<grid, block, 0, ctx.stream>>>((const T*)in, w, bias, (T*)out, (T*)qk, sumsq, gelu, H, W, Cn, C, Ppad,
                                                       total);
 }
 

@@ -9,23 +9,17 @@
 
 namespace rf {
 
-constexpr int FLCA_PIX = 2;
+constexpr int FLCA_SLOTS = 32;   // partial-sum slots per image (atomically accumulated, then summed by se_finalize)
+constexpr int FLCA_LS = 32;      // pixels per warp strip
 
 int flca_num_partials(int C, int B, i64 P) {
-  int cv = C / 8;
-  int ppb = 256 / cv;
-  if (ppb < 1) ppb = 1;
-  i64 per_iter = (i64)ppb * FLCA_PIX;
-  i64 want = cdivl(P, per_iter * 4);  // >= 4 iterations per block
-  i64 cap = (i64)num_sms() * 8 / (B > 0 ? B : 1);
-  if (cap < 1) cap = 1;
-  i64 n = want < cap ? want : cap;
-  return (int)(n < 1 ? 1 : n);
+  (void)C; (void)B; (void)P;
+  return FLCA_SLOTS;
 }
 
-template <typename T>
-__device__ __forceinline__ float act_sig(float x) { return sigmoid_f(x); }
-
+// One warp = 32 channels (one per lane) x a strip of FLCA_LS pixels of one row.  Each lane keeps the 9 x NM tap weights
+// of ITS channel in registers; the guidance column (3 rows x NM maps) is a warp-uniform load that feeds the three
+// outputs it touches (sliding window), so the inner loop is register-only FFMA + 3 MUFU per output.
 // G: [B,Hf,Wf,NG] guidance.  MODE 0: FLCA (maps 0..3 of NG=4): xmod = feat*(1 + a*sig(low) + b*tanh(high) + g*sig(chr)).
 // MODE 1: pyramid level (maps 2l, 2l+1 of NG=8): xs = x*(ga*sig(low_l) + gb*tanh(high_l)).
 // MODE 2: pyramid chroma (maps 4,5 of NG=8): xs = x*(gc*sig(chr)).
@@ -33,143 +27,142 @@ __device__ __forceinline__ float act_sig(float x) { return sigmoid_f(x); }
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 k_flca_mod(const T* __restrict__ feat, const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ coef,
-           T* __restrict__ xmod, float* __restrict__ partial, int Hf, int Wf, int C, int level) {
+           T* __restrict__ xmod, float* __restrict__ partial, int Hf, int Wf, int C, int level, i64 tasks) {
   constexpr int NG = MODE == 0 ? 4 : 8;
   constexpr int NW = MODE == 0 ? 4 : 6;
-  constexpr int NA = MODE == 0 ? 3 : (MODE == 1 ? 2 : 1);  // pre-activations per channel
-  constexpr int PIX = FLCA_PIX;
-  extern __shared__ float smem[];
-  float* sw = smem;  // [9][NW][C]
-  const int cv = blockDim.x, ppb = blockDim.y;
-  const int tid = threadIdx.y * cv + threadIdx.x, nthr = cv * ppb;
-  for (int i = tid; i < 9 * NW * C; i += nthr) sw[i] = w[i];
-  __syncthreads();
+  constexpr int NM = MODE == 0 ? 4 : 2;                      // maps used
+  constexpr int NA = MODE == 0 ? 3 : (MODE == 1 ? 2 : 1);    // pre-activations
+  constexpr int LS = FLCA_LS;
+  const int lane = threadIdx.x & 31;
   const i64 b = blockIdx.y;
-  const int c0 = threadIdx.x * 8;
-  float k0, k1, k2;
+  const i64 task = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= tasks) return;
+  const int CG = (C + 31) >> 5, SW = (Wf + LS - 1) / LS;
+  const int cg = (int)(task % CG);
+  const i64 t2 = task / CG;
+  const int x0 = (int)(t2 % SW) * LS, y = (int)(t2 / SW);
+  const int c = cg * 32 + lane;
+  const bool c_ok = c < C;
+  const int cc = c_ok ? c : C - 1;
+  const int m0 = MODE == 0 ? 0 : (MODE == 1 ? 2 * level : 4);   // first map used (guidance pixel and weight row)
+  float wv[9][NM];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int g = 0; g < NM; ++g) wv[t][g] = w[(t * NW + m0 + g) * C + cc];
+  float k0, k1 = 0.f, k2 = 0.f;
   if constexpr (MODE == 0) { k0 = coef[0]; k1 = coef[1]; k2 = coef[2]; }
-  else if constexpr (MODE == 1) { k0 = coef[b * 6 + 2 * level]; k1 = coef[b * 6 + 2 * level + 1]; k2 = 0.f; }
-  else { k0 = coef[b * 6 + 4]; k1 = 0.f; k2 = 0.f; }
-  // map indices inside a guidance pixel and inside the weight row
-  const int gA = MODE == 0 ? 0 : (MODE == 1 ? 2 * level : 4);
-  const int gB = gA + 1;
-  const int Wp = (Wf + PIX - 1) / PIX;           // pixel groups per row
-  const i64 groups = (i64)Hf * Wp;
-  float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const float* Gb = G + b * (i64)Hf * Wf * NG;
-  for (i64 g = (i64)blockIdx.x * ppb + threadIdx.y; g < groups; g += (i64)gridDim.x * ppb) {
-    const int y = (int)(g / Wp), x0 = (int)(g % Wp) * PIX;
-    float acc[PIX][NA][8];
+  else if constexpr (MODE == 1) { k0 = coef[b * 6 + 2 * level]; k1 = coef[b * 6 + 2 * level + 1]; }
+  else { k0 = coef[b * 6 + 4]; }
+  const float* Gb = G + b * (i64)Hf * Wf * NG + m0;
+  const T* fb = feat + b * (i64)Hf * Wf * C;
+  T* ob = xmod + b * (i64)Hf * Wf * C;
+  // stage the warp's guidance window (3 rows x LS+2 columns x NM maps) in shared memory with coalesced loads, and
+  // prefetch the strip's feature values, so that every global request of the warp is in flight before the FMA loop
+  __shared__ float sG[8][3][LS + 2][NM];
+  const int wslot = threadIdx.x >> 5;
+  for (int idx = lane; idx < 3 * (LS + 2); idx += 32) {
+    const int r = idx / (LS + 2), j = idx - r * (LS + 2);
+    const int yy = y + r - 1, xc = x0 - 1 + j;
+    float gv[NM];
 #pragma unroll
-    for (int p = 0; p < PIX; ++p)
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[p][a][j] = 0.f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= Hf) continue;
-#pragma unroll
-      for (int dxx = -1; dxx <= PIX; ++dxx) {  // guidance column x0 + dxx feeds pixels p with tap dx = dxx - p
-        const int xx = x0 + dxx;
-        if (xx < 0 || xx >= Wf) continue;
-        const float* gp = Gb + ((i64)yy * Wf + xx) * NG;
-        float ga, gb, gc = 0.f, gd = 0.f;
-        if constexpr (MODE == 0) {
-          float4 q = *reinterpret_cast<const float4*>(gp);
-          ga = q.x; gb = q.y; gc = q.z; gd = q.w;
-        } else {
-          float2 q = *reinterpret_cast<const float2*>(gp + gA);
-          ga = q.x; gb = q.y;
-        }
-#pragma unroll
-        for (int p = 0; p < PIX; ++p) {
-          const int dx = dxx - p;
-          if (dx < -1 || dx > 1) continue;
-          const int t = (dy + 1) * 3 + (dx + 1);
-          const float* wr = sw + (t * NW) * C + c0;
-          if constexpr (MODE == 0) {
-            float wl[8], wh[8], w2[8], w3[8];
-            load8(wr, wl); load8(wr + C, wh); load8(wr + 2 * C, w2); load8(wr + 3 * C, w3);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc[p][0][j] = fmaf(wl[j], ga, acc[p][0][j]);
-              acc[p][1][j] = fmaf(wh[j], gb, acc[p][1][j]);
-              acc[p][2][j] = fmaf(w2[j], gc, fmaf(w3[j], gd, acc[p][2][j]));
-            }
-          } else if constexpr (MODE == 1) {
-            float wl[8], wh[8];
-            load8(wr + gA * C, wl); load8(wr + gB * C, wh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc[p][0][j] = fmaf(wl[j], ga, acc[p][0][j]);
-              acc[p][1 % NA][j] = fmaf(wh[j], gb, acc[p][1 % NA][j]);
-            }
-          } else {
-            float w2[8], w3[8];
-            load8(wr + 4 * C, w2); load8(wr + 5 * C, w3);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p][0][j] = fmaf(w2[j], ga, fmaf(w3[j], gb, acc[p][0][j]));
-          }
-        }
+    for (int m = 0; m < NM; ++m) gv[m] = 0.f;
+    if (yy >= 0 && yy < Hf && xc >= 0 && xc < Wf) {
+      const float* gp = Gb + ((i64)yy * Wf + xc) * NG;
+      if constexpr (NM == 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(gp);
+        gv[0] = q4.x; gv[1] = q4.y; gv[2] = q4.z; gv[3] = q4.w;
+      } else {
+        const float2 q2 = *reinterpret_cast<const float2*>(gp);
+        gv[0] = q2.x; gv[1] = q2.y;
       }
     }
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) {
-      const int x = x0 + p;
-      if (x >= Wf) continue;
-      const i64 off = ((b * Hf + y) * (i64)Wf + x) * C + c0;
-      float f[8], o[8];
-      load8(feat + off, f);
+    for (int m = 0; m < NM; ++m) sG[wslot][r][j][m] = gv[m];
+  }
+  T fv[LS];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+  for (int q = 0; q < LS; ++q) {
+    if (c_ok && x0 + q < Wf) fv[q] = fb[((i64)y * Wf + x0 + q) * C + c];
+    else from_f(fv[q], 0.f);
+  }
+  __syncwarp();
+  float a[3][NA];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int q = 0; q < NA; ++q) a[s][q] = 0.f;
+  float csum = 0.f;
+  const int ncol = min(LS, Wf - x0) + 2;
+#pragma unroll
+  for (int j0 = 0; j0 < LS + 2; j0 += 3) {
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {       // the accumulator rotation is static
+      const int j = j0 + jj;
+      if (j >= LS + 2) break;
+      if (j >= ncol) break;
+      float g[3][NM];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) g[r][m] = sG[wslot][r][j][m];
+      float* aN = a[(jj + 2) % 3];  // output q = j      (kx = 0)
+      float* aC = a[(jj + 1) % 3];  // output q = j - 1  (kx = 1)
+      float* aD = a[jj % 3];        // output q = j - 2  (kx = 2), complete after this column
+      // pre-activation index per map: MODE 0: maps (LL, hi, cr, cb) -> (0, 1, 2, 2); MODE 1: (0, 1); MODE 2: (0, 0)
+#pragma unroll
+      for (int q = 0; q < NA; ++q) aN[q] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          const int q = MODE == 0 ? (m < 2 ? m : 2) : (MODE == 1 ? m : 0);
+          aN[q] = fmaf(wv[r * 3 + 0][m], g[r][m], aN[q]);
+          aC[q] = fmaf(wv[r * 3 + 1][m], g[r][m], aC[q]);
+          aD[q] = fmaf(wv[r * 3 + 2][m], g[r][m], aD[q]);
+        }
+      const int qo = j - 2;
+      if (qo >= 0) {
+        const int x = x0 + qo;
         float sp;
-        if constexpr (MODE == 0)
-          sp = 1.f + k0 * sigmoid_f(acc[p][0][j]) + k1 * tanhf(acc[p][1][j]) + k2 * sigmoid_f(acc[p][2][j]);
-        else if constexpr (MODE == 1)
-          sp = k0 * sigmoid_f(acc[p][0][j]) + k1 * tanhf(acc[p][1 % NA][j]);
-        else
-          sp = k0 * sigmoid_f(acc[p][0][j]);
-        o[j] = f[j] * sp;
-        csum[j] += o[j];
+        if constexpr (MODE == 0) {
+          if (FastMath<T>::value)
+            sp = 1.f + k0 * sigmoid_fast(aD[0]) + k1 * tanh_fast(aD[1]) + k2 * sigmoid_fast(aD[2]);
+          else
+            sp = 1.f + k0 * sigmoid_f(aD[0]) + k1 * tanhf(aD[1]) + k2 * sigmoid_f(aD[2]);
+        } else if constexpr (MODE == 1) {
+          sp = FastMath<T>::value ? k0 * sigmoid_fast(aD[0]) + k1 * tanh_fast(aD[1 % NA])
+                                  : k0 * sigmoid_f(aD[0]) + k1 * tanhf(aD[1 % NA]);
+        } else {
+          sp = FastMath<T>::value ? k0 * sigmoid_fast(aD[0]) : k0 * sigmoid_f(aD[0]);
+        }
+        if (c_ok) {
+          const i64 off = ((i64)y * Wf + x) * C + c;
+          const float o = to_f(fv[qo]) * sp;
+          from_f(ob[off], o);
+          csum += o;
+        }
       }
-      store8(xmod + off, o);
     }
   }
-  if (partial != nullptr) {
-    // reduce csum over the ppb pixel lanes of the block (reuse the weight smem after a barrier)
-    __syncthreads();
-    float* red = smem;  // [ppb][C]
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.y * C + c0 + j] = csum[j];
-    __syncthreads();
-    for (int c = tid; c < C; c += nthr) {
-      float s = 0.f;
-      for (int r = 0; r < ppb; ++r) s += red[r * C + c];
-      partial[(b * gridDim.x + blockIdx.x) * C + c] = s;
-    }
-  }
+  if (partial != nullptr && c_ok) atomicAdd(partial + (b * FLCA_SLOTS + (task % FLCA_SLOTS)) * C + c, csum);
 }
 
 template <typename T, int MODE>
 static void run_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w, const float* coef, void* xmod,
                          float* partial, int nblk, int B, int Hf, int Wf, int C, int level, int kid) {
-  const int cv = C / 8;
-  int ppb = 256 / cv;
-  if (ppb < 1) ppb = 1;
-  constexpr int NW = MODE == 0 ? 4 : 6;
-  size_t smem = sizeof(float) * (size_t)C * (9 * NW > ppb ? 9 * NW : ppb);
-  auto kern = k_flca_mod<T, MODE>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  (void)nblk;
+  const i64 tasks = (i64)Hf * cdiv(Wf, FLCA_LS) * cdiv(C, 32);
   double px = (double)B * Hf * Wf;
   ScopedLaunch sl(kid, px * C * 2.0 * sizeof(T) + px * 16.0, px * C * 2.0 * (MODE == 0 ? 36 : 18));
-  kern<<<dim3(nblk, B), dim3(cv, ppb), smem, ctx.stream>>>((const T*)feat, G, w, coef, (T*)xmod, partial, Hf, Wf, C, level);
+  k_flca_mod<T, MODE><<<dim3((unsigned)cdivl(tasks, 8), B), 256, 0, ctx.stream>>>((const T*)feat, G, w, coef, (T*)xmod, partial,
+                                                                                 Hf, Wf, C, level, tasks);
 }
 
 void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
                      float* partial, int nblk, int B, int Hf, int Wf, int C) {
   if (ctx.dry) return;
+  launch_fill_f32(ctx, partial, 0.f, (i64)B * FLCA_SLOTS * C);
   if (ctx.dtype == RF_BF16)
     run_flca_mod<bf16, 0>(ctx, feat, G, w36, abg, xmod, partial, nblk, B, Hf, Wf, C, 0, RF_K_FLCA_MOD);
   else
@@ -179,13 +172,12 @@ void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w3
 void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,
                         int level, int B, int Hf, int Wf, int C) {
   if (ctx.dry) return;
-  int nblk = flca_num_partials(C, B, (i64)Hf * Wf);
   if (ctx.dtype == RF_BF16) {
-    if (mode == 0) run_flca_mod<bf16, 1>(ctx, x, G8, w54, gates, xs, nullptr, nblk, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
-    else run_flca_mod<bf16, 2>(ctx, x, G8, w54, gates, xs, nullptr, nblk, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
+    if (mode == 0) run_flca_mod<bf16, 1>(ctx, x, G8, w54, gates, xs, nullptr, 0, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
+    else run_flca_mod<bf16, 2>(ctx, x, G8, w54, gates, xs, nullptr, 0, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
   } else {
-    if (mode == 0) run_flca_mod<float, 1>(ctx, x, G8, w54, gates, xs, nullptr, nblk, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
-    else run_flca_mod<float, 2>(ctx, x, G8, w54, gates, xs, nullptr, nblk, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
+    if (mode == 0) run_flca_mod<float, 1>(ctx, x, G8, w54, gates, xs, nullptr, 0, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
+    else run_flca_mod<float, 2>(ctx, x, G8, w54, gates, xs, nullptr, 0, B, Hf, Wf, C, level, RF_K_PYR_SPATIAL);
   }
 }
 
