@@ -5,9 +5,9 @@
 // weights stay in registers.  That is 3(L+2)/L vector loads per output instead of 9 + weights, which is what moves
 // these kernels from L1-bound to HBM-bound.
 //   MODE 0: out = [gelu](dw(in) + bias), NHWC                       (conv_ffn.depthwise + GELU, FLCA_RF.py:206-207)
-//   MODE 1: in = qkv_pre [.,3C]: v -> NHWC [.,C]; q,k -> channel-major planes qk[b][2C][Ppad] (so the Gram
-//           q k^T over pixels is a K-major tensor-core GEMM) and their squared norms -> sumsq[b][2C]
-//           (Attention.qkv_dwconv + F.normalize statistics, FLCA_RF.py:223-229)
+//   MODE 1: in = qkv_pre [.,3C] -> out = dw(in)+bias [.,3C] (q | k | v interleaved per pixel, NHWC) and the squared
+//           norms of the q,k channels -> sumsq[b][2C]  (Attention.qkv_dwconv + F.normalize statistics,
+//           FLCA_RF.py:223-229); the Gram q k^T is then a tensor-core kernel with MN-major operands (rf_tc_gemm.cu)
 #include "rf_kernels.cuh"
 
 namespace rf {
@@ -58,7 +58,6 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
 #pragma unroll
       for (int k = 0; k < 4; ++k) a[s][k] = 0.f;
     float sq[4] = {0.f, 0.f, 0.f, 0.f};
-    __align__(16) T buf[4][L];
     const bool is_qk = MODE == 1 && c0 < 2 * C;
 #pragma unroll
     for (int j = 0; j < L + 2; ++j) {
@@ -89,35 +88,25 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
             for (int k = 0; k < 4; ++k) o[k] = FastMath<T>::value ? gelu_erf_fast(o[k]) : gelu_erf_f(o[k]);
           }
           store4(out + (b * P + (i64)y * W + x0 + q) * Cn + c0, o);
-        } else if (is_qk) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            from_f(buf[k][q], o[k]);
-            const float r = to_f(buf[k][q]);  // statistics of the values the Gram GEMM will actually read
-            sq[k] = fmaf(r, r, sq[k]);
-          }
         } else {
-          store4(out + (b * P + (i64)y * W + x0 + q) * C + (c0 - 2 * C), o);
+          // MODE 1: q,k,v all stay NHWC; squared norms of the ROUNDED q,k values (what the Gram kernel reads)
+          T ob[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) from_f(ob[k], o[k]);
+          if (is_qk) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float r = to_f(ob[k]);
+              sq[k] = fmaf(r, r, sq[k]);
+            }
+          }
+          store4(out + (b * P + (i64)y * W + x0 + q) * Cn + c0, o);
         }
       }
     }
     if (is_qk) {
-      const i64 pix = (i64)y * W + x0;
-      const int nv = min(L, W - x0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        T* dst = qk + (b * 2 * C + c0 + k) * Ppad + pix;
-        if (nv == L && (((uintptr_t)dst) & 15) == 0) {
-#pragma unroll
-          for (int q = 0; q < L; q += 16 / (int)sizeof(T))
-            *reinterpret_cast<uint4*>(dst + q) = *reinterpret_cast<const uint4*>(&buf[k][q]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < L; ++q)
-            if (q < nv) dst[q] = buf[k][q];
-        }
-        s_sq[threadIdx.y * 2 * C + c0 + k] = sq[k];
-      }
+      for (int k = 0; k < 4; ++k) s_sq[threadIdx.y * 2 * C + c0 + k] = sq[k];
     }
   }
   if (MODE == 1) {
@@ -151,13 +140,13 @@ void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_
   else run_dw_strip<float, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
 }
 
-void launch_dwqkv_planes(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, void* qk, float* sumsq,
-                         int B, int H, int W, int C, i64 Ppad) {
+void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qkv, float* sumsq, int B,
+                       int H, int W, int C) {
   if (ctx.dry) return;
   double px = (double)B * H * W;
   ScopedLaunch sl(RF_K_DW_QKV_GRAM, 6.0 * px * C * esize(ctx.dtype), 54.0 * px * C);
-  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, v, qk, sumsq, 0, B, H, W, 3 * C, C, Ppad);
-  else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, v, qk, sumsq, 0, B, H, W, 3 * C, C, Ppad);
+  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, qkv, nullptr, sumsq, 0, B, H, W, 3 * C, C, 0);
+  else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qkv, nullptr, sumsq, 0, B, H, W, 3 * C, C, 0);
 }
 
 __global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict__ stats, int C) {

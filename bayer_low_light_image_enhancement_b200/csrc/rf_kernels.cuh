@@ -134,9 +134,11 @@ void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, v
 void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, float* stats, int B,
                        int H, int W, int C);
 inline i64 attn_stats_floats(int C) { return (i64)C * C + 2 * C; }
-// strip-mined variant for the tensor-core Gram: v NHWC, q/k as channel-major planes qk[b][2C][Ppad], sumsq[b][2C]
-void launch_dwqkv_planes(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, void* qk,
-                         float* sumsq, int B, int H, int W, int C, i64 Ppad);
+// strip-mined variant for the tensor-core Gram: qkv = dw(qkv_pre) NHWC [.,3C], sumsq[b][2C] = squared norms of q,k
+void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qkv, float* sumsq, int B,
+                       int H, int W, int C);
+// G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qkv [P][3C]); false if the tcgen05 path is unavailable
+bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P);
 bool tcgen05_enabled();
 // stats[b][C*C + i] = sumsq[b][i], i < 2C
 void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C);

@@ -220,44 +220,35 @@ static void attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const vo
   const size_t mk = A.mark();
   void* qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
   launch_gemm(ctx, gemm_rows(xin, C, pb.qkv_w, pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV));
-  void* v = A.elems((size_t)B * P * C, ctx.dtype);
   const i64 nst = attn_stats_floats(C);
   float* stats = A.get<float>((size_t)B * nst);
   launch_fill_f32(ctx, stats, 0.f, B * nst);
-  if (ctx.dtype == RF_BF16 && tcgen05_enabled() && C % 16 == 0) {
-    // tensor-core Gram: depthwise pass writes q,k as channel-major planes, then G = q k^T is a split-K tcgen05 GEMM
-    // over the pixel axis with an fp32 atomic epilogue (rows = q channels, columns = k channels).
-    const i64 Ppad = (P + 7) & ~(i64)7;      // 16-byte row pitch for the TMA tensor map
-    void* qk = A.elems((size_t)B * 2 * C * Ppad, ctx.dtype);
+  const void* v = nullptr;
+  i64 ldv = C;
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+    // depthwise pass keeps q|k|v interleaved (NHWC, coalesced) and reduces |q|^2,|k|^2; the Gram is a split-K
+    // tcgen05 kernel with MN-major operands reading q,k straight from that tensor; v is a strided view of it.
+    void* qkvd = A.elems((size_t)B * P * 3 * C, ctx.dtype);
     float* sumsq = A.get<float>((size_t)B * 2 * C);
     launch_fill_f32(ctx, sumsq, 0.f, (i64)B * 2 * C);
-    launch_dwqkv_planes(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, v, qk, sumsq, B, H, W, C, Ppad);
-    GemmP gg;
-    gg.A1 = qk; gg.K1 = (int)P; gg.lda1 = Ppad; gg.a1_img = 2 * C * Ppad;
-    gg.Wt = (const char*)qk + (size_t)C * Ppad * esize(ctx.dtype); gg.ldw = Ppad; gg.w_img = 2 * C * Ppad;
-    gg.Y = stats; gg.ldy = C; gg.M = C; gg.N = C; gg.B = B;
-    gg.omode = OMODE_ATOMIC_F32;
-    const int tiles = cdiv(C, 128) * cdiv(C, 256);
-    gg.ksplit = 2 * num_sms() / tiles > 1 ? 2 * num_sms() / tiles : 1;
-    gg.kernel_id = RF_K_GEMM_GRAM;
-    // the gram rows of image b live at stats + b*nst, not b*M*ldy: launch per image
-    for (int b = 0; b < B; ++b) {
-      GemmP g1 = gg;
-      g1.B = 1;
-      g1.A1 = (const char*)qk + (size_t)b * 2 * C * Ppad * esize(ctx.dtype);
-      g1.Wt = (const char*)g1.A1 + (size_t)C * Ppad * esize(ctx.dtype);
-      g1.w_img = 0;
-      g1.Y = stats + b * nst;
-      launch_gemm(ctx, g1);
+    launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qkvd, sumsq, B, H, W, C);
+    if (!ctx.dry) {
+      for (int b = 0; b < B; ++b)
+        if (!launch_gram_tcgen05(ctx, (const char*)qkvd + (size_t)b * P * 3 * C * 2, stats + b * nst, C, P))
+          recorder().last_cuda_error = (int)cudaErrorNotSupported;
     }
-    // squared norms next to the Gram (same layout as the fused CUDA-core kernel)
     launch_copy_norms(ctx, sumsq, stats, B, C);
+    v = (const char*)qkvd + (size_t)2 * C * 2;
+    ldv = 3 * C;
   } else {
-    launch_dwqkv_gram(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, v, stats, B, H, W, C);
+    void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
+    launch_dwqkv_gram(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, vbuf, stats, B, H, W, C);
+    v = vbuf;
   }
   void* Mw = A.elems((size_t)B * C * C, ctx.dtype);
   launch_attn_finalize(ctx, stats, pb.temperature, pb.proj_w, Mw, B, C);
   GemmP g = gemm_rows(v, C, Mw, pb.proj_b, out, C, B, P, RF_K_GEMM_PROJ);
+  g.lda1 = ldv;
   g.w_img = (i64)C * C;
   g.R = resid; g.ldr = C;
   launch_gemm(ctx, g);

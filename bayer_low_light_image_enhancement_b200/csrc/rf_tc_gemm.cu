@@ -391,6 +391,126 @@ static int pick_bn(int N) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Gram kernel of the transposed attention:  G[i][j] += sum_p q[p][i] * k[p][j]   (FLCA_RF.py:230, before softmax)
+// q,k live interleaved in the NHWC depthwise output [P][3C] (q = channels [0,C), k = [C,2C)).  Pixels are the
+// contraction axis, so both operands are "MN-major" for UMMA: a TMA box of 64 channels x 128 pixels lands as 128 rows
+// (pixels) of 128 B, which is exactly the canonical MN-major SWIZZLE_128B atom stack (SBO = 1024 B between 8-pixel
+// groups, LBO = one 16 KB chunk tile between 64-channel groups).  One CTA owns a 128x128 tile of G and a slice of the
+// pixel range (split-K); the accumulator stays in TMEM over the whole slice and only the per-head diagonal blocks
+// are added to global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int GR_STAGES = 3;
+constexpr int GR_PIX = 128;                    // pixels per k-block
+constexpr uint32_t GR_CHUNK = GR_PIX * 128;    // bytes of one 64-channel x 128-pixel chunk tile
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(GR_CHUNK >> 4) << 16;   // LBO: next 64-element group along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row group along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS)
+k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int C, i64 P, int ksplit) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = 4 * GR_CHUNK;   // A: 2 chunks, B: 2 chunks
+  const uint32_t bars = base + GR_STAGES * stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (GR_STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * GR_STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * GR_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int c = C >> 3;  // head width
+  // heads touched by the rows / columns of this tile: skip tiles without a common head
+  const int hr0 = m0 / c, hr1 = (min(m0 + 128, C) - 1) / c, hc0 = n0 / c, hc1 = (min(n0 + 128, C) - 1) / c;
+  if (hr1 < hc0 || hc1 < hr0) return;
+  const int nkb_all = (int)((P + GR_PIX - 1) / GR_PIX);
+  const int kb_per = (nkb_all + ksplit - 1) / ksplit;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int nkb = min(nkb_all, kb_begin + kb_per) - kb_begin;
+  if (nkb <= 0) return;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQK);
+    for (int s = 0; s < GR_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int il = 0; il < nkb; ++il) {
+        const int s = il % GR_STAGES, it = il / GR_STAGES;
+        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t dst = base + s * stage_bytes;
+        const int p0 = (kb_begin + il) * GR_PIX;
+        tma_load_3d(dst, &mapQK, full_bar(s), m0, p0, 0);
+        tma_load_3d(dst + GR_CHUNK, &mapQK, full_bar(s), m0 + 64, p0, 0);
+        tma_load_3d(dst + 2 * GR_CHUNK, &mapQK, full_bar(s), C + n0, p0, 0);
+        tma_load_3d(dst + 3 * GR_CHUNK, &mapQK, full_bar(s), C + n0 + 64, p0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // kind::f16, D=f32, A=B=bf16, both MN-major (bits 15, 16), M = N = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      for (int il = 0; il < nkb; ++il) {
+        const int s = il % GR_STAGES, it = il / GR_STAGES;
+        mbar_wait(full_bar(s), it & 1);
+        tc_fence_after();
+        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + 2 * GR_CHUNK;
+        const uint64_t adesc = make_sw128_mn_desc(a0), bdesc = make_sw128_mn_desc(b0);
+#pragma unroll
+        for (int k = 0; k < GR_PIX / 16; ++k)   // 16 pixels = 16 rows of 128 B = 2048 B per MMA
+          umma_f16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (il | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;   // q channel
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int h = row < C ? row / c : -1;
+    for (int cc = 0; cc < 128; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + cc, v);
+      tmem_ld_wait();
+      if (h < 0) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = n0 + cc + j;   // k channel
+        if (col < C && col / c == h) atomicAdd(G + (i64)row * C + col, __uint_as_float(v[j]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 static bool g_tc_enabled = true;
 static bool g_tc_checked = false;
 void set_tcgen05_enabled(bool on) { g_tc_enabled = on; g_tc_checked = true; }
@@ -409,7 +529,7 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   if (g.lda1 % 8 || (g.A2 && g.lda2 % 8) || (g.ldw % 8)) return false;
   if (g.omode == OMODE_CONVT && ((g.N / 4) % 16)) return false;
   if (g.amode == AMODE_CONV3 && g.A2) return false;
-  if (g.amode != AMODE_CONV3 && g.omode != OMODE_ATOMIC_F32 && (g.lda1 != g.K1 || (g.A2 && g.lda2 != g.K2))) return false;
+  if (g.amode != AMODE_CONV3 && (g.lda1 < g.K1 || (g.A2 && g.lda2 < g.K2))) return false;
   if (g.omode == OMODE_ATOMIC_F32 && (g.amode != AMODE_ROWS || g.A2 || g.bias || g.R || g.act != ACT_NONE)) return false;
 
   TcParams p;
@@ -485,6 +605,30 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
   dim3 grid(grid_x, g.N / BN, g.B * p.ksplit);
   k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, p);
+  return true;
+}
+
+// qkv: bf16 NHWC [P][3C] of ONE image; G: fp32 [C][C], zero-initialised by the caller
+bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
+  if (!g_tc_enabled || ctx.dtype != RF_BF16 || C % 8) return false;
+  CUtensorMap m;
+  const i64 d[3] = {3 * (i64)C, P, 1};
+  const i64 st[3] = {1, 3 * (i64)C, 3 * (i64)C * P};
+  const int bx[3] = {64, GR_PIX, 1};
+  if (!make_map(&m, qkv, 3, d, st, bx)) return false;
+  const int mt = cdiv(C, 128);
+  const int nkb = (int)((P + GR_PIX - 1) / GR_PIX);
+  int ksplit = 2 * num_sms() / (mt * mt);
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > nkb) ksplit = nkb;
+  const size_t smem = 1024 + (size_t)GR_STAGES * 4 * GR_CHUNK + 8 * (2 * GR_STAGES + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    attr_set = true;
+  }
+  ScopedLaunch sl(RF_K_GEMM_GRAM, 4.0 * C * P, 2.0 * P * C * (C / 8.0));
+  k_tc_gram<<<dim3(mt, mt, ksplit), TC_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit);
   return true;
 }
 
