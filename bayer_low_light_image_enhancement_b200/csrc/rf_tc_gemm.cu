@@ -5,7 +5,8 @@
 // One CTA = one 128-row pixel tile x one BN-column slice.  Warp roles (192 threads):
 //   warp 0   : TMA producer  (one elected lane; full/empty mbarrier ring of `stages` k-blocks)
 //   warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16)
-//   warps 2-5: epilogue  (tcgen05.ld 32x32b -> bias / activation / residual -> bf16 -> global)
+//   warps 2-9: epilogue  (tcgen05.ld 32x32b -> bias / activation / residual -> bf16 -> global); two warps share
+//              each TMEM lane quadrant and split the 16-column chunks between them
 // A operand forms:
 //   rows  : 3-d tensor map [K, M, B]; k-blocks run over A1 then A2 (K-concatenation = the cat fusions)
 //   conv3 : 4-d tensor map [C, W, H, B]; the M tile is a th x tw pixel patch and every 3x3 tap is the same box
@@ -21,8 +22,9 @@ namespace rf {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_THREADS = 320;      // 2 control warps + 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_MAX_STAGES = 8;
 
 struct TcParams {
   const float* bias;
@@ -41,7 +43,9 @@ struct TcParams {
   int stages;
   int w_per_image;     // 1: weight tensor map coordinate 2 = image index
   int ksplit;          // split-K factor: blockIdx.z = b*ksplit + split (OMODE_ATOMIC_F32)
-  int tmem_cols;
+  int tmem_cols;       // allocated TMEM columns (two accumulator buffers)
+  int acc_cols;        // column offset of the second accumulator buffer
+  int tiles_m, tiles_n, total_tiles;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -66,6 +70,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -141,6 +148,37 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+struct TileCoord {
+  int b, split, n0, m0, px0, py0, kb_begin, nkb;
+};
+
+// tile index -> coordinates; N slices of the same pixel tile are adjacent so that they share the A tile through L2
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord tc;
+  const int ny = t % p.tiles_n;
+  int r = t / p.tiles_n;
+  const int mx = r % p.tiles_m;
+  const int z = r / p.tiles_m;
+  tc.b = z / p.ksplit;
+  tc.split = z - tc.b * p.ksplit;
+  tc.n0 = ny * p.BN;
+  tc.m0 = 0; tc.px0 = 0; tc.py0 = 0;
+  if (p.amode == AMODE_CONV3) {
+    tc.px0 = (mx % p.tiles_x) * p.tw;
+    tc.py0 = (mx / p.tiles_x) * p.th;
+  } else {
+    tc.m0 = mx * TC_BM;
+  }
+  const int nkb_all = p.taps * p.kb1 + p.kb2;
+  const int kb_per = (nkb_all + p.ksplit - 1) / p.ksplit;
+  tc.kb_begin = tc.split * kb_per;
+  tc.nkb = min(nkb_all, tc.kb_begin + kb_per) - tc.kb_begin;
+  return tc;
+}
+
+// Persistent, warp-specialised: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer
+// runs ahead across tile boundaries through the smem ring; the accumulator is double-buffered in tensor memory so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapW, const TcParams p) {
@@ -152,26 +190,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   const uint32_t bars = sW + p.stages * w_bytes;          // 8-byte aligned (multiples of 128)
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
-  const uint32_t tmem_full = bars + 8u * (2 * TC_MAX_STAGES);
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 1);
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb_all = p.taps * p.kb1 + p.kb2;
-  const int b = blockIdx.z / p.ksplit, split = blockIdx.z - b * p.ksplit;
-  const int kb_per = (nkb_all + p.ksplit - 1) / p.ksplit;
-  const int kb_begin = split * kb_per;
-  const int nkb = min(nkb_all, kb_begin + kb_per) - kb_begin;   // k-blocks of this CTA
-  if (nkb <= 0) return;                                         // uniform for the whole CTA
-  const int n0 = blockIdx.y * p.BN;
-  // tile origin
-  int m0 = 0, px0 = 0, py0 = 0;
-  if (p.amode == AMODE_CONV3) {
-    px0 = (blockIdx.x % p.tiles_x) * p.tw;
-    py0 = (blockIdx.x / p.tiles_x) * p.th;
-  } else {
-    m0 = blockIdx.x * TC_BM;
-  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA1);
@@ -181,7 +205,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -194,23 +221,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t tx = a_bytes + w_bytes;
-      for (int il = 0; il < nkb; ++il) {
-        const int i = kb_begin + il;
-        const int s = il % p.stages, it = il / p.stages;
-        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
-        mbar_expect_tx(full_bar(s), tx);
-        const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
-        if (p.amode == AMODE_CONV3) {
-          const int tap = i / p.kb1, cb = i - tap * p.kb1;
-          tma_load_4d(dstA, &mapA1, full_bar(s), cb * TC_BK, px0 + tap % 3 - 1, py0 + tap / 3 - 1, b);
-          tma_load_3d(dstW, &mapW, full_bar(s), cb * TC_BK, tap, n0);
-        } else if (i < p.kb1) {
-          tma_load_3d(dstA, &mapA1, full_bar(s), i * TC_BK, m0, b);
-          tma_load_3d(dstW, &mapW, full_bar(s), i * TC_BK, n0, p.w_per_image ? b : 0);
-        } else {
-          const int j = i - p.kb1;
-          tma_load_3d(dstA, &mapA2, full_bar(s), j * TC_BK, m0, b);
-          tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * TC_BK, n0, p.w_per_image ? b : 0);
+      int g = 0;  // k-blocks issued so far (ring position)
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int il = 0; il < tc.nkb; ++il, ++g) {
+          const int i = tc.kb_begin + il;
+          const int s = g % p.stages, it = g / p.stages;
+          if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+          mbar_expect_tx(full_bar(s), tx);
+          const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
+          if (p.amode == AMODE_CONV3) {
+            const int tap = i / p.kb1, cb = i - tap * p.kb1;
+            tma_load_4d(dstA, &mapA1, full_bar(s), cb * TC_BK, tc.px0 + tap % 3 - 1, tc.py0 + tap / 3 - 1, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), cb * TC_BK, tap, tc.n0);
+          } else if (i < p.kb1) {
+            tma_load_3d(dstA, &mapA1, full_bar(s), i * TC_BK, tc.m0, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), i * TC_BK, tc.n0, p.w_per_image ? tc.b : 0);
+          } else {
+            const int j = i - p.kb1;
+            tma_load_3d(dstA, &mapA2, full_bar(s), j * TC_BK, tc.m0, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * TC_BK, tc.n0, p.w_per_image ? tc.b : 0);
+          }
         }
       }
     }
@@ -218,121 +249,160 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN);
-      for (int il = 0; il < nkb; ++il) {
-        const int i = kb_begin + il;
-        const int s = il % p.stages, it = il / p.stages;
-        mbar_wait(full_bar(s), it & 1);
-        tc_fence_after();
-        // valid K in this block (zero-filled beyond): skip all-zero 16-wide slices
-        int kvalid;
-        if (p.amode == AMODE_CONV3) {
-          const int cb = i % p.kb1;
-          kvalid = min(TC_BK, p.K1 - cb * TC_BK);
-        } else if (i < p.kb1) {
-          kvalid = min(TC_BK, p.K1 - i * TC_BK);
-        } else {
-          kvalid = min(TC_BK, p.K2 - (i - p.kb1) * TC_BK);
+      int g = 0, ti = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        if (tc.nkb <= 0) continue;
+        const int acc = ti & 1, u = ti >> 1;
+        if (u > 0) {                                  // wait until the epilogue drained this accumulator buffer
+          mbar_wait(tempty_bar(acc), (u - 1) & 1);
+          tc_fence_after();
         }
-        const int ksteps = (kvalid + 15) >> 4;
-        const uint64_t adesc = make_sw128_desc(sA + s * a_bytes);
-        const uint64_t bdesc = make_sw128_desc(sW + s * w_bytes);
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (il | k) ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+        for (int il = 0; il < tc.nkb; ++il, ++g) {
+          const int i = tc.kb_begin + il;
+          const int s = g % p.stages, it = g / p.stages;
+          mbar_wait(full_bar(s), it & 1);
+          tc_fence_after();
+          // valid K in this block (zero-filled beyond): skip all-zero 16-wide slices
+          int kvalid;
+          if (p.amode == AMODE_CONV3) {
+            const int cb = i % p.kb1;
+            kvalid = min(TC_BK, p.K1 - cb * TC_BK);
+          } else if (i < p.kb1) {
+            kvalid = min(TC_BK, p.K1 - i * TC_BK);
+          } else {
+            kvalid = min(TC_BK, p.K2 - (i - p.kb1) * TC_BK);
+          }
+          const int ksteps = (kvalid + 15) >> 4;
+          const uint64_t adesc = make_sw128_desc(sA + s * a_bytes);
+          const uint64_t bdesc = make_sw128_desc(sW + s * w_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (il | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
+        umma_commit(tfull_bar(acc));          // accumulator complete
+        ++ti;
       }
-      umma_commit(tmem_full);               // accumulator complete
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the 16-column chunks this warp handles
     const int r = quad * 32 + lane;         // row of the tile
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    // output row
-    bool row_ok;
-    i64 orow = 0;        // OMODE_ROWS: row index into R/Y
-    int oy = 0, ox = 0;  // pixel coordinates (conv / scatter modes)
-    if (p.amode == AMODE_CONV3) {
-      oy = py0 + r / p.tw;
-      ox = px0 + r % p.tw;
-      row_ok = oy < p.H && ox < p.W;
-      orow = (i64)b * p.M + (i64)oy * p.W + ox;
-    } else {
-      const int m = m0 + r;
-      row_ok = m < p.M;
-      orow = (i64)b * p.M + m;
-      if (p.omode != OMODE_ROWS) { oy = m / p.W; ox = m - oy * p.W; }
-    }
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const int n = n0 + c;
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
-          f[j] += bq.x; f[j + 1] += bq.y; f[j + 2] += bq.z; f[j + 3] += bq.w;
-        }
-      }
-      if (p.act == ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = lrelu_f(f[j]);
-      } else if (p.act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-      } else if (p.act == ACT_TANH_RES) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = 0.2f * tanhf(f[j]);
-      }
-      if (p.omode == OMODE_ATOMIC_F32) {
-        float* yf = reinterpret_cast<float*>(p.Y) + orow * p.ldy + n;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n + j < p.N) atomicAdd(yf + j, f[j]);
-      } else if (p.omode == OMODE_ROWS) {
-        if (p.R) {
-          float r8[8];
-          load8(p.R + orow * p.ldr + n, r8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += r8[j];
-          load8(p.R + orow * p.ldr + n + 8, r8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
-        }
-        float o8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = f[j];
-        store8(p.Y + orow * p.ldy + n, o8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
-        store8(p.Y + orow * p.ldy + n + 8, o8);
-      } else if (p.omode == OMODE_CONVT) {
-        const int Co = p.N >> 2;
-        const int ij = n / Co, co = n - ij * Co;   // 16-wide chunk never straddles ij (Co % 16 == 0)
-        const i64 dst = (((i64)b * 2 * p.H + 2 * oy + (ij >> 1)) * (2 * p.W) + 2 * ox + (ij & 1)) * p.ldy + co;
-        float o8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = f[j];
-        store8(p.Y + dst, o8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
-        store8(p.Y + dst + 8, o8);
+    int ti = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      if (tc.nkb <= 0) continue;
+      const int acc = ti & 1, u = ti >> 1;
+      const int b = tc.b, n0 = tc.n0;
+      mbar_wait(tfull_bar(acc), u & 1);
+      tc_fence_after();
+      // output row
+      bool row_ok;
+      i64 orow = 0;        // OMODE_ROWS: row index into R/Y
+      int oy = 0, ox = 0;  // pixel coordinates (conv / scatter modes)
+      if (p.amode == AMODE_CONV3) {
+        oy = tc.py0 + r / p.tw;
+        ox = tc.px0 + r % p.tw;
+        row_ok = oy < p.H && ox < p.W;
+        orow = (i64)b * p.M + (i64)oy * p.W + ox;
       } else {
-        const i64 dst = (((i64)b * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1)) * p.ldy + 2 * (oy & 1) + (ox & 1);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) p.Y[dst + (i64)(n + j) * 4] = __float2bfloat16_rn(f[j]);
+        const int m = tc.m0 + r;
+        row_ok = m < p.M;
+        orow = (i64)b * p.M + m;
+        if (p.omode != OMODE_ROWS) { oy = m / p.W; ox = m - oy * p.W; }
       }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      for (int c = half * 16; c < p.BN; c += 32) {
+        const int n = n0 + c;
+        const int nvalid = p.N - n;          // < 16 only in the last chunk when N % 16 == 8
+        // residual prefetch (global) is issued before the TMEM load so both latencies overlap
+        uint4 rr0 = make_uint4(0u, 0u, 0u, 0u), rr1 = rr0;
+        const bool use_r = p.R != nullptr && p.omode == OMODE_ROWS && row_ok && nvalid > 0;
+        if (use_r) {
+          rr0 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n);
+          if (nvalid > 8) rr1 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n + 8);
+        }
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (!row_ok || nvalid <= 0) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (j < nvalid) {
+              const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
+              f[j] += bq.x; f[j + 1] += bq.y; f[j + 2] += bq.z; f[j + 3] += bq.w;
+            }
+          }
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = lrelu_f(f[j]);
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == ACT_TANH_RES) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = 0.2f * tanh_fast(f[j]);
+        }
+        if (p.omode == OMODE_ATOMIC_F32) {
+          float* yf = reinterpret_cast<float*>(p.Y) + orow * p.ldy + n;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.N) atomicAdd(yf + j, f[j]);
+        } else if (p.omode == OMODE_ROWS) {
+          if (use_r) {
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&rr0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&rr1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x0 = __bfloat1622float2(h0[j]), x1 = __bfloat1622float2(h1[j]);
+              f[2 * j] += x0.x; f[2 * j + 1] += x0.y;
+              f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+            }
+          }
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = f[j];
+          store8(p.Y + orow * p.ldy + n, o8);
+          if (nvalid > 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
+            store8(p.Y + orow * p.ldy + n + 8, o8);
+          }
+        } else if (p.omode == OMODE_CONVT) {
+          const int Co = p.N >> 2;
+          const int ij = n / Co, co = n - ij * Co;   // 16-wide chunk never straddles ij (Co % 16 == 0)
+          const i64 dst = (((i64)b * 2 * p.H + 2 * oy + (ij >> 1)) * (2 * p.W) + 2 * ox + (ij & 1)) * p.ldy + co;
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = f[j];
+          store8(p.Y + dst, o8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
+          store8(p.Y + dst + 8, o8);
+        } else {
+          const i64 dst = (((i64)b * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1)) * p.ldy + 2 * (oy & 1) + (ox & 1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) p.Y[dst + (i64)(n + j) * 4] = __float2bfloat16_rn(f[j]);
+        }
+      }
+      // this warp is done reading the accumulator buffer: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      ++ti;
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -381,8 +451,9 @@ static bool make_map(CUtensorMap* m, const void* base, int rank, const i64* dims
 }
 
 static int pick_bn(int N) {
+  if (N % 8) return 0;
+  if (N <= 256) return (N + 15) & ~15;   // N % 16 == 8: the last 8 columns are zero weights (TMA OOB) and masked stores
   if (N % 16) return 0;
-  if (N <= 256) return N;
   for (int parts = 2; parts <= 64; ++parts) {
     if (N % parts) continue;
     int bn = N / parts;
@@ -402,6 +473,7 @@ static int pick_bn(int N) {
 // are added to global memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int GR_STAGES = 3;
+constexpr int GR_THREADS = 192;               // TMA warp, MMA warp, 4 epilogue warps
 constexpr int GR_PIX = 128;                    // pixels per k-block
 constexpr uint32_t GR_CHUNK = GR_PIX * 128;    // bytes of one 64-channel x 128-pixel chunk tile
 
@@ -415,7 +487,7 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(GR_THREADS)
 k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int C, i64 P, int ksplit) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -587,12 +659,22 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   }
   const int nkb_all = p.taps * p.kb1 + p.kb2;
   p.ksplit = (g.omode == OMODE_ATOMIC_F32 && g.ksplit > 1) ? (g.ksplit < nkb_all ? g.ksplit : nkb_all) : 1;
-  const int nkb = cdiv(nkb_all, p.ksplit);
-  p.stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
+  // smem ring: as deep as ~190 KB allows (the producer prefetches across tile boundaries), at most TC_MAX_STAGES
+  const size_t stage_bytes = (size_t)TC_BM * 128 + (size_t)BN * 128;
   int cols = 32;
   while (cols < BN) cols *= 2;
-  p.tmem_cols = cols;
-  const size_t smem = 1024 + (size_t)p.stages * (TC_BM * 128 + (size_t)BN * 128) + 8 * (2 * TC_MAX_STAGES + 2);
+  // two CTAs per SM (two producer / MMA / epilogue sets) when the accumulators fit twice in tensor memory
+  const int ctas_per_sm = (2 * cols <= 256) ? 2 : 1;
+  int stages = (int)(((ctas_per_sm == 2 ? 104 : 200) * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.acc_cols = cols;
+  p.tmem_cols = 2 * cols;                     // BN <= 256 -> <= 512 columns
+  p.tiles_m = grid_x;
+  p.tiles_n = cdiv(g.N, BN);
+  p.total_tiles = p.tiles_m * p.tiles_n * g.B * p.ksplit;
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 8 * (2 * TC_MAX_STAGES + 6);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
@@ -603,7 +685,8 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   const double abytes = rows * (g.amode == AMODE_CONV3 ? g.K1 / 9 : K) * es;
   const double bytes = abytes + rows * g.N * es * (g.R ? 2.0 : 1.0) + (double)g.N * K * es * (g.w_img ? g.B : 1);
   ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
-  dim3 grid(grid_x, g.N / BN, g.B * p.ksplit);
+  const int max_ctas = num_sms() * ctas_per_sm;
+  const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
   k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, p);
   return true;
 }
@@ -628,7 +711,7 @@ bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
     attr_set = true;
   }
   ScopedLaunch sl(RF_K_GEMM_GRAM, 4.0 * C * P, 2.0 * P * C * (C / 8.0));
-  k_tc_gram<<<dim3(mt, mt, ksplit), TC_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit);
+  k_tc_gram<<<dim3(mt, mt, ksplit), GR_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit);
   return true;
 }
 

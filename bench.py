@@ -271,7 +271,7 @@ def run_ours(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
     roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
                 avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=None)
-    breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])[:8]
+    breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])
 
     frames_total = args.steps * B * world
     value = frames_total * MP_FRAME / (ms_total * 1e-3)
