@@ -1,0 +1,108 @@
+"""Operators either side of the forward and the WFB gated-GELU FFN, as C-ABI calls.
+
+* ``postprocess_u8``   -- test.py:117-118: clamp(pred,0,1) -> *255 -> uint8 (truncation) -> HWC.
+* ``preprocess_u16``   -- WFB/load_dataset.py:88-89 + correctdataloader.py:103 on a uint16 Bayer frame.
+* ``FeedForward``      -- RawFomer_WFB_FFAB/model.py:42-87 (eval mode): the two Conv2d_BN branches and the identity are folded
+  into one depthwise 3x3 exactly like the reference's own ``fuse()``; hidden = int(dim*factor) is zero-padded to a multiple of 8.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, f32c, ptr, stream_ptr
+from .modules import _Op
+
+
+def postprocess_u8(pred: torch.Tensor) -> torch.Tensor:
+    """[B,3,H,W] float -> [B,H,W,3] uint8, the arithmetic of test.py:117-118 on the device."""
+    pred = _Op._prep(pred, "pred", 3)
+    b, _, h, w = pred.shape
+    out = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred.device)
+    if out.numel():
+        check(_lib.load().rf_postprocess_u8(ptr(pred), ptr(out), b, h, w, stream_ptr(pred.device)), "rf_postprocess_u8")
+    return out
+
+
+def preprocess_u16(raw: torch.Tensor, black: float = 512.0, white: float = 16383.0, ratio: float = 100.0) -> torch.Tensor:
+    """uint16 Bayer [B,H,W] -> float32 [B,1,H,W] in [0,1] (black-level subtract, white-level scale, exposure ratio, clip)."""
+    if raw.dim() != 3:
+        raise ValueError("raw must be [B,H,W]")
+    _lib.init_device(raw.device)
+    if raw.dtype not in (torch.uint16, torch.int16):
+        raise ValueError("raw must be a 16-bit integer tensor")
+    raw = raw.contiguous()
+    b, h, w = raw.shape
+    out = torch.empty(b, 1, h, w, dtype=torch.float32, device=raw.device)
+    if out.numel():
+        check(_lib.load().rf_preprocess_u16(ptr(raw), ptr(out), float(black), float(white), float(ratio), b, h, w,
+                                            stream_ptr(raw.device)), "rf_preprocess_u16")
+    return out
+
+
+class _Conv2dBN(nn.Sequential):
+    """Parameter container with the reference's names ('c', 'bn').  Reference: WFB/model.py:17-25."""
+
+    def __init__(self, ch, ks):
+        super().__init__()
+        self.add_module("c", nn.Conv2d(ch, ch, ks, 1, ks // 2, groups=ch, bias=False))
+        self.add_module("bn", nn.BatchNorm2d(ch))
+
+
+class FeedForward(_Op):
+    """Gated-GELU FFN of the WFB variant, inference (eval-mode BatchNorm).  Reference: WFB/model.py:42-65."""
+
+    def __init__(self, dim, ffn_expansion_factor, bias):
+        super().__init__()
+        hidden = int(dim * ffn_expansion_factor)
+        self.dim, self.hidden = dim, hidden
+        self.rep_conv1 = _Conv2dBN(hidden, 3)
+        self.rep_conv2 = _Conv2dBN(hidden, 1)
+        self.project_in = nn.Conv2d(dim, hidden, 1, bias=bias)
+        self.dwconv = nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden, bias=bias)
+        self.project_out = nn.Conv2d(hidden, dim, 1, bias=bias)
+
+    @torch.no_grad()
+    def _folded(self, device):
+        """x1 = x + BN(dw3(x)) + BN(dw1(x)) as one depthwise 3x3 + bias (the reference's fuse(), WFB/model.py:67-87)."""
+        def bn_fold(seq):
+            s = seq.bn.weight / torch.sqrt(seq.bn.running_var + seq.bn.eps)
+            return seq.c.weight * s[:, None, None, None], seq.bn.bias - seq.bn.running_mean * s
+
+        w3, b3 = bn_fold(self.rep_conv1)
+        w1, b1 = bn_fold(self.rep_conv2)
+        wa = w3.clone()
+        wa[:, :, 1, 1] += w1[:, :, 0, 0] + 1.0
+        ba = b3 + b1
+        hp = (self.hidden + 7) // 8 * 8
+        pad = hp - self.hidden
+
+        def padn(t, dim=0):
+            if pad == 0 or t is None:
+                return None if t is None else f32c(t.to(device))
+            shape = list(t.shape)
+            shape[dim] = pad
+            return f32c(torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim).to(device))
+
+        return dict(
+            hp=hp, w_in=padn(self.project_in.weight), b_in=padn(self.project_in.bias), wa=padn(wa), ba=padn(ba),
+            wb=padn(self.dwconv.weight), bb=padn(self.dwconv.bias), w_out=padn(self.project_out.weight, 1),
+            b_out=None if self.project_out.bias is None else f32c(self.project_out.bias.to(device)))
+
+    def forward(self, x):
+        if self.training:
+            raise RuntimeError("FeedForward kernels implement inference (call .eval()): BatchNorm uses running statistics")
+        x = self._prep(x, "x", self.dim)
+        b, c, h, w = x.shape
+        f = self._folded(x.device)
+        hp = f["hp"]
+        lib = _lib.load()
+        es = 2 if self._dtype() == _lib.RF_BF16 else 4
+        nbytes = (b * h * w * (2 * c + 2 * hp) + 2 * hp * c) * es + 4 * (24 * hp + 2 * c) + (1 << 16)
+        ws = _lib.shared_workspace(nbytes, x.device)
+        out = torch.empty_like(x)
+        check(lib.rf_feedforward_gated(ptr(f["w_in"]), ptr(f["b_in"]), ptr(f["wa"]), ptr(f["ba"]), ptr(f["wb"]), ptr(f["bb"]),
+                                       ptr(f["w_out"]), ptr(f["b_out"]), c, hp, self._dtype(), ptr(x), ptr(out), b, h, w,
+                                       ptr(ws), ws.numel(), stream_ptr(x.device)), "rf_feedforward_gated")
+        return out

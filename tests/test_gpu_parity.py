@@ -284,3 +284,31 @@ def test_full_frame_properties(rf):
     # crop consistency away from the borders is NOT expected (global statistics) -- but the top-left 64x64 of the
     # frame must equal the oracle-checked small-model path in its index work: out[2y+i,2x+j] channel layout.
     assert float(o32.abs().max()) < 1e4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# callers either side of the forward and the WFB gated FFN
+# ---------------------------------------------------------------------------------------------------------
+def test_postprocess_preprocess(rf):
+    pred = torch.randn(2, 3, 20, 28, device=dev()) * 0.8 + 0.4
+    got = rf.postprocess_u8(pred).cpu().numpy()
+    ref = (torch.clamp(pred, 0, 1).cpu().numpy().transpose(0, 2, 3, 1) * 255).astype(np.uint8)  # test.py:117-118
+    assert np.array_equal(got, ref)
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 16384, size=(2, 16, 24)).astype(np.uint16)
+    for ap in (100, 300):
+        x = np.clip(raw.astype(np.float32), 512, 16383)                       # WFB/load_dataset.py:88-89
+        x = (x - 512) / (16383 - 512 + 1e-6) * ap
+        x = np.minimum(x, 1.0).astype(np.float32)                              # correctdataloader.py:103
+        got = rf.preprocess_u16(torch.from_numpy(raw.view(np.int16)).to(dev()).view(torch.uint16), 512.0, 16383.0, float(ap))
+        assert_close("preprocess", got.cpu().numpy()[:, 0], x, 1e-6, scaled=False)
+
+
+def test_wfb_feedforward_gated(rf):
+    keys = [str(k) for k in OPS["wfb_ffn_keys"]]
+    sd = {k: torch.from_numpy(OPS["wfb_ffn_sd." + k]) for k in keys}
+    ff = rf.FeedForward(32, 2.66, False)
+    ff.load_state_dict(sd, strict=True)
+    ff = ff.to(dev()).eval()
+    out = ff(cu(T.gen_input("randn", (2, 32, 6, 9), 25)))
+    assert_close("wfb_ffn", npy(out), OPS["wfb_ffn_c32"], 1e-4)
