@@ -5,8 +5,8 @@
 // weights stay in registers.  That is 3(L+2)/L vector loads per output instead of 9 + weights, which is what moves
 // these kernels from L1-bound to HBM-bound.
 //   MODE 0: out = [gelu](dw(in) + bias), NHWC                       (conv_ffn.depthwise + GELU, FLCA_RF.py:206-207)
-//   MODE 1: in = qkv_pre [.,3C] -> out = dw(in)+bias [.,3C] (q | k | v interleaved per pixel, NHWC) and the squared
-//           norms of the q,k channels -> sumsq[b][2C]  (Attention.qkv_dwconv + F.normalize statistics,
+//   MODE 1: in = qkv_pre [.,3C] -> dw(in)+bias split into out = q|k [.,2C] and vout = v [.,C] (both dense NHWC) and the
+//           squared norms of the q,k channels -> sumsq[b][2C]  (Attention.qkv_dwconv + F.normalize statistics,
 //           FLCA_RF.py:223-229); the Gram q k^T is then a tensor-core kernel with MN-major operands (rf_tc_gemm.cu)
 #include "rf_kernels.cuh"
 
@@ -31,7 +31,7 @@ template <> struct RawVec<float> {
 template <typename T, int MODE, int L>
 __global__ void __launch_bounds__(384, 2)
 k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-           T* __restrict__ qk, float* __restrict__ sumsq, int gelu, int H, int W, int Cn, int C, i64 Ppad, i64 total) {
+           T* __restrict__ vout, float* __restrict__ sumsq, int gelu, int H, int W, int Cn, int C, i64 Ppad, i64 total) {
   // block = (Cn/4 channel groups, SY strips); total = strips per image
   __shared__ float s_sq[MODE == 1 ? 1024 : 1];  // [SY][2C] partial squared norms (SY*2C <= 1024)
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
@@ -100,7 +100,9 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
               sq[k] = fmaf(r, r, sq[k]);
             }
           }
-          store4(out + (b * P + (i64)y * W + x0 + q) * Cn + c0, o);
+          const i64 pix = b * P + (i64)y * W + x0 + q;
+          if (is_qk) store4(out + pix * 2 * C + c0, o);
+          else store4(vout + pix * C + (c0 - 2 * C), o);
         }
       }
     }
@@ -120,14 +122,14 @@ k_dw_strip(const T* __restrict__ in, const float* __restrict__ w, const float* _
 }
 
 template <typename T, int MODE>
-static void run_dw_strip(Ctx& ctx, const void* in, const float* w, const float* bias, void* out, void* qk, float* sumsq,
+static void run_dw_strip(Ctx& ctx, const void* in, const float* w, const float* bias, void* out, void* vout, float* sumsq,
                          int gelu, int B, int H, int W, int Cn, int C, i64 Ppad) {
   constexpr int L = 8;
   const i64 total = (i64)H * cdiv(W, L);   // strips per image
   const int V4 = Cn / 4;
   const int SY = V4 >= 256 ? 1 : 256 / V4;
   dim3 grid((unsigned)cdivl(total, SY), B), block(V4, SY);
-  k_dw_strip<T, MODE, L><<<grid, block, 0, ctx.stream>>>((const T*)in, w, bias, (T*)out, (T*)qk, sumsq, gelu, H, W, Cn, C, Ppad,
+  k_dw_strip<T, MODE, L><<<grid, block, 0, ctx.stream>>>((const T*)in, w, bias, (T*)out, (T*)vout, sumsq, gelu, H, W, Cn, C, Ppad,
                                                       total);
 }
 
@@ -136,17 +138,19 @@ void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_
   if (ctx.dry) return;
   double px = (double)B * H * W;
   ScopedLaunch sl(kernel_id, 2.0 * px * Cn * esize(ctx.dtype), 18.0 * px * Cn);
+  if (ctx.dtype == RF_BF16 && launch_dwconv_tma(ctx, in, dw_w, dw_b, out, gelu, B, H, W, Cn)) return;
   if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
   else run_dw_strip<float, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
 }
 
-void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qkv, float* sumsq, int B,
-                       int H, int W, int C) {
+void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
+                       int B, int H, int W, int C) {
   if (ctx.dry) return;
   double px = (double)B * H * W;
   ScopedLaunch sl(RF_K_DW_QKV_GRAM, 6.0 * px * C * esize(ctx.dtype), 54.0 * px * C);
-  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, qkv, nullptr, sumsq, 0, B, H, W, 3 * C, C, 0);
-  else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qkv, nullptr, sumsq, 0, B, H, W, 3 * C, C, 0);
+  if (ctx.dtype == RF_BF16 && launch_dwqkv_tma(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, C)) return;
+  if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
+  else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
 }
 
 __global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict__ stats, int C) {

@@ -134,11 +134,17 @@ void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, v
 void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* v, float* stats, int B,
                        int H, int W, int C);
 inline i64 attn_stats_floats(int C) { return (i64)C * C + 2 * C; }
-// strip-mined variant for the tensor-core Gram: qkv = dw(qkv_pre) NHWC [.,3C], sumsq[b][2C] = squared norms of q,k
-void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qkv, float* sumsq, int B,
-                       int H, int W, int C);
-// G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qkv [P][3C]); false if the tcgen05 path is unavailable
-bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P);
+// variant for the tensor-core Gram: dw(qkv_pre) split into qk [.,2C] (q | k) and v [.,C], both dense NHWC;
+// sumsq[b][2C] = squared norms of q,k (must be zeroed)
+void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
+                       int B, int H, int W, int C);
+// TMA-staged bf16 depthwise kernels (rf_dw_tma.cu); false when the shape is not supported
+bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H, int W,
+                       int Cn);
+bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
+                      int B, int H, int W, int C);
+// G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qk [P][2C]); false if the tcgen05 path is unavailable
+bool launch_gram_tcgen05(Ctx& ctx, const void* qk, float* G, int C, i64 P);
 bool tcgen05_enabled();
 // stats[b][C*C + i] = sumsq[b][i], i < 2C
 void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C);

@@ -226,20 +226,20 @@ static void attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const vo
   const void* v = nullptr;
   i64 ldv = C;
   if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
-    // depthwise pass keeps q|k|v interleaved (NHWC, coalesced) and reduces |q|^2,|k|^2; the Gram is a split-K
-    // tcgen05 kernel with MN-major operands reading q,k straight from that tensor; v is a strided view of it.
-    void* qkvd = A.elems((size_t)B * P * 3 * C, ctx.dtype);
+    // depthwise pass writes q|k [P][2C] and v [P][C] (dense NHWC, coalesced) and reduces |q|^2,|k|^2; the Gram is a
+    // split-K tcgen05 kernel with MN-major operands reading q,k straight from that tensor.
+    void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+    void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     float* sumsq = A.get<float>((size_t)B * 2 * C);
     launch_fill_f32(ctx, sumsq, 0.f, (i64)B * 2 * C);
-    launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qkvd, sumsq, B, H, W, C);
+    launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
     if (!ctx.dry) {
       for (int b = 0; b < B; ++b)
-        if (!launch_gram_tcgen05(ctx, (const char*)qkvd + (size_t)b * P * 3 * C * 2, stats + b * nst, C, P))
+        if (!launch_gram_tcgen05(ctx, (const char*)qk + (size_t)b * P * 2 * C * 2, stats + b * nst, C, P))
           recorder().last_cuda_error = (int)cudaErrorNotSupported;
     }
     launch_copy_norms(ctx, sumsq, stats, B, C);
-    v = (const char*)qkvd + (size_t)2 * C * 2;
-    ldv = 3 * C;
+    v = vbuf;
   } else {
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     launch_dwqkv_gram(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, vbuf, stats, B, H, W, C);

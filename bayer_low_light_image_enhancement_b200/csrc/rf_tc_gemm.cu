@@ -12,11 +12,11 @@
 //   conv3 : 4-d tensor map [C, W, H, B]; the M tile is a th x tw pixel patch and every 3x3 tap is the same box
 //           shifted by (dx,dy) -- out-of-bounds rows/columns are zero-filled by TMA = the conv's zero padding.
 // K tails (K % 64 != 0) are zero-filled by TMA on both operands; the MMA loop skips all-zero 16-wide slices.
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "rf_kernels.cuh"
+#include "rf_tma.cuh"
 
 namespace rf {
 
@@ -47,86 +47,6 @@ struct TcParams {
   int acc_cols;        // column offset of the second accumulator buffer
   int tiles_m, tiles_n, total_tiles;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B stacked with SBO = 1024 B.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
@@ -413,43 +333,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-
-// bf16 tensor, dims[0] contiguous; strides in elements for dims 1..rank-1; box = elements per dim
-static bool make_map(CUtensorMap* m, const void* base, int rank, const i64* dims, const i64* strides_elems, const int* box) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gd[5];
-  cuuint64_t gs[4];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) {
-    gd[i] = (cuuint64_t)dims[i];
-    bx[i] = (cuuint32_t)box[i];
-    es[i] = 1;
-    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * 2;
-  }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 static int pick_bn(int N) {
   if (N % 8) return 0;
   if (N <= 256) return (N + 15) & ~15;   // N % 16 == 8: the last 8 columns are zero weights (TMA OOB) and masked stores
@@ -465,7 +348,7 @@ static int pick_bn(int N) {
 
 // ---------------------------------------------------------------------------------------------
 // Gram kernel of the transposed attention:  G[i][j] += sum_p q[p][i] * k[p][j]   (FLCA_RF.py:230, before softmax)
-// q,k live interleaved in the NHWC depthwise output [P][3C] (q = channels [0,C), k = [C,2C)).  Pixels are the
+// q,k live interleaved in the NHWC depthwise output [P][2C] (q = channels [0,C), k = [C,2C)).  Pixels are the
 // contraction axis, so both operands are "MN-major" for UMMA: a TMA box of 64 channels x 128 pixels lands as 128 rows
 // (pixels) of 128 B, which is exactly the canonical MN-major SWIZZLE_128B atom stack (SBO = 1024 B between 8-pixel
 // groups, LBO = one 16 KB chunk tile between 64-channel groups).  One CTA owns a 128x128 tile of G and a slice of the
@@ -691,12 +574,12 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   return true;
 }
 
-// qkv: bf16 NHWC [P][3C] of ONE image; G: fp32 [C][C], zero-initialised by the caller
+// qk: bf16 NHWC [P][2C] (q | k) of ONE image; G: fp32 [C][C], zero-initialised by the caller
 bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
   if (!g_tc_enabled || ctx.dtype != RF_BF16 || C % 8) return false;
   CUtensorMap m;
-  const i64 d[3] = {3 * (i64)C, P, 1};
-  const i64 st[3] = {1, 3 * (i64)C, 3 * (i64)C * P};
+  const i64 d[3] = {2 * (i64)C, P, 1};
+  const i64 st[3] = {1, 2 * (i64)C, 2 * (i64)C * P};
   const int bx[3] = {64, GR_PIX, 1};
   if (!make_map(&m, qkv, 3, d, st, bx)) return false;
   const int mt = cdiv(C, 128);

@@ -312,3 +312,38 @@ def test_wfb_feedforward_gated(rf):
     ff = ff.to(dev()).eval()
     out = ff(cu(T.gen_input("randn", (2, 32, 6, 9), 25)))
     assert_close("wfb_ffn", npy(out), OPS["wfb_ffn_c32"], 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16 kernels at sizes that span several tiles / chunks (odd sizes, ragged edges): bf16 mode vs fp32 mode of the
+# same sub-module (the fp32 mode is itself checked against the reference goldens above)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,hf,wf,b", [(32, 70, 90, 1), (64, 37, 50, 2), (48, 41, 100, 1), (128, 19, 45, 1),
+                                       (256, 18, 34, 1)])
+def test_bf16_submodules_multitile(rf, C, hf, wf, b):
+    blk = T.build_block("flca", C)
+    blk.load_state_dict(T.make_state_dict(blk, seed=50 + C, scale=1.5), strict=True)
+    blk = blk.to(dev()).eval()
+    feat = cu(T.gen_input("randn", (b, C, hf, wf), 60 + C))
+    x_ds = cu(T.gen_input("rand", (b, 4, hf, wf), 61 + C))
+    y, cr, cb = rf.BayerLumaChroma().to(dev())(x_ds)
+
+    def run(precision):
+        for m in blk.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+        with torch.no_grad():
+            return {
+                "ffn": npy(blk.Transformer.ffn(feat)),
+                "attn": npy(blk.Transformer.attn(feat)),
+                "flca": npy(blk.FLCA(feat, y, cr, cb)),
+                "trans": npy(blk.Transformer(feat)),
+                "out": npy(blk(feat, y, cr, cb)),
+            }
+
+    ref, got = run("fp32"), run("bf16")
+    for k in ref:
+        assert np.isfinite(got[k]).all(), k
+        rng = float(ref[k].max() - ref[k].min())
+        p = psnr(got[k], ref[k], rng)
+        assert p >= 40.0, f"{k} (C={C}, {hf}x{wf}): bf16 vs fp32 PSNR {p:.1f} dB; " + report(k, got[k], ref[k])
