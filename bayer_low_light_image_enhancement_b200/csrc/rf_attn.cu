@@ -413,6 +413,10 @@ void launch_embed(Ctx& ctx, const float* x_ds, const float* w, const float* b, v
   unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
   double px = (double)B * h * w_;
   ScopedLaunch sl(RF_K_EMBED, px * (16.0 + d * esize(ctx.dtype)), 72.0 * px * d);
+  if (im2col_tc_supported(ctx, d)) {
+    if (!launch_embed_tc(ctx, x_ds, w, b, out, B, h, w_, d)) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   size_t smem = sizeof(float) * 36 * d;
   if (ctx.dtype == RF_BF16)
     k_embed<bf16><<<dim3(gx, B), 256, smem, ctx.stream>>>((const float4*)x_ds, w, b, (bf16*)out, h, w_, d);

@@ -11,7 +11,7 @@
 //   MODE 1: same on qkv_pre [.,3C], written as q|k [.,2C] and v [.,C]; additionally sumsq[b][2C] += squared norms of the
 //           (bf16-rounded) q,k channels
 //           (Attention.qkv_dwconv + F.normalize statistics, FLCA_RF.py:223-229)
-//   MODE 2: out = gelu_erf(dw(in) + bias)            (conv_ffn.depthwise + nn.GELU, FLCA_RF.py:206-207)
+//   MODE 2: out = gelu_erf(dw(in) + bias)            (conv_ffn.depthwise + nn.GELU, FLCA_RF.py:206-207); see gelu_erf2
 #include "rf_kernels.cuh"
 #include "rf_tma.cuh"
 
@@ -29,7 +29,8 @@ struct DwTmaParams {
   int H, W, Cn, C2;
   int CC, nvec, TW;    // channel chunk, 4-channel vectors per pixel of a chunk, tile width
   int tiles_x, tiles_y, nchunks, B;
-  int total_tiles;
+  int sp_tiles;        // spatial tiles per chunk = B * tiles_y * tiles_x
+  int lanes;           // CTAs per chunk: CTA = (chunk = blockIdx.x % nchunks, lane = blockIdx.x / nchunks)
   uint32_t tile_bytes; // (TH+2)*(TW+2)*CC*2
   uint32_t buf_stride; // tile_bytes rounded up to 128
 };
@@ -39,11 +40,40 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void unpack_bf16x4(const uint2& t, float (&v)[4]) {
-  v[0] = __uint_as_float(t.x << 16);
-  v[1] = __uint_as_float(t.x & 0xffff0000u);
-  v[2] = __uint_as_float(t.y << 16);
-  v[3] = __uint_as_float(t.y & 0xffff0000u);
+// 4 bf16 -> two packed fp32 pairs (channel pairs (0,1), (2,3)); the conv runs on packed FFMA2 (fma.rn.f32x2)
+__device__ __forceinline__ void unpack_bf16x4(const uint2& t, float2 (&v)[2]) {
+  // PRMT / LOP3 run on the ALU pipe (a plain shift is turned into IMAD.U32, which competes with the FFMA2s)
+  v[0] = make_float2(__uint_as_float(__byte_perm(t.x, 0u, 0x1044u)), __uint_as_float(t.x & 0xffff0000u));
+  v[1] = make_float2(__uint_as_float(__byte_perm(t.y, 0u, 0x1044u)), __uint_as_float(t.y & 0xffff0000u));
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU of two values in packed fp32:  gelu(x) = x * Phi(x),  Phi(x) = 1 / (1 + exp(-x * P(min(x^2, 64)))),
+// P = degree-4 minimax fit of logit(Phi(x)) / x on |x| <= 8 (tools/fit_gelu.py): |gelu error| <= 1.2e-5 absolute and
+// <= 7.5e-5 of max(|gelu|, 0.02), i.e. < 1/10 of a bf16 half-ulp; no cancellation in the negative tail (x -> -inf
+// gives x * 0), exact identity for x >= 8.  8 packed FMA-pipe ops + 2 MUFU per value pair (the Abramowitz-Stegun
+// erfc form needs 12 + 2); coefficients are pre-multiplied by -log2(e) so the exponential is a bare ex2.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float k0 = -1.4426950408889634f * 1.5954254501877632f, k1 = -1.4426950408889634f * 0.07325994800505611f,
+              k2 = -1.4426950408889634f * -0.00036788829074290585f, k3 = -1.4426950408889634f * -4.5953771468195396e-05f,
+              k4 = -1.4426950408889634f * 1.6250086403938804e-06f;
+  float2 t = __fmul2_rn(x, x);
+  t = make_float2(fminf(t.x, 64.f), fminf(t.y, 64.f));
+  float2 pz = __ffma2_rn(make_float2(k4, k4), t, make_float2(k3, k3));
+  pz = __ffma2_rn(pz, t, make_float2(k2, k2));
+  pz = __ffma2_rn(pz, t, make_float2(k1, k1));
+  pz = __ffma2_rn(pz, t, make_float2(k0, k0));
+  const float2 w = __fmul2_rn(x, pz);
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(w.x), ex2_approx(w.y)), make_float2(1.f, 1.f));
+  return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
 }
 
 template <int MODE>
@@ -52,7 +82,9 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t bars = base + 2 * p.buf_stride;                 // two mbarriers
-  float* s_sum = reinterpret_cast<float*>(smem_raw + (bars + 16 - smem_u32(smem_raw)));   // [CC] flush scratch (MODE 1)
+  uint8_t* tail = smem_raw + (bars + 16 - smem_u32(smem_raw));
+  int4* s_tile = reinterpret_cast<int4*>(tail);                  // [2] decoded tile (tx, ty, chunk, b) of each stage
+  float* s_sum = reinterpret_cast<float*>(tail + 32);            // [CC] flush scratch (MODE 1)
   const int tid = threadIdx.x;
   const int x = tid / p.nvec, cv = tid - x * p.nvec;
   const bool active = x < p.TW;
@@ -65,30 +97,53 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
   }
   __syncthreads();
 
-  const int stride = gridDim.x;
+  // Every CTA owns ONE channel chunk and walks the spatial tiles lane, lane + lanes, ...  CTAs of the same lane run
+  // the other chunks of the same pixels at the same time, so a 128-byte line that holds two chunks is fetched from
+  // DRAM once.  The tap weights stay in registers for the whole kernel.
+  const int chunk = blockIdx.x % p.nchunks, lane_id = blockIdx.x / p.nchunks;
+  const int stride = p.lanes;
+  // the issuing thread decodes the tile once and publishes the coordinates with the stage (the mbarrier's
+  // release/acquire orders the plain store before the consumers' loads)
   auto issue = [&](int t, int s) {
     int r = t;
     const int tx = r % p.tiles_x; r /= p.tiles_x;
-    const int ty = r % p.tiles_y; r /= p.tiles_y;
-    const int chunk = r % p.nchunks;
-    const int b = r / p.nchunks;
+    const int ty = r % p.tiles_y;
+    const int b = r / p.tiles_y;
+    s_tile[s] = make_int4(tx, ty, b, 0);
     mbar_expect_tx(bars + 8 * s, p.tile_bytes);
     tma_load_4d(base + s * p.buf_stride, &mapIn, bars + 8 * s, chunk * p.CC, tx * p.TW - 1, ty * DT_TH - 1, b);
   };
   if (tid == 0) {
-    if ((int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
-    if ((int)blockIdx.x + stride < p.total_tiles) issue(blockIdx.x + stride, 1);
+    if (lane_id < p.sp_tiles) issue(lane_id, 0);
+    if (lane_id + stride < p.sp_tiles) issue(lane_id + stride, 1);
   }
 
-  float wv[9][4], bs[4];
+  float2 wv[9][2], bs[2];
   float sq[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur_key = -1;
+  const int c0 = chunk * p.CC + cv * 4;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 w4 = *reinterpret_cast<const float4*>(p.w + (i64)k * p.Cn + c0);
+      wv[k][0] = make_float2(w4.x, w4.y);
+      wv[k][1] = make_float2(w4.z, w4.w);
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0);
+    bs[0] = make_float2(b4.x, b4.y);
+    bs[1] = make_float2(b4.z, b4.w);
+  }
+  const bool is_qk = MODE == 1 && c0 < p.C2;
+  // MODE 1 splits the channels into two dense tensors (chunks never straddle C2: CC divides C)
+  const int ocn = MODE == 1 ? (is_qk ? p.C2 : p.Cn - p.C2) : p.Cn;
+  bf16* const obase = (MODE == 1 && !is_qk ? p.vout : p.out) + (MODE == 1 && !is_qk ? c0 - p.C2 : c0);
+  const i64 opitch = (i64)p.W * ocn;
+  int cur_b = -1;
   const uint32_t pitch = (uint32_t)(p.TW + 2) * p.CC * 2;       // bytes per halo row
   const uint32_t toff = (uint32_t)(x * p.CC + cv * 4) * 2;      // this thread's column (kx = 0) inside a halo row
+  const uint32_t cstep = (uint32_t)p.CC * 2;                    // bytes between horizontally adjacent pixels
 
-  // MODE 1: add this thread's squared-norm partials of image/chunk `key` to sumsq (block-uniform call)
-  auto flush = [&](int key) {
-    const int chunk = key % p.nchunks, b = key / p.nchunks;
+  // MODE 1: add this thread's squared-norm partials of image b to sumsq (block-uniform call)
+  auto flush = [&](int b) {
     for (int i = tid; i < p.CC; i += DT_THREADS) s_sum[i] = 0.f;
     __syncthreads();
     if (active) {
@@ -105,89 +160,75 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
   };
 
   int it = 0;
-  for (int t = blockIdx.x; t < p.total_tiles; t += stride, ++it) {
-    int r0 = t;
-    const int tx = r0 % p.tiles_x; r0 /= p.tiles_x;
-    const int ty = r0 % p.tiles_y; r0 /= p.tiles_y;
-    const int chunk = r0 % p.nchunks;
-    const int b = r0 / p.nchunks;
-    const int key = b * p.nchunks + chunk;
-    const int c0 = chunk * p.CC + cv * 4;
-    if (key != cur_key) {
-      if (MODE == 1 && cur_key >= 0) flush(cur_key);
-      cur_key = key;
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) load4(p.w + (i64)k * p.Cn + c0, wv[k]);
-        load4(p.bias + c0, bs);
-      }
-    }
+  for (int t = lane_id; t < p.sp_tiles; t += stride, ++it) {
     const int s = it & 1;
     mbar_wait(bars + 8 * s, (it >> 1) & 1);
+    const int4 tc = s_tile[s];
+    const int tx = tc.x, ty = tc.y, b = tc.z;
+    if (MODE == 1 && b != cur_b) {
+      if (cur_b >= 0 && is_qk) flush(cur_b);     // is_qk is uniform over the CTA (one chunk per CTA)
+      cur_b = b;
+    }
     if (active) {
-      const uint32_t src = base + s * p.buf_stride + toff;
+      uint32_t src = base + s * p.buf_stride + toff;
       const int xo = tx * p.TW + x;
-      const bool x_ok = xo < p.W;
-      const bool is_qk = MODE == 1 && c0 < p.C2;
-      // MODE 1 splits the channels into two dense tensors (chunks never straddle C2: CC divides C)
-      const int ocn = MODE == 1 ? (is_qk ? p.C2 : p.Cn - p.C2) : p.Cn;
-      const int oc0 = MODE == 1 && !is_qk ? c0 - p.C2 : c0;
-      bf16* orow = (MODE == 1 && !is_qk ? p.vout : p.out) + (((i64)b * p.H + (i64)ty * DT_TH) * p.W + xo) * ocn + oc0;
-      const i64 opitch = (i64)p.W * ocn;
-      const int rows_ok = min(DT_TH, p.H - ty * DT_TH);
-      float acc[3][4];
+      bf16* optr = obase + (((i64)b * p.H + (i64)ty * DT_TH) * p.W + xo) * ocn - 2 * opitch;   // row of output r - 2
+      const unsigned rows_ok = xo < p.W ? (unsigned)min(DT_TH, p.H - ty * DT_TH) : 0u;
+      float2 acc[3][2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int g = 0; g < (DT_TH + 2) / 3; ++g) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int r = 3 * g + j;                    // halo row: feeds outputs r (ky=0), r-1 (ky=1), r-2 (ky=2)
-          float v[3][4];
+          float2 v[3][2];
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) unpack_bf16x4(lds64(src + (uint32_t)r * pitch + (uint32_t)kx * p.CC * 2), v[kx]);
-          float* aN = acc[j];                 // output r      (r % 3 == j)
-          float* aM = acc[(j + 2) % 3];       // output r - 1
-          float* aD = acc[(j + 1) % 3];       // output r - 2
-          if (r < DT_TH) {
+          for (int kx = 0; kx < 3; ++kx) unpack_bf16x4(lds64(src + (uint32_t)kx * cstep), v[kx]);
+          src += pitch;
+          float2* aN = acc[j];                 // output r      (r % 3 == j)
+          float2* aM = acc[(j + 2) % 3];       // output r - 1
+          float2* aD = acc[(j + 1) % 3];       // output r - 2
+          // rows beyond the tile (r >= TH for ky=0, r > TH for ky=1) and before it (r < 1, r < 2) only produce
+          // accumulators that are never emitted, so the FMAs run unconditionally (no divergence, no branches)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              aN[k] = fmaf(wv[2][k], v[2][k], fmaf(wv[1][k], v[1][k], fmaf(wv[0][k], v[0][k], bs[k])));
+          for (int k = 0; k < 2; ++k) {
+            aN[k] = __ffma2_rn(wv[2][k], v[2][k], __ffma2_rn(wv[1][k], v[1][k], __ffma2_rn(wv[0][k], v[0][k], bs[k])));
+            aM[k] = __ffma2_rn(wv[5][k], v[2][k], __ffma2_rn(wv[4][k], v[1][k], __ffma2_rn(wv[3][k], v[0][k], aM[k])));
+            aD[k] = __ffma2_rn(wv[8][k], v[2][k], __ffma2_rn(wv[7][k], v[1][k], __ffma2_rn(wv[6][k], v[0][k], aD[k])));
           }
-          if (r >= 1 && r <= DT_TH) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              aM[k] = fmaf(wv[5][k], v[2][k], fmaf(wv[4][k], v[1][k], fmaf(wv[3][k], v[0][k], aM[k])));
+          // output o = r - 2; o < 0 wraps to a huge unsigned, so one compare masks both ends.  Everything but the
+          // store is unconditional (straight-line code); masked rows are zeroed so the norms stay exact.
+          const bool ok = (unsigned)(r - 2) < rows_ok;
+          float2 o0 = aD[0], o1 = aD[1];
+          if (MODE == 2) {
+            o0 = gelu_erf2(o0);
+            o1 = gelu_erf2(o1);
           }
-          if (r >= 2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              aD[k] = fmaf(wv[8][k], v[2][k], fmaf(wv[7][k], v[1][k], fmaf(wv[6][k], v[0][k], aD[k])));
-            const int o = r - 2;
-            if (x_ok && o < rows_ok) {
-              float ov[4] = {aD[0], aD[1], aD[2], aD[3]};
-              if (MODE == 2) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ov[k] = gelu_erf_fast(ov[k]);
-              }
-              uint2 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-              h[0] = __floats2bfloat162_rn(ov[0], ov[1]);
-              h[1] = __floats2bfloat162_rn(ov[2], ov[3]);
-              if (is_qk) {
-                float rv[4];
-                unpack_bf16x4(pk, rv);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) sq[k] = fmaf(rv[k], rv[k], sq[k]);
-              }
-              *reinterpret_cast<uint2*>(orow + (i64)o * opitch) = pk;
+          uint2 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+          h[0] = __floats2bfloat162_rn(o0.x, o0.y);
+          h[1] = __floats2bfloat162_rn(o1.x, o1.y);
+          if (MODE == 1) {
+            if (!ok) pk = make_uint2(0u, 0u);
+            if (is_qk) {
+              float2 rv[2];
+              unpack_bf16x4(pk, rv);
+              sq[0] = fmaf(rv[0].x, rv[0].x, sq[0]);
+              sq[1] = fmaf(rv[0].y, rv[0].y, sq[1]);
+              sq[2] = fmaf(rv[1].x, rv[1].x, sq[2]);
+              sq[3] = fmaf(rv[1].y, rv[1].y, sq[3]);
             }
           }
+          if (ok) *reinterpret_cast<uint2*>(optr) = pk;
+          optr += opitch;
         }
       }
     }
-    __syncthreads();                                  // every read of stage s is done
-    if (tid == 0 && t + 2 * stride < p.total_tiles) issue(t + 2 * stride, s);
+    __syncthreads();                                  // every read of stage s (tile and coordinates) is done
+    if (tid == 0 && t + 2 * stride < p.sp_tiles) issue(t + 2 * stride, s);
   }
-  if (MODE == 1 && cur_key >= 0) flush(cur_key);
+  if (MODE == 1 && cur_b >= 0 && is_qk) flush(cur_b);
 }
 
 // false when the shape is not supported by the TMA path (caller falls back to the register-strip kernel)
@@ -207,18 +248,20 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
   p.TW = DT_THREADS / p.nvec;
   if (p.TW > 254) p.TW = 254;
   p.tiles_x = cdiv(W, p.TW); p.tiles_y = cdiv(H, DT_TH); p.nchunks = Cn / CC;
-  const i64 total = (i64)p.tiles_x * p.tiles_y * p.nchunks * B;
-  if (total > 0x7fffffff) return false;
-  p.total_tiles = (int)total;
+  const i64 sp = (i64)p.tiles_x * p.tiles_y * B;
+  if (sp > 0x7fffffff || p.nchunks > num_sms()) return false;
+  p.sp_tiles = (int)sp;
+  p.lanes = num_sms() / p.nchunks;
+  if (p.lanes > p.sp_tiles) p.lanes = p.sp_tiles;
   p.tile_bytes = (uint32_t)((DT_TH + 2) * (p.TW + 2) * CC * 2);
   p.buf_stride = (p.tile_bytes + 127u) & ~127u;
-  const size_t smem = 128 + 2 * (size_t)p.buf_stride + 16 + sizeof(float) * CC;
+  const size_t smem = 128 + 2 * (size_t)p.buf_stride + 16 + 32 + sizeof(float) * CC;
   if (smem > 227 * 1024) return false;
   CUtensorMap m;
   const i64 d[4] = {Cn, W, H, B};
   const i64 st[4] = {1, Cn, (i64)Cn * W, (i64)Cn * W * H};
   const int bx[4] = {CC, p.TW + 2, DT_TH + 2, 1};
-  if (!make_map_ex(&m, in, 4, d, st, bx, 2, false)) return false;
+  if (!make_map_ex(&m, in, 4, d, st, bx, 2, 0)) return false;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_dw_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -227,7 +270,7 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
       return false;
     attr_set = true;
   }
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int grid = p.lanes * p.nchunks;
   if (mode == 0) k_dw_tma<0><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);
   else if (mode == 1) k_dw_tma<1><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);
   else k_dw_tma<2><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);

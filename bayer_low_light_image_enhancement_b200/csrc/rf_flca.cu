@@ -163,6 +163,13 @@ void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w3
                      float* partial, int nblk, int B, int Hf, int Wf, int C) {
   if (ctx.dry) return;
   launch_fill_f32(ctx, partial, 0.f, (i64)B * FLCA_SLOTS * C);
+  if (im2col_tc_supported(ctx, C)) {
+    const double px = (double)B * Hf * Wf;
+    ScopedLaunch sl(RF_K_FLCA_MOD, px * C * 4.0 + px * 16.0, px * C * 72.0);
+    if (!launch_flca_mod_tc(ctx, feat, G, w36, abg, xmod, partial, B, Hf, Wf, C))
+      recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   if (ctx.dtype == RF_BF16)
     run_flca_mod<bf16, 0>(ctx, feat, G, w36, abg, xmod, partial, nblk, B, Hf, Wf, C, 0, RF_K_FLCA_MOD);
   else

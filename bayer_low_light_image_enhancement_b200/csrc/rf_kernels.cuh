@@ -111,6 +111,11 @@ int flca_num_partials(int C, int B, i64 P);
 // xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][nblk][C] channel sums
 void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
                      float* partial, int nblk, int B, int Hf, int Wf, int C);
+// tensor-core im2col forms (rf_im2col_tc.cu, bf16 only); false when the shape is not supported
+bool im2col_tc_supported(const Ctx& ctx, int C);
+bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
+                        float* partial, int B, int Hf, int Wf, int C);
+bool launch_embed_tc(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d);
 // ML: xs = x * (ga * sig(conv(mapA)) + gb * tanh(conv(mapB)))  [mode 0, level l] or xs = x * gc*sig(conv(cr,cb)) [mode 1]
 void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,
                         int level, int B, int Hf, int Wf, int C);

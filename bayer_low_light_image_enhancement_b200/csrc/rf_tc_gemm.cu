@@ -48,22 +48,7 @@ struct TcParams {
   int tiles_m, tiles_n, total_tiles;
 };
 
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B stacked with SBO = 1024 B.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major), canonical value 1
-  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
-  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-  return d;
-}
-
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
+__device__ __forceinline__ uint32_t make_idesc(int n) { return make_idesc_m128(n); }
 
 // ---------------------------------------------------------------------------------------------
 // kernel

@@ -86,7 +86,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B stacked with SBO = 1024 B.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc_m128(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 
 // smem -> global tensor store (bulk async group), and its completion
@@ -134,9 +155,9 @@ inline PFN_encodeTiled get_encode() {
 }
 
 // dims[0] contiguous; strides in elements for dims 1..rank-1; box = elements per dim.
-// esz = 2 (bf16) or 4 (fp32); swizzle128 = 128-byte swizzle (UMMA operand tiles) or none (plain staging tiles).
+// esz = 2 (bf16) or 4 (fp32); swz = 128 (UMMA operand tiles / 128-byte rows), 64 (64-byte rows) or 0 (dense staging tiles).
 inline bool make_map_ex(CUtensorMap* m, const void* base, int rank, const i64* dims, const i64* strides_elems, const int* box,
-                        int esz, bool swizzle128) {
+                        int esz, int swz) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gd[5];
@@ -150,13 +171,13 @@ inline bool make_map_ex(CUtensorMap* m, const void* base, int rank, const i64* d
   }
   CUresult r = enc(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                    const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 // bf16, 128-byte swizzle (the UMMA operand form)
 inline bool make_map(CUtensorMap* m, const void* base, int rank, const i64* dims, const i64* strides_elems, const int* box) {
-  return make_map_ex(m, base, rank, dims, strides_elems, box, 2, true);
+  return make_map_ex(m, base, rank, dims, strides_elems, box, 2, 128);
 }
 
 }  // namespace rf
