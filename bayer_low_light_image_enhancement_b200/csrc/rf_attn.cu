@@ -99,6 +99,92 @@ void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, v
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm folded into the following 1x1 conv (bf16 mode): per-row (sum, sumsq) and the weight fold
+// ---------------------------------------------------------------------------------------------
+template <typename T, int GS, int VPL>
+__global__ void __launch_bounds__(256)
+k_row_stats(const T* __restrict__ x, float2* __restrict__ stats, i64 rows, int C) {
+  const int lane = threadIdx.x & (GS - 1);
+  const i64 row = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+  const bool row_ok = row < rows;
+  const int cv = C >> 3;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * GS;
+    if (row_ok && vec < cv) {
+      float v[8];
+      load8(x + row * C + vec * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += v[j];
+        q = fmaf(v[j], v[j], q);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = GS >> 1; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (row_ok && lane == 0) stats[row] = make_float2(s, q);
+}
+
+void launch_row_stats(Ctx& ctx, const void* x, float* stats, i64 rows, int C) {
+  if (ctx.dry || rows <= 0) return;
+  ScopedLaunch sl(RF_K_LAYERNORM, rows * (C * (double)esize(ctx.dtype) + 8.0));
+  const int cv = C / 8;
+#define RF_RS(T, GS, VPL) \
+  k_row_stats<T, GS, VPL><<<(unsigned)cdivl(rows * GS, 256), 256, 0, ctx.stream>>>((const T*)x, (float2*)stats, rows, C)
+#define RF_RS_ALL(T)                   \
+  do {                                 \
+    if (cv <= 4) RF_RS(T, 4, 1);       \
+    else if (cv <= 8) RF_RS(T, 8, 1);  \
+    else if (cv <= 16) RF_RS(T, 16, 1); \
+    else if (cv <= 32) RF_RS(T, 32, 1); \
+    else if (cv <= 64) RF_RS(T, 32, 2); \
+    else if (cv <= 128) RF_RS(T, 32, 4); \
+    else RF_RS(T, 32, 8);              \
+  } while (0)
+  if (ctx.dtype == RF_BF16) RF_RS_ALL(bf16);
+  else RF_RS_ALL(float);
+#undef RF_RS_ALL
+#undef RF_RS
+}
+
+// one warp per output row n
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fold_ln(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+          const float* __restrict__ bias, T* __restrict__ Wf, float* __restrict__ cs, float* __restrict__ bf, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float c = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(i64)n * K + k];
+    T r;
+    from_f(r, w * gamma[k]);
+    Wf[(i64)n * K + k] = r;
+    c += to_f(r);
+    bb = fmaf(w, beta[k], bb);
+  }
+  c = warp_sum(c);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    cs[n] = c;
+    bf[n] = (bias ? bias[n] : 0.f) + bb;
+  }
+}
+
+void launch_fold_ln(Ctx& ctx, const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* cs,
+                    float* bf, int N, int K) {
+  if (ctx.dry || !W || !gamma || !beta) return;
+  ScopedLaunch sl(RF_K_WEIGHT_PACK);
+  if (ctx.dtype == RF_BF16) k_fold_ln<bf16><<<cdiv(N, 8), 256, 0, ctx.stream>>>(W, gamma, beta, bias, (bf16*)Wf, cs, bf, N, K);
+  else k_fold_ln<float><<<cdiv(N, 8), 256, 0, ctx.stream>>>(W, gamma, beta, bias, (float*)Wf, cs, bf, N, K);
+}
+
+// ---------------------------------------------------------------------------------------------
 // depthwise 3x3 (+bias, optional exact-erf GELU) on NHWC; one thread = 8 channels of one pixel
 // ---------------------------------------------------------------------------------------------
 template <typename T>

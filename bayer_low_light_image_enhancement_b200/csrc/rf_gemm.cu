@@ -120,6 +120,15 @@ k_gemm(GemmP p) {
     const int m = m0 + ty * 8 + i;
     if (m >= p.M) continue;
     float v[4];
+    if (p.ln_stats) {
+      float su = 0.f, sq = 0.f;
+      const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (b * p.M + m) * p.ln_npart;
+      for (int q = 0; q < p.ln_npart; ++q) { su += st[q].x; sq += st[q].y; }
+      const float mu = su / (float)p.ln_C;
+      const float rs = rsqrtf(fmaxf(sq / (float)p.ln_C - mu * mu, 0.f) + p.ln_eps);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = rs * (acc[i][j] - mu * p.ln_cs[n + j]);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
     if (p.act == ACT_LRELU) {
@@ -173,16 +182,29 @@ void launch_gemm_cuda_core(Ctx& ctx, const GemmP& p) {
 }
 
 // Implemented in rf_tc_gemm.cu: returns true when it launched a tcgen05 kernel for this problem.
-bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& p);
+// returns the number of stats_out partials per row it wrote (0 = stats_out not handled), < 0 when it did not launch
+int launch_gemm_tcgen05(Ctx& ctx, const GemmP& p);
 
-void launch_gemm(Ctx& ctx, const GemmP& p) {
-  if (ctx.dry || p.M <= 0 || p.N <= 0 || p.B <= 0) return;
-  if (ctx.dtype == RF_BF16 && launch_gemm_tcgen05(ctx, p)) return;
+int launch_gemm(Ctx& ctx, const GemmP& p) {
+  if (ctx.dry || p.M <= 0 || p.N <= 0 || p.B <= 0) return p.stats_out ? 1 : 0;
+  if (ctx.dtype == RF_BF16) {
+    const int np = launch_gemm_tcgen05(ctx, p);
+    if (np > 0 || (np == 0 && !p.stats_out)) return np;
+    if (np == 0) {  // the kernel ran but its epilogue could not emit the row statistics: one extra pass over Y
+      launch_row_stats(ctx, p.Y, p.stats_out, (i64)p.B * p.M, p.N);
+      return 1;
+    }
+  }
   if (p.omode == OMODE_ATOMIC_F32) {  // only the tcgen05 kernel implements the split-K atomic epilogue
     recorder().last_cuda_error = (int)cudaErrorNotSupported;
-    return;
+    return 0;
   }
   launch_gemm_cuda_core(ctx, p);
+  if (p.stats_out) {
+    launch_row_stats(ctx, p.Y, p.stats_out, (i64)p.B * p.M, p.N);
+    return 1;
+  }
+  return 0;
 }
 
 }  // namespace rf

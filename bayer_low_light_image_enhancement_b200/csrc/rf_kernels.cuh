@@ -18,6 +18,9 @@ struct PackedBlock {
   float* ln1_g = nullptr; float* ln1_b = nullptr;
   void* qkv_w = nullptr;       // T [3C][C]
   float* qkv_b = nullptr;
+  void* qkv_wf = nullptr;      // T [3C][C]: qkv_w * diag(ln1_g)   (LayerNorm folded, bf16 mode)
+  float* qkv_cs = nullptr;     // [3C] row sums of qkv_wf
+  float* qkv_bf = nullptr;     // [3C] qkv_b + qkv_w * ln1_b
   float* qkv_dw_w = nullptr;   // [9][3C]
   float* qkv_dw_b = nullptr;
   float* temperature = nullptr;  // [8]
@@ -26,6 +29,9 @@ struct PackedBlock {
   float* ln2_g = nullptr; float* ln2_b = nullptr;
   void* pw1_w = nullptr;       // T [2C][C]
   float* pw1_b = nullptr;
+  void* pw1_wf = nullptr;      // T [2C][C]: pw1_w * diag(ln2_g)
+  float* pw1_cs = nullptr;
+  float* pw1_bf = nullptr;
   float* ffn_dw_w = nullptr;   // [9][2C]
   float* ffn_dw_b = nullptr;
   void* pw2_w = nullptr;       // T [C][2C]
@@ -80,8 +86,25 @@ struct GemmP {
   int act = ACT_NONE, amode = AMODE_ROWS, omode = OMODE_ROWS;
   int H = 0, W = 0;                                     // image size of the rows (m = y*W + x) for CONV3/CONVT/UNSHUFFLE
   int kernel_id = RF_K_MISC;
+  // LayerNorm folded into the contraction (bf16 mode, FLCA_RF.py:183-187 + the 1x1 conv that follows): Wt / bias are the
+  // folded weights W*diag(g) and b + W*beta, ln_cs[n] = sum_k Wt[n][k], and
+  //   Y = rstd[m] * (acc - mean[m] * ln_cs[n]) + bias[n],  mean/rstd from ln_stats[row][ln_npart] = partial (sum, sumsq)
+  const float* ln_stats = nullptr;
+  const float* ln_cs = nullptr;
+  int ln_npart = 0, ln_C = 0;
+  float ln_eps = 0.f;
+  // optional (OMODE_ROWS): partial (sum, sum of squares) of the stored (rounded) output rows -> stats_out[row][npart]
+  // (float2 each); launch_gemm returns npart (0 when not requested)
+  float* stats_out = nullptr;
 };
-void launch_gemm(Ctx& ctx, const GemmP& p);
+int launch_gemm(Ctx& ctx, const GemmP& p);
+// (sum, sum of squares) over the C channels of every pixel row -> stats[row] (float2); the LayerNorm statistics of the
+// folded form above when no producer epilogue emitted them
+void launch_row_stats(Ctx& ctx, const void* x, float* stats, i64 rows, int C);
+// fold LayerNorm(gamma, beta) into the 1x1 conv W [N][K] (fp32, PyTorch layout): Wf = T(W*gamma), cs = rowsum(Wf),
+// bf = bias + W*beta
+void launch_fold_ln(Ctx& ctx, const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* cs,
+                    float* bf, int N, int K);
 
 // ---- layout / index kernels (rf_index_ops.cu) --------------------------------------------------------------
 void launch_nchw_to_nhwc(Ctx& ctx, const float* in, void* out, int B, int C, i64 HW);   // fp32 NCHW -> T NHWC

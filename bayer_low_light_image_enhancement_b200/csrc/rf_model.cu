@@ -40,11 +40,13 @@ static PackedBlock layout_block(Layout& L, int C, int dtype, int variant) {
   pb.se_w2 = L.f32(c * pb.hid); pb.se_b2 = L.f32(c);
   pb.ln1_g = L.f32(c); pb.ln1_b = L.f32(c);
   pb.qkv_w = L.elems(3 * c * c, dtype); pb.qkv_b = L.f32(3 * c);
+  pb.qkv_wf = L.elems(3 * c * c, dtype); pb.qkv_cs = L.f32(3 * c); pb.qkv_bf = L.f32(3 * c);
   pb.qkv_dw_w = L.f32(27 * c); pb.qkv_dw_b = L.f32(3 * c);
   pb.temperature = L.f32(8);
   pb.proj_w = L.f32(c * c); pb.proj_b = L.f32(c);
   pb.ln2_g = L.f32(c); pb.ln2_b = L.f32(c);
   pb.pw1_w = L.elems(2 * c * c, dtype); pb.pw1_b = L.f32(2 * c);
+  pb.pw1_wf = L.elems(2 * c * c, dtype); pb.pw1_cs = L.f32(2 * c); pb.pw1_bf = L.f32(2 * c);
   pb.ffn_dw_w = L.f32(18 * c); pb.ffn_dw_b = L.f32(2 * c);
   pb.pw2_w = L.elems(2 * c * c, dtype); pb.pw2_b = L.f32(c);
   pb.red_w = L.f32(2 * c * c); pb.red_b = L.f32(c);
@@ -132,6 +134,7 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
   copy_f32(ctx, w.norm1_b, pb.ln1_b, C);
   copy_T(ctx, w.qkv_w, pb.qkv_w, (i64)3 * C * C);
   copy_f32(ctx, w.qkv_b, pb.qkv_b, 3 * C);
+  launch_fold_ln(ctx, w.qkv_w, w.norm1_w, w.norm1_b, w.qkv_b, pb.qkv_wf, pb.qkv_cs, pb.qkv_bf, 3 * C, C);
   pack_taps(ctx, w.qkv_dw_w, 1, 0, pb.qkv_dw_w, 1, 0, 3 * C);
   copy_f32(ctx, w.qkv_dw_b, pb.qkv_dw_b, 3 * C);
   copy_f32(ctx, w.temperature, pb.temperature, 8);
@@ -141,6 +144,7 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
   copy_f32(ctx, w.norm2_b, pb.ln2_b, C);
   copy_T(ctx, w.pw1_w, pb.pw1_w, (i64)2 * C * C);
   copy_f32(ctx, w.pw1_b, pb.pw1_b, 2 * C);
+  launch_fold_ln(ctx, w.pw1_w, w.norm2_w, w.norm2_b, w.pw1_b, pb.pw1_wf, pb.pw1_cs, pb.pw1_bf, 2 * C, C);
   pack_taps(ctx, w.ffn_dw_w, 1, 0, pb.ffn_dw_w, 1, 0, 2 * C);
   copy_f32(ctx, w.ffn_dw_b, pb.ffn_dw_b, 2 * C);
   copy_T(ctx, w.pw2_w, pb.pw2_w, (i64)2 * C * C);
@@ -212,14 +216,26 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   *scale_out = scale;
 }
 
-// out = (resid ? resid : 0) + Attention(xin)   (xin is already normalised when called from the transformer block)
-static void attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W) {
+// LayerNorm statistics of the input rows when the norm is folded into the first 1x1 conv of a branch (bf16 mode)
+struct LnFold {
+  const float* stats = nullptr;   // [rows][npart] float2 (sum, sumsq)
+  int npart = 0;
+};
+
+// out = (resid ? resid : 0) + Attention(xin).  xin is the normalised input, or -- with `ln` -- the raw block input
+// whose LayerNorm (norm1) is folded into the qkv projection.  stats_out (optional): row statistics of `out`.
+static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W,
+                     const LnFold* ln = nullptr, float* stats_out = nullptr) {
   const int C = pb.C;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
   void* qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
-  launch_gemm(ctx, gemm_rows(xin, C, pb.qkv_w, pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV));
+  {
+    GemmP gq = gemm_rows(xin, C, ln ? pb.qkv_wf : pb.qkv_w, ln ? pb.qkv_bf : pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV);
+    if (ln) { gq.ln_stats = ln->stats; gq.ln_npart = ln->npart; gq.ln_cs = pb.qkv_cs; gq.ln_C = C; gq.ln_eps = 1e-5f; }
+    launch_gemm(ctx, gq);
+  }
   const i64 nst = attn_stats_floats(C);
   float* stats = A.get<float>((size_t)B * nst);
   launch_fill_f32(ctx, stats, 0.f, B * nst);
@@ -251,18 +267,25 @@ static void attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const vo
   g.lda1 = ldv;
   g.w_img = (i64)C * C;
   g.R = resid; g.ldr = C;
-  launch_gemm(ctx, g);
+  g.stats_out = stats_out;
+  const int np = launch_gemm(ctx, g);
   A.release(mk);
+  return np;
 }
 
-// out = (resid ? resid : 0) + conv_ffn(xin)
-static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W) {
+// out = (resid ? resid : 0) + conv_ffn(xin); with `ln`, xin is the raw input and norm2 is folded into pointwise1
+static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W,
+                const LnFold* ln = nullptr) {
   const int C = pb.C;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
   void* hpre = A.elems((size_t)B * P * 2 * C, ctx.dtype);
-  launch_gemm(ctx, gemm_rows(xin, C, pb.pw1_w, pb.pw1_b, hpre, 2 * C, B, P, RF_K_GEMM_PW1));
+  {
+    GemmP g1 = gemm_rows(xin, C, ln ? pb.pw1_wf : pb.pw1_w, ln ? pb.pw1_bf : pb.pw1_b, hpre, 2 * C, B, P, RF_K_GEMM_PW1);
+    if (ln) { g1.ln_stats = ln->stats; g1.ln_npart = ln->npart; g1.ln_cs = pb.pw1_cs; g1.ln_C = C; g1.ln_eps = 1e-5f; }
+    launch_gemm(ctx, g1);
+  }
   void* h = A.elems((size_t)B * P * 2 * C, ctx.dtype);
   launch_dwconv(ctx, hpre, pb.ffn_dw_w, pb.ffn_dw_b, h, 1, B, H, W, 2 * C, RF_K_DW_GELU);
   GemmP g = gemm_rows(h, 2 * C, pb.pw2_w, pb.pw2_b, out, C, B, P, RF_K_GEMM_PW2);
@@ -276,12 +299,27 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
-  void* ln = A.elems((size_t)B * P * C, ctx.dtype);
   void* x1 = A.elems((size_t)B * P * C, ctx.dtype);
-  launch_layernorm(ctx, feat, pb.ln1_g, pb.ln1_b, ln, 1e-5f, 0, B * P, C);
-  attention(ctx, pb, ln, feat, x1, B, H, W);
-  launch_layernorm(ctx, x1, pb.ln2_g, pb.ln2_b, ln, 1e-5f, 0, B * P, C);
-  ffn(ctx, pb, ln, x1, out, B, H, W);
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+    // bf16 mode: both LayerNorms are folded into the 1x1 conv that follows them (W*diag(g), per-row mean/rstd applied in
+    // the GEMM epilogue), so the normalised tensors never exist.  norm1 statistics: one read pass over the block input;
+    // norm2 statistics: emitted by the project_out GEMM epilogue that produces x1.
+    float* st1 = A.get<float>((size_t)B * P * 2);
+    float* st2 = A.get<float>((size_t)B * P * 2 * 2);     // up to two N tiles of partials
+    launch_row_stats(ctx, feat, st1, B * P, C);
+    LnFold l1;
+    l1.stats = st1; l1.npart = 1;
+    LnFold l2;
+    l2.stats = st2;
+    l2.npart = attention(ctx, pb, feat, feat, x1, B, H, W, &l1, st2);
+    ffn(ctx, pb, x1, x1, out, B, H, W, &l2);
+  } else {
+    void* ln = A.elems((size_t)B * P * C, ctx.dtype);
+    launch_layernorm(ctx, feat, pb.ln1_g, pb.ln1_b, ln, 1e-5f, 0, B * P, C);
+    attention(ctx, pb, ln, feat, x1, B, H, W);
+    launch_layernorm(ctx, x1, pb.ln2_g, pb.ln2_b, ln, 1e-5f, 0, B * P, C);
+    ffn(ctx, pb, ln, x1, out, B, H, W);
+  }
   A.release(mk);
 }
 

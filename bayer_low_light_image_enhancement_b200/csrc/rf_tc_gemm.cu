@@ -46,6 +46,16 @@ struct TcParams {
   int tmem_cols;       // allocated TMEM columns (two accumulator buffers)
   int acc_cols;        // column offset of the second accumulator buffer
   int tiles_m, tiles_n, total_tiles;
+  int tma_store;       // OMODE_ROWS: stage the bf16 output tile in shared memory and write it with TMA
+  int nslab;           // 64-column slabs of the staged tile
+  int nbuf;            // staging buffers (1 or 2); tile ti uses buffer ti % nbuf
+  int r_tma;           // the residual tile is TMA-loaded into the staging buffer and updated in place
+  // folded LayerNorm (see GemmP) and row statistics of the output
+  const float* ln_stats;
+  const float* ln_cs;
+  int ln_npart;
+  float ln_invC, ln_eps;
+  float* stats_out;    // [rows][tiles_n] float2 (sum, sumsq) of the rounded outputs (tma_store mode only)
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int n) { return make_idesc_m128(n); }
@@ -84,20 +94,26 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
 // Persistent, warp-specialised: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer
 // runs ahead across tile boundaries through the smem ring; the accumulator is double-buffered in tensor memory so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
-          const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+          const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
+          const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x A tile 16 KB][stages x W tile BN*128 B][barriers]
+  // carve: [stages x A tile 16 KB][stages x W tile BN*128 B][nbuf x nslab x 16 KB residual/output staging][barriers]
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)p.BN * 128;
   const uint32_t sA = base, sW = base + p.stages * a_bytes;
-  const uint32_t bars = sW + p.stages * w_bytes;          // 8-byte aligned (multiples of 128)
+  const uint32_t sY = sW + p.stages * w_bytes;            // 1024-aligned (a_bytes, w_bytes are multiples of 2048)
+  const uint32_t y_bytes = (uint32_t)p.nslab * 16384u;
+  const uint32_t sStat = sY + (uint32_t)p.nbuf * y_bytes; // [128] float2: half-1 warps' row partials (stats_out)
+  const uint32_t bars = sStat + (p.stats_out ? 1024u : 0u);  // 8-byte aligned
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 4);
+  auto yfull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 4 + q); };
+  auto yempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 6 + q); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 8);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,6 +122,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     tma_prefetch_desc(&mapA1);
     if (p.kb2) tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapW);
+    if (p.tma_store) tma_prefetch_desc(&mapY);
+    if (p.r_tma) tma_prefetch_desc(&mapR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -113,6 +131,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), TC_EPI_WARPS);      // one arrival per epilogue warp
+      mbar_init(yfull_bar(a), 1);
+      mbar_init(yempty_bar(a), 1);
     }
     fence_barrier_init();
   }
@@ -127,8 +147,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     if (lane == 0) {
       const uint32_t tx = a_bytes + w_bytes;
       int g = 0;  // k-blocks issued so far (ring position)
+      int ti = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
+        if (tc.nkb <= 0) continue;
+        if (p.r_tma) {
+          // residual tile -> staging buffer ti % nbuf (the epilogue adds the accumulator in place); the buffer is free
+          // once the TMA store of its previous tile has finished reading it (yempty, arrived by the storing thread)
+          const int q = ti % p.nbuf, use = ti / p.nbuf;
+          if (use > 0) mbar_wait(yempty_bar(q), (use - 1) & 1);
+          int ns = 0;
+          for (int sl = 0; sl < p.nslab; ++sl) ns += (tc.n0 + sl * 64 < p.N) ? 1 : 0;
+          mbar_expect_tx(yfull_bar(q), (uint32_t)ns * 16384u);
+          for (int sl = 0; sl < ns; ++sl) {
+            const uint32_t dst = sY + q * y_bytes + sl * 16384u;
+            if (p.amode == AMODE_CONV3) tma_load_4d(dst, &mapR, yfull_bar(q), tc.n0 + sl * 64, tc.px0, tc.py0, tc.b);
+            else tma_load_3d(dst, &mapR, yfull_bar(q), tc.n0 + sl * 64, tc.m0, tc.b);
+          }
+        }
+        ++ti;
         for (int il = 0; il < tc.nkb; ++il, ++g) {
           const int i = tc.kb_begin + il;
           const int s = g % p.stages, it = g / p.stages;
@@ -221,23 +258,77 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         if (p.omode != OMODE_ROWS) { oy = m / p.W; ox = m - oy * p.W; }
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      float ln_mu = 0.f, ln_rs = 1.f;
+      if (p.ln_stats != nullptr && row_ok) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow * p.ln_npart;
+        float su = 0.f, sq = 0.f;
+        for (int q = 0; q < p.ln_npart; ++q) {
+          const float2 t2 = st[q];
+          su += t2.x; sq += t2.y;
+        }
+        ln_mu = su * p.ln_invC;
+        ln_rs = rsqrtf(fmaxf(sq * p.ln_invC - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
+      const int yq = ti % p.nbuf;
+      const uint32_t sYq = sY + yq * y_bytes;
+      if (p.tma_store) {
+        if (p.r_tma) {
+          // the storing thread releases the buffer(s) whose TMA stores have finished READING them to the producer,
+          // then everybody waits for this tile's residual
+          if (warp == 2 && lane == 0 && ti > 0) {
+            if (p.nbuf == 2) {
+              tma_store_wait_read<0>();                     // store(ti-1) (and older) done reading
+              mbar_arrive(yempty_bar((ti - 1) & 1));
+            } else {
+              tma_store_wait_read<0>();
+              mbar_arrive(yempty_bar(0));
+            }
+          }
+          mbar_wait(yfull_bar(yq), (ti / p.nbuf) & 1);
+        } else {
+          // the staging buffer is free once the TMA store of tile ti - nbuf has finished READING it
+          if (warp == 2 && lane == 0) {
+            if (p.nbuf == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       for (int c = half * 16; c < p.BN; c += 32) {
         const int n = n0 + c;
         const int nvalid = p.N - n;          // < 16 only in the last chunk when N % 16 == 8
         // residual prefetch (global) is issued before the TMEM load so both latencies overlap
         uint4 rr0 = make_uint4(0u, 0u, 0u, 0u), rr1 = rr0;
         const bool use_r = p.R != nullptr && p.omode == OMODE_ROWS && row_ok && nvalid > 0;
-        if (use_r) {
+        const uint32_t rowp = sYq + (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u;
+        const uint32_t j0 = (uint32_t)(c & 63) >> 3, sw = (uint32_t)(r & 7);
+        if (p.r_tma) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr0.x), "=r"(rr0.y), "=r"(rr0.z), "=r"(rr0.w)
+                       : "r"(rowp + ((j0 ^ sw) << 4)));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr1.x), "=r"(rr1.y), "=r"(rr1.z), "=r"(rr1.w)
+                       : "r"(rowp + (((j0 + 1) ^ sw) << 4)));
+        } else if (use_r) {
           rr0 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n);
           if (nvalid > 8) rr1 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n + 8);
         }
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
-        if (!row_ok || nvalid <= 0) continue;
+        if ((!row_ok && !p.tma_store) || nvalid <= 0) continue;   // (TMA clips rows outside the tensor itself)
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.ln_stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (j < nvalid) {
+              const float4 cq = *reinterpret_cast<const float4*>(p.ln_cs + n + j);
+              f[j] = ln_rs * fmaf(-ln_mu, cq.x, f[j]); f[j + 1] = ln_rs * fmaf(-ln_mu, cq.y, f[j + 1]);
+              f[j + 2] = ln_rs * fmaf(-ln_mu, cq.z, f[j + 2]); f[j + 3] = ln_rs * fmaf(-ln_mu, cq.w, f[j + 3]);
+            }
+          }
+        }
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -263,7 +354,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           for (int j = 0; j < 16; ++j)
             if (n + j < p.N) atomicAdd(yf + j, f[j]);
         } else if (p.omode == OMODE_ROWS) {
-          if (use_r) {
+          if (use_r || p.r_tma) {
             const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&rr0);
             const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&rr1);
 #pragma unroll
@@ -273,14 +364,46 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
               f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
             }
           }
-          float o8[8];
+          if (p.tma_store) {
+            // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk position j ^ (r & 7); a quarter
+            // warp (8 consecutive rows) therefore hits all 32 banks once
+            uint4 q0, q1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&q0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&q1);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o8[j] = f[j];
-          store8(p.Y + orow * p.ldy + n, o8);
-          if (nvalid > 8) {
+            for (int j = 0; j < 4; ++j) {
+              h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            }
+            if (p.stats_out != nullptr) {                    // statistics of the ROUNDED values (what the consumer reads)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
-            store8(p.Y + orow * p.ldy + n + 8, o8);
+              for (int j = 0; j < 4; ++j) {
+                const float2 a0 = __bfloat1622float2(h0[j]);
+                st_sum += a0.x + a0.y;
+                st_sq = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, st_sq));
+                if (nvalid > 8) {
+                  const float2 a1 = __bfloat1622float2(h1[j]);
+                  st_sum += a1.x + a1.y;
+                  st_sq = fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, st_sq));
+                }
+              }
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j0 ^ sw) << 4)), "r"(q0.x), "r"(q0.y),
+                         "r"(q0.z), "r"(q0.w)
+                         : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (((j0 + 1) ^ sw) << 4)), "r"(q1.x),
+                         "r"(q1.y), "r"(q1.z), "r"(q1.w)
+                         : "memory");
+          } else {
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = f[j];
+            store8(p.Y + orow * p.ldy + n, o8);
+            if (nvalid > 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
+              store8(p.Y + orow * p.ldy + n + 8, o8);
+            }
           }
         } else if (p.omode == OMODE_CONVT) {
           const int Co = p.N >> 2;
@@ -304,9 +427,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (p.tma_store) {
+        if (p.stats_out != nullptr && half == 1)
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sStat + 8u * r), "f"(st_sum), "f"(st_sq) : "memory");
+        fence_proxy_async();                               // staged tile (generic stores) -> TMA store (async proxy)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (p.stats_out != nullptr && half == 0 && row_ok) {
+          float ox, oy2;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ox), "=f"(oy2) : "r"(sStat + 8u * r));
+          reinterpret_cast<float2*>(p.stats_out)[orow * p.tiles_n + n0 / p.BN] = make_float2(st_sum + ox, st_sq + oy2);
+        }
+        if (warp == 2 && lane == 0) {
+          for (int sl = 0; sl < p.nslab; ++sl) {
+            if (n0 + sl * 64 >= p.N) break;
+            if (p.amode == AMODE_CONV3) tma_store_4d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.px0, tc.py0, b);
+            else tma_store_3d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.m0, b);
+          }
+          tma_store_commit();
+        }
+      }
       ++ti;
     }
   }
+  if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -322,12 +465,15 @@ static int pick_bn(int N) {
   if (N % 8) return 0;
   if (N <= 256) return (N + 15) & ~15;   // N % 16 == 8: the last 8 columns are zero weights (TMA OOB) and masked stores
   if (N % 16) return 0;
-  for (int parts = 2; parts <= 64; ++parts) {
-    if (N % parts) continue;
-    int bn = N / parts;
-    if (bn <= 256 && bn % 16 == 0) return bn;
+  // several N tiles: multiples of 64 (the TMA-store slabs of neighbouring tiles must not overlap); the last tile may
+  // be ragged (W rows beyond N are zero-filled by TMA, stores are clipped).  Least padded work, then the widest tile.
+  int best = 0;
+  i64 best_pad = 0;
+  for (int bn = 256; bn >= 128; bn -= 64) {
+    const i64 pad = (i64)((N + bn - 1) / bn) * bn;
+    if (best == 0 || pad < best_pad) { best = bn; best_pad = pad; }
   }
-  return 0;
+  return best;
 }
 
 
@@ -454,30 +600,37 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
 static bool g_tc_enabled = true;
 static bool g_tc_checked = false;
 void set_tcgen05_enabled(bool on) { g_tc_enabled = on; g_tc_checked = true; }
-bool tcgen05_enabled() { return g_tc_enabled; }
-
-bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
+bool tcgen05_enabled() {
   if (!g_tc_checked) {
     g_tc_checked = true;
     const char* e = getenv("RAWFORMER_B200_NO_TCGEN05");
     if (e && e[0] == '1') g_tc_enabled = false;
   }
-  if (!g_tc_enabled || ctx.dtype != RF_BF16) return false;
+  return g_tc_enabled;
+}
+
+int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
+  if (!tcgen05_enabled() || ctx.dtype != RF_BF16) return -1;
   const int BN = pick_bn(g.N);
-  if (BN == 0) return false;
-  if (g.omode != OMODE_ATOMIC_F32 && (g.K1 % 8 || g.K2 % 8)) return false;  // (Gram: pitch is padded, TMA zero-fills the K tail)
-  if (g.lda1 % 8 || (g.A2 && g.lda2 % 8) || (g.ldw % 8)) return false;
-  if (g.omode == OMODE_CONVT && ((g.N / 4) % 16)) return false;
-  if (g.amode == AMODE_CONV3 && g.A2) return false;
-  if (g.amode != AMODE_CONV3 && (g.lda1 < g.K1 || (g.A2 && g.lda2 < g.K2))) return false;
-  if (g.omode == OMODE_ATOMIC_F32 && (g.amode != AMODE_ROWS || g.A2 || g.bias || g.R || g.act != ACT_NONE)) return false;
+  if (BN == 0) return -1;
+  if (g.omode != OMODE_ATOMIC_F32 && (g.K1 % 8 || g.K2 % 8)) return -1;  // (Gram: pitch is padded, TMA zero-fills the K tail)
+  if (g.lda1 % 8 || (g.A2 && g.lda2 % 8) || (g.ldw % 8)) return -1;
+  if (g.omode == OMODE_CONVT && ((g.N / 4) % 16)) return -1;
+  if (g.amode == AMODE_CONV3 && g.A2) return -1;
+  if (g.amode != AMODE_CONV3 && (g.lda1 < g.K1 || (g.A2 && g.lda2 < g.K2))) return -1;
+  if (g.omode == OMODE_ATOMIC_F32 && (g.amode != AMODE_ROWS || g.A2 || g.bias || g.R || g.act != ACT_NONE)) return -1;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.bias = g.bias; p.R = (const bf16*)g.R; p.Y = (bf16*)g.Y; p.ldr = g.ldr; p.ldy = g.ldy;
   p.M = g.M; p.N = g.N; p.B = g.B; p.BN = BN; p.act = g.act; p.amode = g.amode; p.omode = g.omode; p.H = g.H; p.W = g.W;
   p.w_per_image = g.w_img != 0;
-  CUtensorMap mA1, mA2, mW;
+  p.ln_stats = g.ln_stats; p.ln_cs = g.ln_cs; p.ln_npart = g.ln_npart; p.ln_eps = g.ln_eps;
+  p.ln_invC = g.ln_C > 0 ? 1.0f / (float)g.ln_C : 0.f;
+  CUtensorMap mA1, mA2, mW, mY, mR;
+  p.tma_store = (g.omode == OMODE_ROWS && g.ldy % 8 == 0 && (!g.R || g.ldr % 8 == 0)) ? 1 : 0;
+  p.nslab = p.tma_store ? cdiv(BN, 64) : 0;
+  p.r_tma = (p.tma_store && g.R != nullptr) ? 1 : 0;
   int grid_x;
   if (g.amode == AMODE_CONV3) {
     const int Cin = g.K1 / 9;
@@ -496,12 +649,22 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 dA[4] = {Cin, g.W, g.H, g.B};
     const i64 sA[4] = {1, g.lda1, g.lda1 * g.W, g.lda1 * g.W * g.H};
     const int bA[4] = {TC_BK, p.tw, p.th, 1};
-    if (!make_map(&mA1, g.A1, 4, dA, sA, bA)) return false;
+    if (!make_map(&mA1, g.A1, 4, dA, sA, bA)) return -1;
     mA2 = mA1;
     const i64 dW[3] = {Cin, 9, g.N};
     const i64 sW[3] = {1, Cin, (i64)9 * Cin};
     const int bW[3] = {TC_BK, 1, BN};
-    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return false;
+    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return -1;
+    if (p.tma_store) {
+      const i64 dY[4] = {g.N, g.W, g.H, g.B};
+      const i64 sY[4] = {1, g.ldy, g.ldy * g.W, g.ldy * g.W * g.H};
+      const int bY[4] = {64, p.tw, p.th, 1};
+      if (!make_map(&mY, g.Y, 4, dY, sY, bY)) return -1;
+      if (p.r_tma) {
+        const i64 sR[4] = {1, g.ldr, g.ldr * g.W, g.ldr * g.W * g.H};
+        if (!make_map(&mR, g.R, 4, dY, sR, bY)) return -1;
+      }
+    }
   } else {
     p.taps = 1; p.K1 = g.K1; p.K2 = g.A2 ? g.K2 : 0;
     p.kb1 = cdiv(g.K1, TC_BK); p.kb2 = g.A2 ? cdiv(g.K2, TC_BK) : 0;
@@ -510,11 +673,11 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 dA[3] = {g.K1, g.M, g.B};
     const i64 sA[3] = {1, g.lda1, g.a1_img ? g.a1_img : g.lda1 * g.M};
     const int bA[3] = {TC_BK, TC_BM, 1};
-    if (!make_map(&mA1, g.A1, 3, dA, sA, bA)) return false;
+    if (!make_map(&mA1, g.A1, 3, dA, sA, bA)) return -1;
     if (g.A2) {
       const i64 dA2[3] = {g.K2, g.M, g.B};
       const i64 sA2[3] = {1, g.lda2, g.lda2 * g.M};
-      if (!make_map(&mA2, g.A2, 3, dA2, sA2, bA)) return false;
+      if (!make_map(&mA2, g.A2, 3, dA2, sA2, bA)) return -1;
     } else {
       mA2 = mA1;
     }
@@ -523,17 +686,51 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 dW[3] = {K, g.N, g.w_img ? g.B : 1};
     const i64 sW[3] = {1, ldw, g.w_img ? g.w_img : ldw * g.N};
     const int bW[3] = {TC_BK, BN, 1};
-    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return false;
+    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return -1;
+    if (p.tma_store) {
+      const i64 dY[3] = {g.N, g.M, g.B};
+      const i64 sY[3] = {1, g.ldy, g.ldy * g.M};
+      const int bY[3] = {64, TC_BM, 1};
+      if (!make_map(&mY, g.Y, 3, dY, sY, bY)) return -1;
+      if (p.r_tma) {
+        const i64 sR[3] = {1, g.ldr, g.ldr * g.M};
+        if (!make_map(&mR, g.R, 3, dY, sR, bY)) return -1;
+      }
+    }
   }
+  if (!p.tma_store) mY = mW;
+  if (!p.r_tma) mR = mW;
+  p.stats_out = p.tma_store ? g.stats_out : nullptr;
   const int nkb_all = p.taps * p.kb1 + p.kb2;
   p.ksplit = (g.omode == OMODE_ATOMIC_F32 && g.ksplit > 1) ? (g.ksplit < nkb_all ? g.ksplit : nkb_all) : 1;
-  // smem ring: as deep as ~190 KB allows (the producer prefetches across tile boundaries), at most TC_MAX_STAGES
+  // smem: operand ring + residual/output staging.  Two CTAs per SM (two producer / MMA / epilogue sets) when the
+  // accumulators fit twice in tensor memory AND a >= 2-deep ring plus the staging fits in half the shared memory.
   const size_t stage_bytes = (size_t)TC_BM * 128 + (size_t)BN * 128;
   int cols = 32;
   while (cols < BN) cols *= 2;
-  // two CTAs per SM (two producer / MMA / epilogue sets) when the accumulators fit twice in tensor memory
-  const int ctas_per_sm = (2 * cols <= 256) ? 2 : 1;
-  int stages = (int)(((ctas_per_sm == 2 ? 104 : 200) * 1024) / stage_bytes);
+  const size_t staging1 = (size_t)p.nslab * 16384;
+  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 10);
+  const int nkb_tile = p.taps * p.kb1 + p.kb2;
+  const int want = nkb_tile > 1 ? 3 : 2;
+  int ctas_per_sm = 1, stages = 0;
+  p.nbuf = 1;
+  if (2 * cols <= 256) {
+    for (int nb = p.tma_store ? 2 : 1; nb >= 1 && stages == 0; --nb) {
+      if (nb == 1 && p.r_tma) break;                       // in-place residual wants two buffers: run one CTA per SM
+      const size_t used = fixed + nb * staging1;
+      if (used + want * stage_bytes <= 115712) {
+        ctas_per_sm = 2; p.nbuf = nb;
+        stages = (int)((115712 - used) / stage_bytes);
+      }
+    }
+  }
+  if (stages == 0) {
+    ctas_per_sm = 1;
+    p.nbuf = p.tma_store ? 2 : 1;
+    if (fixed + p.nbuf * staging1 + 2 * stage_bytes > 232448) p.nbuf = 1;
+    stages = (int)((232448 - fixed - p.nbuf * staging1) / stage_bytes);
+  }
+  const size_t staging = p.nbuf * staging1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -542,10 +739,10 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.tiles_m = grid_x;
   p.tiles_n = cdiv(g.N, BN);
   p.total_tiles = p.tiles_m * p.tiles_n * g.B * p.ksplit;
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 8 * (2 * TC_MAX_STAGES + 6);
+  const size_t smem = fixed + (size_t)p.stages * stage_bytes + staging;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
     smem_set = 227 * 1024;
   }
   const int K = g.K1 + g.K2;
@@ -555,13 +752,13 @@ bool launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
   const int max_ctas = num_sms() * ctas_per_sm;
   const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-  k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, p);
-  return true;
+  k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, mY, mR, p);
+  return p.stats_out ? p.tiles_n : 0;
 }
 
 // qk: bf16 NHWC [P][2C] (q | k) of ONE image; G: fp32 [C][C], zero-initialised by the caller
 bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
-  if (!g_tc_enabled || ctx.dtype != RF_BF16 || C % 8) return false;
+  if (!tcgen05_enabled() || ctx.dtype != RF_BF16 || C % 8) return false;
   CUtensorMap m;
   const i64 d[3] = {2 * (i64)C, P, 1};
   const i64 st[3] = {1, 2 * (i64)C, 2 * (i64)C * P};
