@@ -36,6 +36,7 @@ struct TcParams {
   int act, amode, omode;
   int H, W;            // image size of the rows (conv / convT / unshuffle addressing)
   int tw, th;          // conv patch (tw*th == 128)
+  int tw_log2;
   int tiles_x;         // conv: patches per image row
   int kb1, kb2;        // k-blocks from A1 (per tap for conv) and A2
   int K1, K2;          // K of A1 (per tap for conv: Cin) and A2
@@ -70,30 +71,35 @@ struct TileCoord {
 // tile index -> coordinates; N slices of the same pixel tile are adjacent so that they share the A tile through L2
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   TileCoord tc;
-  const int ny = t % p.tiles_n;
-  int r = t / p.tiles_n;
-  const int mx = r % p.tiles_m;
-  const int z = r / p.tiles_m;
-  tc.b = z / p.ksplit;
-  tc.split = z - tc.b * p.ksplit;
+  int ny = 0, r = t;
+  if (p.tiles_n > 1) { ny = t % p.tiles_n; r = t / p.tiles_n; }
+  int mx = r, z = 0;
+  if (p.B * p.ksplit > 1) { mx = r % p.tiles_m; z = r / p.tiles_m; }
+  tc.b = z; tc.split = 0;
+  if (p.ksplit > 1) { tc.b = z / p.ksplit; tc.split = z - tc.b * p.ksplit; }
   tc.n0 = ny * p.BN;
   tc.m0 = 0; tc.px0 = 0; tc.py0 = 0;
   if (p.amode == AMODE_CONV3) {
-    tc.px0 = (mx % p.tiles_x) * p.tw;
-    tc.py0 = (mx / p.tiles_x) * p.th;
+    const int ty = mx / p.tiles_x;
+    tc.px0 = (mx - ty * p.tiles_x) * p.tw;
+    tc.py0 = ty * p.th;
   } else {
     tc.m0 = mx * TC_BM;
   }
   const int nkb_all = p.taps * p.kb1 + p.kb2;
-  const int kb_per = (nkb_all + p.ksplit - 1) / p.ksplit;
-  tc.kb_begin = tc.split * kb_per;
-  tc.nkb = min(nkb_all, tc.kb_begin + kb_per) - tc.kb_begin;
+  tc.kb_begin = 0; tc.nkb = nkb_all;
+  if (p.ksplit > 1) {
+    const int kb_per = (nkb_all + p.ksplit - 1) / p.ksplit;
+    tc.kb_begin = tc.split * kb_per;
+    tc.nkb = min(nkb_all, tc.kb_begin + kb_per) - tc.kb_begin;
+  }
   return tc;
 }
 
 // Persistent, warp-specialised: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer
 // runs ahead across tile boundaries through the smem ring; the accumulator is double-buffered in tensor memory so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
+template <int OM, bool LN, bool HR, bool ST, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
@@ -112,8 +118,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
   auto yfull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 4 + q); };
-  auto yempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 6 + q); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 8);
+  auto yempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 8 + q); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 12);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,8 +137,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), TC_EPI_WARPS);      // one arrival per epilogue warp
-      mbar_init(yfull_bar(a), 1);
-      mbar_init(yempty_bar(a), 1);
+    }
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(yfull_bar(q), 1);
+      mbar_init(yempty_bar(q), 1);
     }
     fence_barrier_init();
   }
@@ -231,181 +239,178 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     }
   } else {
     // ================= epilogue (warps 2..9) =================
+    // Specialised at compile time (OM, LN, HR, ST, ACT): the tiles of the HBM-bound shapes are small (128 x 32..96), so
+    // the epilogue's instruction count per tile bounds the kernel -- no runtime mode switches inside the chunk code.
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;       // which half of the 16-column chunks this warp handles
     const int r = quad * 32 + lane;         // row of the tile
+    const uint32_t sw = (uint32_t)(r & 7);  // 128-byte-swizzle phase of this row in the staging tile
+    const int rty = r >> p.tw_log2, rtx = r & (p.tw - 1);   // conv patch coordinates of this row
     int ti = 0;
+    float2 ln_next = make_float2(0.f, 0.f);
+    auto row_of = [&](const TileCoord& tn, bool& ok, int& oy, int& ox) -> i64 {
+      if (p.amode == AMODE_CONV3) {
+        oy = tn.py0 + rty;
+        ox = tn.px0 + rtx;
+        ok = oy < p.H && ox < p.W;
+        return (i64)tn.b * p.M + (i64)oy * p.W + ox;
+      }
+      const int m = tn.m0 + r;
+      ok = m < p.M;
+      if (OM == OMODE_CONVT || OM == OMODE_UNSHUFFLE) { oy = m / p.W; ox = m - oy * p.W; }
+      return (i64)tn.b * p.M + m;
+    };
+    // (sum, sumsq) of this thread's row in tile t (folded LayerNorm); rows outside the tensor give zeros
+    auto ln_fetch = [&](int t) {
+      const TileCoord tn = decode_tile(p, t);
+      bool ok;
+      int yy, xx;
+      const i64 row = row_of(tn, ok, yy, xx);
+      float su = 0.f, sq = 0.f;
+      if (ok) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + row * p.ln_npart;
+        for (int q = 0; q < p.ln_npart; ++q) {
+          const float2 t2 = __ldg(st + q);
+          su += t2.x; sq += t2.y;
+        }
+      }
+      return make_float2(su, sq);
+    };
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       if (tc.nkb <= 0) continue;
       const int acc = ti & 1, u = ti >> 1;
       const int b = tc.b, n0 = tc.n0;
+      // the storing thread hands the staging buffer of the previous tile back to the producer as soon as its TMA store
+      // has finished READING it -- before waiting for this tile's accumulator, so that the producer (which fetches the
+      // residual of a later tile into that buffer before issuing that tile's operands) can never wait on this tile
+      if (HR && warp == 2 && lane == 0 && ti > 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(yempty_bar((ti - 1) % p.nbuf));
+      }
+      // folded LayerNorm: this tile's row statistics were fetched one tile ago (the global-load latency hides under the
+      // previous tile's epilogue); fetch the next tile's now
+      float ln_rs = 1.f, ln_nm = 0.f;
+      if (LN) {
+        if (ti == 0) ln_next = ln_fetch(t);
+        const float2 cur = ln_next;
+        if (t + (int)gridDim.x < p.total_tiles) ln_next = ln_fetch(t + gridDim.x);
+        const float mu = cur.x * p.ln_invC;
+        ln_rs = rsqrtf(fmaxf(cur.y * p.ln_invC - mu * mu, 0.f) + p.ln_eps);
+        ln_nm = -ln_rs * mu;
+      }
+      bool row_ok;
+      int oy = 0, ox = 0;
+      const i64 orow = row_of(tc, row_ok, oy, ox);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      const int yq = ti % p.nbuf;
+      const uint32_t srow = sY + yq * y_bytes + (uint32_t)r * 128u;   // this row in slab 0 of the staging buffer
       mbar_wait(tfull_bar(acc), u & 1);
       tc_fence_after();
-      // output row
-      bool row_ok;
-      i64 orow = 0;        // OMODE_ROWS: row index into R/Y
-      int oy = 0, ox = 0;  // pixel coordinates (conv / scatter modes)
-      if (p.amode == AMODE_CONV3) {
-        oy = tc.py0 + r / p.tw;
-        ox = tc.px0 + r % p.tw;
-        row_ok = oy < p.H && ox < p.W;
-        orow = (i64)b * p.M + (i64)oy * p.W + ox;
-      } else {
-        const int m = tc.m0 + r;
-        row_ok = m < p.M;
-        orow = (i64)b * p.M + m;
-        if (p.omode != OMODE_ROWS) { oy = m / p.W; ox = m - oy * p.W; }
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-      float ln_mu = 0.f, ln_rs = 1.f;
-      if (p.ln_stats != nullptr && row_ok) {
-        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow * p.ln_npart;
-        float su = 0.f, sq = 0.f;
-        for (int q = 0; q < p.ln_npart; ++q) {
-          const float2 t2 = st[q];
-          su += t2.x; sq += t2.y;
-        }
-        ln_mu = su * p.ln_invC;
-        ln_rs = rsqrtf(fmaxf(sq * p.ln_invC - ln_mu * ln_mu, 0.f) + p.ln_eps);
-      }
-      float st_sum = 0.f, st_sq = 0.f;
-      const int yq = ti % p.nbuf;
-      const uint32_t sYq = sY + yq * y_bytes;
-      if (p.tma_store) {
-        if (p.r_tma) {
-          // the storing thread releases the buffer(s) whose TMA stores have finished READING them to the producer,
-          // then everybody waits for this tile's residual
-          if (warp == 2 && lane == 0 && ti > 0) {
-            if (p.nbuf == 2) {
-              tma_store_wait_read<0>();                     // store(ti-1) (and older) done reading
-              mbar_arrive(yempty_bar((ti - 1) & 1));
-            } else {
-              tma_store_wait_read<0>();
-              mbar_arrive(yempty_bar(0));
-            }
-          }
-          mbar_wait(yfull_bar(yq), (ti / p.nbuf) & 1);
+      if (OM == OMODE_ROWS) {
+        if (HR) {
+          mbar_wait(yfull_bar(yq), (ti / p.nbuf) & 1);       // this tile's residual has landed in the staging buffer
         } else {
           // the staging buffer is free once the TMA store of tile ti - nbuf has finished READING it
           if (warp == 2 && lane == 0) {
-            if (p.nbuf == 2) tma_store_wait_read<1>();
+            if (p.nbuf >= 2) tma_store_wait_read<1>();
             else tma_store_wait_read<0>();
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }
-      for (int c = half * 16; c < p.BN; c += 32) {
+      float st_sum = 0.f, st_sq = 0.f;
+      // one 16-column chunk of this thread's row: v = its accumulator values
+      auto chunk = [&](const int c, const uint32_t (&v)[16]) {
         const int n = n0 + c;
         const int nvalid = p.N - n;          // < 16 only in the last chunk when N % 16 == 8
-        // residual prefetch (global) is issued before the TMEM load so both latencies overlap
-        uint4 rr0 = make_uint4(0u, 0u, 0u, 0u), rr1 = rr0;
-        const bool use_r = p.R != nullptr && p.omode == OMODE_ROWS && row_ok && nvalid > 0;
-        const uint32_t rowp = sYq + (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u;
-        const uint32_t j0 = (uint32_t)(c & 63) >> 3, sw = (uint32_t)(r & 7);
-        if (p.r_tma) {
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr0.x), "=r"(rr0.y), "=r"(rr0.z), "=r"(rr0.w)
-                       : "r"(rowp + ((j0 ^ sw) << 4)));
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr1.x), "=r"(rr1.y), "=r"(rr1.z), "=r"(rr1.w)
-                       : "r"(rowp + (((j0 + 1) ^ sw) << 4)));
-        } else if (use_r) {
-          rr0 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n);
-          if (nvalid > 8) rr1 = *reinterpret_cast<const uint4*>(p.R + orow * p.ldr + n + 8);
-        }
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
-        if ((!row_ok && !p.tma_store) || nvalid <= 0) continue;   // (TMA clips rows outside the tensor itself)
+        if (nvalid <= 0) return;
+        if (OM != OMODE_ROWS && !row_ok) return;              // (rows mode: TMA clips rows outside the tensor)
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.ln_stats != nullptr) {
+        if (LN) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (j < nvalid) {
-              const float4 cq = *reinterpret_cast<const float4*>(p.ln_cs + n + j);
-              f[j] = ln_rs * fmaf(-ln_mu, cq.x, f[j]); f[j + 1] = ln_rs * fmaf(-ln_mu, cq.y, f[j + 1]);
-              f[j + 2] = ln_rs * fmaf(-ln_mu, cq.z, f[j + 2]); f[j + 3] = ln_rs * fmaf(-ln_mu, cq.w, f[j + 3]);
+              const float4 cq = __ldg(reinterpret_cast<const float4*>(p.ln_cs + n + j));
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              f[j] = fmaf(ln_rs, f[j], fmaf(ln_nm, cq.x, bq.x));
+              f[j + 1] = fmaf(ln_rs, f[j + 1], fmaf(ln_nm, cq.y, bq.y));
+              f[j + 2] = fmaf(ln_rs, f[j + 2], fmaf(ln_nm, cq.z, bq.z));
+              f[j + 3] = fmaf(ln_rs, f[j + 3], fmaf(ln_nm, cq.w, bq.w));
             }
           }
-        }
-        if (p.bias) {
+        } else if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (j < nvalid) {
-              const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
               f[j] += bq.x; f[j + 1] += bq.y; f[j + 2] += bq.z; f[j + 3] += bq.w;
             }
           }
         }
-        if (p.act == ACT_LRELU) {
+        if (ACT == ACT_LRELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = lrelu_f(f[j]);
-        } else if (p.act == ACT_RELU) {
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);
+        } else if (ACT == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        } else if (p.act == ACT_TANH_RES) {
+        } else if (ACT == ACT_TANH_RES) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = 0.2f * tanh_fast(f[j]);
         }
-        if (p.omode == OMODE_ATOMIC_F32) {
+        if (OM == OMODE_ROWS) {
+          // staging tile: 64-column slabs of 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk
+          // position j ^ (r & 7); a quarter warp (8 consecutive rows) hits all 32 banks once
+          const uint32_t rowp = srow + (uint32_t)(c >> 6) * 16384u;
+          const uint32_t j0 = (uint32_t)(c & 63) >> 3;
+          const uint32_t a0 = rowp + ((j0 ^ sw) << 4), a1 = rowp + (((j0 + 1) ^ sw) << 4);
+          if (HR) {                                          // residual, TMA-loaded into the same place
+            uint4 rr0, rr1;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr0.x), "=r"(rr0.y), "=r"(rr0.z), "=r"(rr0.w) : "r"(a0));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rr1.x), "=r"(rr1.y), "=r"(rr1.z), "=r"(rr1.w) : "r"(a1));
+            const uint32_t w0[4] = {rr0.x, rr0.y, rr0.z, rr0.w}, w1[4] = {rr1.x, rr1.y, rr1.z, rr1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[2 * j] += __uint_as_float(w0[j] << 16);
+              f[2 * j + 1] += __uint_as_float(w0[j] & 0xffff0000u);
+              f[8 + 2 * j] += __uint_as_float(w1[j] << 16);
+              f[8 + 2 * j + 1] += __uint_as_float(w1[j] & 0xffff0000u);
+            }
+          }
+          uint32_t q0[4], q1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            q0[j] = *reinterpret_cast<uint32_t*>(&h0);
+            q1[j] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          if (ST) {                                          // statistics of the ROUNDED values (what the consumer reads)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = __uint_as_float(q0[j] << 16), x1 = __uint_as_float(q0[j] & 0xffff0000u);
+              st_sum += x0 + x1;
+              st_sq = fmaf(x0, x0, fmaf(x1, x1, st_sq));
+            }
+            if (nvalid > 8) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x0 = __uint_as_float(q1[j] << 16), x1 = __uint_as_float(q1[j] & 0xffff0000u);
+                st_sum += x0 + x1;
+                st_sq = fmaf(x0, x0, fmaf(x1, x1, st_sq));
+              }
+            }
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(q0[0]), "r"(q0[1]), "r"(q0[2]), "r"(q0[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(q1[0]), "r"(q1[1]), "r"(q1[2]), "r"(q1[3]) : "memory");
+        } else if (OM == OMODE_ATOMIC_F32) {
           float* yf = reinterpret_cast<float*>(p.Y) + orow * p.ldy + n;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (n + j < p.N) atomicAdd(yf + j, f[j]);
-        } else if (p.omode == OMODE_ROWS) {
-          if (use_r || p.r_tma) {
-            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&rr0);
-            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&rr1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 x0 = __bfloat1622float2(h0[j]), x1 = __bfloat1622float2(h1[j]);
-              f[2 * j] += x0.x; f[2 * j + 1] += x0.y;
-              f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
-            }
-          }
-          if (p.tma_store) {
-            // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk position j ^ (r & 7); a quarter
-            // warp (8 consecutive rows) therefore hits all 32 banks once
-            uint4 q0, q1;
-            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&q0);
-            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&q1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-            }
-            if (p.stats_out != nullptr) {                    // statistics of the ROUNDED values (what the consumer reads)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a0 = __bfloat1622float2(h0[j]);
-                st_sum += a0.x + a0.y;
-                st_sq = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, st_sq));
-                if (nvalid > 8) {
-                  const float2 a1 = __bfloat1622float2(h1[j]);
-                  st_sum += a1.x + a1.y;
-                  st_sq = fmaf(a1.x, a1.x, fmaf(a1.y, a1.y, st_sq));
-                }
-              }
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j0 ^ sw) << 4)), "r"(q0.x), "r"(q0.y),
-                         "r"(q0.z), "r"(q0.w)
-                         : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (((j0 + 1) ^ sw) << 4)), "r"(q1.x),
-                         "r"(q1.y), "r"(q1.z), "r"(q1.w)
-                         : "memory");
-          } else {
-            float o8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = f[j];
-            store8(p.Y + orow * p.ldy + n, o8);
-            if (nvalid > 8) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
-              store8(p.Y + orow * p.ldy + n + 8, o8);
-            }
-          }
-        } else if (p.omode == OMODE_CONVT) {
+        } else if (OM == OMODE_CONVT) {
           const int Co = p.N >> 2;
           const int ij = n / Co, co = n - ij * Co;   // 16-wide chunk never straddles ij (Co % 16 == 0)
           const i64 dst = (((i64)b * 2 * p.H + 2 * oy + (ij >> 1)) * (2 * p.W) + 2 * ox + (ij & 1)) * p.ldy + co;
@@ -422,22 +427,33 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           for (int j = 0; j < 16; ++j)
             if (j < nvalid) p.Y[dst + (i64)(n + j) * 4] = __float2bfloat16_rn(f[j]);
         }
+      };
+      // two chunks per TMEM round trip (32 accumulator registers in flight)
+      for (int c = half * 16; c < p.BN; c += 64) {
+        uint32_t va[16], vb[16];
+        const bool two = c + 32 < p.BN;      // warp-uniform
+        tmem_ld16(taddr + c, va);
+        if (two) tmem_ld16(taddr + c + 32, vb);
+        tmem_ld_wait();
+        chunk(c, va);
+        if (two) chunk(c + 32, vb);
       }
       // this warp is done reading the accumulator buffer: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (p.tma_store) {
-        if (p.stats_out != nullptr && half == 1)
+      if (OM == OMODE_ROWS) {
+        if (ST && half == 1)
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sStat + 8u * r), "f"(st_sum), "f"(st_sq) : "memory");
         fence_proxy_async();                               // staged tile (generic stores) -> TMA store (async proxy)
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (p.stats_out != nullptr && half == 0 && row_ok) {
-          float ox, oy2;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ox), "=f"(oy2) : "r"(sStat + 8u * r));
-          reinterpret_cast<float2*>(p.stats_out)[orow * p.tiles_n + n0 / p.BN] = make_float2(st_sum + ox, st_sq + oy2);
+        if (ST && half == 0 && row_ok) {
+          float ox2, oy2;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ox2), "=f"(oy2) : "r"(sStat + 8u * r));
+          reinterpret_cast<float2*>(p.stats_out)[orow * p.tiles_n + n0 / p.BN] = make_float2(st_sum + ox2, st_sq + oy2);
         }
         if (warp == 2 && lane == 0) {
+          const uint32_t sYq = sY + yq * y_bytes;
           for (int sl = 0; sl < p.nslab; ++sl) {
             if (n0 + sl * 64 >= p.N) break;
             if (p.amode == AMODE_CONV3) tma_store_4d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.px0, tc.py0, b);
@@ -449,7 +465,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       ++ti;
     }
   }
-  if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's reads
+  if (OM == OMODE_ROWS && warp == 2 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -644,6 +660,8 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       if (best < 0 || area < best) { best = area; best_tw = tw; }
     }
     p.tw = best_tw; p.th = 128 / best_tw;
+    p.tw_log2 = 0;
+    while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
     p.tiles_x = cdiv(g.W, p.tw);
     grid_x = p.tiles_x * cdiv(g.H, p.th);
     const i64 dA[4] = {Cin, g.W, g.H, g.B};
@@ -668,7 +686,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   } else {
     p.taps = 1; p.K1 = g.K1; p.K2 = g.A2 ? g.K2 : 0;
     p.kb1 = cdiv(g.K1, TC_BK); p.kb2 = g.A2 ? cdiv(g.K2, TC_BK) : 0;
-    p.tw = 128; p.th = 1; p.tiles_x = 1;
+    p.tw = 128; p.th = 1; p.tw_log2 = 7; p.tiles_x = 1;
     grid_x = cdiv(g.M, TC_BM);
     const i64 dA[3] = {g.K1, g.M, g.B};
     const i64 sA[3] = {1, g.lda1, g.a1_img ? g.a1_img : g.lda1 * g.M};
@@ -709,14 +727,19 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   int cols = 32;
   while (cols < BN) cols *= 2;
   const size_t staging1 = (size_t)p.nslab * 16384;
-  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 10);
+  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 14);
   const int nkb_tile = p.taps * p.kb1 + p.kb2;
   const int want = nkb_tile > 1 ? 3 : 2;
+  static int nbuf_r = -1;                 // debugging aid: RAWFORMER_B200_RBUF=2|3 (residual staging depth)
+  if (nbuf_r < 0) {
+    const char* e = getenv("RAWFORMER_B200_RBUF");
+    nbuf_r = (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 3;
+  }
   int ctas_per_sm = 1, stages = 0;
   p.nbuf = 1;
   if (2 * cols <= 256) {
-    for (int nb = p.tma_store ? 2 : 1; nb >= 1 && stages == 0; --nb) {
-      if (nb == 1 && p.r_tma) break;                       // in-place residual wants two buffers: run one CTA per SM
+    for (int nb = p.tma_store ? (p.r_tma ? nbuf_r : 2) : 1; nb >= 1 && stages == 0; --nb) {
+      if (nb == 1 && p.r_tma) break;                       // in-place residual wants >= two buffers: one CTA per SM
       const size_t used = fixed + nb * staging1;
       if (used + want * stage_bytes <= 115712) {
         ctas_per_sm = 2; p.nbuf = nb;
@@ -726,8 +749,10 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   }
   if (stages == 0) {
     ctas_per_sm = 1;
-    p.nbuf = p.tma_store ? 2 : 1;
-    if (fixed + p.nbuf * staging1 + 2 * stage_bytes > 232448) p.nbuf = 1;
+    p.nbuf = p.tma_store ? (p.r_tma ? nbuf_r : 2) : 1;
+    // keep two staging buffers if at all possible (a 2-deep operand ring is enough for that)
+    while (p.nbuf > 2 && fixed + p.nbuf * staging1 + want * stage_bytes > 232448) --p.nbuf;
+    if (p.nbuf == 2 && fixed + 2 * staging1 + 2 * stage_bytes > 232448) p.nbuf = 1;
     stages = (int)((232448 - fixed - p.nbuf * staging1) / stage_bytes);
   }
   const size_t staging = p.nbuf * staging1;
@@ -740,20 +765,51 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.tiles_n = cdiv(g.N, BN);
   p.total_tiles = p.tiles_m * p.tiles_n * g.B * p.ksplit;
   const size_t smem = fixed + (size_t)p.stages * stage_bytes + staging;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    if (cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-    smem_set = 227 * 1024;
-  }
   const int K = g.K1 + g.K2;
   const double es = 2.0, rows = (double)g.B * g.M;
   const double abytes = rows * (g.amode == AMODE_CONV3 ? g.K1 / 9 : K) * es;
   const double bytes = abytes + rows * g.N * es * (g.R ? 2.0 : 1.0) + (double)g.N * K * es * (g.w_img ? g.B : 1);
-  ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);
   const int max_ctas = num_sms() * ctas_per_sm;
   const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-  k_tc_gemm<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, mY, mR, p);
-  return p.stats_out ? p.tiles_n : 0;
+  const bool ln = g.ln_stats != nullptr, hr = p.r_tma != 0;
+  bool st = p.stats_out != nullptr;
+  if (ln && (!g.ln_cs || !g.bias)) return -1;
+#define RF_TC_LAUNCH(OM, LN, HR, ST, ACT)                                                                                   \
+  do {                                                                                                                      \
+    static bool attr = false;                                                                                               \
+    auto kern = k_tc_gemm<OM, LN, HR, ST, ACT>;                                                                             \
+    if (!attr) {                                                                                                            \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;   \
+      attr = true;                                                                                                          \
+    }                                                                                                                       \
+    ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);                                                              \
+    kern<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, mY, mR, p);                                                  \
+    return p.stats_out ? p.tiles_n : 0;                                                                                     \
+  } while (0)
+  if (g.omode == OMODE_ROWS) {
+    if (!p.tma_store) return -1;
+    if (st && (ln || g.act != ACT_NONE)) { st = false; p.stats_out = nullptr; }   // (the caller runs a stats pass instead)
+    if (ln) {
+      if (hr || g.act != ACT_NONE) return -1;
+      RF_TC_LAUNCH(OMODE_ROWS, true, false, false, ACT_NONE);
+    }
+    if (g.act == ACT_NONE) {
+      if (hr && st) RF_TC_LAUNCH(OMODE_ROWS, false, true, true, ACT_NONE);
+      if (hr) RF_TC_LAUNCH(OMODE_ROWS, false, true, false, ACT_NONE);
+      if (st) RF_TC_LAUNCH(OMODE_ROWS, false, false, true, ACT_NONE);
+      RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_NONE);
+    }
+    if (g.act == ACT_LRELU && !hr) RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_LRELU);
+    if (g.act == ACT_RELU && !hr) RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_RELU);
+    if (g.act == ACT_TANH_RES && hr) RF_TC_LAUNCH(OMODE_ROWS, false, true, false, ACT_TANH_RES);
+    return -1;
+  }
+  if (ln || g.act != ACT_NONE || g.R) return -1;
+  if (g.omode == OMODE_CONVT) RF_TC_LAUNCH(OMODE_CONVT, false, false, false, ACT_NONE);
+  if (g.omode == OMODE_UNSHUFFLE) RF_TC_LAUNCH(OMODE_UNSHUFFLE, false, false, false, ACT_NONE);
+  if (g.omode == OMODE_ATOMIC_F32) RF_TC_LAUNCH(OMODE_ATOMIC_F32, false, false, false, ACT_NONE);
+#undef RF_TC_LAUNCH
+  return -1;
 }
 
 // qk: bf16 NHWC [P][2C] (q | k) of ONE image; G: fp32 [C][C], zero-initialised by the caller

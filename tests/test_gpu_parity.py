@@ -347,3 +347,27 @@ def test_bf16_submodules_multitile(rf, C, hf, wf, b):
         rng = float(ref[k].max() - ref[k].min())
         p = psnr(got[k], ref[k], rng)
         assert p >= 40.0, f"{k} (C={C}, {hf}x{wf}): bf16 vs fp32 PSNR {p:.1f} dB; " + report(k, got[k], ref[k])
+
+
+@pytest.mark.parametrize("C,hw", [(32, 448), (64, 320), (128, 224), (256, 160)])
+def test_bf16_pipeline_wraparound(rf, C, hw):
+    """Images large enough that every persistent CTA walks several tiles (ring / staging-buffer / TMEM-buffer reuse in
+    the tcgen05 GEMM, the depthwise and the im2col kernels): bf16 mode against fp32 mode of the same block."""
+    blk = T.build_block("flca", C)
+    blk.load_state_dict(T.make_state_dict(blk, seed=70 + C, scale=1.5), strict=True)
+    blk = blk.to(dev()).eval()
+    g = torch.Generator(device="cpu").manual_seed(C)
+    feat = torch.randn(1, C, hw, hw + 16, generator=g).to(dev())
+    x_ds = torch.rand(1, 4, hw, hw + 16, generator=g).to(dev())
+    y, cr, cb = rf.BayerLumaChroma().to(dev())(x_ds)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        for m in blk.modules():
+            if hasattr(m, "precision"):
+                m.precision = prec
+        with torch.no_grad():
+            outs[prec] = npy(blk(feat, y, cr, cb))
+    ref, got = outs["fp32"], outs["bf16"]
+    assert np.isfinite(got).all()
+    p = psnr(got, ref, float(ref.max() - ref.min()))
+    assert p >= 40.0, f"C={C}: bf16 vs fp32 PSNR {p:.1f} dB; " + report("out", got, ref)
