@@ -63,13 +63,16 @@ struct PackedModel {
   float* red_b[3] = {};
   float* head_w = nullptr;     // [9][d][12]
   float* head_b = nullptr;     // [12]
+  void* head_wt = nullptr;     // T [16][9][d] (rows 12..15 zero): implicit-GEMM form of conv_out for the tensor cores
+  float* head_b16 = nullptr;   // [16] (12 used)
   float* haar = nullptr;       // [16] analysis filter (a,b,c,d taps of LL,LH,HL,HH)
 };
 
 // ---- generic "pixel-row" GEMM / implicit conv (rf_gemm.cu) ----------------------------------------------
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH_RES = 3 /* Y = R + 0.2*tanh(acc+bias) */ };
 enum { AMODE_ROWS = 0, AMODE_CONV3 = 1 };
-enum { OMODE_ROWS = 0, OMODE_CONVT = 1, OMODE_UNSHUFFLE = 2, OMODE_ATOMIC_F32 = 3 /* split-K: atomicAdd into fp32 Y */ };
+enum { OMODE_ROWS = 0, OMODE_CONVT = 1, OMODE_UNSHUFFLE = 2, OMODE_ATOMIC_F32 = 3 /* split-K: atomicAdd into fp32 Y */,
+       OMODE_HEAD = 4 /* N = 16 (12 used): LeakyReLU(0.2) + PixelShuffle(2) into fp32 NCHW [B,3,2H,2W] (FLCA_RF.py:368-369) */ };
 
 struct GemmP {
   const void* A1 = nullptr; const void* A2 = nullptr;  // [B][M][K1], [B][M][K2] (A2 optional: concatenated K)

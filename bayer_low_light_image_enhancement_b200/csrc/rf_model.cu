@@ -9,6 +9,7 @@
 
 namespace rf {
 
+int launch_gemm_tcgen05(Ctx& ctx, const GemmP& p);
 int profile_begin(cudaStream_t stream, int cap);
 int profile_end(float* ms_host, int* ids_host, int cap_out, int* n_host);
 
@@ -79,6 +80,7 @@ static PackedModel layout_model(Layout& L, int dim, int dtype, int variant) {
     pm.red_b[n] = L.f32(Co);
   }
   pm.head_w = L.f32(9 * d * 12); pm.head_b = L.f32(12);
+  pm.head_wt = L.elems(16 * 9 * d, dtype); pm.head_b16 = L.f32(16);
   return pm;
 }
 
@@ -445,7 +447,16 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
     conv_transformer(ctx, pm.blocks[4 + n], variant, fused, st[s], dec, B);
     cur = dec;
   }
-  launch_head(ctx, cur, pm.head_w, pm.head_b, out, B, h, w, d);
+  bool head_done = false;
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+    // conv_out + LeakyReLU + PixelShuffle as an implicit GEMM (N padded to 16) with a scatter epilogue
+    GemmP hp;
+    hp.A1 = cur; hp.K1 = 9 * d; hp.lda1 = d; hp.amode = AMODE_CONV3;
+    hp.Wt = pm.head_wt; hp.bias = pm.head_b16; hp.Y = out; hp.ldy = 0;
+    hp.M = h * w; hp.N = 16; hp.B = B; hp.H = h; hp.W = w; hp.omode = OMODE_HEAD; hp.kernel_id = RF_K_HEAD;
+    head_done = ctx.dry || launch_gemm_tcgen05(ctx, hp) >= 0;
+  }
+  if (!head_done) launch_head(ctx, cur, pm.head_w, pm.head_b, out, B, h, w, d);
   if (variant == RF_VARIANT_ML) {
     float* sums = A.get<float>((size_t)B * 8);
     launch_fill_f32(ctx, sums, 0.f, (i64)B * 8);
@@ -686,6 +697,10 @@ int rf_model_pack(const rf_model_weights* w, int dim, int dtype, int variant, vo
   }
   launch_pack3(ctx, w->conv_out_w, pm.head_w, RF_F32, 9, dim, 12, 1, 9, (i64)dim * 9, (i64)dim * 12, 12, 1, 0);
   copy_f32(ctx, w->conv_out_b, pm.head_b, 12);
+  RF_CUDA(cudaMemsetAsync(pm.head_wt, 0, (size_t)16 * 9 * dim * esize(dtype), ctx.stream));
+  RF_CUDA(cudaMemsetAsync(pm.head_b16, 0, 16 * sizeof(float), ctx.stream));
+  pack_conv3(ctx, w->conv_out_w, pm.head_wt, 12, dim);
+  copy_f32(ctx, w->conv_out_b, pm.head_b16, 12);
   return finish(ctx);
 }
 

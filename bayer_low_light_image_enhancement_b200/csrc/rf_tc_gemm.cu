@@ -410,6 +410,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (n + j < p.N) atomicAdd(yf + j, f[j]);
+        } else if (OM == OMODE_HEAD) {
+          // conv_out: channel n = 4*ch + 2*i + j of packed pixel (oy, ox) -> out[b, ch, 2*oy + i, 2*ox + j], fp32 NCHW
+          float* outp = reinterpret_cast<float*>(p.Y);
+          const i64 Wo = 2 * (i64)p.W, Ho = 2 * (i64)p.H;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float a = f[4 * ch + 2 * i], bq = f[4 * ch + 2 * i + 1];
+              *reinterpret_cast<float2*>(outp + (((i64)b * 3 + ch) * Ho + 2 * oy + i) * Wo + 2 * ox) =
+                  make_float2(fmaxf(a, 0.2f * a), fmaxf(bq, 0.2f * bq));
+            }
         } else if (OM == OMODE_CONVT) {
           const int Co = p.N >> 2;
           const int ij = n / Co, co = n - ij * Co;   // 16-wide chunk never straddles ij (Co % 16 == 0)
@@ -808,6 +820,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   if (g.omode == OMODE_CONVT) RF_TC_LAUNCH(OMODE_CONVT, false, false, false, ACT_NONE);
   if (g.omode == OMODE_UNSHUFFLE) RF_TC_LAUNCH(OMODE_UNSHUFFLE, false, false, false, ACT_NONE);
   if (g.omode == OMODE_ATOMIC_F32) RF_TC_LAUNCH(OMODE_ATOMIC_F32, false, false, false, ACT_NONE);
+  if (g.omode == OMODE_HEAD && g.N == 16 && g.amode == AMODE_CONV3) RF_TC_LAUNCH(OMODE_HEAD, false, false, false, ACT_NONE);
 #undef RF_TC_LAUNCH
   return -1;
 }

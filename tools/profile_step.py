@@ -20,3 +20,9 @@ with torch.no_grad():
     for _ in range(a.iters): y = m(x)
     e1.record(); torch.cuda.synchronize()
 print("ms/frame", e0.elapsed_time(e1) / a.iters, float(y.abs().max()))
+import time
+with torch.no_grad():
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5): y = m(x)
+    t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print("host enqueue ms/frame", (t1 - t0) / 5 * 1e3, "total ms/frame", (t2 - t0) / 5 * 1e3)
