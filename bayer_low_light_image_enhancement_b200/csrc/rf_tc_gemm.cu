@@ -47,6 +47,7 @@ struct TcParams {
   int tmem_cols;       // allocated TMEM columns (two accumulator buffers)
   int acc_cols;        // column offset of the second accumulator buffer
   int tiles_m, tiles_n, total_tiles;
+  int bk;              // K elements per k-block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int tma_store;       // OMODE_ROWS: stage the bf16 output tile in shared memory and write it with TMA
   int nslab;           // 64-column slabs of the staged tile
   int nbuf;            // staging buffers (1 or 2); tile ti uses buffer ti % nbuf
@@ -60,6 +61,18 @@ struct TcParams {
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int n) { return make_idesc_m128(n); }
+// K-major operand tile with rows of bk bf16: bk = 64 -> SWIZZLE_128B (8-row atoms of 1024 B), bk = 32 -> SWIZZLE_64B
+// (8-row atoms of 512 B); cute::UMMA::LayoutType 2 / 4
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
+  if (bk == 64) return make_sw128_desc(smem_addr);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;        // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+  return d;
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -107,9 +120,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A tile 16 KB][stages x W tile BN*128 B][nbuf x nslab x 16 KB residual/output staging][barriers]
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)p.BN * 128;
+  const uint32_t a_bytes = TC_BM * 2u * p.bk, w_bytes = (uint32_t)p.BN * 2u * p.bk;
   const uint32_t sA = base, sW = base + p.stages * a_bytes;
-  const uint32_t sY = sW + p.stages * w_bytes;            // 1024-aligned (a_bytes, w_bytes are multiples of 2048)
+  const uint32_t sY = sW + p.stages * w_bytes;            // 1024-aligned (a_bytes, w_bytes are multiples of 1024)
   const uint32_t y_bytes = (uint32_t)p.nslab * 16384u;
   const uint32_t sStat = sY + (uint32_t)p.nbuf * y_bytes; // [128] float2: half-1 warps' row partials (stats_out)
   const uint32_t bars = sStat + (p.stats_out ? 1024u : 0u);  // 8-byte aligned
@@ -182,15 +195,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
           if (p.amode == AMODE_CONV3) {
             const int tap = i / p.kb1, cb = i - tap * p.kb1;
-            tma_load_4d(dstA, &mapA1, full_bar(s), cb * TC_BK, tc.px0 + tap % 3 - 1, tc.py0 + tap / 3 - 1, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), cb * TC_BK, tap, tc.n0);
+            tma_load_4d(dstA, &mapA1, full_bar(s), cb * p.bk, tc.px0 + tap % 3 - 1, tc.py0 + tap / 3 - 1, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), cb * p.bk, tap, tc.n0);
           } else if (i < p.kb1) {
-            tma_load_3d(dstA, &mapA1, full_bar(s), i * TC_BK, tc.m0, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), i * TC_BK, tc.n0, p.w_per_image ? tc.b : 0);
+            tma_load_3d(dstA, &mapA1, full_bar(s), i * p.bk, tc.m0, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), i * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
           } else {
             const int j = i - p.kb1;
-            tma_load_3d(dstA, &mapA2, full_bar(s), j * TC_BK, tc.m0, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * TC_BK, tc.n0, p.w_per_image ? tc.b : 0);
+            tma_load_3d(dstA, &mapA2, full_bar(s), j * p.bk, tc.m0, tc.b);
+            tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
           }
         }
       }
@@ -218,15 +231,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           int kvalid;
           if (p.amode == AMODE_CONV3) {
             const int cb = i % p.kb1;
-            kvalid = min(TC_BK, p.K1 - cb * TC_BK);
+            kvalid = min(p.bk, p.K1 - cb * p.bk);
           } else if (i < p.kb1) {
-            kvalid = min(TC_BK, p.K1 - i * TC_BK);
+            kvalid = min(p.bk, p.K1 - i * p.bk);
           } else {
-            kvalid = min(TC_BK, p.K2 - (i - p.kb1) * TC_BK);
+            kvalid = min(p.bk, p.K2 - (i - p.kb1) * p.bk);
           }
           const int ksteps = (kvalid + 15) >> 4;
-          const uint64_t adesc = make_sw128_desc(sA + s * a_bytes);
-          const uint64_t bdesc = make_sw128_desc(sW + s * w_bytes);
+          const uint64_t adesc = make_kmajor_desc(sA + s * a_bytes, p.bk);
+          const uint64_t bdesc = make_kmajor_desc(sW + s * w_bytes, p.bk);
           for (int k = 0; k < ksteps; ++k) {
             // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
             umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (il | k) ? 1u : 0u);
@@ -305,11 +318,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
       const int yq = ti % p.nbuf;
       const uint32_t srow = sY + yq * y_bytes + (uint32_t)r * 128u;   // this row in slab 0 of the staging buffer
-      mbar_wait(tfull_bar(acc), u & 1);
+      mbar_wait_sleep(tfull_bar(acc), u & 1);
       tc_fence_after();
       if (OM == OMODE_ROWS) {
         if (HR) {
-          mbar_wait(yfull_bar(yq), (ti / p.nbuf) & 1);       // this tile's residual has landed in the staging buffer
+          mbar_wait_sleep(yfull_bar(yq), (ti / p.nbuf) & 1); // this tile's residual has landed in the staging buffer
         } else {
           // the staging buffer is free once the TMA store of tile ti - nbuf has finished READING it
           if (warp == 2 && lane == 0) {
@@ -656,13 +669,19 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.ln_stats = g.ln_stats; p.ln_cs = g.ln_cs; p.ln_npart = g.ln_npart; p.ln_eps = g.ln_eps;
   p.ln_invC = g.ln_C > 0 ? 1.0f / (float)g.ln_C : 0.f;
   CUtensorMap mA1, mA2, mW, mY, mR;
+  // k-block width: narrow (32) blocks when every operand source has K <= 32 -- half the smem per stage, so the ring is
+  // twice as deep for the same bytes (the 9-tap implicit conv and the C = 32 row GEMMs are TMA-latency bound)
+  const int kmax = g.amode == AMODE_CONV3 ? g.K1 / 9 : (g.K1 > g.K2 ? g.K1 : g.K2);
+  const int BK = (kmax <= 32 && g.omode != OMODE_ATOMIC_F32) ? 32 : 64;
+  p.bk = BK;
+  const int kswz = BK * 2;
   p.tma_store = (g.omode == OMODE_ROWS && g.ldy % 8 == 0 && (!g.R || g.ldr % 8 == 0)) ? 1 : 0;
   p.nslab = p.tma_store ? cdiv(BN, 64) : 0;
   p.r_tma = (p.tma_store && g.R != nullptr) ? 1 : 0;
   int grid_x;
   if (g.amode == AMODE_CONV3) {
     const int Cin = g.K1 / 9;
-    p.taps = 9; p.K1 = Cin; p.K2 = 0; p.kb1 = cdiv(Cin, TC_BK); p.kb2 = 0;
+    p.taps = 9; p.K1 = Cin; p.K2 = 0; p.kb1 = cdiv(Cin, BK); p.kb2 = 0;
     // patch shape: minimise padded area
     int best_tw = 16;
     i64 best = -1;
@@ -678,13 +697,13 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     grid_x = p.tiles_x * cdiv(g.H, p.th);
     const i64 dA[4] = {Cin, g.W, g.H, g.B};
     const i64 sA[4] = {1, g.lda1, g.lda1 * g.W, g.lda1 * g.W * g.H};
-    const int bA[4] = {TC_BK, p.tw, p.th, 1};
-    if (!make_map(&mA1, g.A1, 4, dA, sA, bA)) return -1;
+    const int bA[4] = {BK, p.tw, p.th, 1};
+    if (!make_map_ex(&mA1, g.A1, 4, dA, sA, bA, 2, kswz)) return -1;
     mA2 = mA1;
     const i64 dW[3] = {Cin, 9, g.N};
     const i64 sW[3] = {1, Cin, (i64)9 * Cin};
-    const int bW[3] = {TC_BK, 1, BN};
-    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return -1;
+    const int bW[3] = {BK, 1, BN};
+    if (!make_map_ex(&mW, g.Wt, 3, dW, sW, bW, 2, kswz)) return -1;
     if (p.tma_store) {
       const i64 dY[4] = {g.N, g.W, g.H, g.B};
       const i64 sY[4] = {1, g.ldy, g.ldy * g.W, g.ldy * g.W * g.H};
@@ -697,17 +716,17 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     }
   } else {
     p.taps = 1; p.K1 = g.K1; p.K2 = g.A2 ? g.K2 : 0;
-    p.kb1 = cdiv(g.K1, TC_BK); p.kb2 = g.A2 ? cdiv(g.K2, TC_BK) : 0;
+    p.kb1 = cdiv(g.K1, BK); p.kb2 = g.A2 ? cdiv(g.K2, BK) : 0;
     p.tw = 128; p.th = 1; p.tw_log2 = 7; p.tiles_x = 1;
     grid_x = cdiv(g.M, TC_BM);
     const i64 dA[3] = {g.K1, g.M, g.B};
     const i64 sA[3] = {1, g.lda1, g.a1_img ? g.a1_img : g.lda1 * g.M};
-    const int bA[3] = {TC_BK, TC_BM, 1};
-    if (!make_map(&mA1, g.A1, 3, dA, sA, bA)) return -1;
+    const int bA[3] = {BK, TC_BM, 1};
+    if (!make_map_ex(&mA1, g.A1, 3, dA, sA, bA, 2, kswz)) return -1;
     if (g.A2) {
       const i64 dA2[3] = {g.K2, g.M, g.B};
       const i64 sA2[3] = {1, g.lda2, g.lda2 * g.M};
-      if (!make_map(&mA2, g.A2, 3, dA2, sA2, bA)) return -1;
+      if (!make_map_ex(&mA2, g.A2, 3, dA2, sA2, bA, 2, kswz)) return -1;
     } else {
       mA2 = mA1;
     }
@@ -715,8 +734,8 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 ldw = g.ldw ? g.ldw : K;
     const i64 dW[3] = {K, g.N, g.w_img ? g.B : 1};
     const i64 sW[3] = {1, ldw, g.w_img ? g.w_img : ldw * g.N};
-    const int bW[3] = {TC_BK, BN, 1};
-    if (!make_map(&mW, g.Wt, 3, dW, sW, bW)) return -1;
+    const int bW[3] = {BK, BN, 1};
+    if (!make_map_ex(&mW, g.Wt, 3, dW, sW, bW, 2, kswz)) return -1;
     if (p.tma_store) {
       const i64 dY[3] = {g.N, g.M, g.B};
       const i64 sY[3] = {1, g.ldy, g.ldy * g.M};
@@ -735,7 +754,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.ksplit = (g.omode == OMODE_ATOMIC_F32 && g.ksplit > 1) ? (g.ksplit < nkb_all ? g.ksplit : nkb_all) : 1;
   // smem: operand ring + residual/output staging.  Two CTAs per SM (two producer / MMA / epilogue sets) when the
   // accumulators fit twice in tensor memory AND a >= 2-deep ring plus the staging fits in half the shared memory.
-  const size_t stage_bytes = (size_t)TC_BM * 128 + (size_t)BN * 128;
+  const size_t stage_bytes = ((size_t)TC_BM + (size_t)BN) * 2 * BK;
   int cols = 32;
   while (cols < BN) cols *= 2;
   const size_t staging1 = (size_t)p.nslab * 16384;
