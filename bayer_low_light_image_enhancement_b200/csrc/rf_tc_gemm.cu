@@ -47,6 +47,7 @@ struct TcParams {
   int tmem_cols;       // allocated TMEM columns (two accumulator buffers)
   int acc_cols;        // column offset of the second accumulator buffer
   int tiles_m, tiles_n, total_tiles;
+  int w_resident;      // all k-blocks of W (one N tile) stay in shared memory for the whole kernel
   int bk;              // K elements per k-block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int tma_store;       // OMODE_ROWS: stage the bf16 output tile in shared memory and write it with TMA
   int nslab;           // 64-column slabs of the staged tile
@@ -122,9 +123,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 2u * p.bk, w_bytes = (uint32_t)p.BN * 2u * p.bk;
   const uint32_t sA = base, sW = base + p.stages * a_bytes;
-  const uint32_t sY = sW + p.stages * w_bytes;            // 1024-aligned (a_bytes, w_bytes are multiples of 1024)
+  const uint32_t sY = sW + (p.w_resident ? 0u : p.stages * w_bytes);            // 1024-aligned (a_bytes, w_bytes are multiples of 1024)
   const uint32_t y_bytes = (uint32_t)p.nslab * 16384u;
-  const uint32_t sStat = sY + (uint32_t)p.nbuf * y_bytes; // [128] float2: half-1 warps' row partials (stats_out)
+  const uint32_t sWres = sY + (uint32_t)p.nbuf * y_bytes; // resident W: (taps*kb1 + kb2) k-blocks of w_bytes (1024-aligned)
+  const uint32_t sStat = sWres + (p.w_resident ? (uint32_t)(p.taps * p.kb1 + p.kb2) * w_bytes : 0u);  // [128] float2 (stats_out)
   const uint32_t bars = sStat + (p.stats_out ? 1024u : 0u);  // 8-byte aligned
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
@@ -132,7 +134,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
   auto yfull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 4 + q); };
   auto yempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 8 + q); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 12);
+  const uint32_t wres_bar = bars + 8u * (2 * TC_MAX_STAGES + 12);
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 13);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,6 +158,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       mbar_init(yfull_bar(q), 1);
       mbar_init(yempty_bar(q), 1);
     }
+    mbar_init(wres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -166,9 +170,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const uint32_t tx = a_bytes + w_bytes;
-      int g = 0;  // k-blocks issued so far (ring position)
+      const uint32_t tx = a_bytes + (p.w_resident ? 0u : w_bytes);
+      int s = 0, wrap = 0;  // ring slot and how often the ring has wrapped
       int ti = 0;
+      if (p.w_resident) {
+        // the whole weight matrix of this CTA's (only) N tile, once: W rows cost as much TMA time as A rows, and the
+        // HBM-bound shapes have as many W rows as A rows per tile
+        const int nkb_all = p.taps * p.kb1 + p.kb2;
+        mbar_expect_tx(wres_bar, (uint32_t)nkb_all * w_bytes);
+        for (int i = 0; i < nkb_all; ++i) {
+          const uint32_t dstW = sWres + i * w_bytes;
+          if (p.amode == AMODE_CONV3) {
+            const int tap = i / p.kb1, cb = i - tap * p.kb1;
+            tma_load_3d(dstW, &mapW, wres_bar, cb * p.bk, tap, 0);
+          } else if (i < p.kb1) {
+            tma_load_3d(dstW, &mapW, wres_bar, i * p.bk, 0, 0);
+          } else {
+            tma_load_3d(dstW, &mapW, wres_bar, p.K1 + (i - p.kb1) * p.bk, 0, 0);
+          }
+        }
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         if (tc.nkb <= 0) continue;
@@ -187,24 +208,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           }
         }
         ++ti;
-        for (int il = 0; il < tc.nkb; ++il, ++g) {
-          const int i = tc.kb_begin + il;
-          const int s = g % p.stages, it = g / p.stages;
-          if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        // k-block walk with counters only (this single thread's dependent-instruction chain paces the whole CTA when a
+        // tile has many small k-blocks -- no divisions in here)
+        int i = tc.kb_begin;
+        int tap = 0, cb = i, tdy = 0, tdx = 0;
+        if (p.amode == AMODE_CONV3 && i > 0) { tap = i / p.kb1; cb = i - tap * p.kb1; tdy = tap / 3; tdx = tap - 3 * tdy; }
+        for (int il = 0; il < tc.nkb; ++il, ++i) {
+          if (wrap > 0) mbar_wait(empty_bar(s), (wrap - 1) & 1);
           mbar_expect_tx(full_bar(s), tx);
           const uint32_t dstA = sA + s * a_bytes, dstW = sW + s * w_bytes;
           if (p.amode == AMODE_CONV3) {
-            const int tap = i / p.kb1, cb = i - tap * p.kb1;
-            tma_load_4d(dstA, &mapA1, full_bar(s), cb * p.bk, tc.px0 + tap % 3 - 1, tc.py0 + tap / 3 - 1, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), cb * p.bk, tap, tc.n0);
+            tma_load_4d(dstA, &mapA1, full_bar(s), cb * p.bk, tc.px0 + tdx - 1, tc.py0 + tdy - 1, tc.b);
+            if (!p.w_resident) tma_load_3d(dstW, &mapW, full_bar(s), cb * p.bk, tap, tc.n0);
+            if (++cb == p.kb1) {
+              cb = 0; ++tap;
+              if (++tdx == 3) { tdx = 0; ++tdy; }
+            }
           } else if (i < p.kb1) {
             tma_load_3d(dstA, &mapA1, full_bar(s), i * p.bk, tc.m0, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), i * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
+            if (!p.w_resident) tma_load_3d(dstW, &mapW, full_bar(s), i * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
           } else {
             const int j = i - p.kb1;
             tma_load_3d(dstA, &mapA2, full_bar(s), j * p.bk, tc.m0, tc.b);
-            tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
+            if (!p.w_resident) tma_load_3d(dstW, &mapW, full_bar(s), p.K1 + j * p.bk, tc.n0, p.w_per_image ? tc.b : 0);
           }
+          if (++s == p.stages) { s = 0; ++wrap; }
         }
       }
     }
@@ -212,7 +240,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN);
-      int g = 0, ti = 0;
+      int s = 0, wrap = 0, ti = 0;
+      if (p.w_resident) {
+        mbar_wait(wres_bar, 0);
+        tc_fence_after();
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         if (tc.nkb <= 0) continue;
@@ -222,16 +254,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
-        for (int il = 0; il < tc.nkb; ++il, ++g) {
-          const int i = tc.kb_begin + il;
-          const int s = g % p.stages, it = g / p.stages;
-          mbar_wait(full_bar(s), it & 1);
+        int i = tc.kb_begin;
+        int cb = p.amode == AMODE_CONV3 ? i % p.kb1 : 0;
+        for (int il = 0; il < tc.nkb; ++il, ++i) {
+          mbar_wait(full_bar(s), wrap & 1);
           tc_fence_after();
           // valid K in this block (zero-filled beyond): skip all-zero 16-wide slices
           int kvalid;
           if (p.amode == AMODE_CONV3) {
-            const int cb = i % p.kb1;
             kvalid = min(p.bk, p.K1 - cb * p.bk);
+            if (++cb == p.kb1) cb = 0;
           } else if (i < p.kb1) {
             kvalid = min(p.bk, p.K1 - i * p.bk);
           } else {
@@ -239,12 +271,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           }
           const int ksteps = (kvalid + 15) >> 4;
           const uint64_t adesc = make_kmajor_desc(sA + s * a_bytes, p.bk);
-          const uint64_t bdesc = make_kmajor_desc(sW + s * w_bytes, p.bk);
+          const uint64_t bdesc = make_kmajor_desc(p.w_resident ? sWres + i * w_bytes : sW + s * w_bytes, p.bk);
           for (int k = 0; k < ksteps; ++k) {
-            // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            // advance 32 B (16 bf16) inside the swizzle atom: +2 in the (addr >> 4) field
             umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (il | k) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
+          if (++s == p.stages) { s = 0; ++wrap; }
         }
         umma_commit(tfull_bar(acc));          // accumulator complete
         ++ti;
@@ -754,11 +787,15 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.ksplit = (g.omode == OMODE_ATOMIC_F32 && g.ksplit > 1) ? (g.ksplit < nkb_all ? g.ksplit : nkb_all) : 1;
   // smem: operand ring + residual/output staging.  Two CTAs per SM (two producer / MMA / epilogue sets) when the
   // accumulators fit twice in tensor memory AND a >= 2-deep ring plus the staging fits in half the shared memory.
-  const size_t stage_bytes = ((size_t)TC_BM + (size_t)BN) * 2 * BK;
+  // resident W: one N tile, a weight matrix shared by all tiles of the CTA, at most 40 KB
+  const int nkb_tile0 = p.taps * p.kb1 + p.kb2;
+  const size_t wres_bytes = (size_t)nkb_tile0 * BN * 2 * BK;
+  p.w_resident = (cdiv(g.N, BN) == 1 && (!g.w_img || g.B == 1) && wres_bytes <= 40960 && g.omode != OMODE_ATOMIC_F32) ? 1 : 0;
+  const size_t stage_bytes = ((size_t)TC_BM + (p.w_resident ? 0 : (size_t)BN)) * 2 * BK;
   int cols = 32;
   while (cols < BN) cols *= 2;
   const size_t staging1 = (size_t)p.nslab * 16384;
-  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 14);
+  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 14) + (p.w_resident ? wres_bytes : 0);
   const int nkb_tile = p.taps * p.kb1 + p.kb2;
   const int want = nkb_tile > 1 ? 3 : 2;
   static int nbuf_r = -1;                 // debugging aid: RAWFORMER_B200_RBUF=2|3 (residual staging depth)
