@@ -20,6 +20,7 @@ namespace rf {
 
 constexpr int IT_THREADS = 512;
 constexpr int IT_SLOTS = 32;          // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image
+constexpr int IT_NF = 5;              // feature/output ring depth: loads run 3 tiles ahead, stores drain 1 tile behind
 
 struct Im2colTcParams {
   const float* G;        // [B][H][W][4] fp32 (FLCA guidance / packed frame x_ds)
@@ -55,9 +56,9 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                         // 2 x 16 KB im2col tiles (K-major, SWIZZLE_128B)
   const uint32_t sW = base + 2 * 16384;             // SEG*Cc rows x 128 B (<= 24 KB)
-  const uint32_t sF = sW + 24576;                   // 2 x 16 KB feature / output tiles
-  const uint32_t bars = sF + 2 * 16384;             // acc_full[2], feat_full[2], tmem slot
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bars + 32 - smem_u32(smem_raw)));
+  const uint32_t sF = sW + 24576;                   // IT_NF x 16 KB feature / output tiles (ring, updated in place)
+  const uint32_t bars = sF + IT_NF * 16384;         // acc_full[2], feat_full[IT_NF], tmem slot
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bars + 64 - smem_u32(smem_raw)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x % p.nchunks, lane_id = blockIdx.x / p.nchunks;
   const int N = SEG * p.Cc;
@@ -66,10 +67,10 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
   if (tid == 0) {
     tma_prefetch_desc(&mapOut);
     if (MODE == 0) tma_prefetch_desc(&mapIn);
-    for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < 2 + IT_NF; ++i) mbar_init(bars + 8 * i, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(bars + 32, (uint32_t)(2 * p.tmem_cols));
+  if (warp == 0) tmem_alloc(bars + 64, (uint32_t)(2 * p.tmem_cols));
 
   // ---- W tile (once): row n = seg*Cc + cl, K index = tap*4 + map; sigmoid inputs are pre-halved (sigmoid(a) =
   //      0.5*tanh(a/2) + 0.5), so the epilogue needs MUFU.TANH only -------------------------------------------------
@@ -182,7 +183,9 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     load_G(t0);
     store_A(0);
     if (n_my > 1) load_G(t0 + tstep);
-    if (MODE == 0 && tid == 0) issue_feat(t0, 0);
+    if (MODE == 0 && tid == 0) {
+      for (int j = 0; j < 3 && j < n_my; ++j) issue_feat(t0 + j * tstep, j);
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -191,15 +194,18 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     }
   }
   for (int i = 0; i < n_my; ++i) {
-    const int a = i & 1;
+    const int a = i & 1;                             // A stage / TMEM buffer of tile i
+    const int fs = i % IT_NF;                        // feature stage of tile i
     const int gt = t0 + i * tstep;
+    if (tid == 32) {
+      // (bulk-async groups are per thread: this thread also issues the stores)  store(i-2) has finished reading
+      // feature stage (i+3) % IT_NF, so the load that runs 3 tiles ahead may overwrite it
+      tma_store_wait_read<1>();
+      if (MODE == 0 && i + 3 < n_my) issue_feat(gt + 3 * tstep, (i + 3) % IT_NF);
+    }
     if (i + 1 < n_my) {
       store_A(a ^ 1);                                // A stage a^1: MMA(i-1) completed before epilogue(i-1) started
       if (i + 2 < n_my) load_G(gt + 2 * tstep);      // stays in flight under the epilogue
-      if (tid == 0) {
-        tma_store_wait_read<0>();                    // TMA store(i-1) has finished reading feature stage a^1
-        if (MODE == 0) issue_feat(gt + tstep, a ^ 1);
-      }
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -215,10 +221,10 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     }
     mbar_wait(bars + 8 * a, (i >> 1) & 1);
     tc_fence_after();
-    if (MODE == 0) mbar_wait(bars + 16 + 8 * a, (i >> 1) & 1);
+    if (MODE == 0) mbar_wait(bars + 16 + 8 * fs, (i / IT_NF) & 1);
     if (epi) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.tmem_cols);
-      const uint32_t frow = sF + a * 16384 + (uint32_t)erow * p.row_bytes;
+      const uint32_t frow = sF + fs * 16384 + (uint32_t)erow * p.row_bytes;
 #pragma unroll
       for (int u = 0; u < UPT; ++u) {
         const int ui = part * UPT + u;               // 8-channel unit inside the chunk
@@ -255,12 +261,12 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     tc_fence_before();
     fence_proxy_async();                             // output tile (generic stores) -> TMA store (async proxy)
     __syncthreads();
-    if (tid == 0) {
-      tma_store_3d(&mapOut, sF + a * 16384, chunk * p.Cc, tl * 128, b);
+    if (tid == 32) {
+      tma_store_3d(&mapOut, sF + fs * 16384, chunk * p.Cc, tl * 128, b);
       tma_store_commit();
     }
   }
-  if (tid == 0) tma_store_wait_all<0>();
+  if (tid == 32) tma_store_wait_all<0>();
   if (MODE == 0 && cur_b >= 0) flush(cur_b);
   tc_fence_before();
   __syncthreads();
@@ -312,7 +318,7 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const float* G, 
   } else {
     mIn = mOut;
   }
-  const size_t smem = 1024 + 2 * 16384 + 24576 + 2 * 16384 + 64;
+  const size_t smem = 1024 + 2 * 16384 + 24576 + IT_NF * 16384 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_im2col_tc<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
