@@ -371,3 +371,26 @@ def test_bf16_pipeline_wraparound(rf, C, hw):
     assert np.isfinite(got).all()
     p = psnr(got, ref, float(ref.max() - ref.min()))
     assert p >= 40.0, f"C={C}: bf16 vs fp32 PSNR {p:.1f} dB; " + report("out", got, ref)
+
+
+def test_frame_pipeline(rf):
+    """FramePipeline (overlapped H2D / forward / D2H) returns what the direct call returns, frame by frame and in order.
+    (The forward's float atomics make two runs differ in the last bf16 bits, so the comparison is by PSNR, and every
+    pipelined result must match ITS frame's direct result far better than any other frame's.)"""
+    m = rf.RawFormer(dim=32, precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=5, scale=1.5))
+    m = m.to(dev()).eval()
+    frames = [torch.rand(1, 1, 96, 160, generator=torch.Generator().manual_seed(i)).pin_memory() for i in range(5)]
+    outs = [torch.empty(1, 3, 96, 160).pin_memory() for _ in frames]
+    pipe = rf.FramePipeline(m, depth=2)
+    for x, o in zip(frames, outs):
+        pipe.submit(x, o)
+    pipe.flush()
+    with torch.no_grad():
+        direct = [npy(m(x.to(dev()))) for x in frames]
+    for i, o in enumerate(outs):
+        o = o.numpy()
+        rng = float(direct[i].max() - direct[i].min())
+        own = psnr(o, direct[i], rng)
+        others = max(psnr(o, direct[j], rng) for j in range(len(frames)) if j != i)
+        assert own >= 45.0 and own > others + 15.0, f"frame {i}: PSNR vs own direct result {own:.1f} dB, best other {others:.1f} dB"
