@@ -47,6 +47,10 @@ struct TcParams {
   int tmem_cols;       // allocated TMEM columns (two accumulator buffers)
   int acc_cols;        // column offset of the second accumulator buffer
   int tiles_m, tiles_n, total_tiles;
+  // halo conv (3x3, Cin <= 64): ONE TMA box per tile fetches the (th+2) x (tw+2) halo patch (pixel-major); a warp
+  // re-lays it channel-chunk-major ([Cin/8][pixel][16 B]), which is the canonical NO-SWIZZLE K-major UMMA layout with
+  // pixels as rows -- so the nine taps are nine descriptors into the same buffer (start shifted by (dy*pitch+dx)*16 B)
+  int halo, halo_bytes, nh, nt, npix, pitch;
   int w_resident;      // all k-blocks of W (one N tile) stay in shared memory for the whole kernel
   int bk;              // K elements per k-block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int tma_store;       // OMODE_ROWS: stage the bf16 output tile in shared memory and write it with TMA
@@ -122,7 +126,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   // carve: [stages x A tile 16 KB][stages x W tile BN*128 B][nbuf x nslab x 16 KB residual/output staging][barriers]
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 2u * p.bk, w_bytes = (uint32_t)p.BN * 2u * p.bk;
-  const uint32_t sA = base, sW = base + p.stages * a_bytes;
+  const uint32_t halo_stride = ((uint32_t)p.halo_bytes + 127u) & ~127u;
+  const uint32_t sA = base;
+  const uint32_t sW = base + (p.halo ? (((uint32_t)(p.nh + p.nt) * halo_stride + 1023u) & ~1023u) : p.stages * a_bytes);
+  const uint32_t sT = sA + (uint32_t)p.nh * halo_stride;   // halo conv: re-laid-out patches
   const uint32_t sY = sW + (p.w_resident ? 0u : p.stages * w_bytes);            // 1024-aligned (a_bytes, w_bytes are multiples of 1024)
   const uint32_t y_bytes = (uint32_t)p.nslab * 16384u;
   const uint32_t sWres = sY + (uint32_t)p.nbuf * y_bytes; // resident W: (taps*kb1 + kb2) k-blocks of w_bytes (1024-aligned)
@@ -135,7 +142,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   auto yfull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 4 + q); };
   auto yempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 8 + q); };
   const uint32_t wres_bar = bars + 8u * (2 * TC_MAX_STAGES + 12);
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 13);
+  auto afull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 13 + q); };
+  auto aempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 17 + q); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 21);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,6 +168,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       mbar_init(yempty_bar(q), 1);
     }
     mbar_init(wres_bar, 1);
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(afull_bar(q), 1);
+      mbar_init(aempty_bar(q), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -167,7 +180,58 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ================= halo conv: TMA producer + patch re-layout (whole warp) =================
+    // lane 0 keeps nh patch loads in flight; all 32 lanes re-lay every landed patch from pixel-major (what one TMA box
+    // delivers) to channel-chunk-major [Cin/8][pixel][16 B], the no-swizzle K-major UMMA layout the MMA warp reads
+    const int nch = p.K1 >> 3;                   // 8-channel (16-byte) chunks per pixel
+    const int items = p.npix * nch;
+    const int inc_q = 32 / nch, inc_c = 32 - inc_q * nch;
+    const int q0 = lane / nch, c0 = lane - q0 * nch;
+    auto issue = [&](int t, int slot) {          // lane 0 only
+      const TileCoord tn = decode_tile(p, t);
+      mbar_expect_tx(full_bar(slot), (uint32_t)p.halo_bytes);
+      tma_load_4d(sA + slot * halo_stride, &mapA1, full_bar(slot), 0, tn.px0 - 1, tn.py0 - 1, tn.b);
+    };
+    if (lane == 0) {
+      if (p.w_resident) {
+        const int nkb_all = p.taps * p.kb1;
+        mbar_expect_tx(wres_bar, (uint32_t)nkb_all * w_bytes);
+        for (int i = 0; i < nkb_all; ++i) {
+          const int tap = i / p.kb1, cb = i - tap * p.kb1;
+          tma_load_3d(sWres + i * w_bytes, &mapW, wres_bar, cb * p.bk, tap, 0);
+        }
+      }
+      int t = blockIdx.x;
+      for (int j = 0; j < p.nh && t < p.total_tiles; ++j, t += gridDim.x) issue(t, j);
+    }
+    int sh = 0, wh = 0, st = 0, wt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(full_bar(sh), wh & 1);                       // the patch has landed (TMA, pixel-major)
+      if (wt > 0) mbar_wait(aempty_bar(st), (wt - 1) & 1);   // the destination buffer has been consumed by the MMAs
+      const uint32_t src = sA + sh * halo_stride + (uint32_t)lane * 16u, dst = sT + st * halo_stride;
+      int q = q0, c8 = c0;
+      for (int it = lane; it < items; it += 32) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(src + (uint32_t)(it - lane) * 16u));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(c8 * p.npix + q) * 16u), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+        q += inc_q; c8 += inc_c;
+        if (c8 >= nch) { c8 -= nch; ++q; }
+      }
+      fence_proxy_async();                                   // generic stores -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(afull_bar(st));
+        const int tn = t + p.nh * (int)gridDim.x;            // slot sh is free again: refill it nh tiles ahead
+        if (tn < p.total_tiles) issue(tn, sh);
+      }
+      if (++sh == p.nh) { sh = 0; ++wh; }
+      if (++st == p.nt) { st = 0; ++wt; }
+    }
+  } else if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t tx = a_bytes + (p.w_resident ? 0u : w_bytes);
@@ -254,6 +318,36 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+        if (p.halo) {
+          // nine taps x Cin/16 k-steps straight out of the re-laid-out patch: rows = pixels (8-row groups = patch rows,
+          // SBO = pitch*16 B), the two 8-channel chunks of a k-step are LBO = npix*16 B apart, no swizzle
+          mbar_wait(afull_bar(s), wrap & 1);
+          tc_fence_after();
+          const uint32_t At = sT + s * halo_stride;
+          const uint64_t dbase = ((uint64_t)((uint32_t)(p.npix * 16) >> 4) << 16) | ((uint64_t)((uint32_t)(p.pitch * 16) >> 4) << 32) |
+                                 ((uint64_t)1 << 46);
+          const int ksteps = p.K1 >> 4, kpb = p.bk >> 4;      // k-steps per tap / per resident W block
+          const uint64_t wdesc0 = make_kmajor_desc(sWres, p.bk);
+          const uint32_t wstep = w_bytes >> 4, kstep_a = (uint32_t)(2 * p.npix);   // descriptor address units (16 B)
+          uint32_t a_tap = (At & 0x3FFFF) >> 4, wblk = 0, first = 0;
+          int dxc = 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t a_k = a_tap;
+            int kk = 0;
+            for (int cb = 0; cb < p.kb1; ++cb, wblk += wstep) {
+              for (int k = 0; k < kpb && kk < ksteps; ++k, ++kk, a_k += kstep_a) {
+                umma_f16(d_tmem, dbase | (uint64_t)a_k, wdesc0 + wblk + 2u * k, idesc, first);
+                first = 1u;
+              }
+            }
+            if (++dxc == 3) { dxc = 0; a_tap += (uint32_t)(p.pitch - 2); } else { a_tap += 1u; }
+          }
+          umma_commit(aempty_bar(s));         // the patch buffer is free when these MMAs retire
+          if (++s == p.nt) { s = 0; ++wrap; }
+          umma_commit(tfull_bar(acc));
+          ++ti;
+          continue;
+        }
         int i = tc.kb_begin;
         int cb = p.amode == AMODE_CONV3 ? i % p.kb1 : 0;
         for (int il = 0; il < tc.nkb; ++il, ++i) {
@@ -705,6 +799,13 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   // k-block width: narrow (32) blocks when every operand source has K <= 32 -- half the smem per stage, so the ring is
   // twice as deep for the same bytes (the 9-tap implicit conv and the C = 32 row GEMMs are TMA-latency bound)
   const int kmax = g.amode == AMODE_CONV3 ? g.K1 / 9 : (g.K1 > g.K2 ? g.K1 : g.K2);
+  static int halo_ok = -1;                // debugging aid: RAWFORMER_B200_NO_HALO=1 keeps the per-tap TMA conv
+  if (halo_ok < 0) {
+    const char* e = getenv("RAWFORMER_B200_NO_HALO");
+    halo_ok = (e && e[0] == '1') ? 0 : 1;
+  }
+  p.halo = (halo_ok && g.amode == AMODE_CONV3 && kmax <= 64 && kmax % 16 == 0 && g.N <= 256 &&
+            (size_t)9 * BN * kmax * 2 <= 81920) ? 1 : 0;
   const int BK = (kmax <= 32 && g.omode != OMODE_ATOMIC_F32) ? 32 : 64;
   p.bk = BK;
   const int kswz = BK * 2;
@@ -723,6 +824,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       const i64 area = (i64)cdiv(g.W, tw) * tw * cdiv(g.H, th) * th;
       if (best < 0 || area < best) { best = area; best_tw = tw; }
     }
+    if (p.halo) best_tw = 8;              // 8-pixel patch rows = the 8-row core-matrix groups of the UMMA layout
     p.tw = best_tw; p.th = 128 / best_tw;
     p.tw_log2 = 0;
     while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
@@ -731,7 +833,12 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 dA[4] = {Cin, g.W, g.H, g.B};
     const i64 sA[4] = {1, g.lda1, g.lda1 * g.W, g.lda1 * g.W * g.H};
     const int bA[4] = {BK, p.tw, p.th, 1};
-    if (!make_map_ex(&mA1, g.A1, 4, dA, sA, bA, 2, kswz)) return -1;
+    if (p.halo) {
+      p.pitch = p.tw + 2; p.npix = (p.tw + 2) * (p.th + 2);
+      p.halo_bytes = p.npix * Cin * 2;
+      const int bH[4] = {Cin, p.tw + 2, p.th + 2, 1};
+      if (!make_map_ex(&mA1, g.A1, 4, dA, sA, bH, 2, 0)) return -1;
+    } else if (!make_map_ex(&mA1, g.A1, 4, dA, sA, bA, 2, kswz)) return -1;
     mA2 = mA1;
     const i64 dW[3] = {Cin, 9, g.N};
     const i64 sW[3] = {1, Cin, (i64)9 * Cin};
@@ -790,12 +897,14 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   // resident W: one N tile, a weight matrix shared by all tiles of the CTA, at most 40 KB
   const int nkb_tile0 = p.taps * p.kb1 + p.kb2;
   const size_t wres_bytes = (size_t)nkb_tile0 * BN * 2 * BK;
-  p.w_resident = (cdiv(g.N, BN) == 1 && (!g.w_img || g.B == 1) && wres_bytes <= 40960 && g.omode != OMODE_ATOMIC_F32) ? 1 : 0;
+  p.w_resident = (cdiv(g.N, BN) == 1 && (!g.w_img || g.B == 1) && wres_bytes <= (p.halo ? 81920u : 40960u) &&
+                  g.omode != OMODE_ATOMIC_F32) ? 1 : 0;
+  if (p.halo && !p.w_resident) return -1;
   const size_t stage_bytes = ((size_t)TC_BM + (p.w_resident ? 0 : (size_t)BN)) * 2 * BK;
   int cols = 32;
   while (cols < BN) cols *= 2;
   const size_t staging1 = (size_t)p.nslab * 16384;
-  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 14) + (p.w_resident ? wres_bytes : 0);
+  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 22) + (p.w_resident ? wres_bytes : 0);
   const int nkb_tile = p.taps * p.kb1 + p.kb2;
   const int want = nkb_tile > 1 ? 3 : 2;
   static int nbuf_r = -1;                 // debugging aid: RAWFORMER_B200_RBUF=2|3 (residual staging depth)
@@ -805,7 +914,21 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   }
   int ctas_per_sm = 1, stages = 0;
   p.nbuf = 1;
-  if (2 * cols <= 256) {
+  const size_t halo_stride = ((size_t)p.halo_bytes + 127) & ~(size_t)127;
+  if (p.halo) {
+    // patch rings: nh TMA landing buffers + nt re-laid-out buffers; two CTAs per SM when everything fits twice
+    p.nbuf = p.tma_store ? 2 : 1;
+    p.nh = 3; p.nt = 2;
+    size_t need = fixed + p.nbuf * staging1 + (size_t)(p.nh + p.nt) * halo_stride + 1024;
+    if (2 * cols <= 256 && need <= 115712) {
+      ctas_per_sm = 2;
+    } else {
+      if (need > 232448) { p.nh = 2; need = fixed + p.nbuf * staging1 + (size_t)(p.nh + p.nt) * halo_stride + 1024; }
+      if (need > 232448) return -1;
+    }
+    stages = 3;   // (>= nh: sizes the full/empty barrier initialisation; the operand ring itself is unused)
+  }
+  if (!p.halo && 2 * cols <= 256) {
     for (int nb = p.tma_store ? (p.r_tma ? nbuf_r : 2) : 1; nb >= 1 && stages == 0; --nb) {
       if (nb == 1 && p.r_tma) break;                       // in-place residual wants >= two buffers: one CTA per SM
       const size_t used = fixed + nb * staging1;
@@ -815,7 +938,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       }
     }
   }
-  if (stages == 0) {
+  if (!p.halo && stages == 0) {
     ctas_per_sm = 1;
     p.nbuf = p.tma_store ? (p.r_tma ? nbuf_r : 2) : 1;
     // keep two staging buffers if at all possible (a 2-deep operand ring is enough for that)
@@ -832,7 +955,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   p.tiles_m = grid_x;
   p.tiles_n = cdiv(g.N, BN);
   p.total_tiles = p.tiles_m * p.tiles_n * g.B * p.ksplit;
-  const size_t smem = fixed + (size_t)p.stages * stage_bytes + staging;
+  const size_t smem = fixed + staging + (p.halo ? (size_t)(p.nh + p.nt) * halo_stride + 1024 : (size_t)p.stages * stage_bytes);
   const int K = g.K1 + g.K2;
   const double es = 2.0, rows = (double)g.B * g.M;
   const double abytes = rows * (g.amode == AMODE_CONV3 ? g.K1 / 9 : K) * es;
