@@ -129,6 +129,10 @@ struct Ctx {
   Arena arena;
   bool dry = false;   // size the arena only, launch nothing
   int dtype = RF_F32;
+  // region of the workspace that the forward clears with ONE memset up front; the per-block accumulators (Gram, squared
+  // norms, squeeze-excite partial sums) are carved out of it instead of being zeroed by a kernel each
+  char* zero_base = nullptr;
+  size_t zero_cap = 0, zero_off = 0;
   bool fits() const { return dry || arena.peak <= arena.cap; }
 };
 

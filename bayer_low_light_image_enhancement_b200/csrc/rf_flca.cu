@@ -162,7 +162,7 @@ static void run_flca_mod(Ctx& ctx, const void* feat, const float* G, const float
 void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
                      float* partial, int nblk, int B, int Hf, int Wf, int C) {
   if (ctx.dry) return;
-  launch_fill_f32(ctx, partial, 0.f, (i64)B * FLCA_SLOTS * C);
+  // (partial comes zero-initialised from zeroed_f32)
   if (im2col_tc_supported(ctx, C)) {
     const double px = (double)B * Hf * Wf;
     ScopedLaunch sl(RF_K_FLCA_MOD, px * C * 4.0 + px * 16.0, px * C * 72.0);

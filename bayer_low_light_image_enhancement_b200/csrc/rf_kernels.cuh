@@ -113,6 +113,9 @@ void launch_fold_ln(Ctx& ctx, const float* W, const float* gamma, const float* b
 void launch_nchw_to_nhwc(Ctx& ctx, const float* in, void* out, int B, int C, i64 HW);   // fp32 NCHW -> T NHWC
 void launch_nhwc_to_nchw(Ctx& ctx, const void* in, float* out, int B, int C, i64 HW);   // T NHWC -> fp32 NCHW
 void launch_fill_f32(Ctx& ctx, float* p, float v, i64 n);
+// n zero-initialised floats: from the pre-cleared region of the workspace when there is room (no launch), else an arena
+// block cleared by a fill kernel
+float* zeroed_f32(Ctx& ctx, size_t n);
 // generic strided 3-d copy with conversion: dst[doff + a*da + b*db + c*dc] = src[a*sa + b*sb + c*sc]
 void launch_pack3(Ctx& ctx, const float* src, void* dst, int dst_dtype, int A, int Bn, int Cn, i64 sa, i64 sb, i64 sc,
                   i64 da, i64 db, i64 dc, i64 doff);

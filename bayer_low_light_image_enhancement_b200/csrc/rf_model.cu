@@ -181,7 +181,7 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const int nblk = flca_num_partials(C, B, P);
-  float* partial = A.get<float>((size_t)B * nblk * C);
+  float* partial = zeroed_f32(ctx, (size_t)B * nblk * C);
   float* scale = A.get<float>((size_t)B * C);
   void* xmod = nullptr;
   if (variant == RF_VARIANT_FLCA) {
@@ -239,8 +239,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     launch_gemm(ctx, gq);
   }
   const i64 nst = attn_stats_floats(C);
-  float* stats = A.get<float>((size_t)B * nst);
-  launch_fill_f32(ctx, stats, 0.f, B * nst);
+  float* stats = zeroed_f32(ctx, (size_t)B * nst);
   const void* v = nullptr;
   i64 ldv = C;
   if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
@@ -248,8 +247,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     // split-K tcgen05 kernel with MN-major operands reading q,k straight from that tensor.
     void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
-    float* sumsq = A.get<float>((size_t)B * 2 * C);
-    launch_fill_f32(ctx, sumsq, 0.f, (i64)B * 2 * C);
+    float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);
     launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
     if (!ctx.dry) {
       for (int b = 0; b < B; ++b)
@@ -394,10 +392,37 @@ static GuidanceMaps make_pyramid(Ctx& ctx, int variant, const float* y, const fl
 // ---------------------------------------------------------------------------------------------
 // whole model
 // ---------------------------------------------------------------------------------------------
+float* zeroed_f32(Ctx& ctx, size_t n) {
+  const size_t bytes = align_up(n * sizeof(float), 256);
+  if (ctx.zero_off + bytes <= ctx.zero_cap) {
+    float* p = ctx.zero_base ? reinterpret_cast<float*>(ctx.zero_base + ctx.zero_off) : nullptr;
+    ctx.zero_off += bytes;
+    return p;
+  }
+  float* p = ctx.arena.get<float>(n);
+  launch_fill_f32(ctx, p, 0.f, (i64)n);
+  return p;
+}
+
 static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const float* raw, float* out, int B, int H, int W) {
   const int d = pm.dim;
   const int h = H / 2, w = W / 2;
   Arena& A = ctx.arena;
+  {
+    // all per-block accumulators of the frame, cleared by one memset
+    size_t zb = 0;
+    for (int i = 0; i < 7; ++i) {
+      const size_t C = (size_t)d << kBlockStage[i];
+      zb += align_up(B * (C * C + 2 * C) * 4, 256) + align_up(B * 2 * C * 4, 256) + align_up(B * 32 * C * 4, 256);
+    }
+    ctx.zero_cap = zb;
+    ctx.zero_off = 0;
+    ctx.zero_base = (char*)A.alloc(zb);
+    if (!ctx.dry) {
+      if (!ctx.fits()) return RF_ERR_WORKSPACE;
+      RF_CUDA(cudaMemsetAsync(ctx.zero_base, 0, zb, ctx.stream));
+    }
+  }
   const i64 P0 = (i64)h * w;
   float* x_ds = A.get<float>((size_t)B * P0 * 4);
   float* y_raw = A.get<float>((size_t)B * P0);

@@ -387,7 +387,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     const uint32_t sw = (uint32_t)(r & 7);  // 128-byte-swizzle phase of this row in the staging tile
     const int rty = r >> p.tw_log2, rtx = r & (p.tw - 1);   // conv patch coordinates of this row
     int ti = 0;
-    float2 ln_next = make_float2(0.f, 0.f);
+    float4 ln_next = make_float4(0.f, 0.f, 0.f, 0.f);
     auto row_of = [&](const TileCoord& tn, bool& ok, int& oy, int& ox) -> i64 {
       if (p.amode == AMODE_CONV3) {
         oy = tn.py0 + rty;
@@ -406,15 +406,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       bool ok;
       int yy, xx;
       const i64 row = row_of(tn, ok, yy, xx);
-      float su = 0.f, sq = 0.f;
+      // NO arithmetic on the loaded values here: they are consumed one tile later, so the load latency is hidden
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok) {
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + row * p.ln_npart;
-        for (int q = 0; q < p.ln_npart; ++q) {
-          const float2 t2 = __ldg(st + q);
-          su += t2.x; sq += t2.y;
+        const float2 a = __ldg(st);
+        v.x = a.x; v.y = a.y;
+        if (p.ln_npart > 1) {
+          const float2 c = __ldg(st + 1);
+          v.z = c.x; v.w = c.y;
+          for (int q = 2; q < p.ln_npart; ++q) {   // (more than two N tiles of partials: not a hot shape)
+            const float2 t2 = __ldg(st + q);
+            v.z += t2.x; v.w += t2.y;
+          }
         }
       }
-      return make_float2(su, sq);
+      return v;
     };
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
@@ -433,10 +440,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       float ln_rs = 1.f, ln_nm = 0.f;
       if (LN) {
         if (ti == 0) ln_next = ln_fetch(t);
-        const float2 cur = ln_next;
+        const float4 cur = ln_next;
         if (t + (int)gridDim.x < p.total_tiles) ln_next = ln_fetch(t + gridDim.x);
-        const float mu = cur.x * p.ln_invC;
-        ln_rs = rsqrtf(fmaxf(cur.y * p.ln_invC - mu * mu, 0.f) + p.ln_eps);
+        const float mu = (cur.x + cur.z) * p.ln_invC;
+        ln_rs = rsqrtf(fmaxf((cur.y + cur.w) * p.ln_invC - mu * mu, 0.f) + p.ln_eps);
         ln_nm = -ln_rs * mu;
       }
       bool row_ok;
