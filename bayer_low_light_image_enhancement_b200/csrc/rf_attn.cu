@@ -493,14 +493,15 @@ k_embed(const float4* __restrict__ x_ds, const float* __restrict__ w, const floa
   }
 }
 
-void launch_embed(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d) {
+void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
+                  int w_, int d) {
   if (ctx.dry) return;
   i64 total = (i64)h * w_ * (d / 8);
   unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
   double px = (double)B * h * w_;
   ScopedLaunch sl(RF_K_EMBED, px * (16.0 + d * esize(ctx.dtype)), 72.0 * px * d);
-  if (im2col_tc_supported(ctx, d)) {
-    if (!launch_embed_tc(ctx, x_ds, w, b, out, B, h, w_, d)) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+  if (x16 != nullptr && im2col_tc_supported(ctx, d)) {
+    if (!launch_embed_tc(ctx, x16, w, b, out, B, h, w_, d)) recorder().last_cuda_error = (int)cudaErrorNotSupported;
     return;
   }
   size_t smem = sizeof(float) * 36 * d;

@@ -159,14 +159,14 @@ static void run_flca_mod(Ctx& ctx, const void* feat, const float* G, const float
                                                                                  Hf, Wf, C, level, tasks);
 }
 
-void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
-                     float* partial, int nblk, int B, int Hf, int Wf, int C) {
+void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
+                     void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C) {
   if (ctx.dry) return;
   // (partial comes zero-initialised from zeroed_f32)
-  if (im2col_tc_supported(ctx, C)) {
+  if (G16 != nullptr && im2col_tc_supported(ctx, C)) {
     const double px = (double)B * Hf * Wf;
     ScopedLaunch sl(RF_K_FLCA_MOD, px * C * 4.0 + px * 16.0, px * C * 72.0);
-    if (!launch_flca_mod_tc(ctx, feat, G, w36, abg, xmod, partial, B, Hf, Wf, C))
+    if (!launch_flca_mod_tc(ctx, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C))
       recorder().last_cuda_error = (int)cudaErrorNotSupported;
     return;
   }

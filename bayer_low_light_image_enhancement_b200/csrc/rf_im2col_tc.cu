@@ -1,18 +1,22 @@
 // Small-K 3x3 convolutions of the 4-channel fp32 maps on the tensor cores (bf16 mode, sm_100a):
 //   MODE 0 (FLCA, FLCA_RF.py:150-158): the three guidance convolutions low(LL), high(|high|), chroma(cr,cb) are ONE
-//          GEMM  pre[128 pixels x 3*Cc] = im2col(G)[128 x 36] * W^T, K padded to 48 (3 k-steps of tcgen05.mma); the
-//          epilogue reads the three pre-activations of every feature element from tensor memory, applies
-//          x * (1 + a*sigmoid(low) + b*tanh(high) + g*sigmoid(chr)) with MUFU.TANH only, accumulates the squeeze-excite
-//          channel sums and writes the tile back through shared memory with a TMA store.
-//   MODE 1 (embedding, FLCA_RF.py:303,338): out[128 x d] = im2col(x_ds)[128 x 36] * W_embed^T + bias.
-// The CUDA-core kernels these replace spent 36 FMA + 3 transcendentals per element (instruction-bound at 9 % of HBM);
-// here the FMAs are 3 MMAs per 128-pixel tile and the epilogue is ~10 instructions per element.
+//          GEMM  pre[128 pixels x 3*Cc] = patch(G) * W^T; the epilogue reads the three pre-activations of every feature
+//          element from tensor memory, applies x * (1 + a*sigmoid(low) + b*tanh(high) + g*sigmoid(chr)) with MUFU.TANH
+//          only, accumulates the squeeze-excite channel sums and writes the tile back through shared memory by TMA.
+//   MODE 1 (embedding, FLCA_RF.py:303,338): out[128 x d] = patch(x_ds) * W_embed^T + bias.
 //
-// One persistent CTA per SM (512 threads), fixed channel chunk Cc per CTA, software pipeline over 128-pixel tiles:
-//   build A(i+1) (registers prefetched one tile earlier -> bf16 -> swizzled smem) | TMA load feat(i+1)
-//   tcgen05.mma(i+1) -> TMEM buffer (i+1)&1             (async, one thread)
-//   epilogue(i): tcgen05.ld TMEM buffer i&1, feat(i) from smem, result in place, TMA store
-// so the MMA, the TMA traffic and the guidance gathers of the next tiles are in flight under the epilogue math.
+// No im2col is ever built.  The 4 fp32 maps of a pixel are stored once per stage as 8 bf16 = [hi(4) | lo(4)] (hi = bf16(v),
+// lo = bf16(v - hi): 16 significant bits) = ONE 16-byte unit per pixel.  A TMA box of the (16+2) x (8+2) halo patch then
+// lands as [pixel][16 B], which is the canonical NO-SWIZZLE K-major UMMA operand with pixels as rows and one tap as one
+// 8-wide K chunk: core matrix = 8 consecutive pixels, SBO = patch pitch * 16 B, and the second K chunk of a k-step is
+// simply ANOTHER TAP, LBO = (tap offset difference) * 16 B.  Nine taps = 5 tcgen05.mma (K = 16) per 128-pixel tile whose
+// A descriptors differ only in start address and LBO; out-of-image pixels are TMA zero fill = conv padding.
+// The weights are laid out the same way by the CTA once: [K chunk][n][16 B].
+//
+// One persistent CTA per SM (512 threads), fixed channel chunk Cc per CTA, 8 x 16 pixel tiles, ONE CTA barrier per tile:
+//   thread 32: TMA loads (guidance patch + feature tile) 3 tiles ahead, TMA store of the finished tile
+//   thread 0 : tcgen05.mma of tile i+1 into the other TMEM buffer while
+//   all warps: epilogue of tile i (tcgen05.ld, feature tile from smem, result in place)
 #include "rf_kernels.cuh"
 #include "rf_tma.cuh"
 
@@ -21,14 +25,18 @@ namespace rf {
 constexpr int IT_THREADS = 512;
 constexpr int IT_SLOTS = 32;          // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image
 constexpr int IT_NF = 5;              // feature/output ring depth: loads run 3 tiles ahead, stores drain 1 tile behind
+constexpr int IT_NGS = 4;             // guidance patch ring depth
+constexpr int IT_TW = 8, IT_TH = 16;  // tile = 8 x 16 pixels (patch rows = the 8-row core-matrix groups)
+constexpr int IT_PITCH = IT_TW + 2, IT_NPIX = (IT_TW + 2) * (IT_TH + 2);
+constexpr uint32_t IT_PATCH_BYTES = IT_NPIX * 16;                 // 2880
+constexpr uint32_t IT_PATCH_STRIDE = (IT_PATCH_BYTES + 127u) & ~127u;
 
 struct Im2colTcParams {
-  const float* G;        // [B][H][W][4] fp32 (FLCA guidance / packed frame x_ds)
   const float* w;        // [9][4][C] fp32 taps (FLCA: maps LL, |high|, cr, cb; embed: the 4 input channels)
   const float* coef;     // FLCA: alpha, beta, gamma; embed: bias[C]
   float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums (atomicAdd)
   int H, W, C, Cc, nchunks, B;
-  int tiles_per_img, total_tiles, lanes;
+  int tiles_x, tiles_y, tiles_per_img, total_tiles, lanes;
   int parts;             // epilogue column split: warps 4*part .. 4*part+3 own 8*UPT*part .. channels of every row
   int swz;               // swizzle of the feature/output tile: 128, 64 or 0
   uint32_t row_bytes;    // Cc * 2
@@ -48,104 +56,125 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// fp32 x4 per pixel -> [hi x4 | lo x4] bf16 (16 bytes per pixel)
+__global__ void __launch_bounds__(256)
+k_split_bf16x8(const float4* __restrict__ g, uint4* __restrict__ out, i64 n) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const float4 v = g[i];
+    const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+    const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+    out[i] = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3), pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
+  }
+}
+void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix) {
+  if (ctx.dry || npix <= 0) return;
+  ScopedLaunch sl(RF_K_GUIDANCE, 32.0 * npix);
+  const unsigned gx = (unsigned)(cdivl(npix, 256) < 8 * num_sms() ? cdivl(npix, 256) : 8 * num_sms());
+  k_split_bf16x8<<<gx, 256, 0, ctx.stream>>>((const float4*)g4, (uint4*)out16, npix);
+}
+
 template <int MODE, int UPT>
 __global__ void __launch_bounds__(IT_THREADS, 1)
-k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapOut, const Im2colTcParams p) {
+k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapIn,
+            const __grid_constant__ CUtensorMap mapOut, const Im2colTcParams p) {
   constexpr int SEG = MODE == 0 ? 3 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;                         // 2 x 16 KB im2col tiles (K-major, SWIZZLE_128B)
-  const uint32_t sW = base + 2 * 16384;             // SEG*Cc rows x 128 B (<= 24 KB)
-  const uint32_t sF = sW + 24576;                   // IT_NF x 16 KB feature / output tiles (ring, updated in place)
-  const uint32_t bars = sF + IT_NF * 16384;         // acc_full[2], feat_full[IT_NF], tmem slot
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (bars + 64 - smem_u32(smem_raw)));
+  const uint32_t sF = base;                                   // IT_NF x 16 KB feature / output tiles (ring, in place)
+  const uint32_t sW = sF + IT_NF * 16384;                     // [10 K chunks][N rows][16 B] (<= 30 KB)
+  const uint32_t sG = sW + 30720;                             // IT_NGS guidance patches
+  const uint32_t bars = sG + IT_NGS * IT_PATCH_STRIDE;        // acc_full[2], g_full[IT_NGS], f_full[IT_NF], tmem slot
+  auto acc_bar = [&](int a) { return bars + 8u * a; };
+  auto g_bar = [&](int q) { return bars + 8u * (2 + q); };
+  auto f_bar = [&](int q) { return bars + 8u * (2 + IT_NGS + q); };
+  const uint32_t tmem_slot = bars + 8u * (2 + IT_NGS + IT_NF);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x % p.nchunks, lane_id = blockIdx.x / p.nchunks;
   const int N = SEG * p.Cc;
-  const i64 P = (i64)p.H * p.W;
 
   if (tid == 0) {
+    tma_prefetch_desc(&mapG);
     tma_prefetch_desc(&mapOut);
     if (MODE == 0) tma_prefetch_desc(&mapIn);
-    for (int i = 0; i < 2 + IT_NF; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < 2 + IT_NGS + IT_NF; ++i) mbar_init(bars + 8 * i, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(bars + 64, (uint32_t)(2 * p.tmem_cols));
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)(2 * p.tmem_cols));
 
-  // ---- W tile (once): row n = seg*Cc + cl, K index = tap*4 + map; sigmoid inputs are pre-halved (sigmoid(a) =
-  //      0.5*tanh(a/2) + 0.5), so the epilogue needs MUFU.TANH only -------------------------------------------------
-  for (int item = tid; item < N * 6; item += IT_THREADS) {
-    const int n = item / 6, j = item - n * 6;       // 16-byte chunk j = taps 2j, 2j+1
+  // ---- W (once): K chunk kc <-> tap kc for kc < 8, chunk 8 = zeros (it pairs tap 7's pixels a second time), chunk 9 =
+  //      tap 8; inside a chunk [hi weights of the 4 maps | the same weights again for the lo parts].  Row n = seg*Cc + cl.
+  //      Sigmoid inputs are pre-halved (sigmoid(a) = 0.5*tanh(a/2) + 0.5), so the epilogue needs MUFU.TANH only -----------
+  for (int item = tid; item < N * 10; item += IT_THREADS) {
+    const int kc = item / N, n = item - kc * N;
     const int seg = n / p.Cc, cl = n - seg * p.Cc;
     const int c = chunk * p.Cc + cl;
-    float v[8];
+    const int tap = kc < 8 ? kc : (kc == 9 ? 8 : -1);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tap >= 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int tap = 2 * j + (e >> 2), m = e & 3;
-      float wv = 0.f;
-      if (tap < 9) {
-        bool use;
+      for (int m = 0; m < 4; ++m) {
+        bool use = true;
         float sc = 1.f;
         if (MODE == 0) {
           use = seg == 0 ? m == 0 : (seg == 1 ? m == 1 : m >= 2);
           sc = seg == 1 ? 1.f : 0.5f;
-        } else {
-          use = true;
         }
-        if (use) wv = p.w[(i64)(tap * 4 + m) * p.C + c] * sc;
+        if (use) v[m] = p.w[(i64)(tap * 4 + m) * p.C + c] * sc;
       }
-      v[e] = wv;
     }
-    uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    sts128(sW + (uint32_t)n * 128 + (uint32_t)((j ^ (n & 7)) << 4), q);
+    const uint32_t q0 = pack_bf16x2(v[0], v[1]), q1 = pack_bf16x2(v[2], v[3]);
+    sts128(sW + (uint32_t)(kc * N + n) * 16u, make_uint4(q0, q1, q0, q1));
   }
 
-  // ---- im2col builder: 4 threads per tile row; thread q gathers taps 2q, 2q+1 (chunk q), q == 0 also tap 8 ---------
-  const int arow = tid >> 2, aq = tid & 3;
-  float4 g0, g1, g2;                                 // prefetched guidance of the next tile to build
-  auto load_G = [&](int gt) {                        // gt = global tile index
-    const int b = gt / p.tiles_per_img, tl = gt - b * p.tiles_per_img;
-    const i64 pix = (i64)tl * 128 + arow;
-    g0 = g1 = g2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pix < P) {
-      const int y = (int)(pix / p.W), x = (int)(pix - (i64)y * p.W);
-      const float4* Gb = reinterpret_cast<const float4*>(p.G) + (i64)b * P;
-      auto tap_at = [&](int tap) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) return __ldg(Gb + (i64)yy * p.W + xx);
-        return make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      g0 = tap_at(2 * aq);
-      g1 = tap_at(2 * aq + 1);
-      if (aq == 0) g2 = tap_at(8);
+  // ---- tile bookkeeping -------------------------------------------------------------------------------------------
+  const int t0 = lane_id, tstep = p.lanes;
+  const int n_my = t0 < p.total_tiles ? (p.total_tiles - 1 - t0) / tstep + 1 : 0;
+  auto decode = [&](int gt, int& b, int& ty, int& tx) {
+    b = gt / p.tiles_per_img;
+    const int r = gt - b * p.tiles_per_img;
+    ty = r / p.tiles_x;
+    tx = r - ty * p.tiles_x;
+  };
+  auto issue_loads = [&](int j) {                    // thread 32: guidance patch + feature tile of my j-th tile
+    int b, ty, tx;
+    decode(t0 + j * tstep, b, ty, tx);
+    const int gs = j % IT_NGS, fs = j % IT_NF;
+    mbar_expect_tx(g_bar(gs), IT_PATCH_BYTES);
+    tma_load_4d(sG + gs * IT_PATCH_STRIDE, &mapG, g_bar(gs), 0, tx * IT_TW - 1, ty * IT_TH - 1, b);
+    if (MODE == 0) {
+      mbar_expect_tx(f_bar(fs), 128u * p.row_bytes);
+      tma_load_4d(sF + fs * 16384, &mapIn, f_bar(fs), chunk * p.Cc, tx * IT_TW, ty * IT_TH, b);
     }
   };
-  auto store_A = [&](int stage) {
-    const uint32_t rowp = sA + stage * 16384 + (uint32_t)arow * 128;
-    const uint32_t sw = (uint32_t)(arow & 7);
-    sts128(rowp + ((aq ^ sw) << 4),
-           make_uint4(pack_bf16x2(g0.x, g0.y), pack_bf16x2(g0.z, g0.w), pack_bf16x2(g1.x, g1.y), pack_bf16x2(g1.z, g1.w)));
-    if (aq == 0) sts128(rowp + ((4u ^ sw) << 4), make_uint4(pack_bf16x2(g2.x, g2.y), pack_bf16x2(g2.z, g2.w), 0u, 0u));
-    if (aq == 1) sts128(rowp + ((5u ^ sw) << 4), make_uint4(0u, 0u, 0u, 0u));
-  };
-  auto issue_feat = [&](int gt, int stage) {         // one thread
-    const int b = gt / p.tiles_per_img, tl = gt - b * p.tiles_per_img;
-    mbar_expect_tx(bars + 16 + 8 * stage, 128u * p.row_bytes);
-    tma_load_3d(sF + stage * 16384, &mapIn, bars + 16 + 8 * stage, chunk * p.Cc, tl * 128, b);
-  };
   const uint32_t idesc = make_idesc_m128(N);
-  auto issue_mma = [&](int stage, uint32_t tmem_base) {   // one thread
-    const uint64_t adesc = make_sw128_desc(sA + stage * 16384), bdesc = make_sw128_desc(sW);
-    const uint32_t d = tmem_base + (uint32_t)(stage * p.tmem_cols);
+  // no-swizzle K-major descriptors: start | LBO (K-chunk stride) | SBO (8-row-group stride) | version
+  auto nosw_desc = [&](uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46);
+  };
+  auto issue_mma = [&](int j, uint32_t tmem_base) {          // thread 0: the 5 k-steps of my j-th tile
+    mbar_wait(g_bar(j % IT_NGS), (j / IT_NGS) & 1);
+    tc_fence_after();
+    const uint32_t Gp = sG + (j % IT_NGS) * IT_PATCH_STRIDE;
+    const uint32_t d = tmem_base + (uint32_t)((j & 1) * p.tmem_cols);
+    // k-step s: taps (2s, 2s+1); the last one: (tap 7 again with zero weights, tap 8)
+    const int ta[5] = {0, 2, 4, 6, 7};                          // first tap of each k-step
+    const int tb[5] = {1, 3, 5, 7, 8};                          // second tap
 #pragma unroll
-    for (int k = 0; k < 3; ++k) umma_f16(d, adesc + 2u * k, bdesc + 2u * k, idesc, k ? 1u : 0u);
-    umma_commit(bars + 8 * stage);
+    for (int s5 = 0; s5 < 5; ++s5) {
+      const uint32_t oa = (uint32_t)((ta[s5] / 3) * IT_PITCH + ta[s5] % 3), ob = (uint32_t)((tb[s5] / 3) * IT_PITCH + tb[s5] % 3);
+      const uint64_t adesc = nosw_desc(Gp + oa * 16u, (ob - oa) * 16u, IT_PITCH * 16u);
+      const uint64_t bdesc = nosw_desc(sW + (uint32_t)(2 * s5 * N) * 16u, (uint32_t)N * 16u, 128u);
+      umma_f16(d, adesc, bdesc, idesc, s5 ? 1u : 0u);
+    }
+    umma_commit(acc_bar(j & 1));
   };
 
   // ---- epilogue role of this thread -------------------------------------------------------------------------------
   const int quad = warp & 3, part = warp >> 2;
   const bool epi = part < p.parts;
-  const int erow = quad * 32 + lane;
+  const int erow = quad * 32 + lane;                 // tile row = patch pixel (py, px) = (erow >> 3, erow & 7)
   const uint32_t esw = p.swz == 128 ? (uint32_t)(erow & 7) : (p.swz == 64 ? (uint32_t)((erow >> 1) & 3) : 0u);
   float cf[MODE == 0 ? 4 : 8 * UPT];                 // FLCA: base, h0, h1, h2;  embed: bias of this thread's channels
   if (MODE == 0) {
@@ -171,57 +200,39 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     }
   };
 
-  fence_proxy_async();                               // W tile (generic stores) -> tensor-core (async proxy) reads
+  fence_proxy_async();                               // W (generic stores) -> tensor-core (async proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int t0 = lane_id, tstep = p.lanes;
-  const int n_my = t0 < p.total_tiles ? (p.total_tiles - 1 - t0) / tstep + 1 : 0;
-  if (n_my > 0) {
-    load_G(t0);
-    store_A(0);
-    if (n_my > 1) load_G(t0 + tstep);
-    if (MODE == 0 && tid == 0) {
-      for (int j = 0; j < 3 && j < n_my; ++j) issue_feat(t0 + j * tstep, j);
-    }
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma(0, tmem_base);
-    }
+  if (tid == 32) {
+    for (int j = 0; j < 3 && j < n_my; ++j) issue_loads(j);
   }
+  if (tid == 0 && n_my > 0) issue_mma(0, tmem_base);
+
   for (int i = 0; i < n_my; ++i) {
-    const int a = i & 1;                             // A stage / TMEM buffer of tile i
+    const int a = i & 1;                             // TMEM buffer of tile i
     const int fs = i % IT_NF;                        // feature stage of tile i
-    const int gt = t0 + i * tstep;
     if (tid == 32) {
-      // (bulk-async groups are per thread: this thread also issues the stores)  store(i-2) has finished reading
-      // feature stage (i+3) % IT_NF, so the load that runs 3 tiles ahead may overwrite it
+      // (bulk-async groups are per thread: this thread also issues the stores)  store(i-2) has finished reading feature
+      // stage (i+3) % IT_NF, so the load that runs 3 tiles ahead may overwrite it; the guidance slot (i+3) % IT_NGS was
+      // consumed by the MMAs of tile i-1, complete before the epilogue of tile i-1 started
       tma_store_wait_read<1>();
-      if (MODE == 0 && i + 3 < n_my) issue_feat(gt + 3 * tstep, (i + 3) % IT_NF);
+      if (i + 3 < n_my) issue_loads(i + 3);
     }
-    if (i + 1 < n_my) {
-      store_A(a ^ 1);                                // A stage a^1: MMA(i-1) completed before epilogue(i-1) started
-      if (i + 2 < n_my) load_G(gt + 2 * tstep);      // stays in flight under the epilogue
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_mma(a ^ 1, tmem_base);                 // TMEM buffer a^1 was drained by epilogue(i-1)
+    if (tid == 0 && i + 1 < n_my) issue_mma(i + 1, tmem_base);   // TMEM buffer a^1 was drained by epilogue(i-1)
+    int b = 0;
+    if (MODE == 0) {
+      b = (t0 + i * tstep) / p.tiles_per_img;
+      if (b != cur_b) {
+        if (cur_b >= 0) flush(cur_b);
+        cur_b = b;
       }
     }
-    const int b = gt / p.tiles_per_img, tl = gt - b * p.tiles_per_img;
-    if (MODE == 0 && b != cur_b) {
-      if (cur_b >= 0) flush(cur_b);
-      cur_b = b;
-    }
-    mbar_wait(bars + 8 * a, (i >> 1) & 1);
+    mbar_wait(acc_bar(a), (i >> 1) & 1);
     tc_fence_after();
-    if (MODE == 0) mbar_wait(bars + 16 + 8 * fs, (i / IT_NF) & 1);
+    if (MODE == 0) mbar_wait(f_bar(fs), (i / IT_NF) & 1);
     if (epi) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.tmem_cols);
       const uint32_t frow = sF + fs * 16384 + (uint32_t)erow * p.row_bytes;
@@ -260,9 +271,11 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ C
     }
     tc_fence_before();
     fence_proxy_async();                             // output tile (generic stores) -> TMA store (async proxy)
-    __syncthreads();
+    __syncthreads();                                 // (also: TMEM buffer a is drained before MMA(i+2) is issued)
     if (tid == 32) {
-      tma_store_3d(&mapOut, sF + fs * 16384, chunk * p.Cc, tl * 128, b);
+      int bb, ty, tx;
+      decode(t0 + i * tstep, bb, ty, tx);
+      tma_store_4d(&mapOut, sF + fs * 16384, chunk * p.Cc, tx * IT_TW, ty * IT_TH, bb);
       tma_store_commit();
     }
   }
@@ -283,19 +296,20 @@ bool im2col_tc_supported(const Ctx& ctx, int C) {
   return C / Cc <= num_sms();
 }
 
-static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const float* G, const float* w, const float* coef, void* out,
+// G16: [B][H][W] x 16 bytes ([hi x4 | lo x4] bf16 of the 4 fp32 maps, launch_split_bf16x8)
+static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16, const float* w, const float* coef, void* out,
                           float* partial, int B, int H, int W, int C) {
-  if (!tcgen05_enabled() || ctx.dtype != RF_BF16) return false;
+  if (!tcgen05_enabled() || ctx.dtype != RF_BF16 || !G16) return false;
   int Cc, parts, upt;
   if (C % 64 == 0) { Cc = 64; parts = 4; upt = 2; }
   else if (C % 32 == 0) { Cc = 32; parts = 4; upt = 1; }
   else if (C % 48 == 0) { Cc = 48; parts = 3; upt = 2; }
   else return false;
-  const i64 P = (i64)H * W;
   Im2colTcParams p;
-  p.G = G; p.w = w; p.coef = coef; p.partial = partial;
+  p.w = w; p.coef = coef; p.partial = partial;
   p.H = H; p.W = W; p.C = C; p.Cc = Cc; p.nchunks = C / Cc; p.B = B;
-  p.tiles_per_img = (int)cdivl(P, 128);
+  p.tiles_x = cdiv(W, IT_TW); p.tiles_y = cdiv(H, IT_TH);
+  p.tiles_per_img = p.tiles_x * p.tiles_y;
   const i64 total = (i64)p.tiles_per_img * B;
   if (total > 0x7fffffff || p.nchunks > num_sms()) return false;
   p.total_tiles = (int)total;
@@ -308,17 +322,21 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const float* G, 
   int cols = 32;
   while (cols < N) cols *= 2;
   p.tmem_cols = cols;
-  CUtensorMap mIn, mOut;
-  const i64 d[3] = {C, P, B};
-  const i64 st[3] = {1, C, (i64)C * P};
-  const int bx[3] = {Cc, 128, 1};
-  if (!make_map_ex(&mOut, out, 3, d, st, bx, 2, p.swz)) return false;
+  CUtensorMap mG, mIn, mOut;
+  const i64 dg[4] = {8, W, H, B};
+  const i64 sg[4] = {1, 8, (i64)8 * W, (i64)8 * W * H};
+  const int bg[4] = {8, IT_PITCH, IT_TH + 2, 1};
+  if (!make_map_ex(&mG, G16, 4, dg, sg, bg, 2, 0)) return false;
+  const i64 d[4] = {C, W, H, B};
+  const i64 st[4] = {1, C, (i64)C * W, (i64)C * W * H};
+  const int bx[4] = {Cc, IT_TW, IT_TH, 1};
+  if (!make_map_ex(&mOut, out, 4, d, st, bx, 2, p.swz)) return false;
   if (mode == 0) {
-    if (!make_map_ex(&mIn, feat, 3, d, st, bx, 2, p.swz)) return false;
+    if (!make_map_ex(&mIn, feat, 4, d, st, bx, 2, p.swz)) return false;
   } else {
     mIn = mOut;
   }
-  const size_t smem = 1024 + 2 * 16384 + 24576 + IT_NF * 16384 + 128;
+  const size_t smem = 1024 + IT_NF * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + IT_NF) + 64;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_im2col_tc<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -330,24 +348,24 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const float* G, 
   }
   const int grid = p.lanes * p.nchunks;
   if (mode == 0) {
-    if (upt == 1) k_im2col_tc<0, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mIn, mOut, p);
-    else k_im2col_tc<0, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mIn, mOut, p);
+    if (upt == 1) k_im2col_tc<0, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
+    else k_im2col_tc<0, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
   } else {
-    if (upt == 1) k_im2col_tc<1, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mIn, mOut, p);
-    else k_im2col_tc<1, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mIn, mOut, p);
+    if (upt == 1) k_im2col_tc<1, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
+    else k_im2col_tc<1, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
   }
   return true;
 }
 
 // xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][32][C] += channel sums
-bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
+bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
                         float* partial, int B, int Hf, int Wf, int C) {
-  return run_im2col_tc(ctx, 0, feat, G, w36, abg, xmod, partial, B, Hf, Wf, C);
+  return run_im2col_tc(ctx, 0, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C);
 }
 
-// out = conv3x3(x_ds; 4 -> d) + bias, bf16 NHWC
-bool launch_embed_tc(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d) {
-  return run_im2col_tc(ctx, 1, nullptr, x_ds, w, b, out, nullptr, B, h, w_, d);
+// out = conv3x3(x_ds; 4 -> d) + bias, bf16 NHWC; x16 = launch_split_bf16x8(x_ds)
+bool launch_embed_tc(Ctx& ctx, const void* x16, const float* w, const float* b, void* out, int B, int h, int w_, int d) {
+  return run_im2col_tc(ctx, 1, nullptr, x16, w, b, out, nullptr, B, h, w_, d);
 }
 
 }  // namespace rf

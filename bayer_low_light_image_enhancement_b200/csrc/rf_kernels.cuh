@@ -138,13 +138,16 @@ void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1,
 // ---- FLCA (rf_flca.cu) ---------------------------------------------------------------------------------------------
 int flca_num_partials(int C, int B, i64 P);
 // xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][nblk][C] channel sums
-void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
-                     float* partial, int nblk, int B, int Hf, int Wf, int C);
+// G16 (optional): the bf16 [hi|lo] form of G for the tensor-core path (see launch_split_bf16x8)
+void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
+                     void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C);
 // tensor-core im2col forms (rf_im2col_tc.cu, bf16 only); false when the shape is not supported
 bool im2col_tc_supported(const Ctx& ctx, int C);
-bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const float* G, const float* w36, const float* abg, void* xmod,
+// G16 / x16: the 4 fp32 maps of every pixel as [hi x4 | lo x4] bf16 (16 bytes per pixel), made by launch_split_bf16x8
+void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix);
+bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
                         float* partial, int B, int Hf, int Wf, int C);
-bool launch_embed_tc(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d);
+bool launch_embed_tc(Ctx& ctx, const void* x16, const float* w, const float* b, void* out, int B, int h, int w_, int d);
 // ML: xs = x * (ga * sig(conv(mapA)) + gb * tanh(conv(mapB)))  [mode 0, level l] or xs = x * gc*sig(conv(cr,cb)) [mode 1]
 void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,
                         int level, int B, int Hf, int Wf, int C);
@@ -189,7 +192,8 @@ void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature
 void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H,
                    int W, int Cn, int kernel_id);
 // embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
-void launch_embed(Ctx& ctx, const float* x_ds, const float* w, const float* b, void* out, int B, int h, int w_, int d);
+void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
+                  int w_, int d);
 void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float* out, int B, int h, int w_, int d);
 // ML tail: out += 0.12*(mean(up(in_rgb)) - mean(out)); out += 0.03*(up8(LL2) - Y(out))
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_);

@@ -163,6 +163,7 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
 struct Stage {           // guidance of one U-Net stage
   int H = 0, W = 0;
   float* G = nullptr;    // [B,H,W,NG]
+  void* G16 = nullptr;   // FLCA variant, bf16 mode: [B,H,W] x 16 B = [hi x4 | lo x4] bf16 of G (tensor-core FLCA kernel)
   float* sums = nullptr; // ML: [B][8] sums of the guidance maps
 };
 
@@ -186,7 +187,7 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   void* xmod = nullptr;
   if (variant == RF_VARIANT_FLCA) {
     xmod = A.elems((size_t)B * P * C, ctx.dtype);
-    launch_flca_mod(ctx, feat, sg.G, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
+    launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
   } else {
     float* gates = A.get<float>((size_t)B * 6);
     launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
@@ -368,6 +369,11 @@ static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const f
     launch_fill_f32(ctx, sg.sums, 0.f, (i64)B * 8);
   }
   launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf);
+  sg.G16 = nullptr;
+  if (variant == RF_VARIANT_FLCA && ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+    sg.G16 = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
+    launch_split_bf16x8(ctx, sg.G, sg.G16, (i64)B * Hf * Wf);
+  }
 }
 
 struct GuidanceMaps {
@@ -440,7 +446,12 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
                B);
   auto feat_buf = [&](int s) { return A.elems((size_t)B * (P0 >> (2 * s)) * ((size_t)d << s), ctx.dtype); };
   void* x0 = feat_buf(0);
-  launch_embed(ctx, x_ds, pm.embed_w, pm.embed_b, x0, B, h, w, d);
+  void* x16 = nullptr;
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+    x16 = A.alloc((size_t)B * P0 * 16);
+    launch_split_bf16x8(ctx, x_ds, x16, (i64)B * P0);
+  }
+  launch_embed(ctx, x_ds, x16, pm.embed_w, pm.embed_b, x0, B, h, w, d);
   void* enc[4];
   void* cur = x0;
   for (int s = 0; s < 4; ++s) {
