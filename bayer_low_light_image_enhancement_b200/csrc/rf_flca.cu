@@ -211,7 +211,7 @@ void launch_pyr_gates(Ctx& ctx, const float* sums, i64 P, const float* gate_w, c
 
 // per-channel sums of an NHWC tensor -> partial [B][nblk][C]   (blockDim = (C/8, ppb))
 template <typename T>
-__global__ void k_channel_sums(const T* __restrict__ x, float* __restrict__ partial, i64 P, int C) {
+__global__ void k_channel_sums(const T* __restrict__ x, float* __restrict__ partial, i64 P, int C, int nslots) {
   extern __shared__ float smem[];
   const int cv = blockDim.x, ppb = blockDim.y;
   const int tid = threadIdx.y * cv + threadIdx.x, nthr = cv * ppb;
@@ -230,7 +230,7 @@ __global__ void k_channel_sums(const T* __restrict__ x, float* __restrict__ part
   for (int c = tid; c < C; c += nthr) {
     float s = 0.f;
     for (int r = 0; r < ppb; ++r) s += smem[r * C + c];
-    partial[(b * gridDim.x + blockIdx.x) * C + c] = s;
+    atomicAdd(partial + (b * nslots + blockIdx.x % nslots) * C + c, s);   // partial is zero-initialised by the caller
   }
 }
 void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int B, i64 P, int C) {
@@ -239,13 +239,16 @@ void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int 
   int ppb = 256 / cv;
   if (ppb < 1) ppb = 1;
   size_t smem = sizeof(float) * (size_t)C * ppb;
+  // enough CTAs to stream at HBM speed; they add into the nblk partial slots (zero-initialised by the caller)
+  i64 want = cdivl(P, (i64)ppb * 64);
+  const unsigned gx = (unsigned)(want < 1 ? 1 : (want > 8 * num_sms() ? 8 * num_sms() : want));
   ScopedLaunch sl(RF_K_CHANNEL_SUMS, (double)B * P * C * esize(ctx.dtype));
   if (ctx.dtype == RF_BF16) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_channel_sums<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_channel_sums<bf16><<<dim3(nblk, B), dim3(cv, ppb), smem, ctx.stream>>>((const bf16*)x, partial, P, C);
+    k_channel_sums<bf16><<<dim3(gx, B), dim3(cv, ppb), smem, ctx.stream>>>((const bf16*)x, partial, P, C, nblk);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_channel_sums<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_channel_sums<float><<<dim3(nblk, B), dim3(cv, ppb), smem, ctx.stream>>>((const float*)x, partial, P, C);
+    k_channel_sums<float><<<dim3(gx, B), dim3(cv, ppb), smem, ctx.stream>>>((const float*)x, partial, P, C, nblk);
   }
 }
 

@@ -4,6 +4,8 @@
 //          element from tensor memory, applies x * (1 + a*sigmoid(low) + b*tanh(high) + g*sigmoid(chr)) with MUFU.TANH
 //          only, accumulates the squeeze-excite channel sums and writes the tile back through shared memory by TMA.
 //   MODE 1 (embedding, FLCA_RF.py:303,338): out[128 x d] = patch(x_ds) * W_embed^T + bias.
+//   MODE 2 (FLCA_Pyramid level, ML_RF.py:157-166): xs = x * (ga*sigmoid(conv(LL_l)) + gb*tanh(conv(hi_l))), gates per image.
+//   MODE 3 (FLCA_Pyramid chroma, ML_RF.py:171-176): xs = x * gc*sigmoid(conv(cr, cb)).
 //
 // No im2col is ever built.  The 4 fp32 maps of a pixel are stored once per stage as 8 bf16 = [hi(4) | lo(4)] (hi = bf16(v),
 // lo = bf16(v - hi): 16 significant bits) = ONE 16-byte unit per pixel.  A TMA box of the (16+2) x (8+2) halo patch then
@@ -32,8 +34,13 @@ constexpr uint32_t IT_PATCH_BYTES = IT_NPIX * 16;                 // 2880
 constexpr uint32_t IT_PATCH_STRIDE = (IT_PATCH_BYTES + 127u) & ~127u;
 
 struct Im2colTcParams {
-  const float* w;        // [9][4][C] fp32 taps (FLCA: maps LL, |high|, cr, cb; embed: the 4 input channels)
-  const float* coef;     // FLCA: alpha, beta, gamma; embed: bias[C]
+  const float* w;        // [9][wmaps][C] fp32 taps (FLCA: maps LL, |high|, cr, cb; embed: the 4 input channels; ML: 6 maps)
+  const float* coef;     // FLCA: alpha, beta, gamma; embed: bias[C]; ML: gates [B][6]
+  int wmaps;             // weight maps per tap (4, or 6 for the pyramid variant)
+  int seg_of[4];         // pre-activation segment fed by guidance slot m of the 16-byte pixel (-1: unused)
+  int wmap_of[4];        // weight map of slot m
+  float scale_of[4];     // 0.5 for sigmoid inputs (sigmoid(a) = 0.5*tanh(a/2) + 0.5), else 1
+  int coef_off;          // ML: index of the first gate used inside gates[b][6]
   float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums (atomicAdd)
   int H, W, C, Cc, nchunks, B;
   int tiles_x, tiles_y, tiles_per_img, total_tiles, lanes;
@@ -58,26 +65,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // fp32 x4 per pixel -> [hi x4 | lo x4] bf16 (16 bytes per pixel)
 __global__ void __launch_bounds__(256)
-k_split_bf16x8(const float4* __restrict__ g, uint4* __restrict__ out, i64 n) {
+k_split_bf16x8(const float4* __restrict__ g, uint4* __restrict__ out, i64 n, int stride4) {
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-    const float4 v = g[i];
+    const float4 v = g[i * stride4];
     const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
     const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
     out[i] = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3), pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
   }
 }
-void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix) {
+void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix, int stride_floats) {
   if (ctx.dry || npix <= 0) return;
   ScopedLaunch sl(RF_K_GUIDANCE, 32.0 * npix);
   const unsigned gx = (unsigned)(cdivl(npix, 256) < 8 * num_sms() ? cdivl(npix, 256) : 8 * num_sms());
-  k_split_bf16x8<<<gx, 256, 0, ctx.stream>>>((const float4*)g4, (uint4*)out16, npix);
+  k_split_bf16x8<<<gx, 256, 0, ctx.stream>>>((const float4*)g4, (uint4*)out16, npix, stride_floats / 4);
 }
 
 template <int MODE, int UPT>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapIn,
             const __grid_constant__ CUtensorMap mapOut, const Im2colTcParams p) {
-  constexpr int SEG = MODE == 0 ? 3 : 1;
+  constexpr int SEG = MODE == 0 ? 3 : (MODE == 2 ? 2 : 1);
+  constexpr bool MODULATE = MODE != 1;               // multiply the feature tile (vs. bias epilogue)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sF = base;                                   // IT_NF x 16 KB feature / output tiles (ring, in place)
@@ -96,7 +104,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   if (tid == 0) {
     tma_prefetch_desc(&mapG);
     tma_prefetch_desc(&mapOut);
-    if (MODE == 0) tma_prefetch_desc(&mapIn);
+    if (MODULATE) tma_prefetch_desc(&mapIn);
     for (int i = 0; i < 2 + IT_NGS + IT_NF; ++i) mbar_init(bars + 8 * i, 1);
     fence_barrier_init();
   }
@@ -113,15 +121,8 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (tap >= 0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        bool use = true;
-        float sc = 1.f;
-        if (MODE == 0) {
-          use = seg == 0 ? m == 0 : (seg == 1 ? m == 1 : m >= 2);
-          sc = seg == 1 ? 1.f : 0.5f;
-        }
-        if (use) v[m] = p.w[(i64)(tap * 4 + m) * p.C + c] * sc;
-      }
+      for (int m = 0; m < 4; ++m)
+        if (p.seg_of[m] == seg) v[m] = p.w[(i64)(tap * p.wmaps + p.wmap_of[m]) * p.C + c] * p.scale_of[m];
     }
     const uint32_t q0 = pack_bf16x2(v[0], v[1]), q1 = pack_bf16x2(v[2], v[3]);
     sts128(sW + (uint32_t)(kc * N + n) * 16u, make_uint4(q0, q1, q0, q1));
@@ -142,7 +143,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     const int gs = j % IT_NGS, fs = j % IT_NF;
     mbar_expect_tx(g_bar(gs), IT_PATCH_BYTES);
     tma_load_4d(sG + gs * IT_PATCH_STRIDE, &mapG, g_bar(gs), 0, tx * IT_TW - 1, ty * IT_TH - 1, b);
-    if (MODE == 0) {
+    if (MODULATE) {
       mbar_expect_tx(f_bar(fs), 128u * p.row_bytes);
       tma_load_4d(sF + fs * 16384, &mapIn, f_bar(fs), chunk * p.Cc, tx * IT_TW, ty * IT_TH, b);
     }
@@ -176,11 +177,22 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   const bool epi = part < p.parts;
   const int erow = quad * 32 + lane;                 // tile row = patch pixel (py, px) = (erow >> 3, erow & 7)
   const uint32_t esw = p.swz == 128 ? (uint32_t)(erow & 7) : (p.swz == 64 ? (uint32_t)((erow >> 1) & 3) : 0u);
-  float cf[MODE == 0 ? 4 : 8 * UPT];                 // FLCA: base, h0, h1, h2;  embed: bias of this thread's channels
+  float cf[MODE == 1 ? 8 * UPT : 4];                 // modulate: base, h0, h1, h2;  embed: bias of this thread's channels
+  auto set_coef = [&](int b) {                       // modulation = cf0 + cf1*tanh(a0) + cf2*tanh(a1) + cf3*tanh(a2)
+    if (MODE == 0) {
+      const float k0 = p.coef[0], k1 = p.coef[1], k2 = p.coef[2];
+      cf[0] = 1.f + 0.5f * k0 + 0.5f * k2; cf[1] = 0.5f * k0; cf[2] = k1; cf[3] = 0.5f * k2;
+    } else if (MODE == 2) {
+      const float k0 = p.coef[b * 6 + p.coef_off], k1 = p.coef[b * 6 + p.coef_off + 1];
+      cf[0] = 0.5f * k0; cf[1] = 0.5f * k0; cf[2] = k1; cf[3] = 0.f;
+    } else if (MODE == 3) {
+      const float k0 = p.coef[b * 6 + p.coef_off];
+      cf[0] = 0.5f * k0; cf[1] = 0.5f * k0; cf[2] = 0.f; cf[3] = 0.f;
+    }
+  };
   if (MODE == 0) {
-    const float k0 = p.coef[0], k1 = p.coef[1], k2 = p.coef[2];
-    cf[0] = 1.f + 0.5f * k0 + 0.5f * k2; cf[1] = 0.5f * k0; cf[2] = k1; cf[3] = 0.5f * k2;
-  } else if (epi) {
+    set_coef(0);
+  } else if (MODE == 1 && epi) {
 #pragma unroll
     for (int e = 0; e < 8 * UPT; ++e) cf[e] = p.coef[chunk * p.Cc + part * UPT * 8 + e];
   }
@@ -222,17 +234,17 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
       if (i + 3 < n_my) issue_loads(i + 3);
     }
     if (tid == 0 && i + 1 < n_my) issue_mma(i + 1, tmem_base);   // TMEM buffer a^1 was drained by epilogue(i-1)
-    int b = 0;
-    if (MODE == 0) {
-      b = (t0 + i * tstep) / p.tiles_per_img;
+    if (MODULATE) {
+      const int b = (t0 + i * tstep) / p.tiles_per_img;
       if (b != cur_b) {
-        if (cur_b >= 0) flush(cur_b);
+        if (MODE == 0 && cur_b >= 0) flush(cur_b);
+        if (MODE != 0) set_coef(b);
         cur_b = b;
       }
     }
     mbar_wait(acc_bar(a), (i >> 1) & 1);
     tc_fence_after();
-    if (MODE == 0) mbar_wait(f_bar(fs), (i / IT_NF) & 1);
+    if (MODULATE) mbar_wait(f_bar(fs), (i / IT_NF) & 1);
     if (epi) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.tmem_cols);
       const uint32_t frow = sF + fs * 16384 + (uint32_t)erow * p.row_bytes;
@@ -242,24 +254,22 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
         const uint32_t faddr = frow + ((((uint32_t)ui) ^ esw) << 4);
         uint32_t v0[8], v1[8], v2[8];
         tmem_ld8(taddr + ui * 8, v0);
-        if (MODE == 0) {
-          tmem_ld8(taddr + p.Cc + ui * 8, v1);
-          tmem_ld8(taddr + 2 * p.Cc + ui * 8, v2);
-        }
+        if (SEG >= 2) tmem_ld8(taddr + p.Cc + ui * 8, v1);
+        if (SEG >= 3) tmem_ld8(taddr + 2 * p.Cc + ui * 8, v2);
         uint4 fq = make_uint4(0u, 0u, 0u, 0u);
-        if (MODE == 0) fq = lds128(faddr);
+        if (MODULATE) fq = lds128(faddr);
         tmem_ld_wait();
         float o[8];
-        if (MODE == 0) {
+        if (MODULATE) {
           const uint32_t fw[4] = {fq.x, fq.y, fq.z, fq.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float f = (e & 1) ? __uint_as_float(fw[e >> 1] & 0xffff0000u) : __uint_as_float(fw[e >> 1] << 16);
             float m = fmaf(cf[1], tanh_fast(__uint_as_float(v0[e])), cf[0]);
-            m = fmaf(cf[2], tanh_fast(__uint_as_float(v1[e])), m);
-            m = fmaf(cf[3], tanh_fast(__uint_as_float(v2[e])), m);
+            if (SEG >= 2) m = fmaf(cf[2], tanh_fast(__uint_as_float(v1[e])), m);
+            if (SEG >= 3) m = fmaf(cf[3], tanh_fast(__uint_as_float(v2[e])), m);
             o[e] = f * m;
-            csum[u * 8 + e] += o[e];
+            if (MODE == 0) csum[u * 8 + e] += o[e];
           }
         } else {
 #pragma unroll
@@ -298,7 +308,7 @@ bool im2col_tc_supported(const Ctx& ctx, int C) {
 
 // G16: [B][H][W] x 16 bytes ([hi x4 | lo x4] bf16 of the 4 fp32 maps, launch_split_bf16x8)
 static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16, const float* w, const float* coef, void* out,
-                          float* partial, int B, int H, int W, int C) {
+                          float* partial, int B, int H, int W, int C, int level = 0) {
   if (!tcgen05_enabled() || ctx.dtype != RF_BF16 || !G16) return false;
   int Cc, parts, upt;
   if (C % 64 == 0) { Cc = 64; parts = 4; upt = 2; }
@@ -307,6 +317,22 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   else return false;
   Im2colTcParams p;
   p.w = w; p.coef = coef; p.partial = partial;
+  p.wmaps = 4; p.coef_off = 0;
+  for (int m = 0; m < 4; ++m) { p.seg_of[m] = -1; p.wmap_of[m] = m; p.scale_of[m] = 1.f; }
+  if (mode == 0) {          // FLCA: LL -> sigmoid, |high| -> tanh, (cr, cb) -> sigmoid
+    p.seg_of[0] = 0; p.seg_of[1] = 1; p.seg_of[2] = 2; p.seg_of[3] = 2;
+    p.scale_of[0] = 0.5f; p.scale_of[2] = 0.5f; p.scale_of[3] = 0.5f;
+  } else if (mode == 1) {   // embedding: all four input channels -> one pre-activation
+    for (int m = 0; m < 4; ++m) p.seg_of[m] = 0;
+  } else if (mode == 2) {   // pyramid level l on the (LL1, hi1, LL2, hi2) pixels: weight maps 2l, 2l+1 of 6
+    p.wmaps = 6; p.coef_off = 2 * level;
+    p.seg_of[2 * level] = 0; p.wmap_of[2 * level] = 2 * level; p.scale_of[2 * level] = 0.5f;
+    p.seg_of[2 * level + 1] = 1; p.wmap_of[2 * level + 1] = 2 * level + 1;
+  } else {                  // pyramid chroma on the (cr, cb, mag, 0) pixels: weight maps 4, 5 of 6
+    p.wmaps = 6; p.coef_off = 4;
+    p.seg_of[0] = 0; p.wmap_of[0] = 4; p.scale_of[0] = 0.5f;
+    p.seg_of[1] = 0; p.wmap_of[1] = 5; p.scale_of[1] = 0.5f;
+  }
   p.H = H; p.W = W; p.C = C; p.Cc = Cc; p.nchunks = C / Cc; p.B = B;
   p.tiles_x = cdiv(W, IT_TW); p.tiles_y = cdiv(H, IT_TH);
   p.tiles_per_img = p.tiles_x * p.tiles_y;
@@ -318,7 +344,7 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   p.parts = parts;
   p.row_bytes = (uint32_t)Cc * 2;
   p.swz = p.row_bytes == 128 ? 128 : (p.row_bytes == 64 ? 64 : 0);
-  const int N = (mode == 0 ? 3 : 1) * Cc;
+  const int N = (mode == 0 ? 3 : (mode == 2 ? 2 : 1)) * Cc;
   int cols = 32;
   while (cols < N) cols *= 2;
   p.tmem_cols = cols;
@@ -331,29 +357,28 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   const i64 st[4] = {1, C, (i64)C * W, (i64)C * W * H};
   const int bx[4] = {Cc, IT_TW, IT_TH, 1};
   if (!make_map_ex(&mOut, out, 4, d, st, bx, 2, p.swz)) return false;
-  if (mode == 0) {
+  if (mode != 1) {
     if (!make_map_ex(&mIn, feat, 4, d, st, bx, 2, p.swz)) return false;
   } else {
     mIn = mOut;
   }
   const size_t smem = 1024 + IT_NF * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + IT_NF) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_im2col_tc<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_im2col_tc<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_im2col_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_im2col_tc<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return false;
-    attr_set = true;
-  }
+#define RF_IT_LAUNCH(M, U)                                                                                                  \
+  do {                                                                                                                       \
+    static bool attr = false;                                                                                                \
+    if (!attr) {                                                                                                             \
+      if (cudaFuncSetAttribute(k_im2col_tc<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)   \
+        return false;                                                                                                        \
+      attr = true;                                                                                                           \
+    }                                                                                                                        \
+    k_im2col_tc<M, U><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);                                             \
+  } while (0)
   const int grid = p.lanes * p.nchunks;
-  if (mode == 0) {
-    if (upt == 1) k_im2col_tc<0, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
-    else k_im2col_tc<0, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
-  } else {
-    if (upt == 1) k_im2col_tc<1, 1><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
-    else k_im2col_tc<1, 2><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);
-  }
+  if (mode == 0) { if (upt == 1) RF_IT_LAUNCH(0, 1); else RF_IT_LAUNCH(0, 2); }
+  else if (mode == 1) { if (upt == 1) RF_IT_LAUNCH(1, 1); else RF_IT_LAUNCH(1, 2); }
+  else if (mode == 2) { if (upt == 1) RF_IT_LAUNCH(2, 1); else RF_IT_LAUNCH(2, 2); }
+  else { if (upt == 1) RF_IT_LAUNCH(3, 1); else RF_IT_LAUNCH(3, 2); }
+#undef RF_IT_LAUNCH
   return true;
 }
 
@@ -366,6 +391,13 @@ bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float
 // out = conv3x3(x_ds; 4 -> d) + bias, bf16 NHWC; x16 = launch_split_bf16x8(x_ds)
 bool launch_embed_tc(Ctx& ctx, const void* x16, const float* w, const float* b, void* out, int B, int h, int w_, int d) {
   return run_im2col_tc(ctx, 1, nullptr, x16, w, b, out, nullptr, B, h, w_, d);
+}
+
+// FLCA_Pyramid spatial steps: mode 0 = level `level` (GA16 = [hi|lo] of (LL1, hi1, LL2, hi2)), mode 1 = chroma
+// (GB16 = [hi|lo] of (cr, cb, mag, 0)); gates [B][6]
+bool launch_pyr_spatial_tc(Ctx& ctx, const void* x, const void* G16, const float* w54, const float* gates, void* xs, int mode,
+                           int level, int B, int Hf, int Wf, int C) {
+  return run_im2col_tc(ctx, mode == 0 ? 2 : 3, x, G16, w54, gates, xs, nullptr, B, Hf, Wf, C, level);
 }
 
 }  // namespace rf

@@ -144,7 +144,10 @@ void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16
 // tensor-core im2col forms (rf_im2col_tc.cu, bf16 only); false when the shape is not supported
 bool im2col_tc_supported(const Ctx& ctx, int C);
 // G16 / x16: the 4 fp32 maps of every pixel as [hi x4 | lo x4] bf16 (16 bytes per pixel), made by launch_split_bf16x8
-void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix);
+// (g4 points at the first of 4 consecutive floats of pixel 0; pixels are stride_floats apart: 4, or 8 for the ML guidance)
+void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix, int stride_floats = 4);
+bool launch_pyr_spatial_tc(Ctx& ctx, const void* x, const void* G16, const float* w54, const float* gates, void* xs, int mode,
+                           int level, int B, int Hf, int Wf, int C);
 bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
                         float* partial, int B, int Hf, int Wf, int C);
 bool launch_embed_tc(Ctx& ctx, const void* x16, const float* w, const float* b, void* out, int B, int h, int w_, int d);

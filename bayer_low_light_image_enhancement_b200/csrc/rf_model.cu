@@ -163,7 +163,8 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
 struct Stage {           // guidance of one U-Net stage
   int H = 0, W = 0;
   float* G = nullptr;    // [B,H,W,NG]
-  void* G16 = nullptr;   // FLCA variant, bf16 mode: [B,H,W] x 16 B = [hi x4 | lo x4] bf16 of G (tensor-core FLCA kernel)
+  void* G16 = nullptr;   // bf16 mode: [B,H,W] x 16 B = [hi x4 | lo x4] bf16 of G's maps 0..3 (tensor-core FLCA kernels)
+  void* G16b = nullptr;  // ML variant: the same for maps 4..7 (cr, cb, mag, 0)
   float* sums = nullptr; // ML: [B][8] sums of the guidance maps
 };
 
@@ -199,7 +200,19 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     const void* cur = feat;
     void* nxt = xa;
     for (int step = 0; step < 3; ++step) {
-      launch_pyr_spatial(ctx, cur, sg.G, pb.flca_w, gates, xs, step < 2 ? 0 : 1, step < 2 ? step : 0, B, H, W, C);
+      const int smode = step < 2 ? 0 : 1, slevel = step < 2 ? step : 0;
+      bool done = false;
+      if (sg.G16 != nullptr && im2col_tc_supported(ctx, C)) {
+        if (ctx.dry) {
+          done = true;
+        } else {
+          const double px = (double)B * H * W;
+          ScopedLaunch sl(RF_K_PYR_SPATIAL, px * C * 4.0 + px * 16.0, px * C * 2.0 * (smode == 0 ? 18 : 18));
+          done = launch_pyr_spatial_tc(ctx, cur, smode == 0 ? sg.G16 : sg.G16b, pb.flca_w, gates, xs, smode, slevel, B, H, W, C);
+          if (!done) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+        }
+      }
+      if (!done) launch_pyr_spatial(ctx, cur, sg.G, pb.flca_w, gates, xs, smode, slevel, B, H, W, C);
       GemmP g1 = gemm_rows(xs, C, pb.res_w0, pb.res_b0, t1, C, B, P, RF_K_GEMM_PYR_RES1);
       g1.act = ACT_RELU;
       launch_gemm(ctx, g1);
@@ -369,10 +382,14 @@ static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const f
     launch_fill_f32(ctx, sg.sums, 0.f, (i64)B * 8);
   }
   launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf);
-  sg.G16 = nullptr;
-  if (variant == RF_VARIANT_FLCA && ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+  sg.G16 = nullptr; sg.G16b = nullptr;
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
     sg.G16 = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
-    launch_split_bf16x8(ctx, sg.G, sg.G16, (i64)B * Hf * Wf);
+    launch_split_bf16x8(ctx, sg.G, sg.G16, (i64)B * Hf * Wf, NG);
+    if (variant == RF_VARIANT_ML) {
+      sg.G16b = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
+      launch_split_bf16x8(ctx, sg.G + 4, sg.G16b, (i64)B * Hf * Wf, NG);
+    }
   }
 }
 
