@@ -308,7 +308,9 @@ static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* re
   A.release(mk);
 }
 
-static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void* out, int B, int H, int W) {
+// pre (optional): LayerNorm statistics of `feat` already emitted by the kernel that produced it
+static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void* out, int B, int H, int W,
+                        const LnFold* pre = nullptr) {
   const int C = pb.C;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
@@ -318,11 +320,15 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
     // bf16 mode: both LayerNorms are folded into the 1x1 conv that follows them (W*diag(g), per-row mean/rstd applied in
     // the GEMM epilogue), so the normalised tensors never exist.  norm1 statistics: one read pass over the block input;
     // norm2 statistics: emitted by the project_out GEMM epilogue that produces x1.
-    float* st1 = A.get<float>((size_t)B * P * 2);
     float* st2 = A.get<float>((size_t)B * P * 2 * 2);     // up to two N tiles of partials
-    launch_row_stats(ctx, feat, st1, B * P, C);
     LnFold l1;
-    l1.stats = st1; l1.npart = 1;
+    if (pre != nullptr && pre->stats != nullptr && pre->npart > 0) {
+      l1 = *pre;
+    } else {
+      float* st1 = A.get<float>((size_t)B * P * 2);
+      launch_row_stats(ctx, feat, st1, B * P, C);
+      l1.stats = st1; l1.npart = 1;
+    }
     LnFold l2;
     l2.stats = st2;
     l2.npart = attention(ctx, pb, feat, feat, x1, B, H, W, &l1, st2);
@@ -348,7 +354,7 @@ static void conv3x3(Ctx& ctx, const void* in, const void* w, const float* bias, 
 }
 
 static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const void* feat, const Stage& sg, void* out,
-                             int B) {
+                             int B, const LnFold* pre = nullptr) {
   const int C = pb.C, H = sg.H, W = sg.W;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
@@ -359,7 +365,7 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
   launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
   void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
-  transformer(ctx, pb, feat, x2, B, H, W);
+  transformer(ctx, pb, feat, x2, B, H, W, pre);
   void* xr = A.elems((size_t)B * P * C, ctx.dtype);
   GemmP g = gemm_rows(xmod, C, wred, pb.red_b, xr, C, B, P, RF_K_GEMM_CAT_REDUCE);
   g.A2 = x2; g.K2 = C; g.lda2 = C;
@@ -495,9 +501,16 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
     void* fused = feat_buf(s);
     GemmP r = gemm_rows(up, Co, pm.red_w[n], pm.red_b[n], fused, Co, B, Ps, RF_K_SKIP_REDUCE);
     r.A2 = enc[s]; r.K2 = Co; r.lda2 = Co;
-    launch_gemm(ctx, r);
+    // the skip-fusion GEMM's epilogue also emits the LayerNorm statistics of its rows (= norm1 input of the next block)
+    LnFold pre;
+    if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+      float* stf = A.get<float>((size_t)B * Ps * 2 * 2);
+      r.stats_out = stf;
+      pre.stats = stf;
+    }
+    pre.npart = launch_gemm(ctx, r);
     void* dec = feat_buf(s);
-    conv_transformer(ctx, pm.blocks[4 + n], variant, fused, st[s], dec, B);
+    conv_transformer(ctx, pm.blocks[4 + n], variant, fused, st[s], dec, B, pre.stats ? &pre : nullptr);
     cur = dec;
   }
   bool head_done = false;

@@ -661,15 +661,15 @@ static int pick_bn(int N) {
 // pixel range (split-K); the accumulator stays in TMEM over the whole slice and only the per-head diagonal blocks
 // are added to global memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int GR_STAGES = 3;
+constexpr int GR_STAGES = 8;                   // maximum ring depth (barrier slots); the launcher picks nst <= 8
 constexpr int GR_THREADS = 192;               // TMA warp, MMA warp, 4 epilogue warps
 constexpr int GR_PIX = 128;                    // pixels per k-block
 constexpr uint32_t GR_CHUNK = GR_PIX * 128;    // bytes of one 64-channel x 128-pixel chunk tile
 
-__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes = GR_CHUNK) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(GR_CHUNK >> 4) << 16;   // LBO: next 64-element group along M/N
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;  // LBO: next 64-element group along M/N
   d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row group along K
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
@@ -677,11 +677,17 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(GR_THREADS)
-k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int C, i64 P, int ksplit) {
+k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int C, i64 P, int ksplit, int packed, int nst) {
+  // packed = 0: q rows m0.. and k rows n0.. are different channel ranges: 2 + 2 chunks per k-block.
+  // packed = 1|2 (2C <= 64 | 128): the whole q|k pixel row fits `packed` 64-channel chunks, A = B = those chunks and the
+  //   accumulator is the Gram of [q|k] with itself, whose upper-right block is q^T k -- a quarter / half of the TMA
+  //   traffic and shared-memory fill of the general form.  packed = 1 points the second 64-row group of both operands at
+  //   a zeroed chunk behind the ring.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 4 * GR_CHUNK;   // A: 2 chunks, B: 2 chunks
-  const uint32_t bars = base + GR_STAGES * stage_bytes;
+  const uint32_t stage_bytes = (packed ? (uint32_t)packed : 4u) * GR_CHUNK;
+  const uint32_t zero_chunk = base + (uint32_t)nst * stage_bytes;          // packed == 1 only
+  const uint32_t bars = zero_chunk + (packed == 1 ? GR_CHUNK : 0u);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (GR_STAGES + s); };
   const uint32_t tmem_full = bars + 8u * (2 * GR_STAGES);
@@ -692,7 +698,7 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
   const int c = C >> 3;  // head width
   // heads touched by the rows / columns of this tile: skip tiles without a common head
   const int hr0 = m0 / c, hr1 = (min(m0 + 128, C) - 1) / c, hc0 = n0 / c, hc1 = (min(n0 + 128, C) - 1) / c;
-  if (hr1 < hc0 || hc1 < hr0) return;
+  if (!packed && (hr1 < hc0 || hc1 < hr0)) return;
   const int nkb_all = (int)((P + GR_PIX - 1) / GR_PIX);
   const int kb_per = (nkb_all + ksplit - 1) / ksplit;
   const int kb_begin = blockIdx.z * kb_per;
@@ -708,6 +714,11 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
+  if (packed == 1) {
+    for (uint32_t o = threadIdx.x * 16u; o < GR_CHUNK; o += GR_THREADS * 16u)
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(zero_chunk + o), "r"(0u) : "memory");
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
@@ -716,32 +727,40 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0, wrap = 0;
       for (int il = 0; il < nkb; ++il) {
-        const int s = il % GR_STAGES, it = il / GR_STAGES;
-        if (it > 0) mbar_wait(empty_bar(s), (it - 1) & 1);
+        if (wrap > 0) mbar_wait(empty_bar(s), (wrap - 1) & 1);
         mbar_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = base + s * stage_bytes;
         const int p0 = (kb_begin + il) * GR_PIX;
-        tma_load_3d(dst, &mapQK, full_bar(s), m0, p0, 0);
-        tma_load_3d(dst + GR_CHUNK, &mapQK, full_bar(s), m0 + 64, p0, 0);
-        tma_load_3d(dst + 2 * GR_CHUNK, &mapQK, full_bar(s), C + n0, p0, 0);
-        tma_load_3d(dst + 3 * GR_CHUNK, &mapQK, full_bar(s), C + n0 + 64, p0, 0);
+        if (packed) {
+          tma_load_3d(dst, &mapQK, full_bar(s), 0, p0, 0);
+          if (packed == 2) tma_load_3d(dst + GR_CHUNK, &mapQK, full_bar(s), 64, p0, 0);
+        } else {
+          tma_load_3d(dst, &mapQK, full_bar(s), m0, p0, 0);
+          tma_load_3d(dst + GR_CHUNK, &mapQK, full_bar(s), m0 + 64, p0, 0);
+          tma_load_3d(dst + 2 * GR_CHUNK, &mapQK, full_bar(s), C + n0, p0, 0);
+          tma_load_3d(dst + 3 * GR_CHUNK, &mapQK, full_bar(s), C + n0 + 64, p0, 0);
+        }
+        if (++s == nst) { s = 0; ++wrap; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // kind::f16, D=f32, A=B=bf16, both MN-major (bits 15, 16), M = N = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      int s = 0, wrap = 0;
       for (int il = 0; il < nkb; ++il) {
-        const int s = il % GR_STAGES, it = il / GR_STAGES;
-        mbar_wait(full_bar(s), it & 1);
+        mbar_wait(full_bar(s), wrap & 1);
         tc_fence_after();
-        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + 2 * GR_CHUNK;
-        const uint64_t adesc = make_sw128_mn_desc(a0), bdesc = make_sw128_mn_desc(b0);
+        const uint32_t a0 = base + s * stage_bytes, b0 = packed ? a0 : a0 + 2 * GR_CHUNK;
+        const uint32_t lbo = packed == 1 ? zero_chunk - a0 : GR_CHUNK;
+        const uint64_t adesc = make_sw128_mn_desc(a0, lbo), bdesc = make_sw128_mn_desc(b0, lbo);
 #pragma unroll
         for (int k = 0; k < GR_PIX / 16; ++k)   // 16 pixels = 16 rows of 128 B = 2048 B per MMA
           umma_f16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (il | k) ? 1u : 0u);
         umma_commit(empty_bar(s));
+        if (++s == nst) { s = 0; ++wrap; }
       }
       umma_commit(tmem_full);
     }
@@ -759,8 +778,8 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
       if (h < 0) continue;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = n0 + cc + j;   // k channel
-        if (col < C && col / c == h) atomicAdd(G + (i64)row * C + col, __uint_as_float(v[j]));
+        const int col = packed ? cc + j - C : n0 + cc + j;   // k channel (packed: accumulator column = C + k channel)
+        if (col >= 0 && col < C && col / c == h) atomicAdd(G + (i64)row * C + col, __uint_as_float(v[j]));
       }
     }
     tc_fence_before();
@@ -1019,19 +1038,22 @@ bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
   const i64 st[3] = {1, 2 * (i64)C, 2 * (i64)C * P};
   const int bx[3] = {64, GR_PIX, 1};
   if (!make_map(&m, qkv, 3, d, st, bx)) return false;
-  const int mt = cdiv(C, 128);
+  const int packed = 2 * C <= 64 ? 1 : (2 * C <= 128 ? 2 : 0);
+  const int mt = packed ? 1 : cdiv(C, 128);
   const int nkb = (int)((P + GR_PIX - 1) / GR_PIX);
-  int ksplit = 2 * num_sms() / (mt * mt);
+  // packed: two CTAs per SM (<= 113 KB each), ring as deep as that allows; general: one CTA per SM, 3 stages of 64 KB
+  const int nst = packed == 1 ? 5 : (packed == 2 ? 3 : 3);
+  int ksplit = (packed ? 4 : 2) * num_sms() / (mt * mt);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkb) ksplit = nkb;
-  const size_t smem = 1024 + (size_t)GR_STAGES * 4 * GR_CHUNK + 8 * (2 * GR_STAGES + 2);
+  const size_t smem = 1024 + (size_t)nst * (packed ? packed : 4) * GR_CHUNK + (packed == 1 ? GR_CHUNK : 0) + 8 * (2 * GR_STAGES + 2);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
     attr_set = true;
   }
   ScopedLaunch sl(RF_K_GEMM_GRAM, 4.0 * C * P, 2.0 * P * C * (C / 8.0));
-  k_tc_gram<<<dim3(mt, mt, ksplit), GR_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit);
+  k_tc_gram<<<dim3(mt, mt, ksplit), GR_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit, packed, nst);
   return true;
 }
 
