@@ -183,14 +183,6 @@ bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float*
                        int Cn);
 bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
                       int B, int H, int W, int C);
-// fused LayerNorm-folded 1x1 conv -> depthwise 3x3 (rf_pwdw.cu; C in {32, 64}, bf16): the 3C / 2C-wide 1x1 output stays
-// on chip.  x = raw rows [B,H,W,C]; Wf / cs / pbias = folded weights (PackedBlock qkv_wf.. / pw1_wf..); stats = LN partials
-bool pwdw_supported(const Ctx& ctx, int C);
-bool launch_qkv_dw_fused(Ctx& ctx, const void* x, const void* Wf, const float* cs, const float* pbias, const float* stats,
-                         int npart, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq, int B, int H, int W,
-                         int C);
-bool launch_pw1_dw_fused(Ctx& ctx, const void* x, const void* Wf, const float* cs, const float* pbias, const float* stats,
-                         int npart, const float* dw_w, const float* dw_b, void* h, int B, int H, int W, int C);
 // G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qk [P][2C]); false if the tcgen05 path is unavailable
 bool launch_gram_tcgen05(Ctx& ctx, const void* qk, float* G, int C, i64 P);
 bool tcgen05_enabled();

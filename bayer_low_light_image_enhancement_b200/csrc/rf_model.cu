@@ -246,10 +246,8 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
-  const bool fused = ln != nullptr && pwdw_supported(ctx, C);   // norm1 -> qkv -> qkv_dwconv in one kernel
-  void* qkv = nullptr;
-  if (!fused) {
-    qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
+  void* qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
+  {
     GemmP gq = gemm_rows(xin, C, ln ? pb.qkv_wf : pb.qkv_w, ln ? pb.qkv_bf : pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV);
     if (ln) { gq.ln_stats = ln->stats; gq.ln_npart = ln->npart; gq.ln_cs = pb.qkv_cs; gq.ln_C = C; gq.ln_eps = 1e-5f; }
     launch_gemm(ctx, gq);
@@ -264,17 +262,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);
-    if (fused) {
-      if (!ctx.dry) {
-        const double px = (double)B * P;
-        ScopedLaunch sl(RF_K_DW_QKV_GRAM, px * 4.0 * C * 2.0, px * (6.0 * C * C + 54.0 * C));
-        if (!launch_qkv_dw_fused(ctx, xin, pb.qkv_wf, pb.qkv_cs, pb.qkv_bf, ln->stats, ln->npart, pb.qkv_dw_w, pb.qkv_dw_b,
-                                 qk, vbuf, sumsq, B, H, W, C))
-          recorder().last_cuda_error = (int)cudaErrorNotSupported;
-      }
-    } else {
-      launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
-    }
+    launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
     if (!ctx.dry) {
       for (int b = 0; b < B; ++b)
         if (!launch_gram_tcgen05(ctx, (const char*)qk + (size_t)b * P * 2 * C * 2, stats + b * nst, C, P))
@@ -306,23 +294,14 @@ static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* re
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
-  const bool fused = ln != nullptr && pwdw_supported(ctx, C);   // norm2 -> pointwise1 -> depthwise -> GELU in one kernel
-  void* h = A.elems((size_t)B * P * 2 * C, ctx.dtype);
-  if (fused) {
-    if (!ctx.dry) {
-      const double px = (double)B * P;
-      ScopedLaunch sl(RF_K_DW_GELU, px * 3.0 * C * 2.0, px * (4.0 * C * C + 36.0 * C));
-      if (!launch_pw1_dw_fused(ctx, xin, pb.pw1_wf, pb.pw1_cs, pb.pw1_bf, ln->stats, ln->npart, pb.ffn_dw_w, pb.ffn_dw_b, h, B,
-                               H, W, C))
-        recorder().last_cuda_error = (int)cudaErrorNotSupported;
-    }
-  } else {
-    void* hpre = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+  void* hpre = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+  {
     GemmP g1 = gemm_rows(xin, C, ln ? pb.pw1_wf : pb.pw1_w, ln ? pb.pw1_bf : pb.pw1_b, hpre, 2 * C, B, P, RF_K_GEMM_PW1);
     if (ln) { g1.ln_stats = ln->stats; g1.ln_npart = ln->npart; g1.ln_cs = pb.pw1_cs; g1.ln_C = C; g1.ln_eps = 1e-5f; }
     launch_gemm(ctx, g1);
-    launch_dwconv(ctx, hpre, pb.ffn_dw_w, pb.ffn_dw_b, h, 1, B, H, W, 2 * C, RF_K_DW_GELU);
   }
+  void* h = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+  launch_dwconv(ctx, hpre, pb.ffn_dw_w, pb.ffn_dw_b, h, 1, B, H, W, 2 * C, RF_K_DW_GELU);
   GemmP g = gemm_rows(h, 2 * C, pb.pw2_w, pb.pw2_b, out, C, B, P, RF_K_GEMM_PW2);
   g.R = resid; g.ldr = C;
   launch_gemm(ctx, g);

@@ -66,6 +66,19 @@ struct TcParams {
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int n) { return make_idesc_m128(n); }
+// K-major operand tile with rows of bk bf16: bk = 64 -> SWIZZLE_128B (8-row atoms of 1024 B), bk = 32 -> SWIZZLE_64B
+// (8-row atoms of 512 B); cute::UMMA::LayoutType 2 / 4
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
+  if (bk == 64) return make_sw128_desc(smem_addr);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;        // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
