@@ -278,8 +278,14 @@ def run_ours(args):
     else:
         achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
+    # DRAM traffic of that kernel per launch, from the committed ncu capture of the same workload (null if not captured)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.size}_{args.precision}.json")
+    if args.variant == "flca" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top_name, {}).get("dram_bytes_per_launch")
     roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
-                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=None)
+                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=traffic,
+                algorithmic_per_launch=(top["flops"] if is_tensor else top["bytes"]) / top["n"])
     breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])
 
     frames_total = args.steps * B * world
