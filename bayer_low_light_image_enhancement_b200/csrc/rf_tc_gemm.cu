@@ -450,11 +450,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       int oy = 0, ox = 0;
       const i64 orow = row_of(tc, row_ok, oy, ox);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      constexpr bool STAGED = OM == OMODE_ROWS || OM == OMODE_UNSHUFFLE;   // output tile staged in smem, TMA store
       const int yq = ti % p.nbuf;
       const uint32_t srow = sY + yq * y_bytes + (uint32_t)r * 128u;   // this row in slab 0 of the staging buffer
       mbar_wait_sleep(tfull_bar(acc), u & 1);
       tc_fence_after();
-      if (OM == OMODE_ROWS) {
+      if (STAGED) {
         if (HR) {
           mbar_wait_sleep(yfull_bar(yq), (ti / p.nbuf) & 1); // this tile's residual has landed in the staging buffer
         } else {
@@ -472,7 +473,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         const int n = n0 + c;
         const int nvalid = p.N - n;          // < 16 only in the last chunk when N % 16 == 8
         if (nvalid <= 0) return;
-        if (OM != OMODE_ROWS && !row_ok) return;              // (rows mode: TMA clips rows outside the tensor)
+        if (OM != OMODE_ROWS && OM != OMODE_UNSHUFFLE && !row_ok) return;   // (staged modes: TMA clips outside the tensor)
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -581,10 +582,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           for (int j = 0; j < 8; ++j) o8[j] = f[8 + j];
           store8(p.Y + dst + 8, o8);
         } else {
-          const i64 dst = (((i64)b * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1)) * p.ldy + 2 * (oy & 1) + (ox & 1);
+          // pixel-unshuffle: source pixel (rty, rtx) of the patch feeds output pixel (rty/2, rtx/2) of the (th/2 x tw/2)
+          // output tile, channel n*4 + 2*(rty&1) + (rtx&1).  The output tile is staged as 64-channel slabs of 128-byte
+          // rows (SWIZZLE_128B over the output-pixel index) and written with TMA instead of 2-byte scattered stores.
+          const int opix = (rty >> 1) * (p.tw >> 1) + (rtx >> 1);
+          const int sub = 2 * (rty & 1) + (rtx & 1);
+          const uint32_t obase = sY + yq * y_bytes + (uint32_t)opix * 128u;
+          const uint32_t osw = (uint32_t)(opix & 7);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) p.Y[dst + (i64)(n + j) * 4] = __float2bfloat16_rn(f[j]);
+          for (int j = 0; j < 16; ++j) {
+            if (j < nvalid) {
+              const int ch = (c + j) * 4 + sub;                     // channel inside this N tile's 4*BN output channels
+              const uint32_t a = obase + (uint32_t)(ch >> 6) * 16384u + ((((uint32_t)(ch & 63) >> 3) ^ osw) << 4) +
+                                 (uint32_t)(ch & 7) * 2u;
+              const __nv_bfloat16 hv = __float2bfloat16_rn(f[j]);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+            }
+          }
         }
       };
       // two chunks per TMEM round trip (32 accumulator registers in flight)
@@ -601,7 +615,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (OM == OMODE_ROWS) {
+      if (STAGED) {
         if (ST && half == 1)
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sStat + 8u * r), "f"(st_sum), "f"(st_sq) : "memory");
         fence_proxy_async();                               // staged tile (generic stores) -> TMA store (async proxy)
@@ -613,10 +627,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         }
         if (warp == 2 && lane == 0) {
           const uint32_t sYq = sY + yq * y_bytes;
-          for (int sl = 0; sl < p.nslab; ++sl) {
-            if (n0 + sl * 64 >= p.N) break;
-            if (p.amode == AMODE_CONV3) tma_store_4d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.px0, tc.py0, b);
-            else tma_store_3d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.m0, b);
+          if (OM == OMODE_UNSHUFFLE) {
+            for (int sl = 0; sl < p.nslab; ++sl) {
+              if (4 * n0 + sl * 64 >= 4 * p.N) break;
+              tma_store_4d(&mapY, sYq + sl * 16384u, 4 * n0 + sl * 64, tc.px0 >> 1, tc.py0 >> 1, b);
+            }
+          } else {
+            for (int sl = 0; sl < p.nslab; ++sl) {
+              if (n0 + sl * 64 >= p.N) break;
+              if (p.amode == AMODE_CONV3) tma_store_4d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.px0, tc.py0, b);
+              else tma_store_3d(&mapY, sYq + sl * 16384u, n0 + sl * 64, tc.m0, b);
+            }
           }
           tma_store_commit();
         }
@@ -624,7 +645,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       ++ti;
     }
   }
-  if (OM == OMODE_ROWS && warp == 2 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's reads
+  if ((OM == OMODE_ROWS || OM == OMODE_UNSHUFFLE) && warp == 2 && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -835,8 +856,9 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   const int BK = (kmax <= 32 && g.omode != OMODE_ATOMIC_F32) ? 32 : 64;
   p.bk = BK;
   const int kswz = BK * 2;
-  p.tma_store = (g.omode == OMODE_ROWS && g.ldy % 8 == 0 && (!g.R || g.ldr % 8 == 0)) ? 1 : 0;
-  p.nslab = p.tma_store ? cdiv(BN, 64) : 0;
+  const bool unshuf = g.omode == OMODE_UNSHUFFLE && g.amode == AMODE_CONV3 && !(g.H & 1) && !(g.W & 1) && g.ldy % 8 == 0;
+  p.tma_store = ((g.omode == OMODE_ROWS && g.ldy % 8 == 0 && (!g.R || g.ldr % 8 == 0)) || unshuf) ? 1 : 0;
+  p.nslab = p.tma_store ? cdiv(unshuf ? 4 * BN : BN, 64) : 0;
   p.r_tma = (p.tma_store && g.R != nullptr) ? 1 : 0;
   int grid_x;
   if (g.amode == AMODE_CONV3) {
@@ -870,7 +892,13 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const i64 sW[3] = {1, Cin, (i64)9 * Cin};
     const int bW[3] = {BK, 1, BN};
     if (!make_map_ex(&mW, g.Wt, 3, dW, sW, bW, 2, kswz)) return -1;
-    if (p.tma_store) {
+    if (unshuf) {
+      // output [B, H/2, W/2, 4N]: one (th/2 x tw/2)-pixel box of 64 channels per slab
+      const i64 dY[4] = {4 * (i64)g.N, g.W / 2, g.H / 2, g.B};
+      const i64 sY[4] = {1, g.ldy, g.ldy * (g.W / 2), g.ldy * (g.W / 2) * (g.H / 2)};
+      const int bY[4] = {64, p.tw / 2, p.th / 2, 1};
+      if (!make_map(&mY, g.Y, 4, dY, sY, bY)) return -1;
+    } else if (p.tma_store) {
       const i64 dY[4] = {g.N, g.W, g.H, g.B};
       const i64 sY[4] = {1, g.ldy, g.ldy * g.W, g.ldy * g.W * g.H};
       const int bY[4] = {64, p.tw, p.th, 1};
@@ -1023,7 +1051,10 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   }
   if (ln || g.act != ACT_NONE || g.R) return -1;
   if (g.omode == OMODE_CONVT) RF_TC_LAUNCH(OMODE_CONVT, false, false, false, ACT_NONE);
-  if (g.omode == OMODE_UNSHUFFLE) RF_TC_LAUNCH(OMODE_UNSHUFFLE, false, false, false, ACT_NONE);
+  if (g.omode == OMODE_UNSHUFFLE) {
+    if (!p.tma_store) return -1;
+    RF_TC_LAUNCH(OMODE_UNSHUFFLE, false, false, false, ACT_NONE);
+  }
   if (g.omode == OMODE_ATOMIC_F32) RF_TC_LAUNCH(OMODE_ATOMIC_F32, false, false, false, ACT_NONE);
   if (g.omode == OMODE_HEAD && g.N == 16 && g.amode == AMODE_CONV3) RF_TC_LAUNCH(OMODE_HEAD, false, false, false, ACT_NONE);
 #undef RF_TC_LAUNCH
