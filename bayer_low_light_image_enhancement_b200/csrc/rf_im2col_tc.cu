@@ -142,7 +142,9 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     decode(t0 + j * tstep, b, ty, tx);
     const int gs = j % IT_NGS, fs = j % IT_NF;
     mbar_expect_tx(g_bar(gs), IT_PATCH_BYTES);
-    tma_load_4d(sG + gs * IT_PATCH_STRIDE, &mapG, g_bar(gs), 0, tx * IT_TW - 1, ty * IT_TH - 1, b);
+    // (x, 8 bf16) is one flattened dimension of the map: a patch row is ONE 160-byte line instead of ten 16-byte ones
+    // (TMA time goes with the number of lines); element-wise out-of-bounds fill keeps the zero padding exact
+    tma_load_3d(sG + gs * IT_PATCH_STRIDE, &mapG, g_bar(gs), (tx * IT_TW - 1) * 8, ty * IT_TH - 1, b);
     if (MODULATE) {
       mbar_expect_tx(f_bar(fs), 128u * p.row_bytes);
       tma_load_4d(sF + fs * 16384, &mapIn, f_bar(fs), chunk * p.Cc, tx * IT_TW, ty * IT_TH, b);
@@ -349,10 +351,10 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   while (cols < N) cols *= 2;
   p.tmem_cols = cols;
   CUtensorMap mG, mIn, mOut;
-  const i64 dg[4] = {8, W, H, B};
-  const i64 sg[4] = {1, 8, (i64)8 * W, (i64)8 * W * H};
-  const int bg[4] = {8, IT_PITCH, IT_TH + 2, 1};
-  if (!make_map_ex(&mG, G16, 4, dg, sg, bg, 2, 0)) return false;
+  const i64 dg[3] = {(i64)8 * W, H, B};
+  const i64 sg[3] = {1, (i64)8 * W, (i64)8 * W * H};
+  const int bg[3] = {8 * IT_PITCH, IT_TH + 2, 1};
+  if (!make_map_ex(&mG, G16, 3, dg, sg, bg, 2, 0)) return false;
   const i64 d[4] = {C, W, H, B};
   const i64 st[4] = {1, C, (i64)C * W, (i64)C * W * H};
   const int bx[4] = {Cc, IT_TW, IT_TH, 1};

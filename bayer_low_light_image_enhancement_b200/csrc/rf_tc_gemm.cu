@@ -117,7 +117,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
 // Persistent, warp-specialised: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer
 // runs ahead across tile boundaries through the smem ring; the accumulator is double-buffered in tensor memory so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-template <int OM, bool LN, bool HR, bool ST, int ACT>
+template <int OM, bool LN, bool HR, bool ST, int ACT, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
@@ -128,7 +128,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   const uint32_t a_bytes = TC_BM * 2u * p.bk, w_bytes = (uint32_t)p.BN * 2u * p.bk;
   const uint32_t halo_stride = ((uint32_t)p.halo_bytes + 127u) & ~127u;
   const uint32_t sA = base;
-  const uint32_t sW = base + (p.halo ? (((uint32_t)(p.nh + p.nt) * halo_stride + 1023u) & ~1023u) : p.stages * a_bytes);
+  const uint32_t sW = base + (HALO ? (((uint32_t)(p.nh + p.nt) * halo_stride + 1023u) & ~1023u) : p.stages * a_bytes);
   const uint32_t sT = sA + (uint32_t)p.nh * halo_stride;   // halo conv: re-laid-out patches
   const uint32_t sY = sW + (p.w_resident ? 0u : p.stages * w_bytes);            // 1024-aligned (a_bytes, w_bytes are multiples of 1024)
   const uint32_t y_bytes = (uint32_t)p.nslab * 16384u;
@@ -145,6 +145,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   auto afull_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 13 + q); };
   auto aempty_bar = [&](int q) { return bars + 8u * (2 * TC_MAX_STAGES + 17 + q); };
   const uint32_t tmem_slot = bars + 8u * (2 * TC_MAX_STAGES + 21);
+  const uint32_t sDesc = bars + 8u * (2 * TC_MAX_STAGES + 22);   // halo conv: precomputed UMMA descriptor pairs (<= 1 KB)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,19 +181,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0 && p.halo) {
-    // ================= halo conv: TMA producer + patch re-layout (whole warp) =================
-    // lane 0 keeps nh patch loads in flight; all 32 lanes re-lay every landed patch from pixel-major (what one TMA box
-    // delivers) to channel-chunk-major [Cin/8][pixel][16 B], the no-swizzle K-major UMMA layout the MMA warp reads
-    const int nch = p.K1 >> 3;                   // 8-channel (16-byte) chunks per pixel
-    const int items = p.npix * nch;
-    const int inc_q = 32 / nch, inc_c = 32 - inc_q * nch;
-    const int q0 = lane / nch, c0 = lane - q0 * nch;
-    auto issue = [&](int t, int slot) {          // lane 0 only
-      const TileCoord tn = decode_tile(p, t);
-      mbar_expect_tx(full_bar(slot), (uint32_t)p.halo_bytes);
-      tma_load_4d(sA + slot * halo_stride, &mapA1, full_bar(slot), 0, tn.px0 - 1, tn.py0 - 1, tn.b);
-    };
+  if (warp == 0 && HALO) {
+    // ================= halo conv: TMA producer =================
+    // keeps nh patch loads in flight; the patches are re-laid-out by the epilogue warps (256 threads, a few 16-byte units
+    // each), which release the landing slot through empty_bar
     if (lane == 0) {
       if (p.w_resident) {
         const int nkb_all = p.taps * p.kb1;
@@ -202,34 +194,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           tma_load_3d(sWres + i * w_bytes, &mapW, wres_bar, cb * p.bk, tap, 0);
         }
       }
-      int t = blockIdx.x;
-      for (int j = 0; j < p.nh && t < p.total_tiles; ++j, t += gridDim.x) issue(t, j);
-    }
-    int sh = 0, wh = 0, st = 0, wt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      mbar_wait(full_bar(sh), wh & 1);                       // the patch has landed (TMA, pixel-major)
-      if (wt > 0) mbar_wait(aempty_bar(st), (wt - 1) & 1);   // the destination buffer has been consumed by the MMAs
-      const uint32_t src = sA + sh * halo_stride + (uint32_t)lane * 16u, dst = sT + st * halo_stride;
-      int q = q0, c8 = c0;
-      for (int it = lane; it < items; it += 32) {
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "r"(src + (uint32_t)(it - lane) * 16u));
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(c8 * p.npix + q) * 16u), "r"(v.x),
-                     "r"(v.y), "r"(v.z), "r"(v.w)
-                     : "memory");
-        q += inc_q; c8 += inc_c;
-        if (c8 >= nch) { c8 -= nch; ++q; }
+      int s = 0, wrap = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tn = decode_tile(p, t);
+        if (wrap > 0) mbar_wait(empty_bar(s), (wrap - 1) & 1);
+        mbar_expect_tx(full_bar(s), (uint32_t)p.halo_bytes);
+        tma_load_4d(sA + s * halo_stride, &mapA1, full_bar(s), 0, tn.px0 - 1, tn.py0 - 1, tn.b);
+        if (++s == p.nh) { s = 0; ++wrap; }
       }
-      fence_proxy_async();                                   // generic stores -> tensor-core (async proxy) reads
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(afull_bar(st));
-        const int tn = t + p.nh * (int)gridDim.x;            // slot sh is free again: refill it nh tiles ahead
-        if (tn < p.total_tiles) issue(tn, sh);
-      }
-      if (++sh == p.nh) { sh = 0; ++wh; }
-      if (++st == p.nt) { st = 0; ++wt; }
     }
   } else if (warp == 0) {
     // ================= TMA producer =================
@@ -305,6 +277,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.BN);
       int s = 0, wrap = 0, ti = 0;
+      if (HALO) {
+        // table of (A descriptor relative to the patch buffer, B descriptor) for the 9 taps x Cin/16 k-steps
+        const uint64_t dbase0 = ((uint64_t)((uint32_t)(p.npix * 16) >> 4) << 16) | ((uint64_t)((uint32_t)(p.pitch * 16) >> 4) << 32) |
+                                ((uint64_t)1 << 46);
+        const int ksteps = p.K1 >> 4, kpb = p.bk >> 4;
+        const uint64_t wdesc0 = make_kmajor_desc(sWres, p.bk);
+        const uint32_t wstep = w_bytes >> 4;
+        int i = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - 3 * dy;
+          for (int kk = 0; kk < ksteps; ++kk, ++i) {
+            const uint64_t ad = dbase0 | (uint64_t)(uint32_t)((dy * p.pitch + dx) + 2 * kk * p.npix);
+            const uint64_t bd = wdesc0 + (uint64_t)((tap * p.kb1 + kk / kpb) * wstep + 2u * (kk % kpb));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sDesc + (uint32_t)i * 16u), "r"((uint32_t)ad),
+                         "r"((uint32_t)(ad >> 32)), "r"((uint32_t)bd), "r"((uint32_t)(bd >> 32))
+                         : "memory");
+          }
+        }
+      }
       if (p.w_resident) {
         mbar_wait(wres_bar, 0);
         tc_fence_after();
@@ -318,7 +309,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
-        if (p.halo) {
+        if (HALO) {
           // nine taps x Cin/16 k-steps straight out of the re-laid-out patch: rows = pixels (8-row groups = patch rows,
           // SBO = pitch*16 B), the two 8-channel chunks of a k-step are LBO = npix*16 B apart, no swizzle
           mbar_wait(afull_bar(s), wrap & 1);
@@ -326,21 +317,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           const uint32_t At = sT + s * halo_stride;
           const uint64_t dbase = ((uint64_t)((uint32_t)(p.npix * 16) >> 4) << 16) | ((uint64_t)((uint32_t)(p.pitch * 16) >> 4) << 32) |
                                  ((uint64_t)1 << 46);
-          const int ksteps = p.K1 >> 4, kpb = p.bk >> 4;      // k-steps per tap / per resident W block
-          const uint64_t wdesc0 = make_kmajor_desc(sWres, p.bk);
-          const uint32_t wstep = w_bytes >> 4, kstep_a = (uint32_t)(2 * p.npix);   // descriptor address units (16 B)
-          uint32_t a_tap = (At & 0x3FFFF) >> 4, wblk = 0, first = 0;
-          int dxc = 0;
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t a_k = a_tap;
-            int kk = 0;
-            for (int cb = 0; cb < p.kb1; ++cb, wblk += wstep) {
-              for (int k = 0; k < kpb && kk < ksteps; ++k, ++kk, a_k += kstep_a) {
-                umma_f16(d_tmem, dbase | (uint64_t)a_k, wdesc0 + wblk + 2u * k, idesc, first);
-                first = 1u;
-              }
-            }
-            if (++dxc == 3) { dxc = 0; a_tap += (uint32_t)(p.pitch - 2); } else { a_tap += 1u; }
+          // descriptor pairs come from a table built once (below): the single issuing thread's instruction chain per
+          // MMA was the critical path of the whole CTA (~200 cycles per MMA when computed inline)
+          const int nmma = 9 * (p.K1 >> 4);
+          const uint32_t aoff = (At & 0x3FFFF) >> 4;
+          for (int i = 0; i < nmma; ++i) {
+            uint32_t alo, ahi, blo, bhi;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(alo), "=r"(ahi), "=r"(blo), "=r"(bhi)
+                         : "r"(sDesc + (uint32_t)i * 16u));
+            const uint64_t adesc = ((uint64_t)ahi << 32) | (uint64_t)(alo + aoff);
+            const uint64_t bdesc = ((uint64_t)bhi << 32) | (uint64_t)blo;
+            umma_f16(d_tmem, adesc, bdesc, idesc, i ? 1u : 0u);
           }
           umma_commit(aempty_bar(s));         // the patch buffer is free when these MMAs retire
           if (++s == p.nt) { s = 0; ++wrap; }
@@ -423,11 +410,45 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
       }
       return v;
     };
+    // halo conv: the 8 epilogue warps re-lay patch j (pixel-major, as TMA delivers it) into the channel-chunk-major
+    // [Cin/8][pixel][16 B] form (the no-swizzle K-major UMMA layout) one tile AHEAD of their epilogue, so the MMAs of tile
+    // j run under the epilogue of tile j-1
+    const int etid = threadIdx.x - 64;             // 0..255 over the epilogue warps
+    int rl_j = 0, rl_sh = 0, rl_wh = 0, rl_st = 0, rl_wt = 0;
+    const int rl_total = HALO ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto relayout_next = [&]() {
+      if (rl_j >= rl_total) return;                // (uniform over the epilogue warps)
+      const int nch_log2 = p.K1 == 64 ? 3 : (p.K1 == 32 ? 2 : 1);
+      const int nch = 1 << nch_log2, items = p.npix << nch_log2;
+      mbar_wait_sleep(full_bar(rl_sh), rl_wh & 1);                        // the patch has landed
+      if (rl_wt > 0) mbar_wait_sleep(aempty_bar(rl_st), (rl_wt - 1) & 1); // its destination has been consumed by the MMAs
+      const uint32_t src = sA + rl_sh * halo_stride, dst = sT + rl_st * halo_stride;
+      for (int it = etid; it < items; it += 256) {
+        const int q = it >> nch_log2, c8 = it & (nch - 1);
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(src + (uint32_t)it * 16u));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(c8 * p.npix + q) * 16u), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      }
+      fence_proxy_async();                                   // generic stores -> tensor-core (async proxy) reads
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (etid == 0) {
+        mbar_arrive(afull_bar(rl_st));
+        mbar_arrive(empty_bar(rl_sh));
+      }
+      ++rl_j;
+      if (++rl_sh == p.nh) { rl_sh = 0; ++rl_wh; }
+      if (++rl_st == p.nt) { rl_st = 0; ++rl_wt; }
+    };
+    if (HALO) relayout_next();                   // tile 0
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       if (tc.nkb <= 0) continue;
       const int acc = ti & 1, u = ti >> 1;
       const int b = tc.b, n0 = tc.n0;
+      if (HALO) relayout_next();                 // tile ti + 1
       // the storing thread hands the staging buffer of the previous tile back to the producer as soon as its TMA store
       // has finished READING it -- before waiting for this tile's accumulator, so that the producer (which fetches the
       // residual of a later tile into that buffer before issuing that tile's operands) can never wait on this tile
@@ -851,7 +872,9 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     const char* e = getenv("RAWFORMER_B200_NO_HALO");
     halo_ok = (e && e[0] == '1') ? 0 : 1;
   }
-  p.halo = (halo_ok && g.amode == AMODE_CONV3 && kmax <= 64 && kmax % 16 == 0 && g.N <= 256 &&
+  const bool halo_shape = (g.omode == OMODE_ROWS && g.act == ACT_LRELU && !g.R && !g.ln_stats) || g.omode == OMODE_UNSHUFFLE ||
+                          g.omode == OMODE_HEAD;
+  p.halo = (halo_ok && halo_shape && g.amode == AMODE_CONV3 && (kmax == 16 || kmax == 32 || kmax == 64) && g.N <= 256 &&
             (size_t)9 * BN * kmax * 2 <= 81920) ? 1 : 0;
   const int BK = (kmax <= 32 && g.omode != OMODE_ATOMIC_F32) ? 32 : 64;
   p.bk = BK;
@@ -958,7 +981,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   int cols = 32;
   while (cols < BN) cols *= 2;
   const size_t staging1 = (size_t)p.nslab * 16384;
-  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 22) + (p.w_resident ? wres_bytes : 0);
+  const size_t fixed = 1024 + 1024 + 8 * (2 * TC_MAX_STAGES + 22) + 1024 + (p.w_resident ? wres_bytes : 0);
   const int nkb_tile = p.taps * p.kb1 + p.kb2;
   const int want = nkb_tile > 1 ? 3 : 2;
   static int nbuf_r = -1;                 // debugging aid: RAWFORMER_B200_RBUF=2|3 (residual staging depth)
@@ -1019,10 +1042,10 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   const bool ln = g.ln_stats != nullptr, hr = p.r_tma != 0;
   bool st = p.stats_out != nullptr;
   if (ln && (!g.ln_cs || !g.bias)) return -1;
-#define RF_TC_LAUNCH(OM, LN, HR, ST, ACT)                                                                                   \
+#define RF_TC_LAUNCH_H(OM, LN, HR, ST, ACT, HALO)                                                                         \
   do {                                                                                                                      \
     static bool attr = false;                                                                                               \
-    auto kern = k_tc_gemm<OM, LN, HR, ST, ACT>;                                                                             \
+    auto kern = k_tc_gemm<OM, LN, HR, ST, ACT, HALO>;                                                                       \
     if (!attr) {                                                                                                            \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;   \
       attr = true;                                                                                                          \
@@ -1030,6 +1053,14 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
     ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);                                                              \
     kern<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, mY, mR, p);                                                  \
     return p.stats_out ? p.tiles_n : 0;                                                                                     \
+  } while (0)
+  // the halo-conv code (patch re-layout in the epilogue warps, descriptor-table MMA loop) is compiled only into the
+  // three shapes that use it, so the row-GEMM instantiations stay lean
+#define RF_TC_LAUNCH(OM, LN, HR, ST, ACT) RF_TC_LAUNCH_H(OM, LN, HR, ST, ACT, false)
+#define RF_TC_LAUNCH_CONV(OM, ACT)                          \
+  do {                                                      \
+    if (p.halo) RF_TC_LAUNCH_H(OM, false, false, false, ACT, true); \
+    RF_TC_LAUNCH_H(OM, false, false, false, ACT, false);    \
   } while (0)
   if (g.omode == OMODE_ROWS) {
     if (!p.tma_store) return -1;
@@ -1044,7 +1075,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       if (st) RF_TC_LAUNCH(OMODE_ROWS, false, false, true, ACT_NONE);
       RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_NONE);
     }
-    if (g.act == ACT_LRELU && !hr) RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_LRELU);
+    if (g.act == ACT_LRELU && !hr) RF_TC_LAUNCH_CONV(OMODE_ROWS, ACT_LRELU);
     if (g.act == ACT_RELU && !hr) RF_TC_LAUNCH(OMODE_ROWS, false, false, false, ACT_RELU);
     if (g.act == ACT_TANH_RES && hr) RF_TC_LAUNCH(OMODE_ROWS, false, true, false, ACT_TANH_RES);
     return -1;
@@ -1053,11 +1084,13 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   if (g.omode == OMODE_CONVT) RF_TC_LAUNCH(OMODE_CONVT, false, false, false, ACT_NONE);
   if (g.omode == OMODE_UNSHUFFLE) {
     if (!p.tma_store) return -1;
-    RF_TC_LAUNCH(OMODE_UNSHUFFLE, false, false, false, ACT_NONE);
+    RF_TC_LAUNCH_CONV(OMODE_UNSHUFFLE, ACT_NONE);
   }
   if (g.omode == OMODE_ATOMIC_F32) RF_TC_LAUNCH(OMODE_ATOMIC_F32, false, false, false, ACT_NONE);
-  if (g.omode == OMODE_HEAD && g.N == 16 && g.amode == AMODE_CONV3) RF_TC_LAUNCH(OMODE_HEAD, false, false, false, ACT_NONE);
+  if (g.omode == OMODE_HEAD && g.N == 16 && g.amode == AMODE_CONV3) RF_TC_LAUNCH_CONV(OMODE_HEAD, ACT_NONE);
 #undef RF_TC_LAUNCH
+#undef RF_TC_LAUNCH_H
+#undef RF_TC_LAUNCH_CONV
   return -1;
 }
 
