@@ -453,8 +453,49 @@ class RawFormer(_Op):
             raise ValueError(f"raw frame {h}x{w}: H and W must be non-zero multiples of 16")
         return x
 
+    # -- CUDA-graph replay ------------------------------------------------------------------------
+    def enable_cuda_graphs(self, on=True, max_graphs=8):
+        """Replay the forward as ONE CUDA graph per (input buffer, shape) instead of ~130 kernel launches per frame.
+
+        The graph is captured the first time a given input tensor (same storage, same shape) is seen and replayed on the
+        current stream afterwards; the result is the graph's own output tensor, so it is OVERWRITTEN by the next call
+        with the same input buffer (copy it, or hand the model one of several input slots -- ``FramePipeline`` does).
+        Worth it for streams of frames: the whole frame is one launch, so driver-side stalls (monitoring tools polling the
+        GPU, a busy host) can no longer starve the GPU between kernels."""
+        self._graphs_on = bool(on)
+        self._graph_cap = int(max_graphs)
+        self._graphs = {}
+        return self
+
+    def _forward_graph(self, x):
+        dt = self._dtype()
+        blob = self.packed_weights(x.device, dt)
+        key = (x.data_ptr(), tuple(x.shape), dt, blob.data_ptr())
+        hit = self._graphs.get(key)
+        if hit is None:
+            if len(self._graphs) >= self._graph_cap:
+                self._graphs.clear()
+            cur = torch.cuda.current_stream(x.device)
+            side = torch.cuda.Stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # eager warm-up: workspace, function attributes, lazy module loading
+                self._forward_eager(x)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_eager(x)
+            hit = (g, out, x)                      # keeps the captured input storage alive
+            self._graphs[key] = hit
+        hit[0].replay()
+        return hit[1]
+
     def forward(self, x):
         x = self._check_input(x)
+        if getattr(self, "_graphs_on", False):
+            return self._forward_graph(x)
+        return self._forward_eager(x)
+
+    def _forward_eager(self, x):
         b, _, h, w = x.shape
         lib = _lib.load()
         dt = self._dtype()

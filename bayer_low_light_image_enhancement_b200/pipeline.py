@@ -11,21 +11,27 @@ class FramePipeline:
     """``submit(x_host, out_host)`` enqueues H2D copy -> forward -> D2H copy of one batch of frames and returns at once;
     ``flush()`` waits for everything submitted.  ``x_host`` [B,1,H,W] and ``out_host`` [B,3,H,W] should be pinned fp32
     tensors; ``out_host`` is valid after ``flush()`` (or after ``wait(ticket)``).  Frames are processed in order;
-    ``depth`` device-side slots let copy-in of frame i+1 and copy-out of frame i-1 run under the forward of frame i."""
+    ``depth`` device-side slots let copy-in of frame i+1 and copy-out of frame i-1 run under the forward of frame i.
+    With ``graphs`` (default) the model replays one CUDA graph per slot instead of launching ~130 kernels per frame."""
 
-    def __init__(self, model, depth: int = 2):
+    def __init__(self, model, depth: int = 2, graphs: bool = True):
         p = next(model.parameters(), None)
         if p is None or not p.is_cuda:
             raise RuntimeError("FramePipeline needs a model on a CUDA device (there is no CPU path)")
         self.model = model
         self.dev = p.device
         self.depth = max(1, int(depth))
-        self.s_in = torch.cuda.Stream(self.dev)
+        # copies on high-priority streams (a different stream pool than the compute stream): with the default of 8 hardware
+        # connections, three same-priority pool streams can alias one connection and the copies then serialise with the
+        # forward (seen as a bimodal 8 ms / 13 ms per frame); bench.py also raises CUDA_DEVICE_MAX_CONNECTIONS
+        self.s_in = torch.cuda.Stream(self.dev, priority=-1)
         self.s_cmp = torch.cuda.Stream(self.dev)
-        self.s_out = torch.cuda.Stream(self.dev)
+        self.s_out = torch.cuda.Stream(self.dev, priority=-1)
         self.slots = [dict(x=None, out=None, ev_in=torch.cuda.Event(), ev_cmp=torch.cuda.Event(),
                            ev_out=torch.cuda.Event(), used=False) for _ in range(self.depth)]
         self.n = 0
+        if graphs and hasattr(model, "enable_cuda_graphs"):
+            model.enable_cuda_graphs(True, max_graphs=max(8, 2 * self.depth))   # one graph per input slot
 
     def start_after(self, event: torch.cuda.Event):
         """Make the pipeline's streams wait for ``event`` (e.g. a timing event recorded on the current stream)."""

@@ -25,6 +25,8 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# one hardware queue per stream: the copy streams of FramePipeline must not alias the compute stream's connection
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -111,7 +113,10 @@ class ClockSampler:
                 self.samples.append((sm, rs))
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.02)
+            # sparse on purpose: about one NVML query in fifteen stalled for ~100 ms and stalled the GPU work with it (a
+            # 150 ms timed region read 10.1 instead of 7.5 ms/step), so the sampler covers the load window = warm-up steps
+            # + timed steps (the same kernels back to back) with a few queries instead of many inside the timed region
+            self.stop_flag.wait(0.25)
 
     def start(self):
         import threading
@@ -239,6 +244,8 @@ def run_ours(args):
     model = cls(dim=dim, precision=args.precision)
     model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)  # random-init weights
     model = model.to(dev).eval()
+    if not args.no_graph:
+        model.enable_cuda_graphs()      # one graph launch per frame (public API; the per-kernel profile below stays eager)
     B = args.frames
     gen = torch.Generator().manual_seed(rank)
     x_host = torch.rand(B, 1, H_RAW, W_RAW, generator=gen).pin_memory()
@@ -265,17 +272,25 @@ def run_ours(args):
         while time.perf_counter() - t_pre < 1.5:
             model(x_dev)
             torch.cuda.synchronize()
-        for _ in range(args.warmup):
-            model(x_dev)
         sampler = ClockSampler(local)
         barrier()
         if rank == 0:
-            sampler.start()
+            sampler.start()                       # load window: from the first warm-up step to the end of the timed region
+        t_load = time.perf_counter()
+        nw = 0
+        while nw < args.warmup or time.perf_counter() - t_load < 0.6:
+            model(x_dev)
+            nw += 1
+            if nw % 8 == 0:
+                torch.cuda.synchronize()
+        barrier()
         lib.rf_reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host0 = time.perf_counter()
         for _ in range(args.steps):
             out = model(x_dev)
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
         e1.record()
         barrier()
         launches = lib.rf_launch_count()
@@ -358,12 +373,14 @@ def run_ours(args):
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "precision": args.precision,
                    "parallelism": f"image-parallel x{world}" if world > 1 else "single GPU",
-                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush"},
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush",
+                   "launch": "eager" if args.no_graph else "one CUDA graph per frame (model.enable_cuda_graphs)"},
         "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                 "api": "FramePipeline.submit (H2D, forward, D2H of neighbouring steps overlapped on three streams)",
                 "host_binding": numa},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "clocks": clocks,
         "roofline": roof,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in breakdown},
@@ -388,6 +405,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of one CUDA graph per frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

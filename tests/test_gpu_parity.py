@@ -394,3 +394,27 @@ def test_frame_pipeline(rf):
         own = psnr(o, direct[i], rng)
         others = max(psnr(o, direct[j], rng) for j in range(len(frames)) if j != i)
         assert own >= 45.0 and own > others + 15.0, f"frame {i}: PSNR vs own direct result {own:.1f} dB, best other {others:.1f} dB"
+
+
+def test_cuda_graph_replay(rf):
+    """enable_cuda_graphs(): the captured forward reproduces the eager forward, replays follow new input data in the
+    captured buffer, and a second input buffer gets its own graph."""
+    m = rf.RawFormer(dim=32, precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=6, scale=1.5))
+    m = m.to(dev()).eval()
+    xa = torch.rand(1, 1, 96, 160, device=dev())
+    xb = torch.rand(1, 1, 96, 160, device=dev())
+    with torch.no_grad():
+        ea, eb = npy(m(xa)), npy(m(xb))
+        m.enable_cuda_graphs()
+        ga = npy(m(xa))                      # capture + replay
+        ga2 = npy(m(xa))                     # replay
+        xa.copy_(xb)                         # new data in the captured buffer
+        gab = npy(m(xa))
+        gb = npy(m(xb))                      # second buffer: second graph
+        m.enable_cuda_graphs(False)
+    rng = float(ea.max() - ea.min())
+    for name, got, ref in (("first", ga, ea), ("replay", ga2, ea), ("new data", gab, eb), ("second buffer", gb, eb)):
+        p = psnr(got, ref, rng)
+        assert p >= 45.0, f"{name}: graph vs eager PSNR {p:.1f} dB"
+    assert psnr(gab, ea, rng) < 40.0         # (the replay really used the new data)
