@@ -418,13 +418,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     const int rl_total = HALO ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto relayout_next = [&]() {
       if (rl_j >= rl_total) return;                // (uniform over the epilogue warps)
-      const int nch_log2 = p.K1 == 64 ? 3 : (p.K1 == 32 ? 2 : 1);
-      const int nch = 1 << nch_log2, items = p.npix << nch_log2;
+      const int nch = p.K1 >> 3, items = p.npix * nch;     // 16-byte units per pixel (2, 4, 6 or 8)
+      const bool pow2 = (nch & (nch - 1)) == 0;
+      const int nch_log2 = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
       mbar_wait_sleep(full_bar(rl_sh), rl_wh & 1);                        // the patch has landed
       if (rl_wt > 0) mbar_wait_sleep(aempty_bar(rl_st), (rl_wt - 1) & 1); // its destination has been consumed by the MMAs
       const uint32_t src = sA + rl_sh * halo_stride, dst = sT + rl_st * halo_stride;
       for (int it = etid; it < items; it += 256) {
-        const int q = it >> nch_log2, c8 = it & (nch - 1);
+        int q, c8;
+        if (pow2) { q = it >> nch_log2; c8 = it & (nch - 1); }
+        else { q = it / nch; c8 = it - q * nch; }
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                      : "r"(src + (uint32_t)it * 16u));
@@ -874,7 +877,8 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   }
   const bool halo_shape = (g.omode == OMODE_ROWS && g.act == ACT_LRELU && !g.R && !g.ln_stats) || g.omode == OMODE_UNSHUFFLE ||
                           g.omode == OMODE_HEAD;
-  p.halo = (halo_ok && halo_shape && g.amode == AMODE_CONV3 && (kmax == 16 || kmax == 32 || kmax == 64) && g.N <= 256 &&
+  p.halo = (halo_ok && halo_shape && g.amode == AMODE_CONV3 && (kmax == 16 || kmax == 32 || kmax == 48 || kmax == 64) &&
+            g.N <= 256 &&
             (size_t)9 * BN * kmax * 2 <= 81920) ? 1 : 0;
   const int BK = (kmax <= 32 && g.omode != OMODE_ATOMIC_F32) ? 32 : 64;
   p.bk = BK;
