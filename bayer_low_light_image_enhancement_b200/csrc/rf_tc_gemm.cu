@@ -1111,7 +1111,10 @@ bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
   const int nkb = (int)((P + GR_PIX - 1) / GR_PIX);
   // packed: two CTAs per SM (<= 113 KB each), ring as deep as that allows; general: one CTA per SM, 3 stages of 64 KB
   const int nst = packed == 1 ? 5 : (packed == 2 ? 3 : 3);
+  // split-K: enough CTAs to fill the machine, but at least ~24 k-blocks each (TMEM allocation, barrier set-up and the
+  // atomic read-out of the accumulator are per-CTA costs that dominated the small stages)
   int ksplit = (packed ? 4 : 2) * num_sms() / (mt * mt);
+  if (ksplit > nkb / 24) ksplit = nkb / 24;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkb) ksplit = nkb;
   const size_t smem = 1024 + (size_t)nst * (packed ? packed : 4) * GR_CHUNK + (packed == 1 ? GR_CHUNK : 0) + 8 * (2 * GR_STAGES + 2);
