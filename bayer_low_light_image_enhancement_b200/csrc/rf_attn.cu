@@ -429,7 +429,11 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
     for (int j = 0; j < c; ++j) r[j] *= inv;
   }
   __syncthreads();
-  for (int e = tid; e < C * c; e += blockDim.x) {
+  // the fold itself is split over gridDim.z CTAs (slices of the output rows n); the c x c softmax above is recomputed
+  // by each of them (it is tiny), so the 8-CTA latency chain of the large stages becomes 8 * C/32 CTAs
+  const int nper = (C + gridDim.z - 1) / gridDim.z;
+  const int nb = blockIdx.z * nper, ne = min(C, nb + nper);
+  for (int e = tid + nb * c; e < ne * c; e += blockDim.x) {
     const int n = e / c, j = e - n * c;
     const float* pw = proj_w + (i64)n * C + h * c;
     float s = 0.f;
@@ -443,11 +447,12 @@ void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature
   if (ctx.dry) return;
   const int c = C / 8;
   size_t smem = sizeof(float) * (c * (c + 1) + 2 * c);
+  const int nz = C >= 64 ? C / 32 : 1;
   ScopedLaunch sl(RF_K_ATTN_FINALIZE, 4.0 * B * C * c + (4.0 + esize(ctx.dtype)) * B * C * C, 2.0 * B * C * C * c);
   if (ctx.dtype == RF_BF16)
-    k_attn_finalize<bf16><<<dim3(8, B), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (bf16*)Mw, C);
+    k_attn_finalize<bf16><<<dim3(8, B, nz), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (bf16*)Mw, C);
   else
-    k_attn_finalize<float><<<dim3(8, B), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (float*)Mw, C);
+    k_attn_finalize<float><<<dim3(8, B, nz), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (float*)Mw, C);
 }
 
 // ---------------------------------------------------------------------------------------------
