@@ -114,3 +114,16 @@ def test_state_dict_contract():
     assert len(mk) == 310 and "down1.0.weight" in mk and "haar.filt" in mk
     assert sum(p.numel() for p in ml.parameters()) == 2_708_710
     assert rf.WaveTransformBlock is rf.Conv_Transformer
+
+
+def test_streaming_api_surface():
+    """FramePipeline / CUDA-graph mode exist on the public surface and refuse to run without a CUDA device."""
+    import pytest
+    import torch
+
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    m = rf.RawFormer(dim=32)
+    assert hasattr(m, "enable_cuda_graphs") and m.enable_cuda_graphs(False) is m
+    with pytest.raises(RuntimeError):
+        rf.FramePipeline(m)          # parameters on the CPU: there is no CPU path
