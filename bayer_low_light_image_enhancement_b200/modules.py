@@ -481,12 +481,15 @@ class RawFormer(_Op):
             with torch.cuda.stream(side):          # eager warm-up: workspace, function attributes, lazy module loading
                 self._forward_eager(x)
             cur.wait_stream(side)
+            lib = _lib.load()
+            n0 = lib.rf_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._forward_eager(x)
-            hit = (g, out, x)                      # keeps the captured input storage alive
+            hit = (g, out, x, int(lib.rf_launch_count() - n0))   # x: keeps the captured input storage alive
             self._graphs[key] = hit
         hit[0].replay()
+        self.graph_kernels_replayed = getattr(self, "graph_kernels_replayed", 0) + hit[3]   # kernel nodes executed
         return hit[1]
 
     def forward(self, x):
