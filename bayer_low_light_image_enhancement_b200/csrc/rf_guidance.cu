@@ -115,10 +115,21 @@ template <int NG>
 __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __restrict__ yh1, int H1, int W1,
                                  const float* __restrict__ LL2, const float* __restrict__ yh2, int H2, int W2,
                                  const float* __restrict__ cr, const float* __restrict__ cb, int Hy, int Wy,
-                                 float* __restrict__ G, float* sums, int Hf, int Wf) {
+                                 float* __restrict__ G, float* sums, int Hf, int Wf, uint4* __restrict__ G16a,
+                                 uint4* __restrict__ G16b) {
   i64 b = blockIdx.y;
   i64 total = (i64)Hf * Wf;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // [hi x4 | lo x4] bf16 of four fp32 maps = the 16-byte pixel of the tensor-core FLCA kernels (rf_im2col_tc.cu)
+  auto split4 = [](float a, float bq, float c, float d) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(bq), h2 = __float2bfloat16_rn(c),
+                        h3 = __float2bfloat16_rn(d);
+    __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
+    __nv_bfloat162 q0 = __floats2bfloat162_rn(a - __bfloat162float(h0), bq - __bfloat162float(h1));
+    __nv_bfloat162 q1 = __floats2bfloat162_rn(c - __bfloat162float(h2), d - __bfloat162float(h3));
+    return make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&q0),
+                      *reinterpret_cast<uint32_t*>(&q1));
+  };
   for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
     int x = (int)(idx % Wf), y = (int)(idx / Wf);
     int ya, yb, xa, xb;
@@ -141,12 +152,14 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
     v[o] = bilerp(cr + b * (i64)Hy * Wy, Hy, Wy, ya, yb, ly, xa, xb, lx);
     v[o + 1] = bilerp(cb + b * (i64)Hy * Wy, Hy, Wy, ya, yb, ly, xa, xb, lx);
     float* g = G + (b * total + idx) * NG;
+    if (G16a != nullptr) G16a[b * total + idx] = split4(v[0], v[1], v[2], v[3]);
     if (NG == 4) {
       *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
       v[6] = sqrtf(v[4] * v[4] + v[5] * v[5] + 1e-8f);  // chr_mag, ML_RF.py:172
       *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], 0.f);
+      if (G16b != nullptr) G16b[b * total + idx] = split4(v[4], v[5], v[6], 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
@@ -162,17 +175,17 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
 
 void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
                            const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
-                           int NG, float* sums, int B, int Hf, int Wf) {
+                           int NG, float* sums, int B, int Hf, int Wf, void* G16a, void* G16b) {
   if (ctx.dry) return;
   i64 total = (i64)Hf * Wf;
   unsigned gx = (unsigned)(cdivl(total, 256) < 4 * num_sms() ? cdivl(total, 256) : 4 * num_sms());
   ScopedLaunch sl(RF_K_GUIDANCE, 4.0 * NG * B * total + 4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
   if (NG == 4)
     k_guidance_stage<4><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf);
+                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b);
   else
     k_guidance_stage<8><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf);
+                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b);
 }
 
 }  // namespace rf

@@ -133,7 +133,7 @@ void launch_dwt_high(Ctx& ctx, const float* y, const float* filt16, float* LL, f
 // means (optional, ML): [B][8] sums of the NG maps over the stage (divide by Hf*Wf on use); must be zeroed.
 void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
                            const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
-                           int NG, float* sums, int B, int Hf, int Wf);
+                           int NG, float* sums, int B, int Hf, int Wf, void* G16a = nullptr, void* G16b = nullptr);
 
 // ---- FLCA (rf_flca.cu) ---------------------------------------------------------------------------------------------
 int flca_num_partials(int C, int B, i64 P);

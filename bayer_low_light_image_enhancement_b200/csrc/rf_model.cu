@@ -387,16 +387,12 @@ static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const f
     sg.sums = ctx.arena.get<float>((size_t)B * 8);
     launch_fill_f32(ctx, sg.sums, 0.f, (i64)B * 8);
   }
-  launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf);
   sg.G16 = nullptr; sg.G16b = nullptr;
-  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
+  if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {   // the [hi | lo] bf16 pixels of the tensor-core FLCA kernels, same pass
     sg.G16 = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
-    launch_split_bf16x8(ctx, sg.G, sg.G16, (i64)B * Hf * Wf, NG);
-    if (variant == RF_VARIANT_ML) {
-      sg.G16b = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
-      launch_split_bf16x8(ctx, sg.G + 4, sg.G16b, (i64)B * Hf * Wf, NG);
-    }
+    if (variant == RF_VARIANT_ML) sg.G16b = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
   }
+  launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf, sg.G16, sg.G16b);
 }
 
 struct GuidanceMaps {
