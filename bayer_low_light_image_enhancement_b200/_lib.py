@@ -54,12 +54,20 @@ class ModelWeights(C.Structure):
     ]
 
 
+class Band(C.Structure):
+    """Mirror of ``rf_band`` (row-tiled single frame)."""
+
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("row0", C.c_int), ("rows", C.c_int), ("comm", _fp * 8),
+                ("epoch", C.c_uint)]
+
+
 _lib = None
 _lock = threading.Lock()
 _inited_devices = set()
 
 _i, _sz, _f = C.c_int, C.c_size_t, C.c_float
-_BWp, _MWp = C.POINTER(BlockWeights), C.POINTER(ModelWeights)
+_BWp, _MWp, _BDp = C.POINTER(BlockWeights), C.POINTER(ModelWeights), C.POINTER(Band)
+_ubp = C.POINTER(C.c_ubyte)
 
 # name -> (restype, argtypes).  Keep in sync with include/rawformer_b200.h (tests/test_abi.py checks the symbols).
 _SIGS = {
@@ -95,6 +103,15 @@ _SIGS = {
         _i,
         [_fp, _i, _i, _i, _fp, _fp, _i, _i, _i, _fp, _sz, _fp, C.POINTER(_f), C.POINTER(_i), _i, C.POINTER(_i)],
     ),
+    "rf_band_comm_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "rf_band_comm_alloc": (_i, [_sz, C.POINTER(_fp), _ubp]),
+    "rf_band_comm_open": (_i, [_ubp, C.POINTER(_fp)]),
+    "rf_band_comm_close": (_i, [_fp]),
+    "rf_band_comm_free": (_i, [_fp]),
+    "rf_band_comm_status": (_i, [_fp, C.POINTER(_i), _fp]),
+    "rf_band_out_rows": (_i, [_BDp, C.POINTER(_i), C.POINTER(_i)]),
+    "rf_rawformer_band_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _BDp]),
+    "rf_rawformer_forward_band": (_i, [_fp, _i, _i, _i, _fp, _fp, _i, _i, _BDp, _fp, _sz, _fp]),
     "rf_kernel_name": (C.c_char_p, [_i]),
     "rf_profiled_launch_info": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rf_postprocess_u8": (_i, [_fp, _fp, _i, _i, _i, _fp]),

@@ -55,6 +55,8 @@ enum KernelId {
   RF_K_TAIL_APPLY,
   RF_K_INDEX_OP,
   RF_K_GEMM_GRAM,
+  RF_K_BAND_HALO,
+  RF_K_BAND_ALLREDUCE,
   RF_K_COUNT
 };
 
@@ -124,7 +126,29 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
+// Row-tiled single frame (BASELINE config 4): this rank owns a band of whole rows of ONE frame.  Every
+// activation of the band is a "band image" [ht + rows_in + hb][W][C]: the interior rows plus BAND_HALO halo rows towards
+// each neighbour (none at the frame border, where TMA zero fill is the convolution padding).  The kernels run on the band
+// image as if it were a frame; the halo rows of a block input are fetched from the neighbours once per Conv_Transformer
+// and lose one row of validity per 3x3 convolution of the chain (3 in the block + 1 in Downsample / the head).
+constexpr int BAND_MAX_RANKS = RF_BAND_MAX_RANKS;
+constexpr int BAND_HALO = 4;
+constexpr int BAND_MAX_SYNCS = 32;
+constexpr size_t BAND_FLAGS_OFF = 256;       // [BAND_MAX_SYNCS][BAND_MAX_RANKS] u32 arrival counters
+constexpr size_t BAND_MAIL_OFF = 4096;       // mailboxes (bump-allocated in call order, identical on all ranks)
+struct Band {
+  int rank = 0, nranks = 1;
+  char* comm[BAND_MAX_RANKS] = {};   // comm region of every rank as mapped in this process (comm[rank] is local)
+  unsigned epoch = 0;                // 1, 2, 3 ... one per forward, the same on all ranks
+  int next_sync = 0;                 // sync points used so far in this forward
+  size_t mail_off = BAND_MAIL_OFF;   // bump cursor inside the comm region
+  int ht = 0, hb = 0;                // halo rows above / below the interior
+  int rows_in = 0;                   // interior rows at the current stage
+  i64 P_full = 0;                    // pixels of the WHOLE frame at the current stage (squeeze-excite mean)
+};
+
 struct Ctx {
+  Band* band = nullptr;              // non-null: row-tiled forward
   cudaStream_t stream = 0;
   Arena arena;
   bool dry = false;   // size the arena only, launch nothing

@@ -149,6 +149,10 @@ void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const f
   double px = (double)B * H * W;
   ScopedLaunch sl(RF_K_DW_QKV_GRAM, 6.0 * px * C * esize(ctx.dtype), 54.0 * px * C);
   if (ctx.dtype == RF_BF16 && launch_dwqkv_tma(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, C)) return;
+  if (ctx.band != nullptr) {   // only the TMA kernel restricts the norms to the band's interior rows
+    recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
   else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
 }

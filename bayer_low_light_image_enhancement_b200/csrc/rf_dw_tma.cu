@@ -26,6 +26,7 @@ struct DwTmaParams {
   bf16* out;           // [B,H,W,Cn]; MODE 1: q|k [B,H,W,C2]
   bf16* vout;          // MODE 1: v [B,H,W,Cn-C2]
   float* sumsq;        // MODE 1: [B][C2]
+  int ylo, yhi;        // MODE 1: rows that contribute to sumsq (row-tiled forward: the band's interior; else 0, H)
   int H, W, Cn, C2;
   int CC, nvec, TW;    // channel chunk, 4-channel vectors per pixel of a chunk, tile width
   int tiles_x, tiles_y, nchunks, B;
@@ -174,6 +175,9 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
       const int xo = tx * p.TW + x;
       bf16* optr = obase + (((i64)b * p.H + (i64)ty * DT_TH) * p.W + xo) * ocn - 2 * opitch;   // row of output r - 2
       const unsigned rows_ok = xo < p.W ? (unsigned)min(DT_TH, p.H - ty * DT_TH) : 0u;
+      // MODE 1: tile rows [nlo, nlo + nrows) count towards the squared norms
+      const int nlo = max(p.ylo - ty * DT_TH, 0);
+      const unsigned nrows = xo < p.W ? (unsigned)max(min(DT_TH, p.yhi - ty * DT_TH) - nlo, 0) : 0u;
       float2 acc[3][2];
 #pragma unroll
       for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
@@ -210,10 +214,11 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
           h[0] = __floats2bfloat162_rn(o0.x, o0.y);
           h[1] = __floats2bfloat162_rn(o1.x, o1.y);
           if (MODE == 1) {
-            if (!ok) pk = make_uint2(0u, 0u);
             if (is_qk) {
+              // rows outside the image / the band's interior are zeroed so the norms stay exact
+              const uint2 pn = (unsigned)(r - 2 - nlo) < nrows ? pk : make_uint2(0u, 0u);
               float2 rv[2];
-              unpack_bf16x4(pk, rv);
+              unpack_bf16x4(pn, rv);
               sq[0] = fmaf(rv[0].x, rv[0].x, sq[0]);
               sq[1] = fmaf(rv[0].y, rv[0].y, sq[1]);
               sq[2] = fmaf(rv[1].x, rv[1].x, sq[2]);
@@ -244,6 +249,8 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
   DwTmaParams p;
   p.w = w; p.bias = bias; p.out = (bf16*)out; p.vout = (bf16*)vout; p.sumsq = sumsq;
   p.H = H; p.W = W; p.Cn = Cn; p.C2 = C2; p.B = B;
+  p.ylo = 0; p.yhi = H;
+  if (ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
   p.CC = CC; p.nvec = CC / 4;
   p.TW = DT_THREADS / p.nvec;
   if (p.TW > 254) p.TW = 254;

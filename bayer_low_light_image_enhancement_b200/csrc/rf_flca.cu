@@ -170,6 +170,10 @@ void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16
       recorder().last_cuda_error = (int)cudaErrorNotSupported;
     return;
   }
+  if (ctx.band != nullptr) {   // only the tensor-core kernel restricts the channel sums to the band's interior rows
+    recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   if (ctx.dtype == RF_BF16)
     run_flca_mod<bf16, 0>(ctx, feat, G, w36, abg, xmod, partial, nblk, B, Hf, Wf, C, 0, RF_K_FLCA_MOD);
   else

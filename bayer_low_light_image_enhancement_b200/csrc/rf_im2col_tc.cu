@@ -42,6 +42,7 @@ struct Im2colTcParams {
   float scale_of[4];     // 0.5 for sigmoid inputs (sigmoid(a) = 0.5*tanh(a/2) + 0.5), else 1
   int coef_off;          // ML: index of the first gate used inside gates[b][6]
   float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums (atomicAdd)
+  int ylo, yhi;          // FLCA: rows that contribute to the channel sums (row-tiled forward: the band's interior)
   int H, W, C, Cc, nchunks, B;
   int tiles_x, tiles_y, tiles_per_img, total_tiles, lanes;
   int parts;             // epilogue column split: warps 4*part .. 4*part+3 own 8*UPT*part .. channels of every row
@@ -247,6 +248,12 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     mbar_wait(acc_bar(a), (i >> 1) & 1);
     tc_fence_after();
     if (MODULATE) mbar_wait(f_bar(fs), (i / IT_NF) & 1);
+    float smask = 1.f;                               // MODE 0: does this thread's pixel count towards the channel sums
+    if (MODE == 0 && p.yhi - p.ylo < p.H) {
+      const int gt = t0 + i * tstep;
+      const int ty = (gt % p.tiles_per_img) / p.tiles_x;
+      smask = (unsigned)(ty * IT_TH + (erow >> 3) - p.ylo) < (unsigned)(p.yhi - p.ylo) ? 1.f : 0.f;
+    }
     if (epi) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.tmem_cols);
       const uint32_t frow = sF + fs * 16384 + (uint32_t)erow * p.row_bytes;
@@ -271,7 +278,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
             if (SEG >= 2) m = fmaf(cf[2], tanh_fast(__uint_as_float(v1[e])), m);
             if (SEG >= 3) m = fmaf(cf[3], tanh_fast(__uint_as_float(v2[e])), m);
             o[e] = f * m;
-            if (MODE == 0) csum[u * 8 + e] += o[e];
+            if (MODE == 0) csum[u * 8 + e] = fmaf(o[e], smask, csum[u * 8 + e]);
           }
         } else {
 #pragma unroll
@@ -336,6 +343,8 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
     p.seg_of[1] = 0; p.wmap_of[1] = 5; p.scale_of[1] = 0.5f;
   }
   p.H = H; p.W = W; p.C = C; p.Cc = Cc; p.nchunks = C / Cc; p.B = B;
+  p.ylo = 0; p.yhi = H;
+  if (ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
   p.tiles_x = cdiv(W, IT_TW); p.tiles_y = cdiv(H, IT_TH);
   p.tiles_per_img = p.tiles_x * p.tiles_y;
   const i64 total = (i64)p.tiles_per_img * B;

@@ -202,4 +202,10 @@ void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_);
 void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_);
 
+// ---- row-tiled forward: cross-GPU steps over peer-mapped comm regions (rf_band.cu); ctx.band must be set -------------
+// fetch the BAND_HALO halo rows of the band image x [ht + rows_in + hb][W][C] from the band neighbours' interiors
+void band_halo_exchange(Ctx& ctx, void* x, int W, int C);
+// data[i] <- sum over ranks, i < n; diagC > 0: data = attention statistics of C channels (diagonal Gram blocks + norms)
+void band_allreduce(Ctx& ctx, float* data, int n, int diagC);
+
 }  // namespace rf

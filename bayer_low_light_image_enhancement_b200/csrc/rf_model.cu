@@ -189,6 +189,7 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   if (variant == RF_VARIANT_FLCA) {
     xmod = A.elems((size_t)B * P * C, ctx.dtype);
     launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
+    if (ctx.band != nullptr) band_allreduce(ctx, partial, nblk * C, 0);   // channel sums of the whole frame
   } else {
     float* gates = A.get<float>((size_t)B * 6);
     launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
@@ -227,7 +228,8 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     xmod = const_cast<void*>(cur);  // == xa after three steps
     launch_channel_sums(ctx, xmod, partial, nblk, B, P, C);
   }
-  launch_se_finalize(ctx, partial, nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C, pb.hid);
+  launch_se_finalize(ctx, partial, nblk, ctx.band != nullptr ? ctx.band->P_full : P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2,
+                     scale, B, C, pb.hid);
   *xmod_out = xmod;
   *scale_out = scale;
 }
@@ -263,14 +265,19 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);
     launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
+    // row-tiled forward: the Gram and the norms run over the band's interior rows only, then are summed over the ranks
+    const i64 row0 = ctx.band != nullptr ? (i64)ctx.band->ht * W : 0;
+    const i64 Pg = ctx.band != nullptr ? (i64)ctx.band->rows_in * W : P;
     if (!ctx.dry) {
       for (int b = 0; b < B; ++b)
-        if (!launch_gram_tcgen05(ctx, (const char*)qk + (size_t)b * P * 2 * C * 2, stats + b * nst, C, P))
+        if (!launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, stats + b * nst, C, Pg))
           recorder().last_cuda_error = (int)cudaErrorNotSupported;
     }
     launch_copy_norms(ctx, sumsq, stats, B, C);
+    if (ctx.band != nullptr) band_allreduce(ctx, stats, 0, C);
     v = vbuf;
   } else {
+    if (ctx.band != nullptr) recorder().last_cuda_error = (int)cudaErrorNotSupported;
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     launch_dwqkv_gram(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, vbuf, stats, B, H, W, C);
     v = vbuf;
@@ -526,6 +533,151 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
     launch_tail_apply(ctx, out, sums, gm.LL2, gm.H2, gm.W2, B, h, w);
   }
   return RF_OK;
+}
+
+static int check_model_args(int dim, int dtype, int variant, int B, int H, int W);
+
+// ---------------------------------------------------------------------------------------------
+// row-tiled single frame (BASELINE config 4): this rank's band of ONE frame
+// ---------------------------------------------------------------------------------------------
+// Geometry: the frame is cut in units of 16 raw rows (= 8 >> s packed rows at stage s), so every stage has whole rows.
+// Every activation is a band image [ht + n_s + hb][w_s][C_s] (ht, hb = BAND_HALO towards a neighbour, 0 at the frame
+// border).  Validity of the halo rows along one Conv_Transformer (FLCA_RF.py:272-278), starting from 4 exchanged rows:
+//   qkv 1x1 (4) -> dw3x3 (3) -> x1 (3) -> pointwise1 (3) -> dw3x3+GELU (2) -> x2 (2) -> channel_reduce (2) -> Conv_out (1)
+// and Downsample's / conv_out's 3x3 consumes the last one.  The 1-channel guidance (y, cr, cb, Haar pyramid: FLCA_RF.py:
+// 87-97,140-148) is computed for the WHOLE frame on every rank (replicate, 12 MB), so FLCA needs no halo.
+static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw, float* out, int H, int W,
+                              const rf_band& rb) {
+  Band& bd = *ctx.band;
+  const int d = pm.dim, variant = RF_VARIANT_FLCA, B = 1;
+  const int h = H / 2, w = W / 2;
+  Arena& A = ctx.arena;
+  const int u0 = rb.row0 / 16, nu = rb.rows / 16;
+  bd.ht = rb.rank > 0 ? BAND_HALO : 0;
+  bd.hb = rb.rank + 1 < rb.nranks ? BAND_HALO : 0;
+  const int ht = bd.ht, hb = bd.hb;
+  auto rows_in = [&](int s) { return nu * (8 >> s); };           // interior rows at stage s
+  auto rows_img = [&](int s) { return ht + rows_in(s) + hb; };   // rows of the band image
+  auto first_row = [&](int s) { return u0 * (8 >> s) - ht; };    // frame row of band-image row 0
+  auto set_stage = [&](int s) {
+    bd.rows_in = rows_in(s);
+    bd.P_full = (i64)(h >> s) * (w >> s);
+  };
+  {
+    size_t zb = 0;
+    for (int i = 0; i < 7; ++i) {
+      const size_t C = (size_t)d << kBlockStage[i];
+      zb += align_up((C * C + 2 * C) * 4, 256) + align_up(2 * C * 4, 256) + align_up(32 * C * 4, 256);
+    }
+    ctx.zero_cap = zb;
+    ctx.zero_off = 0;
+    ctx.zero_base = (char*)A.alloc(zb);
+    if (!ctx.dry) {
+      if (!ctx.fits()) return RF_ERR_WORKSPACE;
+      RF_CUDA(cudaMemsetAsync(ctx.zero_base, 0, zb, ctx.stream));
+    }
+  }
+  // ---- whole-frame guidance (replicated) --------------------------------------------------------------------------
+  const i64 P0 = (i64)h * w;
+  float* x_ds = A.get<float>((size_t)P0 * 4);
+  float* y_raw = A.get<float>((size_t)P0);
+  float* ymax = A.get<float>(1);
+  float* y = A.get<float>((size_t)P0);
+  float* cr = A.get<float>((size_t)P0);
+  float* cb = A.get<float>((size_t)P0);
+  Band* const band = ctx.band;
+  ctx.band = nullptr;                                   // the guidance kernels see the whole frame
+  launch_fill_f32(ctx, ymax, -INFINITY, 1);
+  launch_pack_luma(ctx, raw, x_ds, y_raw, ymax, pm.rgb_w, B, H, W);
+  launch_luma_finalize(ctx, x_ds, y_raw, ymax, 1e-6f, y, cr, cb, B, h, w);
+  GuidanceMaps gm = make_pyramid(ctx, variant, y, pm.haar, B, h, w);
+  Stage st[4];
+  for (int s = 0; s < 4; ++s) {
+    make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w, B);
+    // the band's view of the stage guidance: rows [first_row, first_row + rows_img)
+    const size_t px0 = (size_t)first_row(s) * (w >> s);
+    if (st[s].G) st[s].G += px0 * 4;
+    if (st[s].G16) st[s].G16 = (char*)st[s].G16 + px0 * 16;
+    st[s].H = rows_img(s);
+  }
+  auto feat_buf = [&](int s) { return A.elems((size_t)rows_img(s) * (w >> s) * ((size_t)d << s), ctx.dtype); };
+  auto row_off = [&](void* p, int rows, int s) {        // p + `rows` rows of a stage-s band image
+    return (void*)((char*)p + (size_t)rows * (w >> s) * ((size_t)d << s) * esize(ctx.dtype));
+  };
+  void* x0 = feat_buf(0);
+  const size_t px0 = (size_t)first_row(0) * w;
+  void* x16 = A.alloc((size_t)rows_img(0) * w * 16);
+  launch_split_bf16x8(ctx, x_ds + px0 * 4, x16, (i64)rows_img(0) * w);
+  launch_embed(ctx, x_ds + px0 * 4, x16, pm.embed_w, pm.embed_b, x0, B, rows_img(0), w, d);
+  ctx.band = band;
+
+  // ---- encoder ---------------------------------------------------------------------------------------------------------
+  void* enc[4];
+  void* cur = x0;
+  for (int s = 0; s < 4; ++s) {
+    set_stage(s);
+    enc[s] = feat_buf(s);
+    band_halo_exchange(ctx, cur, w >> s, d << s);
+    conv_transformer(ctx, pm.blocks[s], variant, cur, st[s], enc[s], B);
+    if (s < 3) {
+      // Downsample over the whole band image: its ht/2 + n_{s+1} + hb/2 output rows land ht/2 rows into the next
+      // stage's band image (the outer rows are filled by that block's halo exchange)
+      void* pooled = feat_buf(s + 1);
+      const int C = d << s;
+      conv3x3(ctx, enc[s], pm.down_w[s], nullptr, row_off(pooled, ht / 2, s + 1), C, C / 2, ACT_NONE, OMODE_UNSHUFFLE, B,
+              rows_img(s), w >> s, RF_K_DOWN_CONV);
+      cur = pooled;
+    }
+  }
+  // ---- decoder ---------------------------------------------------------------------------------------------------------
+  cur = enc[3];
+  for (int n = 0; n < 3; ++n) {
+    const int s = 2 - n;
+    const int Co = d << s, Ci = 2 * Co;
+    const int Ws = w >> s;
+    set_stage(s);
+    // ConvTranspose2d of the coarse band image minus its outer ht/2 (hb/2) rows = exactly the fine band image
+    const int rows_c = rows_img(s + 1) - ht / 2 - hb / 2;
+    void* up = feat_buf(s);
+    GemmP g = gemm_rows(row_off(cur, ht / 2, s + 1), Ci, pm.up_w[n], pm.up_b[n], up, 4 * Co, B, (i64)rows_c * (Ws / 2),
+                        RF_K_UP_CONVT);
+    g.omode = OMODE_CONVT; g.H = rows_c; g.W = Ws / 2; g.ldy = Co;
+    launch_gemm(ctx, g);
+    void* fused = feat_buf(s);
+    GemmP r = gemm_rows(up, Co, pm.red_w[n], pm.red_b[n], fused, Co, B, (i64)rows_img(s) * Ws, RF_K_SKIP_REDUCE);
+    r.A2 = enc[s]; r.K2 = Co; r.lda2 = Co;
+    launch_gemm(ctx, r);
+    band_halo_exchange(ctx, fused, Ws, Co);
+    void* dec = feat_buf(s);
+    conv_transformer(ctx, pm.blocks[4 + n], variant, fused, st[s], dec, B);
+    cur = dec;
+  }
+  // ---- head: conv_out + LeakyReLU + PixelShuffle over the band image (the caller keeps the interior rows) ----------
+  GemmP hp;
+  hp.A1 = cur; hp.K1 = 9 * d; hp.lda1 = d; hp.amode = AMODE_CONV3;
+  hp.Wt = pm.head_wt; hp.bias = pm.head_b16; hp.Y = out; hp.ldy = 0;
+  hp.M = rows_img(0) * w; hp.N = 16; hp.B = B; hp.H = rows_img(0); hp.W = w; hp.omode = OMODE_HEAD; hp.kernel_id = RF_K_HEAD;
+  if (!ctx.dry && launch_gemm_tcgen05(ctx, hp) < 0) return RF_ERR_UNSUPPORTED;
+  return RF_OK;
+}
+
+static int check_band_args(int dim, int dtype, int variant, int H, int W, const rf_band* band) {
+  if (!band) return RF_ERR_BAD_ARG;
+  RF_TRY(check_model_args(dim, dtype, variant, 1, H, W));
+  if (dtype != RF_BF16 || variant != RF_VARIANT_FLCA) return RF_ERR_UNSUPPORTED;
+  if (dim % 32 && dim % 48) return RF_ERR_UNSUPPORTED;            // tensor-core FLCA / embed kernels (dim 32/48/64)
+  if (band->nranks < 1 || band->nranks > RF_BAND_MAX_RANKS || band->rank < 0 || band->rank >= band->nranks)
+    return RF_ERR_BAD_ARG;
+  if (band->row0 % 16 || band->rows % 16 || band->rows < 16 * BAND_HALO) return RF_ERR_BAD_SHAPE;
+  if (band->row0 < 0 || band->row0 + band->rows > H) return RF_ERR_BAD_SHAPE;
+  if ((band->rank == 0) != (band->row0 == 0)) return RF_ERR_BAD_SHAPE;
+  if ((band->rank == band->nranks - 1) != (band->row0 + band->rows == H)) return RF_ERR_BAD_SHAPE;
+  return RF_OK;
+}
+
+static void band_from_abi(const rf_band& rb, Band& bd, bool dry) {
+  bd.rank = rb.rank; bd.nranks = rb.nranks; bd.epoch = rb.epoch;
+  for (int r = 0; r < rb.nranks; ++r) bd.comm[r] = dry ? nullptr : (char*)rb.comm[r];
 }
 
 static int check_model_args(int dim, int dtype, int variant, int B, int H, int W) {
@@ -785,6 +937,69 @@ int rf_rawformer_forward(const void* packed, int dim, int dtype, int variant, co
   Layout L(const_cast<void*>(packed));
   PackedModel pm = layout_model(L, dim, dtype, variant);
   RF_TRY(model_forward(ctx, pm, variant, raw, out, B, H, W));
+  return finish(ctx);
+}
+
+// ---- row-tiled single frame ----------------------------------------------------------------------------------------
+
+int rf_band_out_rows(const rf_band* band, int* out_rows_host, int* interior_row0_host) {
+  if (!band || band->nranks < 1 || band->rank < 0 || band->rank >= band->nranks) return RF_ERR_BAD_ARG;
+  const int ht = band->rank > 0 ? BAND_HALO : 0, hb = band->rank + 1 < band->nranks ? BAND_HALO : 0;
+  if (out_rows_host) *out_rows_host = 2 * (ht + band->rows / 2 + hb);
+  if (interior_row0_host) *interior_row0_host = 2 * ht;
+  return RF_OK;
+}
+
+// dry run of rank `rank`'s plan: workspace peak and comm-region bytes
+static int band_dry_run(int dim, int dtype, int variant, int H, int W, const rf_band& rb, size_t* ws, size_t* comm) {
+  Ctx ctx = make_ctx(nullptr, 0, nullptr, dtype, true);
+  Band bd;
+  band_from_abi(rb, bd, true);
+  ctx.band = &bd;
+  Layout L(nullptr);
+  PackedModel pm = layout_model(L, dim, dtype, variant);
+  RF_TRY(model_forward_band(ctx, pm, nullptr, nullptr, H, W, rb));
+  if (ws) *ws = ctx.arena.peak + 4096;
+  if (comm) *comm = bd.mail_off + 256;
+  return RF_OK;
+}
+
+size_t rf_band_comm_bytes(int dim, int dtype, int variant, int H, int W, int nranks) {
+  if (nranks < 1 || nranks > RF_BAND_MAX_RANKS || H % 16 || H / 16 < nranks * BAND_HALO) return 0;
+  // mailbox sizes depend on (dim, W, nranks) only; size them with rank 0's plan of an even split
+  rf_band rb;
+  memset(&rb, 0, sizeof(rb));
+  rb.rank = 0; rb.nranks = nranks; rb.row0 = 0;
+  rb.rows = nranks == 1 ? H : (H / 16 / nranks) * 16;
+  if (check_band_args(dim, dtype, variant, H, W, &rb) != RF_OK) return 0;
+  size_t comm = 0;
+  if (band_dry_run(dim, dtype, variant, H, W, rb, nullptr, &comm) != RF_OK) return 0;
+  return comm;
+}
+
+size_t rf_rawformer_band_workspace_bytes(int dim, int dtype, int variant, int H, int W, const rf_band* band) {
+  if (check_band_args(dim, dtype, variant, H, W, band) != RF_OK) return 0;
+  size_t ws = 0;
+  if (band_dry_run(dim, dtype, variant, H, W, *band, &ws, nullptr) != RF_OK) return 0;
+  return ws;
+}
+
+int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int H,
+                              int W, const rf_band* band, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!packed || !raw || !out || !workspace) return RF_ERR_BAD_ARG;
+  RF_TRY(check_band_args(dim, dtype, variant, H, W, band));
+  if ((uintptr_t)packed % 256 || (uintptr_t)raw % 16 || (uintptr_t)out % 16) return RF_ERR_BAD_ARG;
+  for (int r = 0; r < band->nranks; ++r)
+    if (!band->comm[r] || (uintptr_t)band->comm[r] % 256) return RF_ERR_BAD_ARG;
+  if (workspace_bytes < rf_rawformer_band_workspace_bytes(dim, dtype, variant, H, W, band) - 4096) return RF_ERR_WORKSPACE;
+  if (!tcgen05_enabled()) return RF_ERR_UNSUPPORTED;
+  Ctx ctx = make_ctx(workspace, workspace_bytes, stream, dtype, false);
+  Band bd;
+  band_from_abi(*band, bd, false);
+  ctx.band = &bd;
+  Layout L(const_cast<void*>(packed));
+  PackedModel pm = layout_model(L, dim, dtype, variant);
+  RF_TRY(model_forward_band(ctx, pm, raw, out, H, W, *band));
   return finish(ctx);
 }
 

@@ -221,6 +221,48 @@ int rf_rawformer_forward(const void* packed, int dim, int dtype, int variant, co
 int rf_rawformer_forward_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out,
                                   int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream,
                                   float* kernel_ms_host, int* kernel_id_host, int cap, int* n_host);
+/* ------------------------------------------------------------------------------------------------
+ * Row-tiled single frame — RawFormer.forward (FLCA_RF.py:330-370) of ONE frame split into bands of whole rows over
+ * the GPUs of a box (BASELINE config 4).  One process per GPU; rank r owns raw rows [row0, row0 + rows) (multiples of
+ * 16, at least 64).  Per Conv_Transformer the ranks exchange RF_BAND_HALO rows of the block input with their band
+ * neighbours and all-reduce the three per-image reductions of the block (squeeze-excite channel sums FLCA_RF.py:160,
+ * |q|^2,|k|^2 and the per-head Gram FLCA_RF.py:228-230) through peer-mapped memory: every rank owns a "comm region"
+ * (flags + mailboxes) that its peers write with plain stores over NVLink; no NCCL call is on the data path.
+ * RF_BF16 / RF_VARIANT_FLCA only.
+ * ---------------------------------------------------------------------------------------------- */
+#define RF_BAND_MAX_RANKS 8
+#define RF_BAND_HALO 4           /* packed rows at every U-Net stage */
+#define RF_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
+
+typedef struct rf_band {
+  int rank, nranks;
+  int row0, rows;                       /* interior raw rows of this rank */
+  void* comm[RF_BAND_MAX_RANKS];        /* comm region of every rank as mapped in THIS process (comm[rank] = own) */
+  unsigned epoch;                       /* 1, 2, 3, ...: one per forward on this comm region, the same on all ranks;
+                                           0 = rehearsal: same launches, but no rank signals or waits (run it once
+                                           per rank before the first frame so that every kernel is loaded) */
+} rf_band;
+
+/* Bytes of one rank's comm region (identical on all ranks). */
+size_t rf_band_comm_bytes(int dim, int dtype, int variant, int H, int W, int nranks);
+/* cudaMalloc + zero a comm region on the current device and export its IPC handle (handle_host may be NULL). */
+int rf_band_comm_alloc(size_t bytes, void** ptr_host, unsigned char* handle_host);
+/* Map a peer's comm region into this process (cudaIpcOpenMemHandle); rf_band_comm_close undoes it. */
+int rf_band_comm_open(const unsigned char* handle_host, void** ptr_host);
+int rf_band_comm_close(void* ptr);
+int rf_band_comm_free(void* ptr);
+/* Sticky error word of the local comm region: 0, or 1 + the index of the sync point whose wait timed out
+ * (a peer never arrived).  Synchronises `stream`. */
+int rf_band_comm_status(const void* comm_own, int* err_host, void* stream);
+/* Rows of the band image the forward writes: out is [1,3,2*(ht+rows/2+hb),W] where ht/hb = RF_BAND_HALO for a
+ * neighbour above/below, else 0; the interior starts at raw row 2*ht of it. */
+int rf_band_out_rows(const rf_band* band, int* out_rows_host, int* interior_row0_host);
+size_t rf_rawformer_band_workspace_bytes(int dim, int dtype, int variant, int H, int W, const rf_band* band);
+/* raw [1,1,H,W] float32 = the WHOLE frame (replicated on every rank: the 1-channel guidance is computed locally);
+ * out = this rank's band image of the result (see rf_band_out_rows). */
+int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int H,
+                              int W, const rf_band* band, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Human-readable name of a kernel id reported by rf_rawformer_forward_profiled. */
 const char* rf_kernel_name(int kernel_id);
 /* Algorithmic (compulsory) bytes and FLOPs the launch `index` of the last profiled forward moved/did. */

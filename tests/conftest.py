@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# LocalBands (tests/test_rowtiled.py) runs the bands of a frame as concurrent streams that wait for each other inside
+# kernels: give every stream its own hardware queue so two of them never share (and serialise on) one connection
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
