@@ -112,6 +112,8 @@ _SIGS = {
     "rf_band_out_rows": (_i, [_BDp, C.POINTER(_i), C.POINTER(_i)]),
     "rf_rawformer_band_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _BDp]),
     "rf_rawformer_forward_band": (_i, [_fp, _i, _i, _i, _fp, _fp, _i, _i, _BDp, _fp, _sz, _fp]),
+    "rf_rawformer_forward_band_profiled": (
+        _i, [_fp, _i, _i, _i, _fp, _fp, _i, _i, _BDp, _fp, _sz, _fp, C.POINTER(_f), C.POINTER(_i), _i, C.POINTER(_i)]),
     "rf_kernel_name": (C.c_char_p, [_i]),
     "rf_profiled_launch_info": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rf_postprocess_u8": (_i, [_fp, _fp, _i, _i, _i, _fp]),

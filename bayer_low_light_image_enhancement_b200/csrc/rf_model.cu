@@ -1003,6 +1003,16 @@ int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int varian
   return finish(ctx);
 }
 
+int rf_rawformer_forward_band_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out,
+                                       int H, int W, const rf_band* band, void* workspace, size_t workspace_bytes,
+                                       void* stream, float* kernel_ms_host, int* kernel_id_host, int cap, int* n_host) {
+  if (cap <= 0) return RF_ERR_BAD_ARG;
+  RF_TRY(profile_begin((cudaStream_t)stream, cap));
+  int st = rf_rawformer_forward_band(packed, dim, dtype, variant, raw, out, H, W, band, workspace, workspace_bytes, stream);
+  int st2 = profile_end(kernel_ms_host, kernel_id_host, cap, n_host);
+  return st != RF_OK ? st : st2;
+}
+
 int rf_rawformer_forward_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int B,
                                   int H, int W, void* workspace, size_t workspace_bytes, void* stream, float* kernel_ms_host,
                                   int* kernel_id_host, int cap, int* n_host) {

@@ -172,6 +172,28 @@ class RowTiledRawFormer:
                                             _lib.stream_ptr(raw.device)), "rf_rawformer_forward_band")
         return out[:, :, self._out_r0:self._out_r0 + self.rows]
 
+    @torch.no_grad()
+    def forward_profiled(self, raw, cap=4096):
+        """One forward with a CUDA-event pair around every launch (synchronises; every rank must call it).  Returns
+        (band, launches) like ``RawFormer.forward_profiled``; band_halo / band_allreduce times include the wait for peers."""
+        m, lib = self.model, _lib.load()
+        raw = m._check_input(raw)
+        blob = m.packed_weights(raw.device, _lib.RF_BF16)
+        out = torch.empty(1, 3, self._out_rows, self.W, dtype=torch.float32, device=raw.device)
+        self.epoch += 1
+        self._band.epoch = self.epoch
+        ms, ids, n = (C.c_float * cap)(), (C.c_int * cap)(), C.c_int(0)
+        check(lib.rf_rawformer_forward_band_profiled(ptr(blob), m.dim, _lib.RF_BF16, m.variant, ptr(raw), ptr(out), self.H,
+                                                     self.W, C.byref(self._band), ptr(self._ws), self._ws.numel(),
+                                                     _lib.stream_ptr(raw.device), ms, ids, cap, C.byref(n)),
+              "rf_rawformer_forward_band_profiled")
+        launches, by, fl = [], C.c_double(0), C.c_double(0)
+        for i in range(min(n.value, cap)):
+            lib.rf_profiled_launch_info(i, C.byref(by), C.byref(fl))
+            launches.append({"name": lib.rf_kernel_name(ids[i]).decode(), "ms": float(ms[i]), "bytes": by.value,
+                             "flops": fl.value})
+        return out[:, :, self._out_r0:self._out_r0 + self.rows], launches
+
     def status(self):
         """Synchronise and raise if a cross-GPU wait of this rank timed out (a peer never reached the sync point)."""
         err = C.c_int(0)
@@ -181,17 +203,23 @@ class RowTiledRawFormer:
             raise RuntimeError(f"row-tiled forward: rank {self.rank} timed out at sync point {err.value - 1}")
 
     def gather(self, band: torch.Tensor, dst: int = 0):
-        """All bands on rank ``dst`` as one [1,3,H,W] frame (NCCL gather); None on the other ranks."""
+        """All bands on rank ``dst`` as one [1,3,H,W] frame (NCCL point-to-point: the bands may differ in height);
+        None on the other ranks."""
         import torch.distributed as dist
 
         band = band.contiguous()
-        if dist.get_rank(self.group) != dst:
-            dist.gather(band, None, dst=dst, group=self.group)
-            return None
-        parts = [torch.empty(1, 3, rows, self.W, dtype=band.dtype, device=band.device)
-                 for _, rows in plan_bands(self.H, self.nranks)]
-        dist.gather(band, parts, dst=dst, group=self.group)
-        return torch.cat(parts, dim=2)
+        me = dist.get_rank(self.group)
+        if me != dst:
+            ops = [dist.P2POp(dist.isend, band, dst, self.group)]
+            parts = None
+        else:
+            parts = [band if r == me else torch.empty(1, 3, rows, self.W, dtype=band.dtype, device=band.device)
+                     for r, (_, rows) in enumerate(plan_bands(self.H, self.nranks))]
+            ops = [dist.P2POp(dist.irecv, parts[r], r, self.group) for r in range(self.nranks) if r != me]
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        return torch.cat(parts, dim=2) if parts is not None else None
 
 
 class LocalBands:

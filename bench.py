@@ -2,6 +2,7 @@
 """Benchmark of the RawFormer inference hot path on B200 (BASELINE.json metric: MP/s of RAW input).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S|B|L] [--variant flca|ml]
+                    [--row-tiled]
 
 A "step" = one forward over one synthetic SID-Sony-shaped frame (raw 2848x4256 -> packed 1424x2128x4) per GPU.
 N = 1 workload = BASELINE configs[1]: RawFormer-S, full frame, bf16.  N > 1 (torchrun) is image-parallel: every rank
@@ -396,6 +397,148 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_rowtiled(args):
+    """BASELINE config 4: ONE frame per step, cut into row bands over the N ranks (strong scaling).  Every rank holds the
+    whole raw frame; halo rows and the per-image reductions cross the GPUs inside kernels of this library (peer-mapped
+    memory over NVLink).  N = 1 runs the same band code with a single band."""
+    import torch
+    import torch.distributed as dist
+
+    import rf_testlib as T
+
+    import bayer_low_light_image_enhancement_b200 as rf
+    from bayer_low_light_image_enhancement_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
+    lib = _lib.load()
+    dim = SIZES[args.size]
+    model = rf.RawFormer(dim=dim, precision="bf16")
+    model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)
+    model = model.to(dev).eval()
+    x_host = torch.rand(1, 1, H_RAW, W_RAW, generator=torch.Generator().manual_seed(0)).pin_memory()   # same frame on all ranks
+    x_dev = x_host.to(dev)
+    tiled = rf.RowTiledRawFormer.from_process_group(model, H_RAW, W_RAW)
+    band_host = torch.empty(1, 3, tiled.rows, W_RAW).pin_memory()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # parity of the decomposition (untimed): bands gathered on rank 0 against the whole-frame forward of the same engine
+        full = tiled.gather(tiled(x_dev), dst=0)
+        tiled.status()
+        parity = None
+        if rank == 0:
+            whole = model(x_dev)
+            rng = float(whole.max() - whole.min())
+            mse = float(((full - whole).double() ** 2).mean())
+            parity = {"psnr_vs_whole_frame_db": 99.0 if mse == 0 else 10.0 * __import__("math").log10(rng * rng / mse),
+                      "max_abs_over_range": float((full - whole).abs().max()) / rng}
+            del whole
+        del full
+        barrier()
+        t_pre = time.perf_counter()
+        n_pre = torch.zeros(1, device=dev)
+        while True:                               # every rank must run the same number of forwards: agree on when to stop
+            tiled(x_dev)
+            n_pre.fill_(1.0 if time.perf_counter() - t_pre < 1.5 else 0.0)
+            dist.all_reduce(n_pre, op=dist.ReduceOp.MIN)
+            if float(n_pre.item()) == 0.0:
+                break
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        for _ in range(max(args.warmup, 8)):
+            tiled(x_dev)
+        barrier()
+        lib.rf_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            band = tiled(x_dev)
+        e1.record()
+        barrier()
+        launches = lib.rf_launch_count()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None
+        tiled.status()
+        # end to end: whole frame host -> every rank, forward, this rank's band -> host, every step, one stream
+        for _ in range(2):
+            x_dev.copy_(x_host, non_blocking=True)
+            band_host.copy_(tiled(x_dev), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            x_dev.copy_(x_host, non_blocking=True)
+            band_host.copy_(tiled(x_dev), non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+        assert float(band_host.abs().max()) > 0.0
+        # per-kernel times of this rank's band (sync-point kernels include the wait for the peers)
+        agg = {}
+        n_prof = 3
+        for _ in range(n_prof):
+            _, lp = tiled.forward_profiled(x_dev)
+            for l in lp:
+                a = agg.setdefault(l["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
+                a["ms"] += l["ms"]; a["bytes"] += l["bytes"]; a["flops"] += l["flops"]; a["n"] += 1
+        tiled.status()
+        barrier()
+    tiled.close()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    pk = peaks()
+    compute = {k: v for k, v in agg.items() if not k.startswith("band_")}
+    top_name, top = max(compute.items(), key=lambda kv: kv[1]["ms"])
+    total_prof_ms = sum(a["ms"] for a in agg.values())
+    if top_name.startswith(TENSOR_KERNELS):
+        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"]}
+    else:
+        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
+    roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
+                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=None, scope="rank 0's band")
+    line = {
+        "metric": METRIC, "value": args.steps * MP_FRAME / (ms_total * 1e-3), "unit": "MP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 8), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"RawFormer-{args.size} (flca) forward, ONE SID Sony frame raw {H_RAW}x{W_RAW} per step, "
+                               f"row-tiled over {world} GPU(s) (bands of {[r // 16 for _, r in rf.plan_bands(H_RAW, world)]} x 16 rows), "
+                               "random-init weights",
+                   "precision": "bf16", "parallelism": f"row-tiled x{world}: 4-row halo exchange + all-reduce of the per-image "
+                   "reductions per Conv_Transformer, peer-mapped memory over NVLink, no NCCL on the data path",
+                   "l2": "per-step working set >> 126 MB L2, no explicit flush", "launch": "eager"},
+        "e2e": {"value": args.steps * MP_FRAME / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": int(x_host.numel() * 4) * world,
+                "d2h_bytes_per_step": 3 * H_RAW * W_RAW * 4, "ms_per_step": ms_e2e / args.steps,
+                "api": "RowTiledRawFormer.forward with pinned host buffers: whole frame H2D on every rank, forward, band D2H",
+                "host_binding": numa},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
+        "kernel_ms_per_step": {k: round(v["ms"] / n_prof, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+        "sync_ms_per_step": round(sum(v["ms"] for k, v in agg.items() if k.startswith("band_")) / n_prof, 4),
+    }
+    print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,10 +551,14 @@ def main():
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of one CUDA graph per frame")
+    ap.add_argument("--row-tiled", action="store_true",
+                    help="BASELINE config 4: one frame per step cut into row bands over the ranks (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.row_tiled:
+        run_rowtiled(args)
     else:
         run_ours(args)
 

@@ -262,6 +262,11 @@ size_t rf_rawformer_band_workspace_bytes(int dim, int dtype, int variant, int H,
  * out = this rank's band image of the result (see rf_band_out_rows). */
 int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int H,
                               int W, const rf_band* band, void* workspace, size_t workspace_bytes, void* stream);
+/* Same with a cudaEvent pair around every launch (see rf_rawformer_forward_profiled); the times of the band_halo /
+ * band_allreduce launches include the wait for the peers.  Every rank must make the same call. */
+int rf_rawformer_forward_band_profiled(const void* packed, int dim, int dtype, int variant, const float* raw, float* out,
+                                       int H, int W, const rf_band* band, void* workspace, size_t workspace_bytes,
+                                       void* stream, float* kernel_ms_host, int* kernel_id_host, int cap, int* n_host);
 
 /* Human-readable name of a kernel id reported by rf_rawformer_forward_profiled. */
 const char* rf_kernel_name(int kernel_id);
