@@ -27,9 +27,18 @@ struct BandSyncP {
   unsigned* flags_local;                 // [BAND_MAX_RANKS] counters of this sync point in the local region
   unsigned* flags_peer[BAND_MAX_RANKS];  // the same counters in every rank's region
   unsigned* err;                         // local sticky error word
-  unsigned target;                       // epoch * gridDim.x
+  const unsigned* frame;                 // local frame counter (k_band_begin); nullptr = rehearsal
+  unsigned target;                       // frame * gridDim.x, filled in by the kernel (0 = rehearsal)
   int rank, nranks, sync_id;
 };
+
+// The frame counter lives in the comm region and is advanced by the first kernel of every real forward, so the launch
+// sequence of a forward has no per-frame host argument and can be replayed as a CUDA graph.
+__global__ void k_band_begin(unsigned* frame) { *frame += 1u; }
+
+__device__ __forceinline__ void band_load_target(BandSyncP& s) {
+  s.target = s.frame != nullptr ? *reinterpret_cast<const volatile unsigned*>(s.frame) * gridDim.x : 0u;
+}
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   unsigned v;
@@ -76,7 +85,8 @@ struct BandHaloP {
 };
 
 __global__ void __launch_bounds__(512)
-k_band_halo(const BandHaloP p) {
+k_band_halo(BandHaloP p) {
+  band_load_target(p.s);
   const i64 n = (i64)BAND_HALO * p.row_u4;
   const i64 i0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, step = (i64)gridDim.x * blockDim.x;
   unsigned mask = 0;
@@ -104,20 +114,22 @@ k_band_halo(const BandHaloP p) {
   }
 }
 
-// ---- all-reduce (sum) of a small fp32 vector ---------------------------------------------------------------------------
+// ---- all-reduce (sum) of the per-image reductions of one Conv_Transformer ---------------------------------------------
+// ONE exchange per block: the attention statistics {gram [C][C], |q|^2 [C], |k|^2 [C]} -- of the Gram only the 8 per-head
+// diagonal blocks are used (FLCA_RF.py:230) and exchanged -- followed by the C squeeze-excite channel sums
+// (FLCA_RF.py:160), which the FLCA kernel leaves as `se_slots` partial rows and which come back reduced into row 0.
 struct BandReduceP {
   BandSyncP s;
-  float* data;
-  int n;                          // elements exchanged
+  float* stats;                   // attention statistics of C channels
+  float* se;                      // [se_slots][C] partial channel sums (nullptr: none)
+  int C, se_slots;
+  int n;                          // elements exchanged = C*C/8 + 2C (+ C)
   int n_pad;                      // slot pitch in floats
-  int diagC;                      // > 0: data is the attention statistics {gram [C][C], |q|^2 [C], |k|^2 [C]} of which only
-                                  // the 8 per-head diagonal blocks of the Gram are used (FLCA_RF.py:230): exchange those
   float* mail_local;              // [nranks][n_pad]
   float* mail_peer[BAND_MAX_RANKS];
 };
 
-__device__ __forceinline__ i64 band_idx(int e, int C) {
-  if (C == 0) return e;
+__device__ __forceinline__ i64 band_stats_idx(int e, int C) {
   const int c = C >> 3;
   if (e >= C * c) return (i64)C * C + (e - C * c);
   const int h = e / (c * c), r = e - h * c * c;
@@ -126,10 +138,18 @@ __device__ __forceinline__ i64 band_idx(int e, int C) {
 }
 
 __global__ void __launch_bounds__(256)
-k_band_allreduce(const BandReduceP p) {
+k_band_allreduce(BandReduceP p) {
+  band_load_target(p.s);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+  const int n_attn = p.C * (p.C >> 3) + 2 * p.C;
   for (int e = i0; e < p.n; e += step) {
-    const float v = p.data[band_idx(e, p.diagC)];
+    float v;
+    if (e < n_attn) {
+      v = p.stats[band_stats_idx(e, p.C)];
+    } else {
+      v = 0.f;
+      for (int k = 0; k < p.se_slots; ++k) v += p.se[(i64)k * p.C + (e - n_attn)];
+    }
     for (int r = 0; r < p.s.nranks; ++r) p.mail_peer[r][(i64)p.s.rank * p.n_pad + e] = v;
   }
   const unsigned mask = (1u << p.s.nranks) - 1u;
@@ -138,7 +158,8 @@ k_band_allreduce(const BandReduceP p) {
   for (int e = i0; e < p.n; e += step) {
     float sum = 0.f;
     for (int r = 0; r < p.s.nranks; ++r) sum += __ldcg(p.mail_local + (i64)r * p.n_pad + e);
-    p.data[band_idx(e, p.diagC)] = sum;
+    if (e < n_attn) p.stats[band_stats_idx(e, p.C)] = sum;
+    else p.se[e - n_attn] = sum;
   }
 }
 
@@ -155,7 +176,9 @@ static bool band_sync_params(Ctx& ctx, BandSyncP& s, int grid) {
     s.flags_peer[r] = reinterpret_cast<unsigned*>(b.comm[r] + BAND_FLAGS_OFF) + (size_t)id * BAND_MAX_RANKS;
   s.flags_local = s.flags_peer[b.rank];
   s.err = reinterpret_cast<unsigned*>(b.comm[b.rank]);
-  s.target = b.epoch * (unsigned)grid;
+  s.frame = b.epoch != 0 ? reinterpret_cast<const unsigned*>(b.comm[b.rank] + BAND_FRAME_OFF) : nullptr;
+  s.target = 0;
+  (void)grid;
   s.rank = b.rank; s.nranks = b.nranks; s.sync_id = id;
   return true;
 }
@@ -169,7 +192,7 @@ void band_halo_exchange(Ctx& ctx, void* x, int W, int C) {
   const int grid = 16;
   BandHaloP p;
   if (!band_sync_params(ctx, p.s, grid) || ctx.dry) return;
-  if (b.nranks == 1) return;
+  if (b.nranks == 1) return;                 // no neighbours: nothing to fetch
   if (row_bytes % 16 || slot != (size_t)BAND_HALO * row_bytes) {   // W*C*2 is a multiple of 256 for every legal shape
     recorder().last_cuda_error = (int)cudaErrorInvalidValue;
     return;
@@ -184,9 +207,16 @@ void band_halo_exchange(Ctx& ctx, void* x, int W, int C) {
   k_band_halo<<<grid, 512, 0, ctx.stream>>>(p);
 }
 
-void band_allreduce(Ctx& ctx, float* data, int n, int diagC) {
+void band_begin(Ctx& ctx) {
   Band& b = *ctx.band;
-  if (diagC > 0) n = diagC * (diagC / 8) + 2 * diagC;
+  if (ctx.dry || b.epoch == 0) return;
+  ScopedLaunch sl(RF_K_MISC);
+  k_band_begin<<<1, 1, 0, ctx.stream>>>(reinterpret_cast<unsigned*>(b.comm[b.rank] + BAND_FRAME_OFF));
+}
+
+void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots) {
+  Band& b = *ctx.band;
+  const int n = C * (C / 8) + 2 * C + (se != nullptr || ctx.dry ? C : 0);
   const int n_pad = (int)align_up((size_t)n, 64);
   const size_t off = b.mail_off;
   b.mail_off += (size_t)b.nranks * n_pad * sizeof(float);
@@ -194,8 +224,7 @@ void band_allreduce(Ctx& ctx, float* data, int n, int diagC) {
   if (grid > 16) grid = 16;
   BandReduceP p;
   if (!band_sync_params(ctx, p.s, grid) || ctx.dry) return;
-  if (b.nranks == 1) return;
-  p.data = data; p.n = n; p.n_pad = n_pad; p.diagC = diagC;
+  p.stats = stats; p.se = se; p.C = C; p.se_slots = se_slots; p.n = n; p.n_pad = n_pad;
   for (int r = 0; r < b.nranks; ++r) p.mail_peer[r] = reinterpret_cast<float*>(b.comm[r] + off);
   p.mail_local = p.mail_peer[b.rank];
   ScopedLaunch sl(RF_K_BAND_ALLREDUCE, 4.0 * n * (2.0 * b.nranks));

@@ -134,17 +134,20 @@ struct Arena {
 constexpr int BAND_MAX_RANKS = RF_BAND_MAX_RANKS;
 constexpr int BAND_HALO = 4;
 constexpr int BAND_MAX_SYNCS = 32;
+constexpr size_t BAND_FRAME_OFF = 64;        // u32 frame counter (advanced by the first kernel of every real forward)
 constexpr size_t BAND_FLAGS_OFF = 256;       // [BAND_MAX_SYNCS][BAND_MAX_RANKS] u32 arrival counters
 constexpr size_t BAND_MAIL_OFF = 4096;       // mailboxes (bump-allocated in call order, identical on all ranks)
 struct Band {
   int rank = 0, nranks = 1;
   char* comm[BAND_MAX_RANKS] = {};   // comm region of every rank as mapped in this process (comm[rank] is local)
-  unsigned epoch = 0;                // 1, 2, 3 ... one per forward, the same on all ranks
+  unsigned epoch = 0;                // 0 = rehearsal (nobody signals or waits), else a real forward
   int next_sync = 0;                 // sync points used so far in this forward
   size_t mail_off = BAND_MAIL_OFF;   // bump cursor inside the comm region
   int ht = 0, hb = 0;                // halo rows above / below the interior
   int rows_in = 0;                   // interior rows at the current stage
   i64 P_full = 0;                    // pixels of the WHOLE frame at the current stage (squeeze-excite mean)
+  float* se_partial = nullptr;       // squeeze-excite partial sums of the current block, reduced with its attention statistics
+  int se_slots = 0;
 };
 
 struct Ctx {

@@ -205,7 +205,10 @@ void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2
 // ---- row-tiled forward: cross-GPU steps over peer-mapped comm regions (rf_band.cu); ctx.band must be set -------------
 // fetch the BAND_HALO halo rows of the band image x [ht + rows_in + hb][W][C] from the band neighbours' interiors
 void band_halo_exchange(Ctx& ctx, void* x, int W, int C);
-// data[i] <- sum over ranks, i < n; diagC > 0: data = attention statistics of C channels (diagonal Gram blocks + norms)
-void band_allreduce(Ctx& ctx, float* data, int n, int diagC);
+// advance the frame counter of the local comm region (first launch of a real forward)
+void band_begin(Ctx& ctx);
+// one all-reduce (sum over ranks) per Conv_Transformer: the attention statistics of C channels (diagonal Gram blocks +
+// squared norms) and the squeeze-excite channel sums se [se_slots][C] (-> row 0 holds the frame's sums)
+void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots);
 
 }  // namespace rf

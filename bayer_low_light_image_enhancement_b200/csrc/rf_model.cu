@@ -189,7 +189,6 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   if (variant == RF_VARIANT_FLCA) {
     xmod = A.elems((size_t)B * P * C, ctx.dtype);
     launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
-    if (ctx.band != nullptr) band_allreduce(ctx, partial, nblk * C, 0);   // channel sums of the whole frame
   } else {
     float* gates = A.get<float>((size_t)B * 6);
     launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
@@ -228,8 +227,14 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     xmod = const_cast<void*>(cur);  // == xa after three steps
     launch_channel_sums(ctx, xmod, partial, nblk, B, P, C);
   }
-  launch_se_finalize(ctx, partial, nblk, ctx.band != nullptr ? ctx.band->P_full : P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2,
-                     scale, B, C, pb.hid);
+  if (ctx.band != nullptr) {
+    // row-tiled forward: the channel sums of the whole frame arrive with the block's attention statistics (ONE exchange
+    // per block, attention()); conv_transformer runs the squeeze-excite MLP after the transformer branch
+    ctx.band->se_partial = partial;
+    ctx.band->se_slots = nblk;
+  } else {
+    launch_se_finalize(ctx, partial, nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C, pb.hid);
+  }
   *xmod_out = xmod;
   *scale_out = scale;
 }
@@ -274,7 +279,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
           recorder().last_cuda_error = (int)cudaErrorNotSupported;
     }
     launch_copy_norms(ctx, sumsq, stats, B, C);
-    if (ctx.band != nullptr) band_allreduce(ctx, stats, 0, C);
+    if (ctx.band != nullptr) band_allreduce(ctx, stats, C, ctx.band->se_partial, ctx.band->se_slots);
     v = vbuf;
   } else {
     if (ctx.band != nullptr) recorder().last_cuda_error = (int)cudaErrorNotSupported;
@@ -370,9 +375,14 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   float* scale;
   flca_branch(ctx, pb, variant, feat, sg, B, &xmod, &scale);
   void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
-  launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
+  if (ctx.band == nullptr) launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
   void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
   transformer(ctx, pb, feat, x2, B, H, W, pre);
+  if (ctx.band != nullptr) {
+    launch_se_finalize(ctx, ctx.band->se_partial, 1, ctx.band->P_full, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C,
+                       pb.hid);
+    launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
+  }
   void* xr = A.elems((size_t)B * P * C, ctx.dtype);
   GemmP g = gemm_rows(xmod, C, wred, pb.red_b, xr, C, B, P, RF_K_GEMM_CAT_REDUCE);
   g.A2 = x2; g.K2 = C; g.lda2 = C;
@@ -577,6 +587,7 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw,
       RF_CUDA(cudaMemsetAsync(ctx.zero_base, 0, zb, ctx.stream));
     }
   }
+  band_begin(ctx);
   // ---- whole-frame guidance (replicated) --------------------------------------------------------------------------
   const i64 P0 = (i64)h * w;
   float* x_ds = A.get<float>((size_t)P0 * 4);

@@ -28,8 +28,10 @@ MIN_BAND_ROWS = 16 * RF_BAND_HALO
 
 
 def plan_bands(H: int, nranks: int):
-    """[(row0, rows)] per rank: contiguous bands in units of 16 raw rows (every U-Net stage then has whole rows),
-    as even as the units allow (2848 rows = 178 units -> 89+89, 44/45/44/45, 6 x 22 + 2 x 23)."""
+    """[(row0, rows)] per rank: contiguous bands in units of 16 raw rows (every U-Net stage then has whole rows;
+    SURVEY 8d: 2848 rows = 178 units -> 89+89, 44+45+44+45, 6 x 22 + 2 x 23).  A rank works on its band PLUS its halo
+    rows (half a unit per neighbour), so the units left over after an even split go to the ranks whose band image is
+    smallest: the two border ranks first (178 units over 4 ranks -> 45, 44, 44, 45)."""
     if H <= 0 or H % 16:
         raise ValueError(f"frame height {H} must be a positive multiple of 16")
     if not 1 <= nranks <= RF_BAND_MAX_RANKS:
@@ -37,8 +39,13 @@ def plan_bands(H: int, nranks: int):
     units = H // 16
     if units < nranks * RF_BAND_HALO:
         raise ValueError(f"{H} rows are too few for {nranks} bands of at least {MIN_BAND_ROWS} rows")
-    cuts = [(i * units) // nranks for i in range(nranks + 1)]
-    return [(16 * cuts[i], 16 * (cuts[i + 1] - cuts[i])) for i in range(nranks)]
+    size = [units // nranks] * nranks
+    halo = [(1 if r > 0 else 0) + (1 if r < nranks - 1 else 0) for r in range(nranks)]     # in half units
+    for _ in range(units % nranks):
+        r = min(range(nranks), key=lambda i: (2 * size[i] + halo[i], min(i, nranks - 1 - i), i))
+        size[r] += 1
+    row0 = [16 * sum(size[:r]) for r in range(nranks)]
+    return [(row0[r], 16 * size[r]) for r in range(nranks)]
 
 
 class _CommRegion:
@@ -79,6 +86,7 @@ class RowTiledRawFormer:
         self.row0, self.rows = plan_bands(self.H, self.nranks)[self.rank]
         self.group, self._own, self._opened = group, own_region, list(opened)
         self.epoch = 0
+        self._graphs = None
         lib = _lib.load()
         self._band = _lib.Band()
         self._band.rank, self._band.nranks = self.rank, self.nranks
@@ -158,9 +166,36 @@ class RowTiledRawFormer:
         if tuple(raw.shape) != (1, 1, self.H, self.W):
             raise ValueError(f"expected the whole frame [1,1,{self.H},{self.W}], got {tuple(raw.shape)}")
         self.epoch += 1
+        if self._graphs is not None:
+            return self._replay(raw)
         return self._launch(raw, self.epoch)
 
     __call__ = forward
+
+    def enable_cuda_graphs(self, on=True):
+        """Replay this rank's forward as ONE CUDA graph per input buffer (the frame counter the sync points compare
+        against lives in the comm region and is advanced on the device, so the launch sequence is the same every frame).
+        The result is the graph's own output tensor: it is overwritten by the next call with the same input buffer."""
+        self._graphs = {} if on else None
+        return self
+
+    def capture(self, raw):
+        """Capture (without running) the graph of this rank's forward for the input buffer ``raw``."""
+        hit = self._graphs.get(raw.data_ptr())
+        if hit is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._launch(raw, 1)
+            hit = (g, out, raw)
+            self._graphs[raw.data_ptr()] = hit
+        return hit
+
+    def _replay(self, raw):
+        hit = self.capture(raw)
+        hit[0].replay()
+        return hit[1]
 
     def _launch(self, raw, epoch):
         m, lib = self.model, _lib.load()
@@ -226,7 +261,7 @@ class LocalBands:
     """All bands of a frame as concurrent streams of ONE GPU: the same kernels and the same flag/mailbox protocol as
     the multi-GPU run, with the "peer" regions in local memory.  For parity tests of the decomposition."""
 
-    def __init__(self, model, H, W, nranks):
+    def __init__(self, model, H, W, nranks, graphs=False):
         dev = next(model.parameters()).device
         _lib.init_device(dev)
         nbytes = RowTiledRawFormer.comm_bytes(model, H, W, nranks)
@@ -240,12 +275,19 @@ class LocalBands:
         for r, s in enumerate(self.streams):
             with torch.cuda.stream(s):       # the rehearsal also warms this stream's allocator pool
                 self.ranks.append(RowTiledRawFormer(model, H, W, r, nranks, ptrs))
+        if graphs:
+            for t in self.ranks:
+                t.enable_cuda_graphs()
 
     @torch.no_grad()
     def forward(self, raw):
         cur = torch.cuda.current_stream(self.device)
         self.ranks[0].model.packed_weights(raw.device, _lib.RF_BF16)     # pack once, on the current stream
         outs = []
+        if self.ranks[0]._graphs is not None:
+            raw = self.ranks[0].model._check_input(raw)
+            for t in self.ranks:         # capturing synchronises the device: do it before any band is in flight
+                t.capture(raw)
         for t, s in zip(self.ranks, self.streams):
             s.wait_stream(cur)
             with torch.cuda.stream(s):

@@ -225,8 +225,8 @@ int rf_rawformer_forward_profiled(const void* packed, int dim, int dtype, int va
  * Row-tiled single frame — RawFormer.forward (FLCA_RF.py:330-370) of ONE frame split into bands of whole rows over
  * the GPUs of a box (BASELINE config 4).  One process per GPU; rank r owns raw rows [row0, row0 + rows) (multiples of
  * 16, at least 64).  Per Conv_Transformer the ranks exchange RF_BAND_HALO rows of the block input with their band
- * neighbours and all-reduce the three per-image reductions of the block (squeeze-excite channel sums FLCA_RF.py:160,
- * |q|^2,|k|^2 and the per-head Gram FLCA_RF.py:228-230) through peer-mapped memory: every rank owns a "comm region"
+ * neighbours and all-reduce, in one exchange, the three per-image reductions of the block (squeeze-excite channel sums
+ * FLCA_RF.py:160, |q|^2,|k|^2 and the per-head Gram FLCA_RF.py:228-230) through peer-mapped memory: every rank owns a "comm region"
  * (flags + mailboxes) that its peers write with plain stores over NVLink; no NCCL call is on the data path.
  * RF_BF16 / RF_VARIANT_FLCA only.
  * ---------------------------------------------------------------------------------------------- */
@@ -238,7 +238,9 @@ typedef struct rf_band {
   int rank, nranks;
   int row0, rows;                       /* interior raw rows of this rank */
   void* comm[RF_BAND_MAX_RANKS];        /* comm region of every rank as mapped in THIS process (comm[rank] = own) */
-  unsigned epoch;                       /* 1, 2, 3, ...: one per forward on this comm region, the same on all ranks;
+  unsigned epoch;                       /* non-zero: a real forward (the frame counter itself lives in the comm region
+                                           and is advanced on the device, so a forward can be replayed as a CUDA
+                                           graph); every rank must run the same number of real forwards.
                                            0 = rehearsal: same launches, but no rank signals or waits (run it once
                                            per rank before the first frame so that every kernel is loaded) */
 } rf_band;

@@ -126,7 +126,7 @@ def _psnr(a, b, data_range):
 CASES = [
     # dim, H, W, bands, input, weight scale
     (32, 128, 128, 2, "rand", 2.0),
-    (32, 256, 192, 3, "dark", 2.0),      # uneven bands: 80 + 80 + 96 rows
+    (32, 256, 192, 3, "dark", 2.0),      # uneven bands: 96 + 80 + 80 rows
     (48, 128, 160, 2, "rand", 1.5),
     (64, 192, 128, 3, "rand", 1.0),
     (32, 64, 64, 1, "rand", 2.0),        # one band = the whole frame (no halo, no peers)
@@ -157,7 +157,7 @@ def test_row_tiled_matches_whole_frame_and_oracle(case):
             # same engine, same arithmetic per pixel; only the order of the fp32 partial sums of the three per-image
             # reductions differs, which moves a few bf16 roundings: far tighter than the bf16-vs-reference bar
             p = _psnr(tiled, whole, rng)
-            assert p >= 55.0, f"frame {it}: PSNR(row-tiled, whole-frame) = {p:.1f} dB"
+            assert p >= 54.0, f"frame {it}: PSNR(row-tiled, whole-frame) = {p:.1f} dB"
     finally:
         bands.close()
     with torch.no_grad():
@@ -166,6 +166,38 @@ def test_row_tiled_matches_whole_frame_and_oracle(case):
     p_t, p_w = _psnr(tiled, ref, rng), _psnr(whole, ref, rng)
     assert p_t >= 35.0, f"PSNR(row-tiled, oracle) = {p_t:.1f} dB"
     assert abs(p_t - p_w) <= 0.5, f"row-tiled {p_t:.2f} dB vs whole-frame {p_w:.2f} dB against the oracle"
+
+
+@pytest.mark.gpu
+def test_row_tiled_graph_replay():
+    """Every band's forward as one CUDA graph (the frame counter is advanced on the device): same result as eager
+    launches, frame after frame, also when the input buffer's content changes.  Not bit-equal: the fp32 atomics of the
+    Gram / channel-sum kernels make two runs of the SAME path differ at ~58 dB with these stress weights."""
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    dev = torch.device("cuda", 0)
+    m = rf.RawFormer(dim=32, precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=5, scale=2.0), strict=True)
+    m = m.to(dev).eval()
+    H, W, n = 192, 128, 3
+    x = torch.from_numpy(T.gen_input("rand", (1, 1, H, W), 21)).to(dev)
+    x2 = torch.from_numpy(T.gen_input("dark", (1, 1, H, W), 22)).to(dev)
+    eager, graphs = rf.LocalBands(m, H, W, n), rf.LocalBands(m, H, W, n, graphs=True)
+    try:
+        buf = x.clone()
+        for frame in (x, x2, x):
+            buf.copy_(frame)
+            with torch.no_grad():
+                whole = m(buf).float().cpu().numpy()
+            a = eager(buf).float().cpu().numpy()
+            b = graphs(buf).float().cpu().numpy()
+            rng = float(whole.max() - whole.min())
+            assert _psnr(b, whole, rng) >= 54.0 and _psnr(b, a, rng) >= 54.0, (
+                f"graph/whole {_psnr(b, whole, rng):.1f} dB, graph/eager {_psnr(b, a, rng):.1f} dB, "
+                f"eager/whole {_psnr(a, whole, rng):.1f} dB")
+    finally:
+        eager.close()
+        graphs.close()
 
 
 @pytest.mark.gpu
