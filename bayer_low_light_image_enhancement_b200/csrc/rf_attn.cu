@@ -104,6 +104,8 @@ void launch_layernorm(Ctx& ctx, const void* x, const float* g, const float* b, v
 template <typename T, int GS, int VPL>
 __global__ void __launch_bounds__(256)
 k_row_stats(const T* __restrict__ x, float2* __restrict__ stats, i64 rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & (GS - 1);
   const i64 row = ((i64)blockIdx.x * blockDim.x + threadIdx.x) / GS;
   const bool row_ok = row < rows;
@@ -135,7 +137,7 @@ void launch_row_stats(Ctx& ctx, const void* x, float* stats, i64 rows, int C) {
   ScopedLaunch sl(RF_K_LAYERNORM, rows * (C * (double)esize(ctx.dtype) + 8.0));
   const int cv = C / 8;
 #define RF_RS(T, GS, VPL) \
-  k_row_stats<T, GS, VPL><<<(unsigned)cdivl(rows * GS, 256), 256, 0, ctx.stream>>>((const T*)x, (float2*)stats, rows, C)
+  launch_pdl(k_row_stats<T, GS, VPL>, dim3((unsigned)cdivl(rows * GS, 256)), dim3(256), 0, ctx.stream, (const T*)x, (float2*)stats, rows, C)
 #define RF_RS_ALL(T)                   \
   do {                                 \
     if (cv <= 4) RF_RS(T, 4, 1);       \
@@ -393,6 +395,8 @@ __global__ void __launch_bounds__(256)
 k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ temperature, const float* __restrict__ proj_w,
                 T* __restrict__ Mw, int C) {
   extern __shared__ float smem[];
+  pdl_trigger();
+  pdl_wait();
   const int c = C >> 3;
   float* attn = smem;           // [c][c+1]
   float* nq = smem + c * (c + 1);
@@ -450,9 +454,9 @@ void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature
   const int nz = C >= 64 ? C / 32 : 1;
   ScopedLaunch sl(RF_K_ATTN_FINALIZE, 4.0 * B * C * c + (4.0 + esize(ctx.dtype)) * B * C * C, 2.0 * B * C * C * c);
   if (ctx.dtype == RF_BF16)
-    k_attn_finalize<bf16><<<dim3(8, B, nz), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (bf16*)Mw, C);
+    launch_pdl(k_attn_finalize<bf16>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (bf16*)Mw, C);
   else
-    k_attn_finalize<float><<<dim3(8, B, nz), 256, smem, ctx.stream>>>(stats, temperature, proj_w, (float*)Mw, C);
+    launch_pdl(k_attn_finalize<float>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (float*)Mw, C);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -86,6 +86,7 @@ struct BandHaloP {
 
 __global__ void __launch_bounds__(512)
 k_band_halo(BandHaloP p) {
+  pdl_wait();           // (no pdl_trigger: the kernels behind a sync point must not occupy SMs while it waits for a peer)
   band_load_target(p.s);
   const i64 n = (i64)BAND_HALO * p.row_u4;
   const i64 i0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, step = (i64)gridDim.x * blockDim.x;
@@ -139,6 +140,7 @@ __device__ __forceinline__ i64 band_stats_idx(int e, int C) {
 
 __global__ void __launch_bounds__(256)
 k_band_allreduce(BandReduceP p) {
+  pdl_wait();
   band_load_target(p.s);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
   const int n_attn = p.C * (p.C >> 3) + 2 * p.C;
@@ -204,7 +206,7 @@ void band_halo_exchange(Ctx& ctx, void* x, int W, int C) {
   p.mail_above = b.rank > 0 ? reinterpret_cast<uint4*>(b.comm[b.rank - 1] + off) : nullptr;
   p.mail_below = b.rank + 1 < b.nranks ? reinterpret_cast<uint4*>(b.comm[b.rank + 1] + off) : nullptr;
   ScopedLaunch sl(RF_K_BAND_HALO, 2.0 * ((b.ht ? 1 : 0) + (b.hb ? 1 : 0)) * BAND_HALO * (double)row_bytes);
-  k_band_halo<<<grid, 512, 0, ctx.stream>>>(p);
+  launch_pdl(k_band_halo, dim3(grid), dim3(512), 0, ctx.stream, p);
 }
 
 void band_begin(Ctx& ctx) {
@@ -228,7 +230,7 @@ void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots) {
   for (int r = 0; r < b.nranks; ++r) p.mail_peer[r] = reinterpret_cast<float*>(b.comm[r] + off);
   p.mail_local = p.mail_peer[b.rank];
   ScopedLaunch sl(RF_K_BAND_ALLREDUCE, 4.0 * n * (2.0 * b.nranks));
-  k_band_allreduce<<<grid, 256, 0, ctx.stream>>>(p);
+  launch_pdl(k_band_allreduce, dim3(grid), dim3(256), 0, ctx.stream, p);
 }
 
 }  // namespace rf

@@ -90,6 +90,35 @@ struct ScopedLaunch {
 int check_cuda(cudaError_t e);
 int num_sms();
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while the previous kernel of the
+// stream is still draining; it runs its prologue (barrier init, tensor-memory allocation, descriptor prefetch) and then
+// blocks in pdl_wait() until that kernel has completed and its memory is visible.  RULES: every kernel launched this
+// way executes pdl_wait() before its first global-memory access (reads AND writes: the previous kernel may still be
+// reading a buffer this one recycles) -- that also keeps the ordering transitive along the chain; pdl_trigger() comes
+// after the kernel's tensor-memory allocation (a dependent that grabbed TMEM first would starve it while waiting for
+// it).  RAWFORMER_B200_PDL=0 turns the launch attribute off (plain stream order; the device-side calls are no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define RF_CUDA(x)                          \
   do {                                      \
     int _s = rf::check_cuda((x));           \

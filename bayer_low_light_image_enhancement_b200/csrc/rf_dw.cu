@@ -158,6 +158,8 @@ void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const f
 }
 
 __global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict__ stats, int C) {
+  pdl_trigger();
+  pdl_wait();
   const i64 b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 2 * C) stats[b * ((i64)C * C + 2 * C) + (i64)C * C + i] = sumsq[b * 2 * C + i];
@@ -165,7 +167,7 @@ __global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict_
 void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C) {
   if (ctx.dry) return;
   ScopedLaunch sl(RF_K_MISC);
-  k_copy_norms<<<dim3(cdiv(2 * C, 256), B), 256, 0, ctx.stream>>>(sumsq, stats, C);
+  launch_pdl(k_copy_norms, dim3(cdiv(2 * C, 256), B), dim3(256), 0, ctx.stream, sumsq, stats, C);
 }
 
 }  // namespace rf

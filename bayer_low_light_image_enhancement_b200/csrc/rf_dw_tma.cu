@@ -97,6 +97,8 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
 
   // Every CTA owns ONE channel chunk and walks the spatial tiles lane, lane + lanes, ...  CTAs of the same lane run
   // the other chunks of the same pixels at the same time, so a 128-byte line that holds two chunks is fetched from
@@ -278,9 +280,9 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
     attr_set = true;
   }
   const int grid = p.lanes * p.nchunks;
-  if (mode == 0) k_dw_tma<0><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);
-  else if (mode == 1) k_dw_tma<1><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);
-  else k_dw_tma<2><<<grid, DT_THREADS, smem, ctx.stream>>>(m, p);
+  if (mode == 0) launch_pdl(k_dw_tma<0>, dim3(grid), dim3(DT_THREADS), smem, ctx.stream, m, p);
+  else if (mode == 1) launch_pdl(k_dw_tma<1>, dim3(grid), dim3(DT_THREADS), smem, ctx.stream, m, p);
+  else launch_pdl(k_dw_tma<2>, dim3(grid), dim3(DT_THREADS), smem, ctx.stream, m, p);
   return true;
 }
 

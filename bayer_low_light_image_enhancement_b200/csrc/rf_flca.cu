@@ -262,6 +262,8 @@ k_se_finalize(const float* __restrict__ partial, int nblk, float invP, const flo
               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
               float* __restrict__ scale, int C, int hid) {
   extern __shared__ float smem[];
+  pdl_trigger();
+  pdl_wait();
   float* mean = smem;       // [C]
   float* hbuf = smem + C;   // [hid]
   const int b = blockIdx.x;
@@ -289,12 +291,14 @@ void launch_se_finalize(Ctx& ctx, const float* partial, int nblk, i64 P, const f
                         const float* w2, const float* b2, float* scale, int B, int C, int hid) {
   if (ctx.dry) return;
   ScopedLaunch sl(RF_K_SE_FINALIZE, 4.0 * B * nblk * C);
-  k_se_finalize<<<B, 256, sizeof(float) * (C + hid), ctx.stream>>>(partial, nblk, 1.0f / (float)P, w1, b1, w2, b2, scale, C,
-                                                                  hid);
+  launch_pdl(k_se_finalize, dim3(B), dim3(256), sizeof(float) * (C + hid), ctx.stream, partial, nblk, 1.0f / (float)P, w1, b1, w2,
+             b2, scale, C, hid);
 }
 
 template <typename T>
 __global__ void k_fold_reduce(const float* __restrict__ red_w, const float* __restrict__ scale, T* __restrict__ wred, int C) {
+  pdl_trigger();
+  pdl_wait();
   const i64 b = blockIdx.y;
   const i64 n2 = (i64)C * 2 * C;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (i64)gridDim.x * blockDim.x) {
@@ -310,9 +314,9 @@ void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* 
   unsigned gx = (unsigned)(cdivl(n2, 256) < 296 ? cdivl(n2, 256) : 296);
   ScopedLaunch sl(RF_K_FOLD_REDUCE, (4.0 + esize(ctx.dtype)) * B * n2);
   if (ctx.dtype == RF_BF16)
-    k_fold_reduce<bf16><<<dim3(gx, B), 256, 0, ctx.stream>>>(red_w, scale, (bf16*)wred, C);
+    launch_pdl(k_fold_reduce<bf16>, dim3(gx, B), dim3(256), 0, ctx.stream, red_w, scale, (bf16*)wred, C);
   else
-    k_fold_reduce<float><<<dim3(gx, B), 256, 0, ctx.stream>>>(red_w, scale, (float*)wred, C);
+    launch_pdl(k_fold_reduce<float>, dim3(gx, B), dim3(256), 0, ctx.stream, red_w, scale, (float*)wred, C);
 }
 
 template <typename T>

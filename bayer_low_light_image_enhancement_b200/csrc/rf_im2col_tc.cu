@@ -67,6 +67,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // fp32 x4 per pixel -> [hi x4 | lo x4] bf16 (16 bytes per pixel)
 __global__ void __launch_bounds__(256)
 k_split_bf16x8(const float4* __restrict__ g, uint4* __restrict__ out, i64 n, int stride4) {
+  pdl_trigger();
+  pdl_wait();
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
     const float4 v = g[i * stride4];
     const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
@@ -78,7 +80,7 @@ void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix, int s
   if (ctx.dry || npix <= 0) return;
   ScopedLaunch sl(RF_K_GUIDANCE, 32.0 * npix);
   const unsigned gx = (unsigned)(cdivl(npix, 256) < 8 * num_sms() ? cdivl(npix, 256) : 8 * num_sms());
-  k_split_bf16x8<<<gx, 256, 0, ctx.stream>>>((const float4*)g4, (uint4*)out16, npix, stride_floats / 4);
+  launch_pdl(k_split_bf16x8, dim3(gx), dim3(256), 0, ctx.stream, (const float4*)g4, (uint4*)out16, npix, stride_floats / 4);
 }
 
 template <int MODE, int UPT>
@@ -110,6 +112,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)(2 * p.tmem_cols));
+  pdl_wait();           // barrier set-up and the TMEM allocation overlapped the previous kernel's tail
 
   // ---- W (once): K chunk kc <-> tap kc for kc < 8, chunk 8 = zeros (it pairs tap 7's pixels a second time), chunk 9 =
   //      tap 8; inside a chunk [hi weights of the 4 maps | the same weights again for the lo parts].  Row n = seg*Cc + cl.
@@ -220,6 +223,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();                                     // (after the TMEM allocation, see launch_pdl)
 
   if (tid == 32) {
     for (int j = 0; j < 3 && j < n_my; ++j) issue_loads(j);
@@ -382,7 +386,7 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
         return false;                                                                                                        \
       attr = true;                                                                                                           \
     }                                                                                                                        \
-    k_im2col_tc<M, U><<<grid, IT_THREADS, smem, ctx.stream>>>(mG, mIn, mOut, p);                                             \
+    launch_pdl(k_im2col_tc<M, U>, dim3(grid), dim3(IT_THREADS), smem, ctx.stream, mG, mIn, mOut, p);                         \
   } while (0)
   const int grid = p.lanes * p.nchunks;
   if (mode == 0) { if (upt == 1) RF_IT_LAUNCH(0, 1); else RF_IT_LAUNCH(0, 2); }

@@ -24,6 +24,15 @@ int num_sms() {
   return g_num_sms;
 }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("RAWFORMER_B200_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 int check_cuda(cudaError_t e) {
   if (e == cudaSuccess) return RF_OK;
   g_rec.last_cuda_error = (int)e;

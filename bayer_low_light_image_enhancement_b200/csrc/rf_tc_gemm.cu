@@ -180,6 +180,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();        // (after the TMEM allocation, see launch_pdl)
+  pdl_wait();           // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0 && HALO) {
     // ================= halo conv: TMA producer =================
@@ -769,6 +771,8 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1055,7 +1059,7 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
       attr = true;                                                                                                          \
     }                                                                                                                       \
     ScopedLaunch sl(g.kernel_id, bytes, 2.0 * rows * g.N * K);                                                              \
-    kern<<<grid, TC_THREADS, smem, ctx.stream>>>(mA1, mA2, mW, mY, mR, p);                                                  \
+    launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, ctx.stream, mA1, mA2, mW, mY, mR, p);                              \
     return p.stats_out ? p.tiles_n : 0;                                                                                     \
   } while (0)
   // the halo-conv code (patch re-layout in the epilogue warps, descriptor-table MMA loop) is compiled only into the
@@ -1124,7 +1128,7 @@ bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
     attr_set = true;
   }
   ScopedLaunch sl(RF_K_GEMM_GRAM, 4.0 * C * P, 2.0 * P * C * (C / 8.0));
-  k_tc_gram<<<dim3(mt, mt, ksplit), GR_THREADS, smem, ctx.stream>>>(m, G, C, P, ksplit, packed, nst);
+  launch_pdl(k_tc_gram, dim3(mt, mt, ksplit), dim3(GR_THREADS), smem, ctx.stream, m, G, C, P, ksplit, packed, nst);
   return true;
 }
 
