@@ -393,7 +393,7 @@ void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const f
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ temperature, const float* __restrict__ proj_w,
-                T* __restrict__ Mw, int C) {
+                T* __restrict__ Mw, int C, const float* __restrict__ norms) {
   extern __shared__ float smem[];
   pdl_trigger();
   pdl_wait();
@@ -405,8 +405,9 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
   const i64 b = blockIdx.y;
   const float* st = stats + b * ((i64)C * C + 2 * C);
   const float* gram = st + ((i64)h * c) * C + h * c;   // diagonal block of head h, row pitch C
-  const float* qn2 = st + (i64)C * C + h * c;
-  const float* kn2 = st + (i64)C * C + C + h * c;
+  const float* nrm = norms != nullptr ? norms + b * 2 * C : st + (i64)C * C;
+  const float* qn2 = nrm + h * c;
+  const float* kn2 = nrm + C + h * c;
   const int tid = threadIdx.x;
   for (int i = tid; i < c; i += blockDim.x) {
     nq[i] = fmaxf(sqrtf(qn2[i]), 1e-12f);
@@ -447,16 +448,16 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
 }
 
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
-                          int C) {
+                          int C, const float* norms) {
   if (ctx.dry) return;
   const int c = C / 8;
   size_t smem = sizeof(float) * (c * (c + 1) + 2 * c);
   const int nz = C >= 64 ? C / 32 : 1;
   ScopedLaunch sl(RF_K_ATTN_FINALIZE, 4.0 * B * C * c + (4.0 + esize(ctx.dtype)) * B * C * C, 2.0 * B * C * C * c);
   if (ctx.dtype == RF_BF16)
-    launch_pdl(k_attn_finalize<bf16>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (bf16*)Mw, C);
+    launch_pdl(k_attn_finalize<bf16>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (bf16*)Mw, C, norms);
   else
-    launch_pdl(k_attn_finalize<float>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (float*)Mw, C);
+    launch_pdl(k_attn_finalize<float>, dim3(8, B, nz), dim3(256), smem, ctx.stream, stats, temperature, proj_w, (float*)Mw, C, norms);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -122,6 +122,7 @@ k_band_halo(BandHaloP p) {
 struct BandReduceP {
   BandSyncP s;
   float* stats;                   // attention statistics of C channels
+  float* norms;                   // [2C] squared norms of q,k when they are kept outside stats (else nullptr)
   float* se;                      // [se_slots][C] partial channel sums (nullptr: none)
   int C, se_slots;
   int n;                          // elements exchanged = C*C/8 + 2C (+ C)
@@ -147,7 +148,7 @@ k_band_allreduce(BandReduceP p) {
   for (int e = i0; e < p.n; e += step) {
     float v;
     if (e < n_attn) {
-      v = p.stats[band_stats_idx(e, p.C)];
+      v = (p.norms != nullptr && e >= n_attn - 2 * p.C) ? p.norms[e - (n_attn - 2 * p.C)] : p.stats[band_stats_idx(e, p.C)];
     } else {
       v = 0.f;
       for (int k = 0; k < p.se_slots; ++k) v += p.se[(i64)k * p.C + (e - n_attn)];
@@ -160,8 +161,9 @@ k_band_allreduce(BandReduceP p) {
   for (int e = i0; e < p.n; e += step) {
     float sum = 0.f;
     for (int r = 0; r < p.s.nranks; ++r) sum += __ldcg(p.mail_local + (i64)r * p.n_pad + e);
-    if (e < n_attn) p.stats[band_stats_idx(e, p.C)] = sum;
-    else p.se[e - n_attn] = sum;
+    if (e >= n_attn) p.se[e - n_attn] = sum;
+    else if (p.norms != nullptr && e >= n_attn - 2 * p.C) p.norms[e - (n_attn - 2 * p.C)] = sum;
+    else p.stats[band_stats_idx(e, p.C)] = sum;
   }
 }
 
@@ -216,7 +218,7 @@ void band_begin(Ctx& ctx) {
   k_band_begin<<<1, 1, 0, ctx.stream>>>(reinterpret_cast<unsigned*>(b.comm[b.rank] + BAND_FRAME_OFF));
 }
 
-void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots) {
+void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots, float* norms) {
   Band& b = *ctx.band;
   const int n = C * (C / 8) + 2 * C + (se != nullptr || ctx.dry ? C : 0);
   const int n_pad = (int)align_up((size_t)n, 64);
@@ -226,7 +228,7 @@ void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots) {
   if (grid > 16) grid = 16;
   BandReduceP p;
   if (!band_sync_params(ctx, p.s, grid) || ctx.dry) return;
-  p.stats = stats; p.se = se; p.C = C; p.se_slots = se_slots; p.n = n; p.n_pad = n_pad;
+  p.stats = stats; p.norms = norms; p.se = se; p.C = C; p.se_slots = se_slots; p.n = n; p.n_pad = n_pad;
   for (int r = 0; r < b.nranks; ++r) p.mail_peer[r] = reinterpret_cast<float*>(b.comm[r] + off);
   p.mail_local = p.mail_peer[b.rank];
   ScopedLaunch sl(RF_K_BAND_ALLREDUCE, 4.0 * n * (2.0 * b.nranks));

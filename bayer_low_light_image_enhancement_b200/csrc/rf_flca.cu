@@ -319,6 +319,71 @@ void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* 
     launch_pdl(k_fold_reduce<float>, dim3(gx, B), dim3(256), 0, ctx.stream, red_w, scale, (float*)wred, C);
 }
 
+// squeeze-excite MLP + fold of its scale into channel_reduce in ONE launch (FLCA_RF.py:160-161,275-276): every CTA
+// recomputes the tiny MLP (C x hid) in shared memory and then scales its slice of W_red [C][2C]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_se_fold(const float* __restrict__ partial, int nblk, float invP, const float* __restrict__ w1, const float* __restrict__ b1,
+          const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ scale_out,
+          const float* __restrict__ red_w, T* __restrict__ wred, int C, int hid) {
+  extern __shared__ float smem[];
+  pdl_trigger();
+  pdl_wait();
+  float* mean = smem;            // [C]
+  float* hbuf = smem + C;        // [hid]
+  float* sc = hbuf + hid;        // [C]
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* pp = partial + (i64)b * nblk * C + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // independent chains: the loads of a channel overlap
+    int k = 0;
+    for (; k + 4 <= nblk; k += 4) {
+      s0 += pp[(i64)k * C]; s1 += pp[(i64)(k + 1) * C]; s2 += pp[(i64)(k + 2) * C]; s3 += pp[(i64)(k + 3) * C];
+    }
+    for (; k < nblk; ++k) s0 += pp[(i64)k * C];
+    mean[c] = ((s0 + s1) + (s2 + s3)) * invP;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < hid; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w1[(i64)j * C + c] * mean[c];
+    s = warp_sum(s);
+    if (lane == 0) hbuf[j] = fmaxf(s + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int j = 0; j < hid; ++j) s += w2[(i64)c * hid + j] * hbuf[j];
+    s = sigmoid_f(s);
+    sc[c] = s;
+    if (blockIdx.x == 0) scale_out[(i64)b * C + c] = s;
+  }
+  __syncthreads();
+  const i64 n2 = (i64)C * 2 * C;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (i64)gridDim.x * blockDim.x) {
+    const int k = (int)(i % (2 * C));
+    float v = red_w[i];
+    if (k < C) v *= sc[k];
+    from_f(wred[b * n2 + i], v);
+  }
+}
+void launch_se_fold(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* scale, const float* red_w, void* wred, int B, int C, int hid) {
+  if (ctx.dry) return;
+  const i64 n2 = (i64)C * 2 * C;
+  unsigned gx = (unsigned)cdivl(n2, 2048);
+  if (gx > (unsigned)num_sms()) gx = num_sms();
+  const size_t smem = sizeof(float) * (2 * C + hid);
+  ScopedLaunch sl(RF_K_SE_FINALIZE, 4.0 * B * nblk * C + (4.0 + esize(ctx.dtype)) * B * n2);
+  if (ctx.dtype == RF_BF16)
+    launch_pdl(k_se_fold<bf16>, dim3(gx, B), dim3(256), smem, ctx.stream, partial, nblk, 1.0f / (float)P, w1, b1, w2, b2, scale,
+               red_w, (bf16*)wred, C, hid);
+  else
+    launch_pdl(k_se_fold<float>, dim3(gx, B), dim3(256), smem, ctx.stream, partial, nblk, 1.0f / (float)P, w1, b1, w2, b2, scale,
+               red_w, (float*)wred, C, hid);
+}
+
 template <typename T>
 __global__ void k_scale_channels(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ out, i64 P, int C) {
   const i64 b = blockIdx.y;

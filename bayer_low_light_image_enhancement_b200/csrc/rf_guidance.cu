@@ -116,9 +116,10 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
                                  const float* __restrict__ LL2, const float* __restrict__ yh2, int H2, int W2,
                                  const float* __restrict__ cr, const float* __restrict__ cb, int Hy, int Wy,
                                  float* __restrict__ G, float* sums, int Hf, int Wf, uint4* __restrict__ G16a,
-                                 uint4* __restrict__ G16b) {
+                                 uint4* __restrict__ G16b, int y_begin, int y_rows) {
   i64 b = blockIdx.y;
-  i64 total = (i64)Hf * Wf;
+  const i64 total = (i64)Hf * Wf;                     // pixels of one image of G
+  const i64 first = (i64)y_begin * Wf, last = first + (i64)y_rows * Wf;   // rows [y_begin, y_begin + y_rows) are produced
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // [hi x4 | lo x4] bf16 of four fp32 maps = the 16-byte pixel of the tensor-core FLCA kernels (rf_im2col_tc.cu)
   auto split4 = [](float a, float bq, float c, float d) {
@@ -130,7 +131,7 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
     return make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&q0),
                       *reinterpret_cast<uint32_t*>(&q1));
   };
-  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+  for (i64 idx = first + (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < last; idx += (i64)gridDim.x * blockDim.x) {
     int x = (int)(idx % Wf), y = (int)(idx / Wf);
     int ya, yb, xa, xb;
     float ly, lx;
@@ -175,17 +176,18 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
 
 void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
                            const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
-                           int NG, float* sums, int B, int Hf, int Wf, void* G16a, void* G16b) {
+                           int NG, float* sums, int B, int Hf, int Wf, void* G16a, void* G16b, int y_begin, int y_rows) {
   if (ctx.dry) return;
-  i64 total = (i64)Hf * Wf;
+  if (y_rows < 0) { y_begin = 0; y_rows = Hf; }
+  i64 total = (i64)y_rows * Wf;
   unsigned gx = (unsigned)(cdivl(total, 256) < 4 * num_sms() ? cdivl(total, 256) : 4 * num_sms());
   ScopedLaunch sl(RF_K_GUIDANCE, 4.0 * NG * B * total + 4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
   if (NG == 4)
     k_guidance_stage<4><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b);
+                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
   else
     k_guidance_stage<8><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b);
+                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
 }
 
 }  // namespace rf

@@ -133,7 +133,8 @@ void launch_dwt_high(Ctx& ctx, const float* y, const float* filt16, float* LL, f
 // means (optional, ML): [B][8] sums of the NG maps over the stage (divide by Hf*Wf on use); must be zeroed.
 void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
                            const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
-                           int NG, float* sums, int B, int Hf, int Wf, void* G16a = nullptr, void* G16b = nullptr);
+                           int NG, float* sums, int B, int Hf, int Wf, void* G16a = nullptr, void* G16b = nullptr,
+                           int y_begin = 0, int y_rows = -1 /* rows of G to produce; default: all */);
 
 // ---- FLCA (rf_flca.cu) ---------------------------------------------------------------------------------------------
 int flca_num_partials(int C, int B, i64 P);
@@ -162,6 +163,9 @@ void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int 
 // s = sigmoid(W2 relu(W1 mean + b1) + b2)  -> scale [B][C]
 void launch_se_finalize(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1,
                         const float* w2, const float* b2, float* scale, int B, int C, int hid);
+// both of the above in one launch (the scale is also written to scale [B][C])
+void launch_se_fold(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* scale, const float* red_w, void* wred, int B, int C, int hid);
 // wred[b][n][k] = red_w[n][k] * (k < C ? scale[b][k] : 1)   (T output)
 void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* wred, int B, int C);
 // out = x * scale[b][c]
@@ -189,8 +193,9 @@ bool tcgen05_enabled();
 // stats[b][C*C + i] = sumsq[b][i], i < 2C
 void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C);
 // Mw[b] = proj_w * blockdiag(softmax(gram / (|q||k|) * temperature))   (T [B][C][C])
+// norms (optional): [B][2C] squared norms of q,k kept outside `stats` (else they are read from stats[b][C*C ..])
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
-                          int C);
+                          int C, const float* norms = nullptr);
 // depthwise 3x3 (+bias) with optional exact GELU: in/out [B,H,W,Cn]
 void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H,
                    int W, int Cn, int kernel_id);
@@ -209,6 +214,7 @@ void band_halo_exchange(Ctx& ctx, void* x, int W, int C);
 void band_begin(Ctx& ctx);
 // one all-reduce (sum over ranks) per Conv_Transformer: the attention statistics of C channels (diagonal Gram blocks +
 // squared norms) and the squeeze-excite channel sums se [se_slots][C] (-> row 0 holds the frame's sums)
-void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots);
+// norms: the [2C] squared norms of q,k (nullptr: inside stats at C*C)
+void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots, float* norms = nullptr);
 
 }  // namespace rf

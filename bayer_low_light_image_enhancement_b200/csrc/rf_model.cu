@@ -177,8 +177,11 @@ static GemmP gemm_rows(const void* A, int K, const void* Wt, const float* bias, 
 }
 
 // FLCA branch: returns xmod (un-scaled) and the SE scale [B][C]
+// With `se_out`, the squeeze-excite MLP is left to the caller (conv_transformer fuses it with the channel_reduce fold):
+// se_out = {partial sums [B][nblk][C], nblk}.
+struct SePartial { float* partial = nullptr; int nblk = 0; };
 static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void* feat, const Stage& sg, int B, void** xmod_out,
-                        float** scale_out) {
+                        float** scale_out, SePartial* se_out = nullptr) {
   const int C = pb.C, H = sg.H, W = sg.W;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
@@ -232,6 +235,10 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     // per block, attention()); conv_transformer runs the squeeze-excite MLP after the transformer branch
     ctx.band->se_partial = partial;
     ctx.band->se_slots = nblk;
+  }
+  if (se_out != nullptr) {
+    se_out->partial = partial;
+    se_out->nblk = nblk;
   } else {
     launch_se_finalize(ctx, partial, nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C, pb.hid);
   }
@@ -262,6 +269,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   const i64 nst = attn_stats_floats(C);
   float* stats = zeroed_f32(ctx, (size_t)B * nst);
   const void* v = nullptr;
+  const float* norms = nullptr;
   i64 ldv = C;
   if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
     // depthwise pass writes q|k [P][2C] and v [P][C] (dense NHWC, coalesced) and reduces |q|^2,|k|^2; the Gram is a
@@ -278,8 +286,8 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
         if (!launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, stats + b * nst, C, Pg))
           recorder().last_cuda_error = (int)cudaErrorNotSupported;
     }
-    launch_copy_norms(ctx, sumsq, stats, B, C);
-    if (ctx.band != nullptr) band_allreduce(ctx, stats, C, ctx.band->se_partial, ctx.band->se_slots);
+    if (ctx.band != nullptr) band_allreduce(ctx, stats, C, ctx.band->se_partial, ctx.band->se_slots, sumsq);
+    norms = sumsq;     // the squared norms stay where the depthwise kernel left them
     v = vbuf;
   } else {
     if (ctx.band != nullptr) recorder().last_cuda_error = (int)cudaErrorNotSupported;
@@ -288,7 +296,7 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     v = vbuf;
   }
   void* Mw = A.elems((size_t)B * C * C, ctx.dtype);
-  launch_attn_finalize(ctx, stats, pb.temperature, pb.proj_w, Mw, B, C);
+  launch_attn_finalize(ctx, stats, pb.temperature, pb.proj_w, Mw, B, C, norms);
   GemmP g = gemm_rows(v, C, Mw, pb.proj_b, out, C, B, P, RF_K_GEMM_PROJ);
   g.lda1 = ldv;
   g.w_img = (i64)C * C;
@@ -373,16 +381,18 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   const size_t mk = A.mark();
   void* xmod;
   float* scale;
-  flca_branch(ctx, pb, variant, feat, sg, B, &xmod, &scale);
+  SePartial se;
+  flca_branch(ctx, pb, variant, feat, sg, B, &xmod, &scale, &se);
   void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
-  if (ctx.band == nullptr) launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
+  // squeeze-excite MLP + fold of its scale into channel_reduce: one launch.  Row-tiled forward: after the transformer
+  // branch, whose all-reduce brings the channel sums of the whole frame (into row 0 of the partial sums)
+  if (ctx.band == nullptr)
+    launch_se_fold(ctx, se.partial, se.nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C, pb.hid);
   void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
   transformer(ctx, pb, feat, x2, B, H, W, pre);
-  if (ctx.band != nullptr) {
-    launch_se_finalize(ctx, ctx.band->se_partial, 1, ctx.band->P_full, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, B, C,
-                       pb.hid);
-    launch_fold_reduce(ctx, pb.red_w, scale, wred, B, C);
-  }
+  if (ctx.band != nullptr)
+    launch_se_fold(ctx, se.partial, 1, ctx.band->P_full, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C,
+                   pb.hid);
   void* xr = A.elems((size_t)B * P * C, ctx.dtype);
   GemmP g = gemm_rows(xmod, C, wred, pb.red_b, xr, C, B, P, RF_K_GEMM_CAT_REDUCE);
   g.A2 = x2; g.K2 = C; g.lda2 = C;
@@ -395,7 +405,7 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
 // guidance of one stage from planar y-derived maps
 static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const float* LL1, const float* yh1, int H1, int W1,
                        const float* LL2, const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy,
-                       int B) {
+                       int B, int y_begin = 0, int y_rows = -1) {
   const int NG = variant == RF_VARIANT_ML ? 8 : 4;
   sg.H = Hf; sg.W = Wf;
   sg.G = ctx.arena.get<float>((size_t)B * Hf * Wf * NG);
@@ -409,7 +419,8 @@ static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const f
     sg.G16 = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
     if (variant == RF_VARIANT_ML) sg.G16b = ctx.arena.alloc((size_t)B * Hf * Wf * 16);
   }
-  launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf, sg.G16, sg.G16b);
+  launch_guidance_stage(ctx, LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, sg.G, NG, sg.sums, B, Hf, Wf, sg.G16, sg.G16b,
+                        y_begin, y_rows);
 }
 
 struct GuidanceMaps {
@@ -604,7 +615,9 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw,
   GuidanceMaps gm = make_pyramid(ctx, variant, y, pm.haar, B, h, w);
   Stage st[4];
   for (int s = 0; s < 4; ++s) {
-    make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w, B);
+    // (the maps are laid out for the whole frame, but only the band's rows are produced)
+    make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w, B,
+               first_row(s), rows_img(s));
     // the band's view of the stage guidance: rows [first_row, first_row + rows_img)
     const size_t px0 = (size_t)first_row(s) * (w >> s);
     if (st[s].G) st[s].G += px0 * 4;

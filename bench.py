@@ -191,6 +191,44 @@ def time_cpu_port(size, variant, budget_s=25.0):
     return best
 
 
+def time_torch_eager_b200(size, variant, dev):
+    """The reference's own operator sequence (oracle/rawformer_torch.py = the ATen calls of the reference modules) run
+    EAGERLY on the B200: the "existing Blackwell path" of SURVEY 8d.  A reported baseline like cpu_baseline, never a
+    product path.  fp32 with TF32 contractions, and the same under torch.autocast(bf16)."""
+    import torch
+
+    import rf_testlib as T
+    from oracle import rawformer_torch as P
+
+    dim = SIZES[size]
+    sd = {k: v.to(dev) for k, v in T.make_state_dict(T.build_model(variant, dim), seed=1234, scale=1.0).items()}
+    x = torch.rand(1, 1, H_RAW, W_RAW, generator=torch.Generator().manual_seed(0)).to(dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    out = {}
+    for name, ctx in (("fp32_tf32", None), ("autocast_bf16", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def step():
+            if ctx is None:
+                return P.rawformer_forward(sd, x, variant)
+            with ctx:
+                return P.rawformer_forward(sd, x, variant)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name] = {"value": MP_FRAME / (ms * 1e-3), "unit": "MP/s", "ms_per_frame": ms}
+        torch.cuda.empty_cache()
+    out["what"] = (f"functional-PyTorch port of the reference forward (same ATen operators, eager, cuDNN/cuBLAS) on this B200, "
+                   f"RawFormer-{size} ({variant}), full frame, 2 warm-ups + 3 timed")
+    return out
+
+
 def run_reference(args):
     """Reference arm: the CPU port of the reference forward on this box's host cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -370,6 +408,11 @@ def run_ours(args):
     value = frames_total * MP_FRAME / (ms_total * 1e-3)
     e2e_val = frames_total * MP_FRAME / (ms_e2e * 1e-3)
     cpu = time_cpu_port(args.size, args.variant) if world == 1 and not args.no_cpu else None
+    eager = None
+    if world == 1 and args.torch_eager:
+        del model, pipe, x_dev
+        torch.cuda.empty_cache()
+        eager = time_torch_eager_b200(args.size, args.variant, dev)
     line = {
         "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -392,6 +435,8 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if eager is not None:
+        line["eager_b200_baseline"] = eager
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -415,9 +460,9 @@ def run_rowtiled(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_cpus(local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29533")
-    dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     dim = SIZES[args.size]
     model = rf.RawFormer(dim=dim, precision="bf16")
@@ -425,21 +470,30 @@ def run_rowtiled(args):
     model = model.to(dev).eval()
     x_host = torch.rand(1, 1, H_RAW, W_RAW, generator=torch.Generator().manual_seed(0)).pin_memory()   # same frame on all ranks
     x_dev = x_host.to(dev)
-    tiled = rf.RowTiledRawFormer.from_process_group(model, H_RAW, W_RAW)
+    if world > 1:
+        tiled = rf.RowTiledRawFormer.from_process_group(model, H_RAW, W_RAW)
+    else:                                         # one band = the whole frame, same band code, no peers
+        from bayer_low_light_image_enhancement_b200.rowtiled import _CommRegion
+
+        region = _CommRegion(rf.RowTiledRawFormer.comm_bytes(model, H_RAW, W_RAW, 1), dev)
+        tiled = rf.RowTiledRawFormer(model, H_RAW, W_RAW, 0, 1, [region.ptr], own_region=region)
     band_host = torch.empty(1, 3, tiled.rows, W_RAW).pin_memory()
 
     def barrier():
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
+        if world == 1:
+            return ms
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     with torch.no_grad():
         # parity of the decomposition (untimed): bands gathered on rank 0 against the whole-frame forward of the same engine
-        full = tiled.gather(tiled(x_dev), dst=0)
+        full = tiled.gather(tiled(x_dev), dst=0) if world > 1 else tiled(x_dev).clone()
         tiled.status()
         parity = None
         if rank == 0:
@@ -456,7 +510,8 @@ def run_rowtiled(args):
         while True:                               # every rank must run the same number of forwards: agree on when to stop
             tiled(x_dev)
             n_pre.fill_(1.0 if time.perf_counter() - t_pre < 1.5 else 0.0)
-            dist.all_reduce(n_pre, op=dist.ReduceOp.MIN)
+            if world > 1:
+                dist.all_reduce(n_pre, op=dist.ReduceOp.MIN)
             if float(n_pre.item()) == 0.0:
                 break
         sampler = ClockSampler(local)
@@ -506,8 +561,9 @@ def run_rowtiled(args):
         tiled.status()
         barrier()
     tiled.close()
-    if rank != 0:
+    if world > 1:
         dist.destroy_process_group()
+    if rank != 0:
         return
     pk = peaks()
     compute = {k: v for k, v in agg.items() if not k.startswith("band_")}
@@ -541,7 +597,6 @@ def run_rowtiled(args):
         "sync_ms_per_step": round(sum(v["ms"] for k, v in agg.items() if k.startswith("band_")) / n_prof, 4),
     }
     print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
 
 
 def main():
@@ -556,6 +611,8 @@ def main():
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of one CUDA graph per frame")
+    ap.add_argument("--torch-eager", action="store_true",
+                    help="also time the reference's operator sequence run eagerly by PyTorch on this B200 (baseline leg)")
     ap.add_argument("--row-tiled", action="store_true",
                     help="BASELINE config 4: one frame per step cut into row bands over the ranks (strong scaling)")
     args = ap.parse_args()

@@ -1,7 +1,9 @@
 """CPU port of the reference forward in functional PyTorch (ATen/MKL-DNN kernels) -- the CPU *baseline*.
 
 TEST / MEASUREMENT INFRASTRUCTURE ONLY (same rules as ``rawformer_oracle.py``): imported by ``tests/`` and by the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``; never by the product package.
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` (and its opt-in ``--torch-eager`` baseline leg, which runs
+the same operator sequence eagerly on the GPU as the "existing Blackwell path" to compare with); never by the product
+package.
 
 Why a second restatement: the reference itself is pure Python/PyTorch (no native code to compile into
 ``oracle/_ref``) and cannot travel to the GPU box, while the numpy oracle is written for clarity, not speed.  This
