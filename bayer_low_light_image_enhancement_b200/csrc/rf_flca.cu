@@ -353,9 +353,20 @@ k_se_fold(const float* __restrict__ partial, int nblk, float invP, const float* 
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = b2[c];
-    for (int j = 0; j < hid; ++j) s += w2[(i64)c * hid + j] * hbuf[j];
-    s = sigmoid_f(s);
+    // the row of W2 as float4s with four independent chains when hid % 4 == 0 (this loop was the kernel's latency)
+    float s0 = b2[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if ((hid & 3) == 0) {
+      const float4* wr = reinterpret_cast<const float4*>(w2 + (i64)c * hid);
+#pragma unroll 4
+      for (int j = 0; j < hid / 4; ++j) {
+        const float4 q = wr[j];
+        s0 = fmaf(q.x, hbuf[4 * j], s0); s1 = fmaf(q.y, hbuf[4 * j + 1], s1);
+        s2 = fmaf(q.z, hbuf[4 * j + 2], s2); s3 = fmaf(q.w, hbuf[4 * j + 3], s3);
+      }
+    } else {
+      for (int j = 0; j < hid; ++j) s0 = fmaf(w2[(i64)c * hid + j], hbuf[j], s0);
+    }
+    const float s = sigmoid_f((s0 + s1) + (s2 + s3));
     sc[c] = s;
     if (blockIdx.x == 0) scale_out[(i64)b * C + c] = s;
   }
