@@ -118,6 +118,9 @@ _SIGS = {
     "rf_profiled_launch_info": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rf_postprocess_u8": (_i, [_fp, _fp, _i, _i, _i, _fp]),
     "rf_preprocess_u16": (_i, [_fp, _fp, _f, _f, _f, _i, _i, _i, _fp]),
+    "rf_postprocess_rgb_u8": (_i, [_fp, _fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
+    "rf_correct_rgb_u8": (_i, [_fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
+    "rf_sse_u8": (_i, [_fp, _fp, _fp, _i, C.c_longlong, _fp]),
 }
 
 

@@ -19,6 +19,71 @@ __global__ void __launch_bounds__(256) k_post_u8(const float* __restrict__ in, u
   }
 }
 
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// test.py:17-40,117-120 -- the same conversion followed by correct_bayer_channels (out channel k = channel perm[k]) and the
+// statistics of auto_correct_rb: sums[b] = {sum of out channel 0, sum of out channel 2} (exact integer sums; comparing them
+// is comparing the means).  SRC_U8: the input already is a uint8 HWC image (the ground-truth side, test.py:111-113; in place).
+template <bool SRC_U8>
+__global__ void __launch_bounds__(256)
+k_post_rgb_u8(const float* __restrict__ in, unsigned char* out, i64 hw, int p0, int p1, int p2, unsigned long long* sums) {
+  const i64 b = blockIdx.y;
+  unsigned long long s0 = 0, s2 = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (i64)gridDim.x * blockDim.x) {
+    unsigned char v[3];
+    unsigned char* o = out + (b * hw + i) * 3;
+    if (SRC_U8) {
+      v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x = in[(b * 3 + c) * hw + i];
+        x = fminf(fmaxf(x, 0.f), 1.f);
+        v[c] = (unsigned char)(int)__fmul_rn(x, 255.f);
+      }
+    }
+    const unsigned char r = v[p0], g = v[p1], bl = v[p2];
+    o[0] = r; o[1] = g; o[2] = bl;
+    s0 += r;
+    s2 += bl;
+  }
+  s0 = warp_sum_u64(s0);
+  s2 = warp_sum_u64(s2);
+  if ((threadIdx.x & 31) == 0 && sums != nullptr) {
+    atomicAdd(sums + b * 2, s0);
+    atomicAdd(sums + b * 2 + 1, s2);
+  }
+}
+
+// auto_correct_rb (test.py:29-38): swap R and B of every image whose red mean is below its blue mean
+__global__ void __launch_bounds__(256) k_swap_rb_if(unsigned char* img, i64 hw, const unsigned long long* __restrict__ sums) {
+  const i64 b = blockIdx.y;
+  if (!(sums[b * 2] < sums[b * 2 + 1])) return;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (i64)gridDim.x * blockDim.x) {
+    unsigned char* o = img + (b * hw + i) * 3;
+    const unsigned char t = o[0];
+    o[0] = o[2];
+    o[2] = t;
+  }
+}
+
+// sum of squared differences of two uint8 images (exact): the mean_squared_error inside skimage's PSNR (test.py:123)
+__global__ void __launch_bounds__(256)
+k_sse_u8(const unsigned char* __restrict__ a, const unsigned char* __restrict__ bimg, i64 n, unsigned long long* sse) {
+  const i64 b = blockIdx.y;
+  unsigned long long s = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const int d = (int)a[b * n + i] - (int)bimg[b * n + i];
+    s += (unsigned)(d * d);
+  }
+  s = warp_sum_u64(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sse + b, s);
+}
+
 // WFB/load_dataset.py:88-89 and correctdataloader.py:103
 __global__ void __launch_bounds__(256)
 k_pre_u16(const unsigned short* __restrict__ raw, float* __restrict__ out, float black, float white, float denom, float ratio,
@@ -85,6 +150,63 @@ int rf_postprocess_u8(const float* in, unsigned char* out, int B, int H, int W, 
   unsigned gx = (unsigned)(cdivl(hw, 256) < 8 * num_sms() ? cdivl(hw, 256) : 8 * num_sms());
   ScopedLaunch sl(RF_K_INDEX_OP, 15.0 * B * hw);
   k_post_u8<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(in, out, hw);
+  return check_cuda(cudaGetLastError());
+}
+
+static int post_rgb(const float* in, unsigned char* img, const int* perm_host, int auto_rb, int B, int H, int W,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!img || !perm_host) return RF_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || W <= 0) return (B < 0 || H < 0 || W < 0) ? RF_ERR_BAD_SHAPE : RF_OK;
+  int seen = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (perm_host[k] < 0 || perm_host[k] > 2) return RF_ERR_BAD_ARG;
+    seen |= 1 << perm_host[k];
+  }
+  if (seen != 7) return RF_ERR_BAD_ARG;
+  unsigned long long* sums = nullptr;
+  if (auto_rb) {
+    if (!workspace || (uintptr_t)workspace % 8) return RF_ERR_BAD_ARG;
+    if (workspace_bytes < (size_t)B * 16) return RF_ERR_WORKSPACE;
+    sums = (unsigned long long*)workspace;
+    RF_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 16, (cudaStream_t)stream));
+  }
+  const i64 hw = (i64)H * W;
+  const unsigned gx = (unsigned)(cdivl(hw, 256) < 8 * num_sms() ? cdivl(hw, 256) : 8 * num_sms());
+  {
+    ScopedLaunch sl(RF_K_INDEX_OP, (in ? 15.0 : 6.0) * B * hw);
+    if (in)
+      k_post_rgb_u8<false><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(in, img, hw, perm_host[0], perm_host[1], perm_host[2], sums);
+    else
+      k_post_rgb_u8<true><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(nullptr, img, hw, perm_host[0], perm_host[1], perm_host[2], sums);
+  }
+  if (auto_rb) {
+    ScopedLaunch sl(RF_K_INDEX_OP, 6.0 * B * hw);
+    k_swap_rb_if<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(img, hw, sums);
+  }
+  return check_cuda(cudaGetLastError());
+}
+
+int rf_postprocess_rgb_u8(const float* in, unsigned char* out, const int* perm_host, int auto_rb, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!in) return RF_ERR_BAD_ARG;
+  return post_rgb(in, out, perm_host, auto_rb, B, H, W, workspace, workspace_bytes, stream);
+}
+
+int rf_correct_rgb_u8(unsigned char* img, const int* perm_host, int auto_rb, int B, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return post_rgb(nullptr, img, perm_host, auto_rb, B, H, W, workspace, workspace_bytes, stream);
+}
+
+int rf_sse_u8(const unsigned char* a, const unsigned char* b, unsigned long long* sse, int B, long long n_per_image,
+              void* stream) {
+  if (!a || !b || !sse || (uintptr_t)sse % 8) return RF_ERR_BAD_ARG;
+  if (B < 0 || n_per_image < 0) return RF_ERR_BAD_SHAPE;
+  if (B == 0) return RF_OK;
+  RF_CUDA(cudaMemsetAsync(sse, 0, (size_t)B * 8, (cudaStream_t)stream));
+  if (n_per_image == 0) return RF_OK;
+  const unsigned gx = (unsigned)(cdivl(n_per_image, 1024) < 8 * num_sms() ? cdivl(n_per_image, 1024) : 8 * num_sms());
+  ScopedLaunch sl(RF_K_INDEX_OP, 2.0 * B * n_per_image);
+  k_sse_u8<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(a, b, n_per_image, sse);
   return check_cuda(cudaGetLastError());
 }
 

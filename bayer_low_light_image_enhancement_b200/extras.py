@@ -7,6 +7,8 @@
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 
@@ -22,6 +24,63 @@ def postprocess_u8(pred: torch.Tensor) -> torch.Tensor:
     out = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred.device)
     if out.numel():
         check(_lib.load().rf_postprocess_u8(ptr(pred), ptr(out), b, h, w, stream_ptr(pred.device)), "rf_postprocess_u8")
+    return out
+
+
+BAYER_PERMS = {"RGGB": (0, 1, 2), "BGGR": (2, 1, 0), "GBRG": (1, 0, 2), "GRBG": (0, 2, 1)}   # test.py:17-27
+
+
+def _perm(pattern):
+    p = BAYER_PERMS.get(str(pattern).upper(), (0, 1, 2))      # unknown patterns are left alone, like the reference
+    return (C.c_int * 3)(*p)
+
+
+def postprocess_rgb_u8(pred: torch.Tensor, pattern: str = "RGGB", auto_rb: bool = True) -> torch.Tensor:
+    """test.py:117-120 on the device: clamp -> *255 -> uint8 -> HWC -> ``correct_bayer_channels(pattern)`` ->
+    ``auto_correct_rb`` (per image).  [B,3,H,W] float -> [B,H,W,3] uint8."""
+    pred = _Op._prep(pred, "pred", 3)
+    b, _, h, w = pred.shape
+    out = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred.device)
+    if out.numel():
+        ws = torch.empty(2 * b, dtype=torch.int64, device=pred.device)
+        check(_lib.load().rf_postprocess_rgb_u8(ptr(pred), ptr(out), _perm(pattern), int(bool(auto_rb)), b, h, w, ptr(ws),
+                                                ws.numel() * 8, stream_ptr(pred.device)), "rf_postprocess_rgb_u8")
+    return out
+
+
+def correct_rgb_u8(img: torch.Tensor, pattern: str = "RGGB", auto_rb: bool = True) -> torch.Tensor:
+    """``auto_correct_rb(correct_bayer_channels(img, pattern))`` (test.py:111-113) for a uint8 [B,H,W,3] image; returns a
+    corrected copy."""
+    if img.dim() != 4 or img.shape[-1] != 3 or img.dtype != torch.uint8:
+        raise ValueError("img must be a uint8 tensor [B,H,W,3]")
+    _lib.init_device(img.device)
+    out = img.contiguous().clone()
+    b, h, w, _ = out.shape
+    if out.numel():
+        ws = torch.empty(2 * b, dtype=torch.int64, device=out.device)
+        check(_lib.load().rf_correct_rgb_u8(ptr(out), _perm(pattern), int(bool(auto_rb)), b, h, w, ptr(ws), ws.numel() * 8,
+                                            stream_ptr(out.device)), "rf_correct_rgb_u8")
+    return out
+
+
+def psnr_u8(a: torch.Tensor, b: torch.Tensor):
+    """``skimage.metrics.peak_signal_noise_ratio(a, b)`` for uint8 images (test.py:123), one value per image of the batch:
+    the squared error is summed exactly (uint64) on the device; 10*log10(255^2 / mse) in float64 on the host."""
+    import math
+
+    if a.shape != b.shape or a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.dim() < 2:
+        raise ValueError("a and b must be uint8 tensors of the same shape [B,...]")
+    _lib.init_device(a.device)
+    a, b = a.contiguous(), b.contiguous()
+    nb = a.shape[0]
+    n = a[0].numel() if nb else 0
+    sse = torch.zeros(max(nb, 1), dtype=torch.int64, device=a.device)
+    if nb:
+        check(_lib.load().rf_sse_u8(ptr(a), ptr(b), ptr(sse), nb, n, stream_ptr(a.device)), "rf_sse_u8")
+    out = []
+    for v in sse[:nb].cpu().tolist():
+        mse = v / n if n else 0.0
+        out.append(math.inf if mse == 0 else 10.0 * math.log10(255.0 ** 2 / mse))
     return out
 
 

@@ -184,6 +184,19 @@ int rf_feedforward_gated(const float* project_in_w, const float* project_in_b, c
  * ---------------------------------------------------------------------------------------------- */
 /* test.py:117-118: clamp(pred,0,1) -> *255 -> uint8 (truncation) -> HWC.  in [B,3,H,W] f32 -> out [B,H,W,3] u8. */
 int rf_postprocess_u8(const float* in, unsigned char* out, int B, int H, int W, void* stream);
+/* test.py:17-40 + 117-120 (prediction side): the conversion above, then correct_bayer_channels -- out channel k =
+ * channel perm_host[k] ({0,1,2} RGGB, {2,1,0} BGGR, {1,0,2} GBRG, {0,2,1} GRBG) -- and, if auto_rb, auto_correct_rb: R and B
+ * of an image are swapped when its red mean is below its blue mean (decided on exact integer sums).
+ * workspace (auto_rb only): 16*B bytes, 8-byte aligned. */
+int rf_postprocess_rgb_u8(const float* in, unsigned char* out, const int* perm_host, int auto_rb, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* test.py:111-113 (ground-truth side): the same two corrections on a uint8 [B,H,W,3] image, in place. */
+int rf_correct_rgb_u8(unsigned char* img, const int* perm_host, int auto_rb, int B, int H, int W, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* test.py:123, skimage.metrics.peak_signal_noise_ratio on uint8 images: sse[b] = sum (a-b)^2 over the n_per_image bytes of
+ * image b (exact, uint64, device); PSNR = 10*log10(255^2 * n_per_image / sse). */
+int rf_sse_u8(const unsigned char* a, const unsigned char* b, unsigned long long* sse, int B, long long n_per_image,
+              void* stream);
 /* WFB/load_dataset.py:88-89: clip(raw,black,white) -> (x-black)/(white-black+1e-6)*ratio, then min(.,1)
  * (correctdataloader.py:103).  raw [B,H,W] u16 -> out [B,1,H,W] f32. */
 int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,

@@ -474,3 +474,39 @@ def layernorm_biasfree(x, w):
     mu = x.mean(axis=1, keepdims=True)
     var = ((x - mu) ** 2).mean(axis=1, keepdims=True)
     return x / np.sqrt(var + x.dtype.type(1e-5)) * w.astype(x.dtype)[None, :, None, None]
+
+
+# ----------------------------------------------------------------------------------------------
+# caller side of the forward: uint8 conversion, Bayer channel order, R/B auto-correction, PSNR  
+# ----------------------------------------------------------------------------------------------
+# Pinned: ``tests/golden/make_golden_post.py`` executes the reference's own ``correct_bayer_channels`` /
+# ``auto_correct_rb`` (cut out of test.py, whose top-level imports need skimage / imageio) and stores their outputs.
+# ``psnr_u8`` restates ``skimage.metrics.peak_signal_noise_ratio`` (scikit-image: version not pinned by the reference and
+# not installed here) from its published definition -- parity UNPINNED for that one function.
+BAYER_PERMS = {"BGGR": (2, 1, 0), "GBRG": (1, 0, 2), "GRBG": (0, 2, 1)}
+
+
+def postprocess_u8(pred):
+    """test.py:117-118: clamp(pred, 0, 1)[b] -> HWC -> * 255 -> astype(uint8).  pred [B,3,H,W] -> [B,H,W,3]."""
+    x = np.clip(np.asarray(pred, np.float32), 0.0, 1.0).transpose(0, 2, 3, 1)
+    return (x * np.float32(255.0)).astype(np.uint8)
+
+
+def correct_bayer_channels(rgb, pattern="RGGB"):
+    """test.py:17-27: channel order by Bayer pattern; unknown patterns (and RGGB) are left alone."""
+    perm = BAYER_PERMS.get(str(pattern).upper())
+    return rgb if perm is None else rgb[..., list(perm)]
+
+
+def auto_correct_rb(rgb):
+    """test.py:29-38: swap R and B when the red mean is below the blue mean (ONE image, HWC)."""
+    if rgb[..., 0].mean() < rgb[..., 2].mean():
+        rgb = rgb[..., [2, 1, 0]]
+    return rgb
+
+
+def psnr_u8(a, b):
+    """skimage.metrics.peak_signal_noise_ratio(a, b) for uint8 images as called in test.py:123: data_range = 255 (from the
+    dtype), mse = mean((a - b)^2) in float64, 10 * log10(data_range^2 / mse)."""
+    err = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2, dtype=np.float64)
+    return math.inf if err == 0 else 10.0 * math.log10(255.0 ** 2 / err)

@@ -1,0 +1,101 @@
+"""Caller side of the forward (test.py:17-40,111-123): uint8 conversion, Bayer channel order, R/B
+auto-correction and PSNR.
+
+CPU: the numpy oracle against golden vectors produced by the reference's own functions (tests/golden/make_golden_post.py).
+GPU: the device operators against the oracle, bit-exact (integer / byte work)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import rf_testlib as T
+from oracle import rawformer_oracle as O
+
+PATTERNS = ("RGGB", "BGGR", "GBRG", "GRBG", "rggb", "XXXX")
+
+
+def _golden():
+    g = T.load_golden("post")
+    names = sorted(k[3:] for k in g if k.startswith("in_"))
+    return g, names
+
+
+def test_oracle_matches_reference_golden():
+    g, names = _golden()
+    assert names == ["blue", "equal", "green", "red", "tiny"]
+    swapped = 0
+    for n in names:
+        img = g["in_" + n]
+        for pat in PATTERNS:
+            ours = O.auto_correct_rb(O.correct_bayer_channels(img.copy(), pat))
+            assert np.array_equal(ours, g[f"out_{n}_{pat}"]), (n, pat)
+            swapped += int(not np.array_equal(g[f"out_{n}_{pat}"], O.correct_bayer_channels(img.copy(), pat)))
+    assert swapped > 0                       # the data-dependent branch is exercised both ways
+    # equal means: strict '<' -> no swap
+    assert np.array_equal(O.auto_correct_rb(g["in_equal"]), g["in_equal"])
+
+
+def test_oracle_u8_conversion_and_psnr_known_answers():
+    pred = np.array([[[[-0.5, 0.0, 0.5]], [[1.0, 1.5, 0.999]], [[0.25, 0.75, 1e-9]]]], np.float32)      # [1,3,1,3]
+    out = O.postprocess_u8(pred)
+    assert out.shape == (1, 1, 3, 3) and out.dtype == np.uint8
+    assert out[0, 0].tolist() == [[0, 255, 63], [0, 255, 191], [127, 254, 0]]      # truncation, not rounding
+    a = np.zeros((4, 4, 3), np.uint8)
+    b = a.copy()
+    assert O.psnr_u8(a, b) == math.inf
+    b[0, 0, 0] = 48                                                                  # mse = 48^2 / 48 = 48
+    assert abs(O.psnr_u8(a, b) - 10.0 * math.log10(255.0 ** 2 / 48.0)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_device_corrections_bit_exact():
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    dev = torch.device("cuda", 0)
+    g, names = _golden()
+    # (a) uint8 images through correct_rgb_u8 against the reference goldens, batched so that one call takes both branches
+    for pat in PATTERNS:
+        batch = np.stack([g["in_" + n] for n in ("red", "blue", "equal", "green")])
+        got = rf.correct_rgb_u8(torch.from_numpy(batch).to(dev), pat).cpu().numpy()
+        for i, n in enumerate(("red", "blue", "equal", "green")):
+            assert np.array_equal(got[i], g[f"out_{n}_{pat}"]), (n, pat)
+        got = rf.correct_rgb_u8(torch.from_numpy(batch).to(dev), pat, auto_rb=False).cpu().numpy()
+        assert np.array_equal(got, O.correct_bayer_channels(batch, pat))
+    tiny = torch.from_numpy(g["in_tiny"][None]).to(dev)
+    assert np.array_equal(rf.correct_rgb_u8(tiny, "BGGR").cpu().numpy()[0], g["out_tiny_BGGR"])
+    # (b) float predictions through postprocess_rgb_u8 against the oracle chain, odd sizes, values outside [0,1]
+    rng = np.random.default_rng(7)
+    for shape in ((3, 3, 37, 53), (1, 3, 128, 256), (2, 3, 1, 1)):
+        pred = (rng.standard_normal(shape) * 0.6 + 0.45).astype(np.float32)
+        pred[0, 2] += 0.3                                     # image 0: blue-heavy -> swapped
+        for pat in ("RGGB", "GBRG"):
+            ref = np.stack([O.auto_correct_rb(O.correct_bayer_channels(im, pat)) for im in O.postprocess_u8(pred)])
+            got = rf.postprocess_rgb_u8(torch.from_numpy(pred).to(dev), pat).cpu().numpy()
+            assert got.dtype == np.uint8 and np.array_equal(got, ref), (shape, pat)
+        assert np.array_equal(rf.postprocess_rgb_u8(torch.from_numpy(pred).to(dev), "RGGB", auto_rb=False).cpu().numpy(),
+                              O.postprocess_u8(pred))
+        assert np.array_equal(rf.postprocess_u8(torch.from_numpy(pred).to(dev)).cpu().numpy(), O.postprocess_u8(pred))
+    with pytest.raises(ValueError):
+        rf.correct_rgb_u8(torch.zeros(1, 4, 4, 3, device=dev))       # not uint8
+
+
+@pytest.mark.gpu
+def test_device_psnr_exact():
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 256, size=(3, 211, 173, 3), dtype=np.uint8)
+    b = a.copy()
+    b[0] = rng.integers(0, 256, size=b[0].shape, dtype=np.uint8)      # unrelated images
+    b[1, ::7, ::5, 1] ^= 3                                             # small sparse error; image 2 identical
+    got = rf.psnr_u8(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    ref = [O.psnr_u8(a[i], b[i]) for i in range(3)]
+    assert got[2] == math.inf and ref[2] == math.inf
+    assert got[0] == ref[0] and got[1] == ref[1], (got, ref)          # exact integer error sums -> identical doubles
+    # full-frame size: sum of squares well beyond 32 bits
+    big_a = torch.full((1, 2848, 4256, 3), 255, dtype=torch.uint8, device=dev)
+    big_b = torch.zeros_like(big_a)
+    assert rf.psnr_u8(big_a, big_b) == [10.0 * math.log10(255.0 ** 2 / 255.0 ** 2)]
