@@ -121,6 +121,7 @@ _SIGS = {
     "rf_postprocess_rgb_u8": (_i, [_fp, _fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_correct_rgb_u8": (_i, [_fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_sse_u8": (_i, [_fp, _fp, _fp, _i, C.c_longlong, _fp]),
+    "rf_ssim_u8": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp]),
 }
 
 

@@ -84,6 +84,65 @@ k_sse_u8(const unsigned char* __restrict__ a, const unsigned char* __restrict__ 
   if ((threadIdx.x & 31) == 0) atomicAdd(sse + b, s);
 }
 
+// skimage.metrics.structural_similarity(a, b, channel_axis=-1) as called in test.py:124 on uint8 HWC images: 7x7 uniform
+// window, data_range 255, K1 = 0.01, K2 = 0.03, sample covariance (x 49/48), mean of S over the pixels whose window lies
+// inside the image (crop by 3) and over the channels.  The five window sums are exact integers; S is evaluated in double.
+// sum_out[b] += sum of S over the valid pixels and the 3 channels (the host divides by 3*(H-6)*(W-6)).
+constexpr int SS_TW = 32, SS_TH = 16, SS_R = 3;
+__global__ void __launch_bounds__(SS_TW * SS_TH)
+k_ssim_u8(const unsigned char* __restrict__ a, const unsigned char* __restrict__ bimg, double* sum_out, int H, int W) {
+  __shared__ unsigned char sa[SS_TH + 2 * SS_R][(SS_TW + 2 * SS_R) * 3];
+  __shared__ unsigned char sb[SS_TH + 2 * SS_R][(SS_TW + 2 * SS_R) * 3];
+  __shared__ double swarp[SS_TW * SS_TH / 32];
+  const i64 img = (i64)blockIdx.z * H * W * 3;
+  // outputs of this block: centres (y, x) with y in [y0, y0 + TH), x in [x0, x0 + TW); valid centres are [3, H-3) x [3, W-3)
+  const int x0 = SS_R + blockIdx.x * SS_TW, y0 = SS_R + blockIdx.y * SS_TH;
+  const int tid = threadIdx.y * SS_TW + threadIdx.x;
+  const int row_bytes = (SS_TW + 2 * SS_R) * 3;
+  for (int i = tid; i < (SS_TH + 2 * SS_R) * row_bytes; i += SS_TW * SS_TH) {
+    const int r = i / row_bytes, cb = i - r * row_bytes;
+    const int gy = y0 - SS_R + r, gxb = (x0 - SS_R) * 3 + cb;      // byte column inside the image row
+    unsigned char va = 0, vb = 0;
+    if (gy < H && gxb < W * 3) {
+      va = a[img + (i64)gy * W * 3 + gxb];
+      vb = bimg[img + (i64)gy * W * 3 + gxb];
+    }
+    sa[r][cb] = va;
+    sb[r][cb] = vb;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  double acc = 0.0;
+  if (x < W - SS_R && y < H - SS_R) {
+    const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0), cov_norm = 49.0 / 48.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int s_a = 0, s_b = 0, s_aa = 0, s_bb = 0, s_ab = 0;
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+          const int pa = sa[threadIdx.y + dy][(threadIdx.x + dx) * 3 + c], pb = sb[threadIdx.y + dy][(threadIdx.x + dx) * 3 + c];
+          s_a += pa; s_b += pb; s_aa += pa * pa; s_bb += pb * pb; s_ab += pa * pb;
+        }
+      }
+      const double ux = s_a / 49.0, uy = s_b / 49.0, uxx = s_aa / 49.0, uyy = s_bb / 49.0, uxy = s_ab / 49.0;
+      const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+      const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2, B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+      acc += (A1 * A2) / (B1 * B2);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) swarp[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < SS_TW * SS_TH / 32; ++i) t += swarp[i];
+    atomicAdd(sum_out + blockIdx.z, t);
+  }
+}
+
 // WFB/load_dataset.py:88-89 and correctdataloader.py:103
 __global__ void __launch_bounds__(256)
 k_pre_u16(const unsigned short* __restrict__ raw, float* __restrict__ out, float black, float white, float denom, float ratio,
@@ -207,6 +266,20 @@ int rf_sse_u8(const unsigned char* a, const unsigned char* b, unsigned long long
   const unsigned gx = (unsigned)(cdivl(n_per_image, 1024) < 8 * num_sms() ? cdivl(n_per_image, 1024) : 8 * num_sms());
   ScopedLaunch sl(RF_K_INDEX_OP, 2.0 * B * n_per_image);
   k_sse_u8<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(a, b, n_per_image, sse);
+  return check_cuda(cudaGetLastError());
+}
+
+int rf_ssim_u8(const unsigned char* a, const unsigned char* b, double* sum_out, int B, int H, int W, void* stream) {
+  if (!a || !b || !sum_out || (uintptr_t)sum_out % 8) return RF_ERR_BAD_ARG;
+  if (B < 0) return RF_ERR_BAD_SHAPE;
+  if (B == 0) return RF_OK;
+  if (H < 7 || W < 7) return RF_ERR_BAD_SHAPE;          // the 7x7 window must fit (skimage raises for smaller images)
+  if (B > 65535) return RF_ERR_UNSUPPORTED;
+  RF_CUDA(cudaMemsetAsync(sum_out, 0, (size_t)B * 8, (cudaStream_t)stream));
+  const dim3 grid(cdiv(W - 6, SS_TW), cdiv(H - 6, SS_TH), B);
+  if (grid.y > 65535) return RF_ERR_UNSUPPORTED;
+  ScopedLaunch sl(RF_K_INDEX_OP, 6.0 * B * H * W);
+  k_ssim_u8<<<grid, dim3(SS_TW, SS_TH), 0, (cudaStream_t)stream>>>(a, b, sum_out, H, W);
   return check_cuda(cudaGetLastError());
 }
 

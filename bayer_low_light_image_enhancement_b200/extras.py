@@ -84,6 +84,23 @@ def psnr_u8(a: torch.Tensor, b: torch.Tensor):
     return out
 
 
+def ssim_u8(a: torch.Tensor, b: torch.Tensor):
+    """``skimage.metrics.structural_similarity(a, b, channel_axis=-1)`` for uint8 [B,H,W,3] images (test.py:124), one value
+    per image: 7x7 uniform window, data_range 255, sample covariance, border of 3 cropped.  H, W >= 7."""
+    if a.shape != b.shape or a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.dim() != 4 or a.shape[-1] != 3:
+        raise ValueError("a and b must be uint8 tensors of the same shape [B,H,W,3]")
+    nb, h, w, _ = a.shape
+    if h < 7 or w < 7:
+        raise ValueError("win_size exceeds image extent: H and W must be at least 7")
+    _lib.init_device(a.device)
+    a, b = a.contiguous(), b.contiguous()
+    acc = torch.zeros(max(nb, 1), dtype=torch.float64, device=a.device)
+    if nb:
+        check(_lib.load().rf_ssim_u8(ptr(a), ptr(b), ptr(acc), nb, h, w, stream_ptr(a.device)), "rf_ssim_u8")
+    n = 3.0 * (h - 6) * (w - 6)
+    return [v / n for v in acc[:nb].cpu().tolist()]
+
+
 def preprocess_u16(raw: torch.Tensor, black: float = 512.0, white: float = 16383.0, ratio: float = 100.0) -> torch.Tensor:
     """uint16 Bayer [B,H,W] -> float32 [B,1,H,W] in [0,1] (black-level subtract, white-level scale, exposure ratio, clip)."""
     if raw.dim() != 3:

@@ -197,6 +197,10 @@ int rf_correct_rgb_u8(unsigned char* img, const int* perm_host, int auto_rb, int
  * image b (exact, uint64, device); PSNR = 10*log10(255^2 * n_per_image / sse). */
 int rf_sse_u8(const unsigned char* a, const unsigned char* b, unsigned long long* sse, int B, long long n_per_image,
               void* stream);
+/* test.py:124, skimage.metrics.structural_similarity(a, b, channel_axis=-1) on uint8 [B,H,W,3] images (7x7 uniform window,
+ * data_range 255, K1 0.01, K2 0.03, sample covariance, border of 3 cropped): sum_out[b] (device, double) = sum of the SSIM
+ * map over the valid pixels and the 3 channels; SSIM = sum_out[b] / (3*(H-6)*(W-6)).  H, W >= 7. */
+int rf_ssim_u8(const unsigned char* a, const unsigned char* b, double* sum_out, int B, int H, int W, void* stream);
 /* WFB/load_dataset.py:88-89: clip(raw,black,white) -> (x-black)/(white-black+1e-6)*ratio, then min(.,1)
  * (correctdataloader.py:103).  raw [B,H,W] u16 -> out [B,1,H,W] f32. */
 int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,

@@ -510,3 +510,28 @@ def psnr_u8(a, b):
     dtype), mse = mean((a - b)^2) in float64, 10 * log10(data_range^2 / mse)."""
     err = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2, dtype=np.float64)
     return math.inf if err == 0 else 10.0 * math.log10(255.0 ** 2 / err)
+
+
+def ssim_u8(a, b, win_size=7, K1=0.01, K2=0.03):
+    """skimage.metrics.structural_similarity(a, b, channel_axis=-1) for uint8 HWC images as called in test.py:124
+    (scikit-image's published algorithm, defaults: uniform 7x7 window, use_sample_covariance=True, data_range from the
+    dtype = 255; float64 arithmetic; mean of the SSIM map cropped by (win_size - 1) // 2, then mean over channels).
+    Parity UNPINNED (scikit-image is not installed here); the windowed means use scipy.ndimage.uniform_filter like skimage."""
+    from scipy.ndimage import uniform_filter
+
+    if min(a.shape[0], a.shape[1]) < win_size:
+        raise ValueError("win_size exceeds image extent")
+    R = 255.0
+    C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+    NP = win_size ** 2
+    cov_norm = NP / (NP - 1)
+    pad = (win_size - 1) // 2
+    vals = []
+    for ch in range(a.shape[-1]):
+        x, y = a[..., ch].astype(np.float64), b[..., ch].astype(np.float64)
+        ux, uy = uniform_filter(x, size=win_size), uniform_filter(y, size=win_size)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win_size), uniform_filter(y * y, size=win_size), uniform_filter(x * y, size=win_size)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        vals.append(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
+    return float(np.mean(vals))

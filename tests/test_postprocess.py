@@ -48,6 +48,21 @@ def test_oracle_u8_conversion_and_psnr_known_answers():
     assert abs(O.psnr_u8(a, b) - 10.0 * math.log10(255.0 ** 2 / 48.0)) < 1e-12
 
 
+def test_oracle_ssim_known_answers():
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=(24, 31, 3), dtype=np.uint8)
+    assert O.ssim_u8(a, a) == 1.0                                   # identical images: every map value is exactly 1
+    flat0, flat1 = np.full((9, 9, 3), 100, np.uint8), np.full((9, 9, 3), 120, np.uint8)
+    # constant images: variances are 0, S = (2*100*120 + C1) / (100^2 + 120^2 + C1) everywhere
+    c1 = (0.01 * 255) ** 2
+    assert abs(O.ssim_u8(flat0, flat1) - (2 * 100 * 120 + c1) / (100 ** 2 + 120 ** 2 + c1)) < 1e-12
+    noisy = np.clip(a.astype(np.int16) + rng.integers(-20, 21, size=a.shape), 0, 255).astype(np.uint8)
+    s = O.ssim_u8(a, noisy)
+    assert 0.5 < s < 1.0 and abs(s - O.ssim_u8(noisy, a)) < 1e-12   # symmetric
+    with pytest.raises(ValueError):
+        O.ssim_u8(a[:5], a[:5])
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_device_corrections_bit_exact():
@@ -99,3 +114,34 @@ def test_device_psnr_exact():
     big_a = torch.full((1, 2848, 4256, 3), 255, dtype=torch.uint8, device=dev)
     big_b = torch.zeros_like(big_a)
     assert rf.psnr_u8(big_a, big_b) == [10.0 * math.log10(255.0 ** 2 / 255.0 ** 2)]
+
+
+@pytest.mark.gpu
+def test_device_ssim():
+    """Windowed integer sums are exact; the map is evaluated in double like skimage: agreement to ~1e-12 (scipy's separable
+    uniform_filter rounds the window means differently in the last bits)."""
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(13)
+    for h, w in ((7, 7), (40, 53), (129, 200)):
+        a = rng.integers(0, 256, size=(3, h, w, 3), dtype=np.uint8)
+        b = a.copy()
+        b[0] = np.clip(a[0].astype(np.int16) + rng.integers(-25, 26, size=a[0].shape), 0, 255).astype(np.uint8)
+        b[1] = rng.integers(0, 256, size=a[1].shape, dtype=np.uint8)
+        got = rf.ssim_u8(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+        ref = [O.ssim_u8(a[i], b[i]) for i in range(3)]
+        assert abs(got[2] - 1.0) <= 1e-12          # identical images (the device may contract a*b+c into FMAs)
+        for g_, r_ in zip(got, ref):
+            assert abs(g_ - r_) <= 1e-10, (h, w, got, ref)
+    with pytest.raises(ValueError):
+        rf.ssim_u8(torch.zeros(1, 6, 9, 3, dtype=torch.uint8, device=dev), torch.zeros(1, 6, 9, 3, dtype=torch.uint8, device=dev))
+    # the reference's evaluation loop (test.py:111-124) end to end on the device against the oracle chain
+    pred = (rng.standard_normal((1, 3, 64, 96)) * 0.4 + 0.5).astype(np.float32)
+    gt = (rng.random((1, 64, 96, 3)) * 255).astype(np.uint8)
+    p_dev = rf.postprocess_rgb_u8(torch.from_numpy(pred).to(dev), "RGGB")
+    g_dev = rf.correct_rgb_u8(torch.from_numpy(gt).to(dev), "RGGB")
+    p_ref = O.auto_correct_rb(O.correct_bayer_channels(O.postprocess_u8(pred)[0], "RGGB"))
+    g_ref = O.auto_correct_rb(O.correct_bayer_channels(gt[0], "RGGB"))
+    assert rf.psnr_u8(p_dev, g_dev)[0] == O.psnr_u8(p_ref, g_ref)
+    assert abs(rf.ssim_u8(p_dev, g_dev)[0] - O.ssim_u8(p_ref, g_ref)) <= 1e-10
