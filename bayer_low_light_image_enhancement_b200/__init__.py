@@ -13,7 +13,7 @@ All compute runs in ``librawformer_b200.so`` (hand-written sm_100a CUDA behind a
 from . import modules_ml as multilevel
 from ._lib import LIB_PATH, exported_symbols
 from .modules import (MODEL_SIZES, Attention, BayerLumaChroma, Conv_Transformer, Downsample, FLCA, HaarDWT, LayerNorm,
-                      PixelShuffle, RawFormer, TransformerBlock, WaveTransformBlock, conv_ffn, downshuffle,
+                      PixelShuffle, RawFormer, TransformerBlock, WaveTransformBlock, bayer_downshuffle, conv_ffn, downshuffle,
                       get_default_precision, set_default_precision)
 from .modules_ml import FLCA_Pyramid
 from .modules_ml import RawFormer as RawFormerMultiLevel
@@ -26,6 +26,6 @@ from .wavelets import DWT, IWT, CustomDWT, CustomIDWT, dwt_init, iwt_init
 __all__ = [
     "RawFormer", "RawFormerMultiLevel", "Conv_Transformer", "WaveTransformBlock", "FLCA", "FLCA_Pyramid", "HaarDWT",
     "BayerLumaChroma", "Attention", "conv_ffn", "TransformerBlock", "LayerNorm", "Downsample", "PixelShuffle",
-    "downshuffle", "CustomDWT", "CustomIDWT", "DWT", "IWT", "dwt_init", "iwt_init", "multilevel", "MODEL_SIZES",
+    "downshuffle", "bayer_downshuffle", "CustomDWT", "CustomIDWT", "DWT", "IWT", "dwt_init", "iwt_init", "multilevel", "MODEL_SIZES",
     "FeedForward", "postprocess_u8", "postprocess_rgb_u8", "correct_rgb_u8", "psnr_u8", "ssim_u8", "preprocess_u16", "FramePipeline", "RowTiledRawFormer", "LocalBands", "plan_bands", "set_default_precision", "get_default_precision", "LIB_PATH", "exported_symbols",
 ]

@@ -74,6 +74,27 @@ def downshuffle(var, r):
     return out
 
 
+_BAYER_PATTERNS = {(0, 1, 1, 2): "RGGB", (2, 1, 1, 0): "BGGR", (1, 0, 2, 1): "GRBG", (1, 2, 0, 1): "GBRG"}
+
+
+def bayer_downshuffle(var, bayer_pattern, r=2):
+    """Space-to-depth of a Bayer frame [B,1,H,W] -> [B,4,H/2,W/2].  Reference: dataloader.py:7-43.
+
+    ``bayer_pattern`` is the 2x2 array of ``rawpy``'s ``raw_pattern``.  The reference validates it (RGGB / BGGR / GRBG /
+    GBRG, ``ValueError`` otherwise) but then always stacks the four phases in positional order top-left, top-right,
+    bottom-left, bottom-right (its ``channel_dict`` is keyed by position, dataloader.py:41-43) -- i.e. exactly
+    ``downshuffle(var, 2)`` for every supported pattern.  Same behaviour here, same errors."""
+    if r != 2:
+        raise ValueError("Bayer S2D only supports r=2")
+    flat = getattr(bayer_pattern, "flatten", None)
+    key = tuple(int(v) for v in (flat() if flat is not None else [x for row in bayer_pattern for x in row]))
+    if key not in _BAYER_PATTERNS:
+        raise ValueError(f"Unsupported Bayer pattern: {bayer_pattern}")
+    if not isinstance(var, torch.Tensor) or var.dim() != 4 or var.shape[1] != 1:
+        raise ValueError("var must be a tensor of size (B,1,H,W)")
+    return downshuffle(var, 2)
+
+
 class PixelShuffle(_Op):
     """nn.PixelShuffle(r).  Reference: FLCA_RF.py:328,369."""
 

@@ -63,6 +63,34 @@ def test_oracle_ssim_known_answers():
         O.ssim_u8(a[:5], a[:5])
 
 
+def test_bayer_downshuffle_validation():
+    """dataloader.py:7-43: r must be 2, the pattern one of the four Bayer layouts (checked before any device work)."""
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    x = torch.zeros(1, 1, 4, 4)
+    with pytest.raises(ValueError):
+        rf.bayer_downshuffle(x, np.array([[0, 1], [1, 2]]), r=4)
+    with pytest.raises(ValueError):
+        rf.bayer_downshuffle(x, np.array([[0, 0], [1, 2]]))
+    with pytest.raises(ValueError):
+        rf.bayer_downshuffle(torch.zeros(1, 3, 4, 4), np.array([[0, 1], [1, 2]]))
+    with pytest.raises(RuntimeError):                      # valid request on a CPU tensor: no fallback
+        rf.bayer_downshuffle(x, np.array([[0, 1], [1, 2]]))
+
+
+@pytest.mark.gpu
+def test_bayer_downshuffle_device():
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(T.gen_input("int", (2, 1, 24, 40), 4)).to(dev)
+    # the reference's arithmetic (dataloader.py:35-43): phases in positional order, whatever the pattern
+    ref = torch.cat([x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]], dim=1)
+    for pat in ([[0, 1], [1, 2]], [[2, 1], [1, 0]], [[1, 0], [2, 1]], [[1, 2], [0, 1]]):
+        assert torch.equal(rf.bayer_downshuffle(x, np.array(pat)), ref)
+    assert torch.equal(rf.bayer_downshuffle(x, [[0, 1], [1, 2]]), rf.downshuffle(x, 2))
+
+
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_device_corrections_bit_exact():
