@@ -5,7 +5,8 @@
 // flags[sync point][source rank] and one mailbox per sync point.  A sync point is ONE kernel per rank:
 //   1. push:   plain 16-byte / coalesced 4-byte stores of the local data into the peers' mailboxes (NVLink writes)
 //   2. signal: per CTA  bar.sync -> fence.sys -> atomicAdd_system on the peer's counter of this rank
-//   3. wait:   spin (bounded, ld.acquire.sys) until every source's counter reached epoch * CTAs
+//   3. wait:   spin (bounded, ld.acquire.sys) until every source's counter reached frame * CTAs (frame = the frame
+//               counter of the local region, advanced on the device by k_band_begin)
 //   4. combine from the LOCAL mailbox (L1-bypassing loads): copy into the halo rows / sum over ranks in rank order,
 //      so every rank computes bit-identical statistics.
 // The mailbox of a sync point is reused every frame: a peer can only reach sync point j of frame f+1 after the last
