@@ -215,6 +215,34 @@ def test_whole_model_bf16(case):
     assert d <= 0.05, f"|PSNR(ours,GT) - PSNR(ref,GT)| = {d:.3f} dB"
 
 
+def test_baseline_config0_packed_512(rf):
+    """BASELINE configs[0]: RawFormer-S, batch 1, packed 512x512x4 crop (raw 1024x1024) against the
+    reference's fp32 CPU forward (oracle/rawformer_torch.py, pinned to the reference by tests/test_oracle_golden.py):
+    fp32 engine max-abs <= 1e-4; bf16 engine PSNR >= 35 dB and |PSNR(ours,GT) - PSNR(ref,GT)| <= 0.05 dB."""
+    from oracle import rawformer_torch as P
+
+    m = rf.RawFormer(model_size="S", precision="fp32")
+    sd = T.make_state_dict(m, seed=1234, scale=1.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev()).eval()
+    x = torch.rand(1, 1, 1024, 1024, generator=torch.Generator().manual_seed(0))
+    ref = P.rawformer_forward(sd, x, "flca").numpy()
+    with torch.no_grad():
+        out32 = npy(m(x.to(dev())))
+    assert_close("config0 fp32", out32, ref, 1e-4)
+    m16 = rf.RawFormer(model_size="S", precision="bf16")
+    m16.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out16 = npy(m16.to(dev()).eval()(x.to(dev())))
+    rng = max(float(ref.max() - ref.min()), 1e-6)
+    p = psnr(out16, ref, rng)
+    assert p >= 35.0, f"config0 bf16 PSNR(ours, ref) = {p:.1f} dB; " + report("config0 bf16", out16, ref)
+    gt = np.clip(ref + np.random.default_rng(5).normal(0, 0.05 * rng, ref.shape), ref.min(), ref.max())
+    d = abs(psnr(out16, gt, rng) - psnr(ref, gt, rng))
+    assert d <= 0.05, f"|PSNR(ours,GT) - PSNR(ref,GT)| = {d:.3f} dB"
+    print(report("config0 fp32", out32, ref), f"; bf16 PSNR {p:.1f} dB")
+
+
 def test_model_size_sugar_and_state_dict(rf):
     for size, dim in rf.MODEL_SIZES.items():
         m = rf.RawFormer(model_size=size)
