@@ -74,6 +74,21 @@ def test_band_sizing_through_the_abi():
     assert lib.rf_rawformer_band_workspace_bytes(64, _lib.RF_BF16, 0, H, W, C.byref(b)) == 0
 
 
+def test_row_tiled_rejects_what_it_does_not_implement():
+    """No silent fallback: CPU models, the fp32 engine and the multi-level variant are refused before any device work."""
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    with pytest.raises(RuntimeError):                                   # model on the CPU
+        rf.RowTiledRawFormer(rf.RawFormer(dim=32, precision="bf16"), 128, 128, 0, 2, [0, 0])
+    with pytest.raises(NotImplementedError):                            # ML_RF variant
+        rf.RowTiledRawFormer(rf.multilevel.RawFormer(dim=32, precision="bf16"), 128, 128, 0, 2, [0, 0])
+    with pytest.raises(ValueError):
+        rf.plan_bands(100, 2)
+    if torch.cuda.is_available():
+        with pytest.raises(NotImplementedError):                        # fp32 parity engine
+            rf.RowTiledRawFormer(rf.RawFormer(dim=32, precision="fp32").cuda(), 128, 128, 0, 2, [0, 0])
+
+
 def _handshake_worker(rank, world, port, q):
     import torch.distributed as dist
 
