@@ -157,17 +157,4 @@ void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const f
   else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
 }
 
-__global__ void k_copy_norms(const float* __restrict__ sumsq, float* __restrict__ stats, int C) {
-  pdl_trigger();
-  pdl_wait();
-  const i64 b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * C) stats[b * ((i64)C * C + 2 * C) + (i64)C * C + i] = sumsq[b * 2 * C + i];
-}
-void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C) {
-  if (ctx.dry) return;
-  ScopedLaunch sl(RF_K_MISC);
-  launch_pdl(k_copy_norms, dim3(cdiv(2 * C, 256), B), dim3(256), 0, ctx.stream, sumsq, stats, C);
-}
-
 }  // namespace rf

@@ -4,7 +4,7 @@
 // 3x3 neighbourhood of the four stage-resolution guidance maps (one float4 per pixel) is gathered through L1, the
 // 36 x C tap weights sit in shared memory.  The three 1->C / 2->C convolutions, sigmoid/tanh, the modulation and
 // the squeeze-excite channel sums are fused; the SE scale itself is folded into channel_reduce's weights
-// (fold_reduce) so the FLCA output is never re-read for a per-channel multiply.
+// (k_se_fold) so the FLCA output is never re-read for a per-channel multiply.
 #include "rf_kernels.cuh"
 
 namespace rf {
@@ -293,30 +293,6 @@ void launch_se_finalize(Ctx& ctx, const float* partial, int nblk, i64 P, const f
   ScopedLaunch sl(RF_K_SE_FINALIZE, 4.0 * B * nblk * C);
   launch_pdl(k_se_finalize, dim3(B), dim3(256), sizeof(float) * (C + hid), ctx.stream, partial, nblk, 1.0f / (float)P, w1, b1, w2,
              b2, scale, C, hid);
-}
-
-template <typename T>
-__global__ void k_fold_reduce(const float* __restrict__ red_w, const float* __restrict__ scale, T* __restrict__ wred, int C) {
-  pdl_trigger();
-  pdl_wait();
-  const i64 b = blockIdx.y;
-  const i64 n2 = (i64)C * 2 * C;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (i64)gridDim.x * blockDim.x) {
-    int k = (int)(i % (2 * C));
-    float v = red_w[i];
-    if (k < C) v *= scale[b * C + k];
-    from_f(wred[b * n2 + i], v);
-  }
-}
-void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* wred, int B, int C) {
-  if (ctx.dry) return;
-  i64 n2 = (i64)C * 2 * C;
-  unsigned gx = (unsigned)(cdivl(n2, 256) < 296 ? cdivl(n2, 256) : 296);
-  ScopedLaunch sl(RF_K_FOLD_REDUCE, (4.0 + esize(ctx.dtype)) * B * n2);
-  if (ctx.dtype == RF_BF16)
-    launch_pdl(k_fold_reduce<bf16>, dim3(gx, B), dim3(256), 0, ctx.stream, red_w, scale, (bf16*)wred, C);
-  else
-    launch_pdl(k_fold_reduce<float>, dim3(gx, B), dim3(256), 0, ctx.stream, red_w, scale, (float*)wred, C);
 }
 
 // squeeze-excite MLP + fold of its scale into channel_reduce in ONE launch (FLCA_RF.py:160-161,275-276): every CTA

@@ -163,11 +163,10 @@ void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int 
 // s = sigmoid(W2 relu(W1 mean + b1) + b2)  -> scale [B][C]
 void launch_se_finalize(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1,
                         const float* w2, const float* b2, float* scale, int B, int C, int hid);
-// both of the above in one launch (the scale is also written to scale [B][C])
+// the squeeze-excite MLP and the fold wred[b][n][k] = red_w[n][k] * (k < C ? scale[b][k] : 1) (T output) in one launch
+// (the scale is also written to scale [B][C])
 void launch_se_fold(Ctx& ctx, const float* partial, int nblk, i64 P, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* scale, const float* red_w, void* wred, int B, int C, int hid);
-// wred[b][n][k] = red_w[n][k] * (k < C ? scale[b][k] : 1)   (T output)
-void launch_fold_reduce(Ctx& ctx, const float* red_w, const float* scale, void* wred, int B, int C);
 // out = x * scale[b][c]
 void launch_scale_channels(Ctx& ctx, const void* x, const float* scale, void* out, int B, i64 P, int C);
 
@@ -190,8 +189,6 @@ bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const fl
 // G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qk [P][2C]); false if the tcgen05 path is unavailable
 bool launch_gram_tcgen05(Ctx& ctx, const void* qk, float* G, int C, i64 P);
 bool tcgen05_enabled();
-// stats[b][C*C + i] = sumsq[b][i], i < 2C
-void launch_copy_norms(Ctx& ctx, const float* sumsq, float* stats, int B, int C);
 // Mw[b] = proj_w * blockdiag(softmax(gram / (|q||k|) * temperature))   (T [B][C][C])
 // norms (optional): [B][2C] squared norms of q,k kept outside `stats` (else they are read from stats[b][C*C ..])
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
