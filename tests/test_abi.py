@@ -41,20 +41,25 @@ def test_struct_layout_matches_header(tmp_path):
     """sizeof/offsetof of the ctypes mirrors against the C compiler's view of include/rawformer_b200.h."""
     import subprocess
 
-    from bayer_low_light_image_enhancement_b200._lib import BlockWeights, ModelWeights
+    from bayer_low_light_image_enhancement_b200._lib import Band, BlockWeights, ModelWeights
 
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "rawformer_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(rf_block_weights), sizeof(rf_model_weights),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(rf_block_weights), sizeof(rf_model_weights),'
         ' offsetof(rf_block_weights, pyr_low_w), offsetof(rf_block_weights, pyr_res_b2),'
-        ' offsetof(rf_model_weights, down_w), offsetof(rf_model_weights, rgb_w_host));return 0;}\n')
+        ' offsetof(rf_model_weights, down_w), offsetof(rf_model_weights, rgb_w_host),'
+        ' sizeof(rf_band), offsetof(rf_band, comm), offsetof(rf_band, epoch), RF_BAND_MAX_RANKS, RF_BAND_HALO);return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(T.ROOT, "include"), str(src), "-o", str(exe)], check=True)
     c = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     ours = [ctypes.sizeof(BlockWeights), ctypes.sizeof(ModelWeights), BlockWeights.pyr_low_w.offset,
-            BlockWeights.pyr_res_b2.offset, ModelWeights.down_w.offset, ModelWeights.rgb_w_host.offset]
-    assert ours == c
+            BlockWeights.pyr_res_b2.offset, ModelWeights.down_w.offset, ModelWeights.rgb_w_host.offset,
+            ctypes.sizeof(Band), Band.comm.offset, Band.epoch.offset]
+    assert ours == c[:9]
+    from bayer_low_light_image_enhancement_b200 import rowtiled
+
+    assert [rowtiled.RF_BAND_MAX_RANKS, rowtiled.RF_BAND_HALO] == c[9:]
 
 
 def test_host_queries(lib):
