@@ -173,3 +173,31 @@ def test_device_ssim():
     g_ref = O.auto_correct_rb(O.correct_bayer_channels(gt[0], "RGGB"))
     assert rf.psnr_u8(p_dev, g_dev)[0] == O.psnr_u8(p_ref, g_ref)
     assert abs(rf.ssim_u8(p_dev, g_dev)[0] - O.ssim_u8(p_ref, g_ref)) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties of the restatement (CPU)
+# ---------------------------------------------------------------------------------------------------------
+def test_oracle_properties():
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    imgs = hnp.arrays(np.uint8, st.tuples(st.integers(7, 12), st.integers(7, 12), st.just(3)))
+
+    @settings(max_examples=40, deadline=None)
+    @given(imgs, st.sampled_from(["RGGB", "BGGR", "GBRG", "GRBG"]))
+    def check(img, pat):
+        out = O.auto_correct_rb(O.correct_bayer_channels(img, pat))
+        # a permutation of the channels: same multiset of planes, and red is never darker than blue afterwards
+        assert sorted(out[..., c].tobytes() for c in range(3)) == sorted(img[..., c].tobytes() for c in range(3))
+        assert out[..., 0].mean() >= out[..., 2].mean()
+        assert np.array_equal(O.auto_correct_rb(out), out)                       # idempotent
+        swap = O.correct_bayer_channels(O.correct_bayer_channels(img, "BGGR"), "BGGR")
+        assert np.array_equal(swap, img)                                         # the three swaps are involutions
+        other = np.roll(img, 1, axis=0)
+        assert O.psnr_u8(img, other) == O.psnr_u8(other, img)
+        s = O.ssim_u8(img, other)
+        assert -1.0 - 1e-12 <= s <= 1.0 + 1e-12 and abs(s - O.ssim_u8(other, img)) < 1e-12
+
+    check()
