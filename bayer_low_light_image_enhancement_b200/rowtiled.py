@@ -147,6 +147,8 @@ class RowTiledRawFormer:
         return cls(model, H, W, rank, world, ptrs, own_region=own, group=group, opened=opened)
 
     def close(self):
+        """Unmap the peers' comm regions and free this rank's.  The peers write into this rank's region until their last
+        forward has finished: synchronise and barrier the group first."""
         lib = _lib.load()
         with torch.cuda.device(self.device):
             for p in self._opened:
