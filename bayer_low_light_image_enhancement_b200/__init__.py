@@ -17,7 +17,7 @@ from .modules import (MODEL_SIZES, Attention, BayerLumaChroma, Conv_Transformer,
                       get_default_precision, set_default_precision)
 from .modules_ml import FLCA_Pyramid
 from .modules_ml import RawFormer as RawFormerMultiLevel
-from .extras import (FeedForward, correct_rgb_u8, postprocess_rgb_u8, postprocess_u8, preprocess_u16, psnr_u8,
+from .extras import (BiasFree_LayerNorm, FeedForward, WFBLayerNorm, WithBias_LayerNorm, correct_rgb_u8, postprocess_rgb_u8, postprocess_u8, preprocess_u16, psnr_u8,
                      ssim_u8)
 from .pipeline import FramePipeline
 from .rowtiled import LocalBands, RowTiledRawFormer, plan_bands
@@ -27,5 +27,5 @@ __all__ = [
     "RawFormer", "RawFormerMultiLevel", "Conv_Transformer", "WaveTransformBlock", "FLCA", "FLCA_Pyramid", "HaarDWT",
     "BayerLumaChroma", "Attention", "conv_ffn", "TransformerBlock", "LayerNorm", "Downsample", "PixelShuffle",
     "downshuffle", "bayer_downshuffle", "CustomDWT", "CustomIDWT", "DWT", "IWT", "dwt_init", "iwt_init", "multilevel", "MODEL_SIZES",
-    "FeedForward", "postprocess_u8", "postprocess_rgb_u8", "correct_rgb_u8", "psnr_u8", "ssim_u8", "preprocess_u16", "FramePipeline", "RowTiledRawFormer", "LocalBands", "plan_bands", "set_default_precision", "get_default_precision", "LIB_PATH", "exported_symbols",
+    "FeedForward", "WithBias_LayerNorm", "BiasFree_LayerNorm", "WFBLayerNorm", "postprocess_u8", "postprocess_rgb_u8", "correct_rgb_u8", "psnr_u8", "ssim_u8", "preprocess_u16", "FramePipeline", "RowTiledRawFormer", "LocalBands", "plan_bands", "set_default_precision", "get_default_precision", "LIB_PATH", "exported_symbols",
 ]

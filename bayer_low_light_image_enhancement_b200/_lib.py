@@ -87,6 +87,7 @@ _SIGS = {
     "rf_iwt_init": (_i, [_fp, _fp, _i, _i, _i, _i, _fp]),
     "rf_luma_chroma": (_i, [_fp, _fp, _fp, _fp, C.POINTER(_f), _f, _i, _i, _i, _fp, _sz, _fp]),
     "rf_layernorm": (_i, [_fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _fp]),
+    "rf_layernorm_rows": (_i, [_fp, _fp, _fp, _fp, _f, _i, C.c_longlong, _i, _fp]),
     "rf_block_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "rf_flca_forward": (_i, [_BWp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_attention_forward": (_i, [_BWp, _i, _i, _fp, _fp, _i, _i, _i, _fp, _sz, _fp]),
@@ -117,7 +118,7 @@ _SIGS = {
     "rf_kernel_name": (C.c_char_p, [_i]),
     "rf_profiled_launch_info": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rf_postprocess_u8": (_i, [_fp, _fp, _i, _i, _i, _fp]),
-    "rf_preprocess_u16": (_i, [_fp, _fp, _f, _f, _f, _i, _i, _i, _fp]),
+    "rf_preprocess_u16": (_i, [_fp, _fp, _f, _f, _f, _i, _i, _i, _i, _fp]),
     "rf_postprocess_rgb_u8": (_i, [_fp, _fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_correct_rgb_u8": (_i, [_fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_sse_u8": (_i, [_fp, _fp, _fp, _i, C.c_longlong, _fp]),

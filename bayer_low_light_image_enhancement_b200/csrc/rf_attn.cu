@@ -670,3 +670,21 @@ void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2
 }
 
 }  // namespace rf
+
+// WithBias_LayerNorm / BiasFree_LayerNorm of the WFB variant (RawFomer_WFB_FFAB/model.py:89-122) on the [.., C] rows they
+// are called with (to_3d: 'b (h w) c'), fp32.  mode 0: (x - mu) / sqrt(var + eps) * w + b; mode 1: x / sqrt(var + eps) * w.
+extern "C" int rf_layernorm_rows(const float* in, const float* weight, const float* bias, float* out, float eps, int mode,
+                                 long long rows, int C, void* stream) {
+  using namespace rf;
+  if (!in || !weight || !out || (mode == 0 && !bias)) return RF_ERR_BAD_ARG;
+  if (mode != 0 && mode != 1) return RF_ERR_BAD_ARG;
+  if (rows < 0 || C <= 0 || C % 8) return RF_ERR_BAD_SHAPE;
+  if ((uintptr_t)in % 16 || (uintptr_t)out % 16) return RF_ERR_BAD_ARG;
+  if (rows == 0) return RF_OK;
+  Ctx ctx;
+  ctx.stream = (cudaStream_t)stream;
+  ctx.dtype = RF_F32;
+  launch_layernorm(ctx, in, weight, bias, out, eps, mode, rows, C);
+  return check_cuda(cudaGetLastError());
+}
+

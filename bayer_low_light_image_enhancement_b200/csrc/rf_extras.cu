@@ -143,15 +143,32 @@ k_ssim_u8(const unsigned char* __restrict__ a, const unsigned char* __restrict__
   }
 }
 
-// WFB/load_dataset.py:88-89 and correctdataloader.py:103
+// WFB/load_dataset.py:88-89 (clip to [black, white], scale by the exposure ratio) and, with `clamp`, correctdataloader.py:103
+// (min(., 1)).  8 pixels per thread (one 16-byte load, two 16-byte stores) when n % 8 == 0.
+__device__ __forceinline__ float pre_u16_one(unsigned v, float black, float white, float denom, float ratio, int clamp) {
+  float x = fminf(fmaxf((float)v, black), white);
+  x = __fmul_rn(__fdiv_rn(__fsub_rn(x, black), denom), ratio);
+  return clamp ? fminf(x, 1.0f) : x;
+}
 __global__ void __launch_bounds__(256)
 k_pre_u16(const unsigned short* __restrict__ raw, float* __restrict__ out, float black, float white, float denom, float ratio,
-          i64 n) {
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-    float x = fminf(fmaxf((float)raw[i], black), white);
-    x = __fmul_rn(__fdiv_rn(__fsub_rn(x, black), denom), ratio);
-    out[i] = fminf(x, 1.0f);
+          int clamp, i64 n) {
+  const i64 n8 = (n & 7) == 0 ? n >> 3 : 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (i64)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw) + i);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = pre_u16_one(w[k] & 0xffffu, black, white, denom, ratio, clamp);
+      f[2 * k + 1] = pre_u16_one(w[k] >> 16, black, white, denom, ratio, clamp);
+    }
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(f[0], f[1], f[2], f[3]);
+    o[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
+  for (i64 i = n8 * 8 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    out[i] = pre_u16_one(raw[i], black, white, denom, ratio, clamp);
 }
 
 // gated-GELU core: x1 = dwA(t)+bA, x2 = dwB(t)+bB, g = gelu(x2)*x1 + gelu(x1)*x2     (WFB/model.py:61-63)
@@ -283,15 +300,16 @@ int rf_ssim_u8(const unsigned char* a, const unsigned char* b, double* sum_out, 
   return check_cuda(cudaGetLastError());
 }
 
-int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,
-                      void* stream) {
-  if (!raw || !out) return RF_ERR_BAD_ARG;
+int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int clamp, int B, int H,
+                      int W, void* stream) {
+  if (!raw || !out || (uintptr_t)raw % 16 || (uintptr_t)out % 16) return RF_ERR_BAD_ARG;
   if (B <= 0 || H <= 0 || W <= 0) return (B < 0 || H < 0 || W < 0) ? RF_ERR_BAD_SHAPE : RF_OK;
   i64 n = (i64)B * H * W;
   const float denom = (float)((double)white - (double)black + 1e-6);
-  unsigned gx = (unsigned)(cdivl(n, 256) < 8 * num_sms() ? cdivl(n, 256) : 8 * num_sms());
+  const i64 work = (n & 7) == 0 ? n >> 3 : n;
+  unsigned gx = (unsigned)(cdivl(work, 256) < 8 * num_sms() ? cdivl(work, 256) : 8 * num_sms());
   ScopedLaunch sl(RF_K_INDEX_OP, 6.0 * n);
-  k_pre_u16<<<gx, 256, 0, (cudaStream_t)stream>>>(raw, out, black, white, denom, ratio, n);
+  k_pre_u16<<<gx, 256, 0, (cudaStream_t)stream>>>(raw, out, black, white, denom, ratio, clamp ? 1 : 0, n);
   return check_cuda(cudaGetLastError());
 }
 

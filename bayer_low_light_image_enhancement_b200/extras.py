@@ -101,8 +101,11 @@ def ssim_u8(a: torch.Tensor, b: torch.Tensor):
     return [v / n for v in acc[:nb].cpu().tolist()]
 
 
-def preprocess_u16(raw: torch.Tensor, black: float = 512.0, white: float = 16383.0, ratio: float = 100.0) -> torch.Tensor:
-    """uint16 Bayer [B,H,W] -> float32 [B,1,H,W] in [0,1] (black-level subtract, white-level scale, exposure ratio, clip)."""
+def preprocess_u16(raw: torch.Tensor, black: float = 512.0, white: float = 16383.0, ratio: float = 100.0,
+                   clamp: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+    """uint16 Bayer [B,H,W] -> float32 [B,1,H,W]: clip to [black, white], subtract the black level, scale by
+    ratio / (white - black + 1e-6) (WFB/load_dataset.py:88-89); ``clamp`` adds min(., 1) (correctdataloader.py:103).
+    ``out`` (optional): a float32 [B,1,H,W] tensor to write into."""
     if raw.dim() != 3:
         raise ValueError("raw must be [B,H,W]")
     _lib.init_device(raw.device)
@@ -110,11 +113,83 @@ def preprocess_u16(raw: torch.Tensor, black: float = 512.0, white: float = 16383
         raise ValueError("raw must be a 16-bit integer tensor")
     raw = raw.contiguous()
     b, h, w = raw.shape
-    out = torch.empty(b, 1, h, w, dtype=torch.float32, device=raw.device)
+    if out is None:
+        out = torch.empty(b, 1, h, w, dtype=torch.float32, device=raw.device)
+    elif tuple(out.shape) != (b, 1, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != raw.device:
+        raise ValueError("out must be a contiguous float32 [B,1,H,W] tensor on the device of raw")
     if out.numel():
-        check(_lib.load().rf_preprocess_u16(ptr(raw), ptr(out), float(black), float(white), float(ratio), b, h, w,
-                                            stream_ptr(raw.device)), "rf_preprocess_u16")
+        check(_lib.load().rf_preprocess_u16(ptr(raw), ptr(out), float(black), float(white), float(ratio), int(bool(clamp)),
+                                            b, h, w, stream_ptr(raw.device)), "rf_preprocess_u16")
     return out
+
+
+class _RowsLayerNorm(_Op):
+    """Shared body of the two hand-written LayerNorms of the WFB variant: normalises the LAST axis of x."""
+
+    _mode = 0
+
+    def __init__(self, normalized_shape):
+        super().__init__()
+        if isinstance(normalized_shape, int):
+            normalized_shape = (normalized_shape,)
+        normalized_shape = torch.Size(normalized_shape)
+        assert len(normalized_shape) == 1
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.normalized_shape = normalized_shape
+
+    def forward(self, x):
+        if not isinstance(x, torch.Tensor) or x.dim() < 1 or x.shape[-1] != self.normalized_shape[0]:
+            raise ValueError(f"last axis of x must have {self.normalized_shape[0]} elements")
+        _lib.init_device(x.device)
+        xin = f32c(x.detach())
+        out = torch.empty_like(xin)
+        c = xin.shape[-1]
+        rows = xin.numel() // c if c else 0
+        bias = getattr(self, "bias", None)
+        wt = f32c(self.weight.detach())
+        bs = None if bias is None else f32c(bias.detach())
+        if rows:
+            check(_lib.load().rf_layernorm_rows(ptr(xin), ptr(wt), ptr(bs), ptr(out), 1e-5, self._mode, rows, c,
+                                                stream_ptr(x.device)), "rf_layernorm_rows")
+        return out
+
+
+class BiasFree_LayerNorm(_RowsLayerNorm):
+    """x / sqrt(var(x) + 1e-5) * weight over the last axis -- the mean is NOT subtracted from x.
+    Reference: RawFomer_WFB_FFAB/model.py:89-103."""
+
+    _mode = 1
+
+
+class WithBias_LayerNorm(_RowsLayerNorm):
+    """(x - mean) / sqrt(var + 1e-5) * weight + bias over the last axis.  Reference: RawFomer_WFB_FFAB/model.py:106-122."""
+
+    _mode = 0
+
+    def __init__(self, normalized_shape):
+        super().__init__(normalized_shape)
+        self.bias = nn.Parameter(torch.zeros(self.normalized_shape))
+
+
+class WFBLayerNorm(_Op):
+    """``LayerNorm(dim, LayerNorm_type)`` of the WFB variant on NCHW tensors ('BiasFree' or anything else = with bias).
+    Reference: RawFomer_WFB_FFAB/model.py:125-135 (to_3d -> body -> to_4d)."""
+
+    def __init__(self, dim, LayerNorm_type):
+        super().__init__()
+        self.body = BiasFree_LayerNorm(dim) if LayerNorm_type == "BiasFree" else WithBias_LayerNorm(dim)
+
+    def forward(self, x):
+        x = self._prep(x, "x", self.body.normalized_shape[0])
+        b, c, h, w = x.shape
+        out = torch.empty_like(x)
+        wt = f32c(self.body.weight.detach())
+        bias = getattr(self.body, "bias", None)
+        bs = None if bias is None else f32c(bias.detach())
+        if out.numel():
+            check(_lib.load().rf_layernorm(ptr(x), ptr(wt), ptr(bs), ptr(out), 1e-5, self.body._mode, b, c, h, w,
+                                           stream_ptr(x.device)), "rf_layernorm")
+        return out
 
 
 class _Conv2dBN(nn.Sequential):

@@ -91,6 +91,10 @@ int rf_luma_chroma(const float* x_ds, float* y, float* cr, float* cb, const floa
  * WithBias_LayerNorm / BiasFree_LayerNorm — WFB/model.py:89-122 (mode 0 / mode 1: no mean subtraction, no bias). */
 int rf_layernorm(const float* in, const float* weight, const float* bias, float* out, float eps, int mode,
                  int B, int C, int H, int W, void* stream);
+/* The same two normalisations on channels-last rows [rows, C] (the 'b (h w) c' tensors WithBias_LayerNorm /
+ * BiasFree_LayerNorm.forward receive, WFB/model.py:102-103,119-122).  C % 8 == 0; bias may be NULL for mode 1. */
+int rf_layernorm_rows(const float* in, const float* weight, const float* bias, float* out, float eps, int mode,
+                      long long rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv_Transformer ("WaveTransformBlock") and its parts.
@@ -201,10 +205,11 @@ int rf_sse_u8(const unsigned char* a, const unsigned char* b, unsigned long long
  * data_range 255, K1 0.01, K2 0.03, sample covariance, border of 3 cropped): sum_out[b] (device, double) = sum of the SSIM
  * map over the valid pixels and the 3 channels; SSIM = sum_out[b] / (3*(H-6)*(W-6)).  H, W >= 7. */
 int rf_ssim_u8(const unsigned char* a, const unsigned char* b, double* sum_out, int B, int H, int W, void* stream);
-/* WFB/load_dataset.py:88-89: clip(raw,black,white) -> (x-black)/(white-black+1e-6)*ratio, then min(.,1)
- * (correctdataloader.py:103).  raw [B,H,W] u16 -> out [B,1,H,W] f32. */
-int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int B, int H, int W,
-                      void* stream);
+/* WFB/load_dataset.py:88-89: clip(raw,black,white) -> (x-black)/(white-black+1e-6)*ratio (fp32 arithmetic, as numpy
+ * evaluates it); clamp != 0 adds min(.,1) (correctdataloader.py:103).  raw [B,H,W] u16 -> out [B,1,H,W] f32; both
+ * pointers 16-byte aligned. */
+int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float white, float ratio, int clamp, int B, int H,
+                      int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole model — RawFormer.forward, FLCA_RF.py:330-370 (variant ML: ML_RF.py:356-416)

@@ -486,6 +486,16 @@ def layernorm_biasfree(x, w):
 BAYER_PERMS = {"BGGR": (2, 1, 0), "GBRG": (1, 0, 2), "GRBG": (0, 2, 1)}
 
 
+def preprocess_u16(raw, black=512.0, white=16383.0, ratio=100.0, clamp=True):
+    """RAW normalisation of the short exposure, WFB/load_dataset.py:88-89: ``np.clip(raw.astype(float32), 512, 16383)`` then
+    ``(x - 512) / (16383 - 512 + 1e-6) * ap`` -- float32 throughout (the Python-float divisor is cast to float32 by numpy's
+    scalar promotion) -- and, with ``clamp``, ``np.minimum(x, 1.0)`` (correctdataloader.py:103).  raw: uint16 array.
+    Pinned by tests/golden/pre.npz (tests/golden/make_golden_pre.py executes the reference's own statements)."""
+    x = np.clip(np.asarray(raw).astype(np.float32), np.float32(black), np.float32(white))
+    x = (x - np.float32(black)) / np.float32(float(white) - float(black) + 1e-6) * np.float32(ratio)
+    return np.minimum(x, np.float32(1.0)) if clamp else x
+
+
 def postprocess_u8(pred):
     """test.py:117-118: clamp(pred, 0, 1)[b] -> HWC -> * 255 -> astype(uint8).  pred [B,3,H,W] -> [B,H,W,3]."""
     x = np.clip(np.asarray(pred, np.float32), 0.0, 1.0).transpose(0, 2, 3, 1)

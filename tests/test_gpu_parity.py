@@ -40,6 +40,18 @@ def assert_close(name, got, ref, tol=1e-4, scaled=True):
     assert err <= lim, report(name, got, ref) + f"  > tol {lim:.3e}"
 
 
+# bf16 mode floors, PSNR(ours, reference) relative to the output's own range (SURVEY 8d expects >= 55 dB).  Measured in
+# round 1 (tools/accuracy_report.py): whole models 57.0-66.9 dB at weight scale <= 1.5, 54.4-54.7 dB with the x2 "stress"
+# weights; Conv_Transformer blocks >= 50 dB.
+BF16_MODEL_DB = 55.0
+BF16_MODEL_STRESS_DB = 52.0
+BF16_BLOCK_DB = 50.0
+
+
+def bf16_model_floor(weight_scale):
+    return BF16_MODEL_STRESS_DB if weight_scale >= 2.0 else BF16_MODEL_DB
+
+
 def psnr(a, b, data_range):
     mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
     return 99.0 if mse == 0 else 10.0 * np.log10(data_range ** 2 / mse)
@@ -177,7 +189,7 @@ def test_block_bf16(rf, case):
     out = npy(blk(cu(feat), y, cr, cb))
     rng = float(g["out"].max() - g["out"].min())
     p = psnr(out, g["out"], rng)
-    assert p >= 38.0, f"bf16 block PSNR vs reference {p:.1f} dB (range {rng:.3f}); " + report("out", out, g["out"])
+    assert p >= BF16_BLOCK_DB, f"bf16 block PSNR vs reference {p:.1f} dB (range {rng:.3f}); " + report("out", out, g["out"])
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -209,7 +221,8 @@ def test_whole_model_bf16(case):
     assert np.isfinite(out).all()
     rng = max(float(ref.max() - ref.min()), 1e-6)
     p = psnr(out, ref, rng)
-    assert p >= 35.0, f"PSNR(ours, ref) = {p:.1f} dB; " + report(case[0], out, ref)
+    floor = bf16_model_floor(case[7])
+    assert p >= floor, f"PSNR(ours, ref) = {p:.1f} dB < {floor}; " + report(case[0], out, ref)
     gt = np.clip(ref + np.random.default_rng(5).normal(0, 0.05 * rng, ref.shape), ref.min(), ref.max())
     d = abs(psnr(out, gt, rng) - psnr(ref, gt, rng))
     assert d <= 0.05, f"|PSNR(ours,GT) - PSNR(ref,GT)| = {d:.3f} dB"
@@ -236,7 +249,7 @@ def test_baseline_config0_packed_512(rf):
         out16 = npy(m16.to(dev()).eval()(x.to(dev())))
     rng = max(float(ref.max() - ref.min()), 1e-6)
     p = psnr(out16, ref, rng)
-    assert p >= 35.0, f"config0 bf16 PSNR(ours, ref) = {p:.1f} dB; " + report("config0 bf16", out16, ref)
+    assert p >= BF16_MODEL_DB, f"config0 bf16 PSNR(ours, ref) = {p:.1f} dB; " + report("config0 bf16", out16, ref)
     gt = np.clip(ref + np.random.default_rng(5).normal(0, 0.05 * rng, ref.shape), ref.min(), ref.max())
     d = abs(psnr(out16, gt, rng) - psnr(ref, gt, rng))
     assert d <= 0.05, f"|PSNR(ours,GT) - PSNR(ref,GT)| = {d:.3f} dB"
@@ -283,35 +296,23 @@ def test_errors(rf):
         rf.RawFormer(dim=36)
 
 
-def test_full_frame_properties(rf):
-    """BASELINE sizes (SID Sony 2848x4256): no NaN/Inf, fp32-vs-bf16 agreement, launch accounting."""
+def test_full_frame_launch_accounting(rf):
+    """BASELINE size (SID Sony 2848x4256): shape, finiteness and launch accounting.  The comparison of the full frame with
+    the reference's CPU forward lives in tests/test_fullframe.py (one test per BASELINE config)."""
     from bayer_low_light_image_enhancement_b200 import _lib
 
     torch.manual_seed(0)
     x = torch.rand(1, 1, 2848, 4256, device=dev())
-    m32 = rf.RawFormer(model_size="S", precision="fp32")
-    sd = T.make_state_dict(m32, seed=99, scale=1.5)
-    m32.load_state_dict(sd)
-    m32 = m32.to(dev()).eval()
     m16 = rf.RawFormer(model_size="S", precision="bf16")
-    m16.load_state_dict(sd)
+    m16.load_state_dict(T.make_state_dict(m16, seed=99, scale=1.5))
     m16 = m16.to(dev()).eval()
     lib = _lib.load()
     lib.rf_reset_launch_count()
     with torch.no_grad():
-        o32 = m32(x)
-        n_launch = lib.rf_launch_count()
         o16 = m16(x)
-    assert n_launch > 50
-    assert tuple(o32.shape) == (1, 3, 2848, 4256)
-    assert torch.isfinite(o32).all() and torch.isfinite(o16).all()
-    rng = float(o32.max() - o32.min())
-    mse = float(((o32 - o16) ** 2).mean())
-    p = 10 * np.log10(rng ** 2 / max(mse, 1e-30))
-    assert p >= 35.0, f"full-frame fp32 vs bf16 PSNR {p:.1f} dB"
-    # crop consistency away from the borders is NOT expected (global statistics) -- but the top-left 64x64 of the
-    # frame must equal the oracle-checked small-model path in its index work: out[2y+i,2x+j] channel layout.
-    assert float(o32.abs().max()) < 1e4
+    assert lib.rf_launch_count() > 50
+    assert tuple(o16.shape) == (1, 3, 2848, 4256)
+    assert torch.isfinite(o16).all()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -322,14 +323,47 @@ def test_postprocess_preprocess(rf):
     got = rf.postprocess_u8(pred).cpu().numpy()
     ref = (torch.clamp(pred, 0, 1).cpu().numpy().transpose(0, 2, 3, 1) * 255).astype(np.uint8)  # test.py:117-118
     assert np.array_equal(got, ref)
-    rng = np.random.default_rng(3)
-    raw = rng.integers(0, 16384, size=(2, 16, 24)).astype(np.uint16)
+    # RAW normalisation: bit-exact against the golden made by executing the reference loader's own statements
+    # (tests/golden/make_golden_pre.py: WFB/load_dataset.py:88-89, optional clamp of correctdataloader.py:103)
+    from oracle import rawformer_oracle as O
+
+    g = T.load_golden("pre")
+    raw = g["raw"]
+    dev_raw = torch.from_numpy(raw.view(np.int16)).to(dev()).view(torch.uint16)
     for ap in (100, 300):
-        x = np.clip(raw.astype(np.float32), 512, 16383)                       # WFB/load_dataset.py:88-89
-        x = (x - 512) / (16383 - 512 + 1e-6) * ap
-        x = np.minimum(x, 1.0).astype(np.float32)                              # correctdataloader.py:103
-        got = rf.preprocess_u16(torch.from_numpy(raw.view(np.int16)).to(dev()).view(torch.uint16), 512.0, 16383.0, float(ap))
-        assert_close("preprocess", got.cpu().numpy()[:, 0], x, 1e-6, scaled=False)
+        for clamp in (False, True):
+            ref = g[f"out_ap{ap}_{'clamp' if clamp else 'noclamp'}"]
+            assert np.array_equal(O.preprocess_u16(raw, 512.0, 16383.0, float(ap), clamp), ref)
+            got = rf.preprocess_u16(dev_raw, 512.0, 16383.0, float(ap), clamp=clamp)
+            assert np.array_equal(got.cpu().numpy()[:, 0], ref), (ap, clamp)
+
+
+def test_wfb_layernorms(rf):
+    """WithBias_LayerNorm / BiasFree_LayerNorm (RawFomer_WFB_FFAB/model.py:89-122) against the goldens made by the
+    reference's own classes, on the [b, hw, c] rows they are called with, and through the NCHW wrapper."""
+    from oracle import rawformer_oracle as O
+
+    xx = T.gen_input("randn", (2, 35, 32), 26) * 2 + 0.5
+    wv = np.random.default_rng(27).uniform(0.5, 1.5, 32).astype(np.float32)
+    bv = np.random.default_rng(28).uniform(-0.2, 0.2, 32).astype(np.float32)
+    lnb, lnw = rf.BiasFree_LayerNorm(32), rf.WithBias_LayerNorm(32)
+    lnb.load_state_dict({"weight": torch.from_numpy(wv)}, strict=True)
+    lnw.load_state_dict({"weight": torch.from_numpy(wv), "bias": torch.from_numpy(bv)}, strict=True)
+    assert_close("wfb_ln_biasfree", npy(lnb.to(dev())(cu(xx))), OPS["wfb_ln_biasfree"], 1e-5)
+    assert_close("wfb_ln_withbias", npy(lnw.to(dev())(cu(xx))), OPS["wfb_ln_withbias"], 1e-5)
+    # NCHW wrapper (to_3d -> body -> to_4d) on a larger ragged shape, against the oracle
+    x4 = T.gen_input("randn", (2, 48, 37, 53), 29) * 1.5 - 0.3
+    w4 = np.random.default_rng(30).uniform(0.5, 1.5, 48).astype(np.float32)
+    b4 = np.random.default_rng(31).uniform(-0.2, 0.2, 48).astype(np.float32)
+    for kind in ("BiasFree", "WithBias"):
+        m = rf.WFBLayerNorm(48, kind)
+        sd = {"body.weight": torch.from_numpy(w4)}
+        if kind == "WithBias":
+            sd["body.bias"] = torch.from_numpy(b4)
+        m.load_state_dict(sd, strict=True)
+        ref = O.layernorm_biasfree(x4, w4) if kind == "BiasFree" else O.layernorm_withbias(x4, w4, b4)
+        assert_close(f"wfb_layernorm_{kind}", npy(m.to(dev())(cu(x4))), ref, 1e-5)
+    assert tuple(lnb.to(dev())(torch.zeros(0, 32, device=dev())).shape) == (0, 32)
 
 
 def test_wfb_feedforward_gated(rf):
@@ -343,62 +377,90 @@ def test_wfb_feedforward_gated(rf):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# bf16 kernels at sizes that span several tiles / chunks (odd sizes, ragged edges): bf16 mode vs fp32 mode of the
-# same sub-module (the fp32 mode is itself checked against the reference goldens above)
+# bf16 kernels at sizes that span several tiles / chunks (odd sizes, ragged edges), both variants, against the ORACLE:
+# the functional-PyTorch CPU port of the reference (oracle/rawformer_torch.py, pinned to the reference goldens by
+# tests/test_oracle_golden.py).  fp32 mode of the same sub-modules is checked against it at 1e-4 as well.
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("C,hf,wf,b", [(32, 70, 90, 1), (64, 37, 50, 2), (48, 41, 100, 1), (128, 19, 45, 1),
-                                       (256, 18, 34, 1)])
-def test_bf16_submodules_multitile(rf, C, hf, wf, b):
-    blk = T.build_block("flca", C)
-    blk.load_state_dict(T.make_state_dict(blk, seed=50 + C, scale=1.5), strict=True)
+def _oracle_block_parts(variant, sd, feat, y, cr, cb):
+    from oracle import rawformer_torch as P
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    sdt = {k: v.detach().cpu().float() for k, v in sd.items()}
+    f, yy, c1, c2 = t(feat), t(y), t(cr), t(cb)
+    tr = P._p(sdt, "Transformer.")
+    lv = 2 if variant == "ml" else 0
+    with torch.no_grad():
+        ffn = P.conv_ffn(P._p(tr, "ffn."), f)
+        attn = P.attention(P._p(tr, "attn."), f)
+        fl = P.flca_pyramid(P._p(sdt, "FLCA."), f, yy, c1, c2, lv) if lv else P.flca(P._p(sdt, "FLCA."), f, yy, c1, c2)
+        x1 = f + P.attention(P._p(tr, "attn."), P.layernorm(f, tr["norm1.body.weight"], tr["norm1.body.bias"]))
+        trans = x1 + P.conv_ffn(P._p(tr, "ffn."), P.layernorm(x1, tr["norm2.body.weight"], tr["norm2.body.bias"]))
+        out = P.conv_transformer(sdt, f, yy, c1, c2, lv)
+    return {k: v.numpy() for k, v in dict(ffn=ffn, attn=attn, flca=fl, trans=trans, out=out).items()}
+
+
+def _run_block_parts(blk, precision, feat, y, cr, cb):
+    for m in blk.modules():
+        if hasattr(m, "precision"):
+            m.precision = precision
+    with torch.no_grad():
+        return {
+            "ffn": npy(blk.Transformer.ffn(feat)),
+            "attn": npy(blk.Transformer.attn(feat)),
+            "flca": npy(blk.FLCA(feat, y, cr, cb)),
+            "trans": npy(blk.Transformer(feat)),
+            "out": npy(blk(feat, y, cr, cb)),
+        }
+
+
+@pytest.mark.parametrize("variant,C,hf,wf,b", [("flca", 32, 70, 90, 1), ("flca", 64, 37, 50, 2), ("flca", 48, 41, 100, 1),
+                                               ("flca", 128, 19, 45, 1), ("flca", 256, 18, 34, 1), ("ml", 32, 70, 90, 1),
+                                               ("ml", 48, 41, 100, 2), ("ml", 64, 37, 50, 1), ("ml", 128, 19, 45, 1)])
+def test_bf16_submodules_multitile(rf, variant, C, hf, wf, b):
+    blk = T.build_block(variant, C)
+    sd = T.make_state_dict(blk, seed=50 + C, scale=1.5)
+    blk.load_state_dict(sd, strict=True)
     blk = blk.to(dev()).eval()
-    feat = cu(T.gen_input("randn", (b, C, hf, wf), 60 + C))
-    x_ds = cu(T.gen_input("rand", (b, 4, hf, wf), 61 + C))
-    y, cr, cb = rf.BayerLumaChroma().to(dev())(x_ds)
-
-    def run(precision):
-        for m in blk.modules():
-            if hasattr(m, "precision"):
-                m.precision = precision
-        with torch.no_grad():
-            return {
-                "ffn": npy(blk.Transformer.ffn(feat)),
-                "attn": npy(blk.Transformer.attn(feat)),
-                "flca": npy(blk.FLCA(feat, y, cr, cb)),
-                "trans": npy(blk.Transformer(feat)),
-                "out": npy(blk(feat, y, cr, cb)),
-            }
-
-    ref, got = run("fp32"), run("bf16")
+    feat = T.gen_input("randn", (b, C, hf, wf), 60 + C)
+    x_ds = T.gen_input("rand", (b, 4, hf, wf), 61 + C)
+    y, cr, cb = rf.BayerLumaChroma().to(dev())(cu(x_ds))
+    ref = _oracle_block_parts(variant, sd, feat, npy(y), npy(cr), npy(cb))
+    got32 = _run_block_parts(blk, "fp32", cu(feat), y, cr, cb)
+    got16 = _run_block_parts(blk, "bf16", cu(feat), y, cr, cb)
     for k in ref:
-        assert np.isfinite(got[k]).all(), k
+        assert_close(f"{variant} {k} fp32 (C={C}, {hf}x{wf})", got32[k], ref[k], 1e-4)
+        assert np.isfinite(got16[k]).all(), k
         rng = float(ref[k].max() - ref[k].min())
-        p = psnr(got[k], ref[k], rng)
-        assert p >= 40.0, f"{k} (C={C}, {hf}x{wf}): bf16 vs fp32 PSNR {p:.1f} dB; " + report(k, got[k], ref[k])
+        p = psnr(got16[k], ref[k], rng)
+        assert p >= 45.0, f"{variant} {k} (C={C}, {hf}x{wf}): bf16 vs oracle PSNR {p:.1f} dB; " + report(k, got16[k], ref[k])
 
 
-@pytest.mark.parametrize("C,hw", [(32, 448), (64, 320), (128, 224), (256, 160)])
-def test_bf16_pipeline_wraparound(rf, C, hw):
+@pytest.mark.parametrize("variant,C,hw", [("flca", 32, 448), ("flca", 64, 320), ("flca", 128, 224), ("flca", 256, 160),
+                                          ("ml", 32, 448), ("ml", 64, 320), ("ml", 96, 224)])
+def test_bf16_pipeline_wraparound(rf, variant, C, hw):
     """Images large enough that every persistent CTA walks several tiles (ring / staging-buffer / TMEM-buffer reuse in
-    the tcgen05 GEMM, the depthwise and the im2col kernels): bf16 mode against fp32 mode of the same block."""
-    blk = T.build_block("flca", C)
-    blk.load_state_dict(T.make_state_dict(blk, seed=70 + C, scale=1.5), strict=True)
+    the tcgen05 GEMM, the depthwise, the im2col and the fused kernels): the bf16 block against the oracle."""
+    blk = T.build_block(variant, C)
+    sd = T.make_state_dict(blk, seed=70 + C, scale=1.5)
+    blk.load_state_dict(sd, strict=True)
     blk = blk.to(dev()).eval()
     g = torch.Generator(device="cpu").manual_seed(C)
-    feat = torch.randn(1, C, hw, hw + 16, generator=g).to(dev())
-    x_ds = torch.rand(1, 4, hw, hw + 16, generator=g).to(dev())
-    y, cr, cb = rf.BayerLumaChroma().to(dev())(x_ds)
-    outs = {}
-    for prec in ("fp32", "bf16"):
-        for m in blk.modules():
-            if hasattr(m, "precision"):
-                m.precision = prec
-        with torch.no_grad():
-            outs[prec] = npy(blk(feat, y, cr, cb))
-    ref, got = outs["fp32"], outs["bf16"]
+    feat = torch.randn(1, C, hw, hw + 16, generator=g)
+    x_ds = torch.rand(1, 4, hw, hw + 16, generator=g)
+    y, cr, cb = rf.BayerLumaChroma().to(dev())(x_ds.to(dev()))
+    from oracle import rawformer_torch as P
+
+    sdt = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = P.conv_transformer(sdt, feat, y.cpu(), cr.cpu(), cb.cpu(), 2 if variant == "ml" else 0).numpy()
+    for m in blk.modules():
+        if hasattr(m, "precision"):
+            m.precision = "bf16"
+    with torch.no_grad():
+        got = npy(blk(feat.to(dev()), y, cr, cb))
     assert np.isfinite(got).all()
     p = psnr(got, ref, float(ref.max() - ref.min()))
-    assert p >= 40.0, f"C={C}: bf16 vs fp32 PSNR {p:.1f} dB; " + report("out", got, ref)
+    assert p >= BF16_BLOCK_DB, f"{variant} C={C}: bf16 vs oracle PSNR {p:.1f} dB; " + report("out", got, ref)
 
 
 def test_frame_pipeline(rf):

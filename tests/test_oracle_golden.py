@@ -166,3 +166,17 @@ def test_torch_port(case):
     out = P.rawformer_forward(sd, x, variant).numpy()
     ref = T.load_golden(name)["out"]
     assert np.abs(out - ref).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_preprocess_u16_oracle_matches_reference_statements():
+    """RAW normalisation: the oracle against tests/golden/pre.npz, which make_golden_pre.py produced by
+    executing the reference loader's own statements (WFB/load_dataset.py:88-89, correctdataloader.py:103)."""
+    g = T.load_golden("pre")
+    raw = g["raw"]
+    assert raw.dtype == np.uint16 and raw.min() == 0 and raw.max() == 65535
+    for ap in (100, 300):
+        for clamp in (False, True):
+            ref = g[f"out_ap{ap}_{'clamp' if clamp else 'noclamp'}"]
+            got = O.preprocess_u16(raw, 512.0, 16383.0, float(ap), clamp)
+            assert got.dtype == np.float32 and np.array_equal(got, ref), (ap, clamp)
+    assert float(g["out_ap300_noclamp"].max()) == 300.0 and float(g["out_ap300_clamp"].max()) == 1.0
