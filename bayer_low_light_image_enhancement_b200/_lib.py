@@ -110,6 +110,7 @@ _SIGS = {
     "rf_band_comm_close": (_i, [_fp]),
     "rf_band_comm_free": (_i, [_fp]),
     "rf_band_comm_status": (_i, [_fp, C.POINTER(_i), _fp]),
+    "rf_band_comm_reset": (_i, [_fp, _fp]),
     "rf_band_out_rows": (_i, [_BDp, C.POINTER(_i), C.POINTER(_i)]),
     "rf_rawformer_band_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _BDp]),
     "rf_rawformer_forward_band": (_i, [_fp, _i, _i, _i, _fp, _fp, _i, _i, _BDp, _fp, _sz, _fp]),
@@ -203,15 +204,26 @@ def dtype_code(precision: str) -> int:
 
 
 class Workspace:
-    """Caller-owned scratch memory (the C ABI never allocates).  Grows monotonically per device."""
+    """Caller-owned scratch memory (the C ABI never allocates): one buffer per (device, stream), grown on demand.
+
+    Stream-ordered work of ONE stream may share a buffer; two streams never do (forwards on different streams would race
+    on it).  A CUDA graph must NOT capture a buffer of this pool -- a later, larger request replaces it and the graph would
+    replay into freed memory; graph owners allocate their own workspace and keep it with the graph
+    (``RawFormer._forward_graph``, ``RowTiledRawFormer``)."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
-        key = (device.type, device.index)
+        stream = torch.cuda.current_stream(device)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the shared workspace must not be captured into a CUDA graph: allocate a workspace that "
+                               "lives as long as the graph")
+        key = (device.type, device.index, stream.cuda_stream)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
+            if b is not None:
+                b.record_stream(stream)          # work already enqueued on this stream may still use the old buffer
             b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._buf[key] = b
         return b

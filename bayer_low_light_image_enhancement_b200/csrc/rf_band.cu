@@ -282,6 +282,14 @@ int rf_band_comm_free(void* ptr) {
   return RF_OK;
 }
 
+int rf_band_comm_reset(void* comm_own, void* stream) {
+  // header of the region: sticky error word, frame counter, arrival counters (the mailboxes need no reset)
+  if (!comm_own) return RF_ERR_BAD_ARG;
+  RF_CUDA(cudaMemsetAsync(comm_own, 0, BAND_MAIL_OFF, (cudaStream_t)stream));
+  RF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return RF_OK;
+}
+
 int rf_band_comm_status(const void* comm_own, int* err_host, void* stream) {
   if (!comm_own || !err_host) return RF_ERR_BAD_ARG;
   unsigned v = 0;

@@ -490,24 +490,30 @@ class RawFormer(_Op):
 
     def _forward_graph(self, x):
         dt = self._dtype()
-        blob = self.packed_weights(x.device, dt)
+        blob = self.packed_weights(x.device, dt)     # (packs outside the capture)
         key = (x.data_ptr(), tuple(x.shape), dt, blob.data_ptr())
         hit = self._graphs.get(key)
         if hit is None:
             if len(self._graphs) >= self._graph_cap:
-                self._graphs.clear()
+                self._graphs.pop(next(iter(self._graphs)))      # oldest entry only: callers may hold the others' outputs
+            lib = _lib.load()
+            b, _, h, w = x.shape
+            # the graph OWNS its scratch memory: the captured pointers stay valid for as long as the cache entry lives,
+            # whatever other models, shapes or streams ask of the shared pool
+            ws = torch.empty(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), dtype=torch.uint8,
+                             device=x.device)
             cur = torch.cuda.current_stream(x.device)
             side = torch.cuda.Stream(x.device)
             side.wait_stream(cur)
-            with torch.cuda.stream(side):          # eager warm-up: workspace, function attributes, lazy module loading
-                self._forward_eager(x)
+            with torch.cuda.stream(side):          # eager warm-up: function attributes, lazy module loading
+                self._forward_eager(x, ws=ws)
             cur.wait_stream(side)
-            lib = _lib.load()
             n0 = lib.rf_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                out = self._forward_eager(x)
-            hit = (g, out, x, int(lib.rf_launch_count() - n0))   # x: keeps the captured input storage alive
+                out = self._forward_eager(x, ws=ws)
+            # x, ws, blob: keep the captured input storage, scratch memory and packed weights alive with the graph
+            hit = (g, out, x, int(lib.rf_launch_count() - n0), ws, blob)
             self._graphs[key] = hit
         hit[0].replay()
         self.graph_kernels_replayed = getattr(self, "graph_kernels_replayed", 0) + hit[3]   # kernel nodes executed
@@ -519,12 +525,13 @@ class RawFormer(_Op):
             return self._forward_graph(x)
         return self._forward_eager(x)
 
-    def _forward_eager(self, x):
+    def _forward_eager(self, x, ws=None):
         b, _, h, w = x.shape
         lib = _lib.load()
         dt = self._dtype()
         blob = self.packed_weights(x.device, dt)
-        ws = _lib.shared_workspace(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), x.device)
+        if ws is None:
+            ws = _lib.shared_workspace(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), x.device)
         out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
         check(lib.rf_rawformer_forward(ptr(blob), self.dim, dt, self.variant, ptr(x), ptr(out), b, h, w, ptr(ws),
                                        ws.numel(), stream_ptr(x.device)), "rf_rawformer_forward")

@@ -87,6 +87,7 @@ class RowTiledRawFormer:
         self.group, self._own, self._opened = group, own_region, list(opened)
         self.epoch = 0
         self._graphs = None
+        self.check_every = 64          # forward() reads the sticky error word every this many frames (synchronises)
         lib = _lib.load()
         self._band = _lib.Band()
         self._band.rank, self._band.nranks = self.rank, self.nranks
@@ -144,7 +145,12 @@ class RowTiledRawFormer:
                 ptrs.append(p.value)
                 opened.append(p.value)
         dist.barrier(group=group)
-        return cls(model, H, W, rank, world, ptrs, own_region=own, group=group, opened=opened)
+        tiled = cls(model, H, W, rank, world, ptrs, own_region=own, group=group, opened=opened)
+        # the constructor allocates GBs, loads every kernel (rehearsal) and packs the weights: without this barrier the
+        # rank skew at the first sync point of the first real frame is unbounded (the waits time out after ~6 s)
+        torch.cuda.current_stream(tiled.device).synchronize()
+        dist.barrier(group=group)
+        return tiled
 
     def close(self):
         """Unmap the peers' comm regions and free this rank's.  The peers write into this rank's region until their last
@@ -168,11 +174,30 @@ class RowTiledRawFormer:
         if tuple(raw.shape) != (1, 1, self.H, self.W):
             raise ValueError(f"expected the whole frame [1,1,{self.H},{self.W}], got {tuple(raw.shape)}")
         self.epoch += 1
-        if self._graphs is not None:
-            return self._replay(raw)
-        return self._launch(raw, self.epoch)
+        out = self._replay(raw) if self._graphs is not None else self._launch(raw, self.epoch)
+        if self.check_every and self.epoch % self.check_every == 0:
+            self.status()          # a peer that never arrived makes every later frame wrong: fail loudly, not silently
+        return out
 
     __call__ = forward
+
+    def reset(self):
+        """Recover from a failed frame (``status()`` raised on some rank, or a rank raised mid-frame): every rank calls
+        this.  Waits for the local stream, meets the group, clears the local region's error word / frame counter / arrival
+        counters, meets the group again and restarts the frame count.  Captured graphs stay valid (the frame counter they
+        compare against lives in the region)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        if self.group is not None or self._opened:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+        check(_lib.load().rf_band_comm_reset(C.c_void_p(self._band.comm[self.rank]), _lib.stream_ptr(self.device)),
+              "rf_band_comm_reset")
+        if self.group is not None or self._opened:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+        self.epoch = 0
 
     def enable_cuda_graphs(self, on=True):
         """Replay this rank's forward as ONE CUDA graph per input buffer (the frame counter the sync points compare
@@ -183,15 +208,17 @@ class RowTiledRawFormer:
 
     def capture(self, raw):
         """Capture (without running) the graph of this rank's forward for the input buffer ``raw``."""
-        hit = self._graphs.get(raw.data_ptr())
+        blob = self.model.packed_weights(raw.device, _lib.RF_BF16)      # pack BEFORE the capture (it synchronises)
+        key = (raw.data_ptr(), tuple(raw.shape), blob.data_ptr())
+        hit = self._graphs.get(key)
         if hit is None:
             if len(self._graphs) >= 8:
-                self._graphs.clear()
+                self._graphs.pop(next(iter(self._graphs)))              # oldest entry only
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._launch(raw, 1)
-            hit = (g, out, raw)
-            self._graphs[raw.data_ptr()] = hit
+            hit = (g, out, raw, blob)                                   # keeps input storage and packed weights alive
+            self._graphs[key] = hit
         return hit
 
     def _replay(self, raw):
@@ -244,6 +271,7 @@ class RowTiledRawFormer:
         None on the other ranks."""
         import torch.distributed as dist
 
+        self.status()                      # never hand out bands of a frame whose sync points timed out
         band = band.contiguous()
         me = dist.get_rank(self.group)
         if me != dst:
@@ -264,8 +292,15 @@ class LocalBands:
     the multi-GPU run, with the "peer" regions in local memory.  For parity tests of the decomposition."""
 
     def __init__(self, model, H, W, nranks, graphs=False):
+        import os
+
         dev = next(model.parameters()).device
         _lib.init_device(dev)
+        # the bands' kernels spin on one another: every band stream needs its own hardware queue, else a waiting sync
+        # kernel blocks the launches of the band it waits for (the variable is read when CUDA initialises)
+        if nranks > 1 and int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")) < 2 * nranks:
+            raise RuntimeError(f"LocalBands({nranks}) needs CUDA_DEVICE_MAX_CONNECTIONS >= {2 * nranks} set BEFORE CUDA is "
+                               "initialised (tests/conftest.py and bench.py set 32)")
         nbytes = RowTiledRawFormer.comm_bytes(model, H, W, nranks)
         self.regions = [_CommRegion(nbytes, dev) for _ in range(nranks)]
         ptrs = [r.ptr for r in self.regions]

@@ -278,6 +278,10 @@ int rf_band_comm_free(void* ptr);
 /* Sticky error word of the local comm region: 0, or 1 + the index of the sync point whose wait timed out
  * (a peer never arrived).  Synchronises `stream`. */
 int rf_band_comm_status(const void* comm_own, int* err_host, void* stream);
+/* Clear the header of the LOCAL comm region (error word, frame counter, arrival counters) after a failed frame.  Every
+ * rank must call it between two barriers of the group (no forward in flight anywhere), then restart its epoch count.
+ * Synchronises `stream`. */
+int rf_band_comm_reset(void* comm_own, void* stream);
 /* Rows of the band image the forward writes: out is [1,3,2*(ht+rows/2+hb),W] where ht/hb = RF_BAND_HALO for a
  * neighbour above/below, else 0; the interior starts at raw row 2*ht of it. */
 int rf_band_out_rows(const rf_band* band, int* out_rows_host, int* interior_row0_host);

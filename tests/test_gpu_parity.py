@@ -486,6 +486,49 @@ def test_frame_pipeline(rf):
         assert own >= 45.0 and own > others + 15.0, f"frame {i}: PSNR vs own direct result {own:.1f} dB, best other {others:.1f} dB"
 
 
+@pytest.mark.parametrize("precision,graphs", [("fp32", False), ("bf16", True)])
+def test_frame_pipeline_u16_in_rgb_u8_out(rf, precision, graphs):
+    """The streaming wire formats of the caller: uint16 sensor frames in (normalised on the device,
+    WFB/load_dataset.py:88-89), uint8 HWC images out (test.py:117-120: clamp, x255, truncation, Bayer channel order,
+    auto_correct_rb), frame by frame and in order, against the numpy oracle applied around the directly called forward."""
+    from oracle import rawformer_oracle as O
+
+    m = rf.RawFormer(dim=32, precision=precision)
+    m.load_state_dict(T.make_state_dict(m, seed=8, scale=2.0))
+    with torch.no_grad():          # spread the output over [0,1] and make red darker than blue (auto_correct_rb swaps)
+        m.conv_out.bias.copy_(torch.tensor([0.25] * 4 + [0.45] * 4 + [0.65] * 4))
+        m.conv_out.weight.mul_(6.0)
+    m = m.to(dev()).eval()
+    rng = np.random.default_rng(11)
+    frames = [torch.from_numpy(rng.integers(400, 2200, size=(1, 96, 160)).astype(np.uint16)).pin_memory() for _ in range(5)]
+    ratios = [100.0, 300.0, 100.0, 250.0, 300.0]
+    outs = [torch.empty(1, 96, 160, 3, dtype=torch.uint8).pin_memory() for _ in frames]
+    pipe = rf.FramePipeline(m, depth=2, graphs=graphs, preprocess={"black": 512, "white": 16383, "clamp": False},
+                            postprocess={"pattern": "GRBG", "auto_rb": True})
+    assert pipe.wire_bytes(1, 96, 160) == (96 * 160 * 2, 96 * 160 * 3)
+    for x, o, r in zip(frames, outs, ratios):
+        pipe.submit(x, o, ratio=r)
+    pipe.flush()
+    m.enable_cuda_graphs(False)
+    swapped = 0
+    for i, (x, o, r) in enumerate(zip(frames, outs, ratios)):
+        xin = O.preprocess_u16(x.numpy(), 512.0, 16383.0, r, clamp=False)[:, None]
+        with torch.no_grad():
+            pred = npy(m(cu(xin)))
+        u8 = O.postprocess_u8(pred)
+        plain = np.stack([O.correct_bayer_channels(u8[b], "GRBG") for b in range(u8.shape[0])])
+        ref = np.stack([O.auto_correct_rb(p_) for p_ in plain])
+        swapped += int(not np.array_equal(ref, plain))
+        got = o.numpy()
+        d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+        # two runs of the forward differ in the last bits (float atomics), so a value next to an integer boundary may
+        # truncate differently: allow |diff| <= 1 on a small fraction of the bytes (bf16: its rounding noise moves more)
+        lim = 2e-3 if precision == "fp32" else 0.08
+        assert d.max() <= 1 and (d > 0).mean() <= lim, f"frame {i}: max diff {d.max()}, differing bytes {(d > 0).mean():.4f}"
+        assert ref.max() - ref.min() > 60, "the test image must span a useful range"
+    assert swapped > 0
+
+
 def test_cuda_graph_replay(rf):
     """enable_cuda_graphs(): the captured forward reproduces the eager forward, replays follow new input data in the
     captured buffer, and a second input buffer gets its own graph."""
