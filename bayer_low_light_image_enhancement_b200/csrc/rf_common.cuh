@@ -57,6 +57,8 @@ enum KernelId {
   RF_K_GEMM_GRAM,
   RF_K_BAND_HALO,
   RF_K_BAND_ALLREDUCE,
+  RF_K_FFN_FUSED,
+  RF_K_QKV_FUSED,
   RF_K_COUNT
 };
 

@@ -14,6 +14,7 @@
 //   MODE 2: out = gelu_erf(dw(in) + bias)            (conv_ffn.depthwise + nn.GELU, FLCA_RF.py:206-207); see gelu_erf2
 #include "rf_kernels.cuh"
 #include "rf_tma.cuh"
+#include "rf_dw_math.cuh"
 
 namespace rf {
 
@@ -35,47 +36,6 @@ struct DwTmaParams {
   uint32_t tile_bytes; // (TH+2)*(TW+2)*CC*2
   uint32_t buf_stride; // tile_bytes rounded up to 128
 };
-
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
-}
-// 4 bf16 -> two packed fp32 pairs (channel pairs (0,1), (2,3)); the conv runs on packed FFMA2 (fma.rn.f32x2)
-__device__ __forceinline__ void unpack_bf16x4(const uint2& t, float2 (&v)[2]) {
-  // PRMT / LOP3 run on the ALU pipe (a plain shift is turned into IMAD.U32, which competes with the FFMA2s)
-  v[0] = make_float2(__uint_as_float(__byte_perm(t.x, 0u, 0x1044u)), __uint_as_float(t.x & 0xffff0000u));
-  v[1] = make_float2(__uint_as_float(__byte_perm(t.y, 0u, 0x1044u)), __uint_as_float(t.y & 0xffff0000u));
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// erf-GELU of two values in packed fp32:  gelu(x) = x * Phi(x),  Phi(x) = 1 / (1 + exp(-x * P(min(x^2, 64)))),
-// P = degree-4 minimax fit of logit(Phi(x)) / x on |x| <= 8 (tools/fit_gelu.py): |gelu error| <= 1.2e-5 absolute and
-// <= 7.5e-5 of max(|gelu|, 0.02), i.e. < 1/10 of a bf16 half-ulp; no cancellation in the negative tail (x -> -inf
-// gives x * 0), exact identity for x >= 8.  8 packed FMA-pipe ops + 2 MUFU per value pair (the Abramowitz-Stegun
-// erfc form needs 12 + 2); coefficients are pre-multiplied by -log2(e) so the exponential is a bare ex2.
-__device__ __forceinline__ float2 gelu_erf2(float2 x) {
-  const float k0 = -1.4426950408889634f * 1.5954254501877632f, k1 = -1.4426950408889634f * 0.07325994800505611f,
-              k2 = -1.4426950408889634f * -0.00036788829074290585f, k3 = -1.4426950408889634f * -4.5953771468195396e-05f,
-              k4 = -1.4426950408889634f * 1.6250086403938804e-06f;
-  float2 t = __fmul2_rn(x, x);
-  t = make_float2(fminf(t.x, 64.f), fminf(t.y, 64.f));
-  float2 pz = __ffma2_rn(make_float2(k4, k4), t, make_float2(k3, k3));
-  pz = __ffma2_rn(pz, t, make_float2(k2, k2));
-  pz = __ffma2_rn(pz, t, make_float2(k1, k1));
-  pz = __ffma2_rn(pz, t, make_float2(k0, k0));
-  const float2 w = __fmul2_rn(x, pz);
-  const float2 d = __fadd2_rn(make_float2(ex2_approx(w.x), ex2_approx(w.y)), make_float2(1.f, 1.f));
-  return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(DT_THREADS, 1)

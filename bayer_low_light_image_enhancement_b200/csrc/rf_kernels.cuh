@@ -196,6 +196,12 @@ void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature
 // depthwise 3x3 (+bias) with optional exact GELU: in/out [B,H,W,Cn]
 void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H,
                    int W, int Cn, int kernel_id);
+// fused conv_ffn (rf_ffn_fused.cu): out = x + pointwise2(gelu(depthwise(pointwise1(norm2(x))))) in ONE kernel, norm2 folded
+// into W1f / cs / b1; stats = [rows][npart] (sum, sumsq) of x's rows.  false when the shape is not supported.
+bool ffn_fused_supported(const Ctx& ctx, int C, int W);
+bool launch_ffn_fused(Ctx& ctx, const void* x, const void* W1f, const float* cs, const float* b1, const float* stats, int npart,
+                      const float* dw_w, const float* dw_b, const void* W2, const float* b2, void* out, int B, int H, int W,
+                      int C);
 // embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
 void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
                   int w_, int d);

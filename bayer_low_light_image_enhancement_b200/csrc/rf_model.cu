@@ -313,6 +313,15 @@ static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* re
   const int C = pb.C;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
+  // one kernel for the whole FFN (hidden tensor in shared / tensor memory) where the shape allows
+  if (ln != nullptr && xin == resid && ffn_fused_supported(ctx, C, W) && ln->npart == 1) {
+    if (ctx.dry) return;
+    if (launch_ffn_fused(ctx, xin, pb.pw1_wf, pb.pw1_cs, pb.pw1_bf, ln->stats, ln->npart, pb.ffn_dw_w, pb.ffn_dw_b, pb.pw2_w,
+                         pb.pw2_b, out, B, H, W, C))
+      return;
+    recorder().last_cuda_error = (int)cudaErrorNotSupported;   // (the dry run sized the arena without the hidden tensors)
+    return;
+  }
   const size_t mk = A.mark();
   void* hpre = A.elems((size_t)B * P * 2 * C, ctx.dtype);
   {

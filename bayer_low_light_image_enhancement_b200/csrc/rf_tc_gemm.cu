@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "rf_kernels.cuh"
 #include "rf_tma.cuh"
 
@@ -66,19 +68,6 @@ struct TcParams {
 };
 
 __device__ __forceinline__ uint32_t make_idesc(int n) { return make_idesc_m128(n); }
-// K-major operand tile with rows of bk bf16: bk = 64 -> SWIZZLE_128B (8-row atoms of 1024 B), bk = 32 -> SWIZZLE_64B
-// (8-row atoms of 512 B); cute::UMMA::LayoutType 2 / 4
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
-  if (bk == 64) return make_sw128_desc(smem_addr);
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;        // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
-  return d;
-}
-
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -319,17 +308,40 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           const uint32_t At = sT + s * halo_stride;
           const uint64_t dbase = ((uint64_t)((uint32_t)(p.npix * 16) >> 4) << 16) | ((uint64_t)((uint32_t)(p.pitch * 16) >> 4) << 32) |
                                  ((uint64_t)1 << 46);
-          // descriptor pairs come from a table built once (below): the single issuing thread's instruction chain per
-          // MMA was the critical path of the whole CTA (~200 cycles per MMA when computed inline)
-          const int nmma = 9 * (p.K1 >> 4);
+          // the single issuing thread's instruction chain per MMA is the critical path of the CTA (a tcgen05.mma costs
+          // ~59 issue cycles by itself): the tap / k-step loops are fully unrolled for the four channel counts of the
+          // halo form, so every descriptor is the base plus a compile-time constant (patch pitch 10, 180 patch pixels)
           const uint32_t aoff = (At & 0x3FFFF) >> 4;
-          for (int i = 0; i < nmma; ++i) {
-            uint32_t alo, ahi, blo, bhi;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(alo), "=r"(ahi), "=r"(blo), "=r"(bhi)
-                         : "r"(sDesc + (uint32_t)i * 16u));
-            const uint64_t adesc = ((uint64_t)ahi << 32) | (uint64_t)(alo + aoff);
-            const uint64_t bdesc = ((uint64_t)bhi << 32) | (uint64_t)blo;
-            umma_f16(d_tmem, adesc, bdesc, idesc, i ? 1u : 0u);
+          const uint64_t abase = dbase + (uint64_t)aoff;
+          const uint64_t wdesc0 = make_kmajor_desc(sWres, p.bk);
+          const uint32_t wstep = w_bytes >> 4;
+          auto issue_all = [&](auto KS, auto KPB) {          // one k-block per tap in the halo form (Cin <= 64)
+            constexpr int ksteps = decltype(KS)::value, kpb = decltype(KPB)::value;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint64_t adesc = abase + (uint64_t)(uint32_t)(((tap / 3) * 10 + (tap % 3)) + 2 * kk * 180);
+                const uint64_t bdesc = wdesc0 + (uint64_t)((uint32_t)(tap + kk / kpb) * wstep + 2u * (uint32_t)(kk % kpb));
+                umma_f16(d_tmem, adesc, bdesc, idesc, (tap | kk) ? 1u : 0u);
+              }
+            }
+          };
+          const bool std_patch = p.pitch == 10 && p.npix == 180 && p.kb1 == 1;
+          if (std_patch && p.K1 == 32 && p.bk == 32) issue_all(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+          else if (std_patch && p.K1 == 64 && p.bk == 64) issue_all(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+          else if (std_patch && p.K1 == 48 && p.bk == 64) issue_all(std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{});
+          else if (std_patch && p.K1 == 16 && p.bk == 32) issue_all(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
+          else {
+            const int nmma = 9 * (p.K1 >> 4);
+            for (int i = 0; i < nmma; ++i) {
+              uint32_t alo, ahi, blo, bhi;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(alo), "=r"(ahi), "=r"(blo), "=r"(bhi)
+                           : "r"(sDesc + (uint32_t)i * 16u));
+              const uint64_t adesc = ((uint64_t)ahi << 32) | (uint64_t)(alo + aoff);
+              const uint64_t bdesc = ((uint64_t)bhi << 32) | (uint64_t)blo;
+              umma_f16(d_tmem, adesc, bdesc, idesc, i ? 1u : 0u);
+            }
           }
           umma_commit(aempty_bar(s));         // the patch buffer is free when these MMAs retire
           if (++s == p.nt) { s = 0; ++wrap; }

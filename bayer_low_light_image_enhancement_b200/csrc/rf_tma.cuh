@@ -122,6 +122,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+// K-major operand tile with rows of bk bf16: bk = 64 -> SWIZZLE_128B (8-row atoms of 1024 B), bk = 32 -> SWIZZLE_64B
+// (8-row atoms of 512 B); cute::UMMA::LayoutType 2 / 4
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
+  if (bk == 64) return make_sw128_desc(smem_addr);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;        // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t make_idesc_m128(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
