@@ -8,11 +8,15 @@ A "step" = one forward over one synthetic SID-Sony-shaped frame (raw 2848x4256 -
 N = 1 workload = BASELINE configs[1]: RawFormer-S, full frame, bf16.  N > 1 (torchrun) is image-parallel: every rank
 runs its own frames, no data-path collective ("weak" scaling); timing = max over ranks of CUDA-event time.
 
-Prints ONE JSON line (see the driver contract): value = device-resident throughput, e2e = same metric through the
-public nn.Module call with pinned HOST buffers (H2D + forward + D2H inside the timed region), roofline = the
-dominant kernel of the step (per-launch CUDA events on the launching stream), cpu_baseline = the functional-PyTorch
-CPU port of the reference timed on this box's host cores on a bounded sample.
-`--impl reference` times that CPU port alone (rank 0 only) and prints the same line with "impl": "reference".
+Prints ONE JSON line (see the driver contract): value = device-resident throughput; e2e = the same metric through the
+package's streaming API with pinned HOST buffers in the caller's wire formats -- uint16 sensor frame in (normalised on
+the device, WFB/load_dataset.py:88-89), uint8 HWC image out (test.py:117-120) -- H2D + forward + D2H inside the timed
+region (e2e_fp32_wires: the same with fp32 tensors both ways); roofline = the dominant CUDA symbol of the step
+(per-launch CUDA events on the launching stream); parity_db = PSNR of the timed frame's output against the reference's
+CPU forward; cpu_baseline = the functional-PyTorch CPU port of the reference on this box's host cores, one full frame.
+N = 1 also reports ms/frame of RawFormer-B / -L and the multi-level variant ("sizes"); N > 1 adds BASELINE config 3
+(RawFormer-B image-parallel) and config 4 (RawFormer-L, ONE frame row-tiled over the N GPUs) as sub-records.
+`--impl reference` times the CPU port alone on the full frame (rank 0 only) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -36,6 +40,19 @@ MP_FRAME = H_RAW * W_RAW / 1e6
 METRIC = "megapixels/sec of RAW input (SID Sony full frame)"
 SIZES = {"S": 32, "B": 48, "L": 64}
 TENSOR_KERNELS = ("gemm_", "conv3x3_out", "down_conv3x3", "up_convT", "skip_reduce")
+# logical launch name -> CUDA symbol family (template instantiation) it runs as, and which roofline bounds that family at
+# the benchmarked sizes: the LayerNorm-folded GEMM is ONE symbol although it appears under two logical names
+SYMBOL_OF = {
+    "gemm_qkv": ("k_tc_gemm<ROWS, LN-fold>", "hbm"), "gemm_pw1": ("k_tc_gemm<ROWS, LN-fold>", "hbm"),
+    "gemm_proj_resid": ("k_tc_gemm<ROWS, residual, stats>", "hbm"), "gemm_pw2_resid": ("k_tc_gemm<ROWS, residual>", "hbm"),
+    "gemm_cat_reduce": ("k_tc_gemm<ROWS>", "hbm"), "skip_reduce": ("k_tc_gemm<ROWS, stats>", "hbm"),
+    "up_convT": ("k_tc_gemm<CONVT>", "hbm"), "conv3x3_out": ("k_tc_gemm<ROWS, lrelu, conv3x3>", "tensor"),
+    "down_conv3x3": ("k_tc_gemm<UNSHUFFLE, conv3x3>", "tensor"), "head": ("k_tc_gemm<HEAD, conv3x3>", "hbm"),
+    "gemm_pyr_res1": ("k_tc_gemm<ROWS, relu>", "hbm"), "gemm_pyr_res2": ("k_tc_gemm<ROWS, residual, tanh>", "hbm"),
+    "dw_qkv_gram": ("k_dw_tma<1>", "hbm"), "dw_gelu": ("k_dw_tma<2>", "hbm"), "ffn_fused": ("k_ffn_fused", "hbm"),
+    "qkv_fused": ("k_qkv_fused", "hbm"), "flca_mod": ("k_im2col_tc<0>", "hbm"), "embed": ("k_im2col_tc<1>", "hbm"),
+    "pyr_spatial": ("k_im2col_tc<2|3>", "hbm"), "gemm_gram": ("k_tc_gram", "hbm"),
+}
 
 
 def workload_name(args, world):
@@ -157,7 +174,30 @@ class ClockSampler:
         return out
 
 
-def cpu_port_setup(size, variant, h, w, seed=0):
+def synthetic_u16_frames(batch, seed):
+    """Synthetic SID-Sony-shaped sensor frames: uint16 [B,H,W] with black level 512, such that the reference
+    normalisation at exposure ratio 100 (WFB/load_dataset.py:88-89) maps them to [0, 1)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    return (512 + torch.randint(0, 159, (batch, H_RAW, W_RAW), generator=g, dtype=torch.int32)).to(torch.uint16)
+
+
+PRE = {"black": 512.0, "white": 16383.0, "ratio": 100.0, "clamp": True}
+
+
+def normalise_cpu(u16):
+    """The reference loader's arithmetic on the host (fp32, numpy semantics) -> float32 [B,1,H,W]."""
+    import numpy as np
+    import torch
+
+    from oracle import rawformer_oracle as O
+
+    x = O.preprocess_u16(u16.numpy(), PRE["black"], PRE["white"], PRE["ratio"], PRE["clamp"])
+    return torch.from_numpy(np.ascontiguousarray(x[:, None]))
+
+
+def cpu_port_setup(size, variant, x):
     import torch
 
     import rf_testlib as T
@@ -166,29 +206,23 @@ def cpu_port_setup(size, variant, h, w, seed=0):
     torch.set_num_threads(os.cpu_count() or 1)
     dim = SIZES[size]
     sd = T.make_state_dict(T.build_model(variant, dim), seed=1234, scale=1.0)
-    g = torch.Generator().manual_seed(seed)
-    x = torch.rand(1, 1, h, w, generator=g)
     return (lambda: P.rawformer_forward(sd, x, variant)), torch.get_num_threads()
 
 
-def time_cpu_port(size, variant, budget_s=25.0):
-    """Bounded CPU sample: 1024x1024 raw crop first; the full frame once if the budget allows."""
-    fn, threads = cpu_port_setup(size, variant, 1024, 1024)
-    fn()  # warm-up
+def time_cpu_port(size, variant, x_full):
+    """cpu_baseline: the CPU port of the reference forward on ONE full frame (the frame the GPU legs time): one timed
+    run after a warm-up on a raw 512x512 crop (thread pool, MKL-DNN primitives).  Returns (record, output)."""
+    fn_small, threads = cpu_port_setup(size, variant, x_full[:, :, :512, :512].contiguous())
+    fn_small()
+    fn, _ = cpu_port_setup(size, variant, x_full)
     t0 = time.perf_counter()
-    fn()
+    out = fn()
     dt = time.perf_counter() - t0
-    mp = 1024 * 1024 / 1e6
-    best = {"value": mp / dt, "sample": f"RawFormer-{size} ({variant}) fp32, 1 frame raw 1024x1024 (1.05 MP), 1 warm-up + 1 timed"}
-    est_full = dt * (MP_FRAME / mp) * 2.2  # the reference is ~2x slower per MP at full frame (BASELINE.md)
-    if est_full < budget_s:
-        fn_full, _ = cpu_port_setup(size, variant, H_RAW, W_RAW)
-        t0 = time.perf_counter()
-        fn_full()
-        dt = time.perf_counter() - t0
-        best = {"value": MP_FRAME / dt, "sample": f"RawFormer-{size} ({variant}) fp32, 1 full frame raw {H_RAW}x{W_RAW} (12.12 MP), 1 timed run"}
-    best.update(unit="MP/s", cores=threads, kind="port")
-    return best
+    rec = {"value": MP_FRAME / dt, "unit": "MP/s", "cores": threads, "kind": "port",
+           "sample": f"RawFormer-{size} ({variant}) fp32 CPU port of the reference forward (oracle/rawformer_torch.py: the "
+                     f"reference's ATen operators; einops rearrange -> permute + F.layer_norm), 1 full frame raw "
+                     f"{H_RAW}x{W_RAW} (12.12 MP), 1 timed run, {threads} threads"}
+    return rec, out
 
 
 def time_torch_eager_b200(size, variant, dev):
@@ -230,27 +264,27 @@ def time_torch_eager_b200(size, variant, dev):
 
 
 def run_reference(args):
-    """Reference arm: the CPU port of the reference forward on this box's host cores, rank 0 only."""
+    """Reference arm: the CPU port of the reference forward on this box's host cores, rank 0 only, the FULL frame per
+    step (same config as the GPU arm: RawFormer-S takes ~6 s per frame on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    h = w = 1024
-    fn, threads = cpu_port_setup(args.size, args.variant, h, w)
+    x = normalise_cpu(synthetic_u16_frames(1, 0))
+    fn, threads = cpu_port_setup(args.size, args.variant, x)
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         fn()
     dt = time.perf_counter() - t0
-    mp = h * w / 1e6
-    val = args.steps * mp / dt
-    sample = (f"CPU port of the reference forward (oracle/rawformer_torch.py, fp32, {threads} threads); each step = "
-              f"one raw {h}x{w} crop (1.05 MP) of the frame")
+    val = args.steps * MP_FRAME / dt
+    sample = (f"CPU port of the reference forward (oracle/rawformer_torch.py, fp32, {threads} threads: the reference's ATen "
+              f"operators, einops rearrange -> permute + F.layer_norm); each step = one FULL frame raw {H_RAW}x{W_RAW} (12.12 MP)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, args.gpus), "cpu_sample": f"raw {h}x{w} crop per step"},
+        "config": {"workload": workload_name(args, args.gpus), "cpu_sample": f"full frame raw {H_RAW}x{W_RAW} per step"},
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -258,218 +292,268 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Env:
+    """Process / device context shared by the legs of one invocation."""
 
-    import rf_testlib as T
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    import bayer_low_light_image_enhancement_b200 as rf
-    from bayer_low_light_image_enhancement_b200 import _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_cpus(self.local)   # pinned host buffers are first-touched on the GPU's own NUMA node
+        self.dist = dist
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_cpus(local)   # pinned host buffers are first-touched on the GPU's own NUMA node
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
+    def barrier(self):
+        import torch
 
-    dim = SIZES[args.size]
-    cls = rf.RawFormer if args.variant == "flca" else rf.multilevel.RawFormer
-    model = cls(dim=dim, precision=args.precision)
-    model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)  # random-init weights
-    model = model.to(dev).eval()
-    if not args.no_graph:
-        model.enable_cuda_graphs()      # one graph launch per frame (public API; the per-kernel profile below stays eager)
-    B = args.frames
-    gen = torch.Generator().manual_seed(rank)
-    x_host = torch.rand(B, 1, H_RAW, W_RAW, generator=gen).pin_memory()
-    out_host = torch.empty(B, 3, H_RAW, W_RAW).pin_memory()
-    x_dev = x_host.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, ms):
+        import torch
+
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             return float(t.item())
         return ms
 
-    with torch.no_grad():
-        # ---- device-resident throughput ----
-        # pre-warm: a fresh box needs ~1 s of work before clocks / HBM / lazily loaded kernels settle (the first timed
-        # run on a cold GPU was 40 % slower than the next ones); then the W warm-up steps of the contract
-        t_pre = time.perf_counter()
-        while time.perf_counter() - t_pre < 1.5:
-            model(x_dev)
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def build_model(env, size, variant, precision, graphs=True):
+    import rf_testlib as T
+
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    cls = rf.RawFormer if variant == "flca" else rf.multilevel.RawFormer
+    model = cls(dim=SIZES[size], precision=precision)
+    model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)  # random-init weights
+    model = model.to(env.dev).eval()
+    if graphs:
+        model.enable_cuda_graphs()      # one graph launch per frame (public API; the per-kernel profile stays eager)
+    return model
+
+
+def time_resident(env, model, x_dev, steps, warmup, prewarm_s=1.5, load_s=0.6, sampler=None):
+    """Device-resident forward: W warm-ups, then exactly `steps` timed steps between barriers; CUDA events, max over ranks."""
+    import torch
+
+    from bayer_low_light_image_enhancement_b200 import _lib
+
+    lib = _lib.load()
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < prewarm_s:       # a fresh box needs ~1 s of work before clocks / HBM settle
+        model(x_dev)
+        torch.cuda.synchronize()
+    env.barrier()
+    if sampler is not None and env.rank == 0:
+        sampler.start()                                   # load window: first warm-up step .. end of the timed region
+    t_load = time.perf_counter()
+    nw = 0
+    while nw < warmup or time.perf_counter() - t_load < load_s:
+        model(x_dev)
+        nw += 1
+        if nw % 8 == 0:
             torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        barrier()
-        if rank == 0:
-            sampler.start()                       # load window: from the first warm-up step to the end of the timed region
-        t_load = time.perf_counter()
-        nw = 0
-        while nw < args.warmup or time.perf_counter() - t_load < 0.6:
-            model(x_dev)
-            nw += 1
-            if nw % 8 == 0:
-                torch.cuda.synchronize()
-        barrier()
-        lib.rf_reset_launch_count()
-        model.graph_kernels_replayed = 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t_host0 = time.perf_counter()
-        for _ in range(args.steps):
-            out = model(x_dev)
-        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
-        e1.record()
-        barrier()
-        # kernels of this library executed in the timed region: launched one by one (eager) or as nodes of the replayed graphs
-        launches = lib.rf_launch_count() + model.graph_kernels_replayed
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop() if rank == 0 else None
+    env.barrier()
+    lib.rf_reset_launch_count()
+    model.graph_kernels_replayed = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_host0 = time.perf_counter()
+    for _ in range(steps):
+        out = model(x_dev)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / steps
+    e1.record()
+    env.barrier()
+    launches = lib.rf_launch_count() + getattr(model, "graph_kernels_replayed", 0)
+    return env.max_over_ranks(e0.elapsed_time(e1)), int(launches), host_ms, out
 
-        # ---- end to end through the public call with host buffers ----
-        # rf.FramePipeline = the package's streaming API: every step copies its frame from pinned host memory to the
-        # device, runs the forward and copies the fp32 result back to pinned host memory; the copies of neighbouring
-        # steps overlap with the forward (three streams), all K steps' copies are inside the timed region.
-        pipe = rf.FramePipeline(model, depth=2)
-        outs = [out_host, torch.empty_like(out_host).pin_memory()]
-        t_pre = time.perf_counter()
-        i = 0
-        while i < 3 or time.perf_counter() - t_pre < 1.0:
-            pipe.submit(x_host, outs[i & 1])
-            i += 1
-            if i % 4 == 0:
-                pipe.flush()
-        pipe.flush()
-        barrier()
-        f0 = torch.cuda.Event(enable_timing=True)
-        f0.record()
-        pipe.start_after(f0)
-        for i in range(args.steps):
-            pipe.submit(x_host, outs[i & 1])
-        f1 = pipe.finish_event()
-        pipe.flush()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
-        e2e_check = float(outs[(args.steps - 1) & 1].abs().max())   # the result really is on the host
-        assert e2e_check == e2e_check and e2e_check > 0.0
 
-        # ---- per-kernel times (CUDA events around every launch, on the launching stream) ----
-        agg = {}
-        n_prof = 3
-        for _ in range(n_prof):
-            _, launches_prof = model.forward_profiled(x_dev)
-            for l in launches_prof:
-                a = agg.setdefault(l["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
-                a["ms"] += l["ms"]
-                a["bytes"] += l["bytes"]
-                a["flops"] += l["flops"]
-                a["n"] += 1
-        barrier()
+def time_pipeline(env, model, x_host, out_hosts, steps, **pipe_kw):
+    """End to end through rf.FramePipeline: every step copies its frame from pinned host memory to the device, runs the
+    forward and copies the result back to pinned host memory; copies of neighbouring steps overlap with the forward
+    (three streams); all K steps' copies are inside the timed region."""
+    import torch
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    import bayer_low_light_image_enhancement_b200 as rf
 
-    pk = peaks()
-    total_prof_ms = sum(a["ms"] for a in agg.values())
-    top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-    is_tensor = top_name.startswith(TENSOR_KERNELS)
-    if is_tensor:
-        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"]}
-    else:
-        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
-    # DRAM traffic of that kernel per launch, from the committed ncu capture of the same workload (null if not captured)
+    pipe = rf.FramePipeline(model, depth=2, **pipe_kw)
+    t_pre = time.perf_counter()
+    i = 0
+    while i < 3 or time.perf_counter() - t_pre < 1.0:
+        pipe.submit(x_host, out_hosts[i & 1])
+        i += 1
+        if i % 4 == 0:
+            pipe.flush()
+    pipe.flush()
+    env.barrier()
+    f0 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    pipe.start_after(f0)
+    for i in range(steps):
+        pipe.submit(x_host, out_hosts[i & 1])
+    f1 = pipe.finish_event()
+    pipe.flush()
+    env.barrier()
+    ms = env.max_over_ranks(f0.elapsed_time(f1))
+    return ms, pipe
+
+
+def roofline_records(agg, n_prof, pk, size, precision, variant):
+    """roofline = the dominant CUDA SYMBOL of the step (launches grouped by the template instantiation they run as);
+    roofline_logical = the dominant logical launch name (round-1 definition, kept for continuity)."""
+    total_ms = sum(a["ms"] for a in agg.values())
+
+    def record(ms, by, fl, n, bound, name):
+        if bound == "tensor":
+            ach = fl / (ms * 1e-3) / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"]}
+        else:
+            ach = by / (ms * 1e-3) / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
+        r.update(kernel=name, launches_per_step=n // n_prof, share_of_step=ms / total_ms, avg_launch_ms=ms / n,
+                 peak_source=pk["src"], algorithmic_per_launch=(fl if bound == "tensor" else by) / n)
+        return r
+
+    groups = {}
+    for name, a in agg.items():
+        sym, bound = SYMBOL_OF.get(name, (name, "tensor" if name.startswith(TENSOR_KERNELS) else "hbm"))
+        g = groups.setdefault(sym, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0, "bound": bound, "names": []})
+        g["ms"] += a["ms"]; g["bytes"] += a["bytes"]; g["flops"] += a["flops"]; g["n"] += a["n"]; g["names"].append(name)
+    sym, g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    roof = record(g["ms"], g["bytes"], g["flops"], g["n"], g["bound"], sym)
+    roof["logical_launches"] = sorted(g["names"])
+    # DRAM traffic of that symbol per launch, from the committed ncu capture of the same workload (null if not captured)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", f"traffic_{args.size}_{args.precision}.json")
-    if args.variant == "flca" and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top_name, {}).get("dram_bytes_per_launch")
-    roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
-                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=traffic,
-                algorithmic_per_launch=(top["flops"] if is_tensor else top["bytes"]) / top["n"])
-    breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])
-
-    frames_total = args.steps * B * world
-    value = frames_total * MP_FRAME / (ms_total * 1e-3)
-    e2e_val = frames_total * MP_FRAME / (ms_e2e * 1e-3)
-    cpu = time_cpu_port(args.size, args.variant) if world == 1 and not args.no_cpu else None
-    eager = None
-    if world == 1 and args.torch_eager:
-        del model, pipe, x_dev
-        torch.cuda.empty_cache()
-        eager = time_torch_eager_b200(args.size, args.variant, dev)
-    line = {
-        "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "precision": args.precision,
-                   "parallelism": f"image-parallel x{world}" if world > 1 else "single GPU",
-                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush",
-                   "launch": "eager" if args.no_graph else "one CUDA graph per frame (model.enable_cuda_graphs)"},
-        "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
-                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
-                "api": "FramePipeline.submit (H2D, forward, D2H of neighbouring steps overlapped on three streams)",
-                "host_binding": numa},
-        "gpu_launches": int(launches),
-        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
-        "clocks": clocks,
-        "roofline": roof,
-        "kernel_ms_per_step": {k: round(v, 4) for k, v in breakdown},
-        "model_roofline": {"flops_per_frame": 320.5 * dim * dim * 3030272 + 875.0 * dim * 3030272,
-                           "achieved_tflops": (320.5 * dim * dim + 875.0 * dim) * 3030272 * frames_total / (ms_total * 1e-3) / 1e12},
-    }
-    if cpu is not None:
-        line["cpu_baseline"] = cpu
-    if eager is not None:
-        line["eager_b200_baseline"] = eager
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    tpath = os.path.join(ROOT, "profiles", f"traffic_{size}_{precision}.json")
+    if variant == "flca" and os.path.exists(tpath):
+        t = json.load(open(tpath))
+        vals = [t[n]["dram_bytes_per_launch"] * agg[n]["n"] for n in g["names"] if n in t and "dram_bytes_per_launch" in t[n]]
+        if len(vals) == len(g["names"]):
+            traffic = sum(vals) / g["n"]
+    roof["traffic"] = traffic
+    top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    logical = record(top["ms"], top["bytes"], top["flops"], top["n"], "tensor" if top_name.startswith(TENSOR_KERNELS) else "hbm",
+                     top_name)
+    by_symbol = {k: round(v["ms"] / n_prof, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+    return roof, logical, by_symbol
 
 
-def run_rowtiled(args):
+def profile_kernels(model, x_dev, n_prof=3):
+    agg = {}
+    for _ in range(n_prof):
+        _, launches_prof = model.forward_profiled(x_dev)
+        for l in launches_prof:
+            a = agg.setdefault(l["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
+            a["ms"] += l["ms"]; a["bytes"] += l["bytes"]; a["flops"] += l["flops"]; a["n"] += 1
+    return agg
+
+
+def psnr_db(a, b):
+    import math
+
+    import torch
+
+    rng = float(b.max() - b.min())
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 99.0 if mse == 0 else 10.0 * math.log10(rng * rng / mse)
+
+
+def model_flops(size, variant):
+    dim = SIZES[size]
+    if variant == "ml":
+        return (404.5 * dim * dim + 1005.75 * dim) * 3030272
+    return (320.5 * dim * dim + 875.0 * dim) * 3030272
+
+
+def leg_image_parallel(env, args, size, variant, main):
+    """One frame (args.frames) per GPU per step, every rank its own frames, no data-path collective.  `main`: the full
+    record of the default workload; else a compact sub-record (BASELINE config 3 at N > 1, the 'sizes' entries at N = 1)."""
+    import torch
+
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    B = args.frames
+    model = build_model(env, size, variant, args.precision, graphs=not args.no_graph)
+    u16_host = synthetic_u16_frames(B, env.rank).pin_memory()
+    x_dev = rf.preprocess_u16(u16_host.to(env.dev), **PRE)          # [B,1,H,W] fp32, the frame every leg times
+    sampler = ClockSampler(env.local) if main else None
+    with torch.no_grad():
+        ms_total, launches, host_ms, out = time_resident(env, model, x_dev, args.steps, args.warmup,
+                                                         prewarm_s=1.5 if main else 0.5, sampler=sampler)
+        clocks = sampler.stop() if (main and env.rank == 0) else None
+        out_keep = out.clone() if main else None
+        # end to end, the caller's wire formats: uint16 in, uint8 HWC image out
+        u8_hosts = [torch.empty(B, H_RAW, W_RAW, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        ms_e2e, pipe = time_pipeline(env, model, u16_host, u8_hosts, args.steps, preprocess=dict(PRE),
+                                     postprocess={"pattern": "RGGB", "auto_rb": True})
+        h2d, d2h = pipe.wire_bytes(B, H_RAW, W_RAW)
+        assert int(u8_hosts[(args.steps - 1) & 1].max()) > 0          # the result really is on the host
+        del pipe
+        frames_total = args.steps * B * env.world
+        rec = {
+            "value": frames_total * MP_FRAME / (ms_total * 1e-3), "unit": "MP/s", "ms_per_step": ms_total / args.steps,
+            "e2e": {"value": frames_total * MP_FRAME / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                    "api": "FramePipeline(preprocess='u16', postprocess='rgb_u8').submit: uint16 sensor frame H2D, normalise "
+                           "(WFB/load_dataset.py:88-89) + forward + clamp/x255/uint8/HWC/channel corrections (test.py:117-120) on "
+                           "the device, uint8 image D2H; copies of neighbouring steps overlapped on three streams",
+                    "host_binding": env.numa},
+            "gpu_launches": launches,
+        }
+        if not main:
+            rec["workload"] = (f"RawFormer-{size} ({variant}), {B} full frame(s) per GPU per step, {args.precision}, "
+                               f"image-parallel x{env.world}")
+            del model
+            torch.cuda.empty_cache()
+            return rec
+        # the same with fp32 tensors both ways (48.5 MB in, 145 MB out per frame: round 1's e2e definition)
+        x_host = x_dev.cpu().pin_memory()
+        f32_hosts = [torch.empty(B, 3, H_RAW, W_RAW).pin_memory() for _ in range(2)]
+        ms_f32, pipe = time_pipeline(env, model, x_host, f32_hosts, args.steps)
+        rec["e2e_fp32_wires"] = {"value": frames_total * MP_FRAME / (ms_f32 * 1e-3), "unit": "MP/s",
+                                 "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(f32_hosts[0].numel() * 4),
+                                 "ms_per_step": ms_f32 / args.steps}
+        del pipe, f32_hosts
+        agg = profile_kernels(model, x_dev)
+        env.barrier()
+    rec.update(host_enqueue_ms_per_step=round(host_ms, 3), clocks=clocks)
+    rec["_agg"] = agg
+    rec["_out"] = out_keep
+    rec["_x_host"] = x_host
+    rec["_model"] = model
+    return rec
+
+
+def leg_rowtiled(env, args, size, main):
     """BASELINE config 4: ONE frame per step, cut into row bands over the N ranks (strong scaling).  Every rank holds the
     whole raw frame; halo rows and the per-image reductions cross the GPUs inside kernels of this library (peer-mapped
     memory over NVLink).  N = 1 runs the same band code with a single band."""
-    import torch
-    import torch.distributed as dist
+    import math
 
-    import rf_testlib as T
+    import torch
 
     import bayer_low_light_image_enhancement_b200 as rf
     from bayer_low_light_image_enhancement_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_cpus(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, dev = env.world, env.rank, env.dev
     lib = _lib.load()
-    dim = SIZES[args.size]
-    model = rf.RawFormer(dim=dim, precision="bf16")
-    model.load_state_dict(T.make_state_dict(model, seed=1234, scale=1.0), strict=True)
-    model = model.to(dev).eval()
-    x_host = torch.rand(1, 1, H_RAW, W_RAW, generator=torch.Generator().manual_seed(0)).pin_memory()   # same frame on all ranks
-    x_dev = x_host.to(dev)
+    model = build_model(env, size, "flca", "bf16", graphs=False)
+    u16_host = synthetic_u16_frames(1, 0).pin_memory()              # the same frame on all ranks
+    x_dev = rf.preprocess_u16(u16_host.to(dev), **PRE)
+    x_host = x_dev.cpu().pin_memory()
     if world > 1:
         tiled = rf.RowTiledRawFormer.from_process_group(model, H_RAW, W_RAW)
     else:                                         # one band = the whole frame, same band code, no peers
@@ -477,20 +561,8 @@ def run_rowtiled(args):
 
         region = _CommRegion(rf.RowTiledRawFormer.comm_bytes(model, H_RAW, W_RAW, 1), dev)
         tiled = rf.RowTiledRawFormer(model, H_RAW, W_RAW, 0, 1, [region.ptr], own_region=region)
+    tiled.check_every = 0                         # (status() synchronises; the bench checks it between its phases)
     band_host = torch.empty(1, 3, tiled.rows, W_RAW).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     with torch.no_grad():
         # parity of the decomposition (untimed): bands gathered on rank 0 against the whole-frame forward of the same engine
         full = tiled.gather(tiled(x_dev), dst=0) if world > 1 else tiled(x_dev).clone()
@@ -500,30 +572,31 @@ def run_rowtiled(args):
             whole = model(x_dev)
             rng = float(whole.max() - whole.min())
             mse = float(((full - whole).double() ** 2).mean())
-            parity = {"psnr_vs_whole_frame_db": 99.0 if mse == 0 else 10.0 * __import__("math").log10(rng * rng / mse),
+            parity = {"psnr_vs_whole_frame_db": 99.0 if mse == 0 else 10.0 * math.log10(rng * rng / mse),
                       "max_abs_over_range": float((full - whole).abs().max()) / rng}
             del whole
         del full
-        barrier()
+        env.barrier()
         t_pre = time.perf_counter()
         n_pre = torch.zeros(1, device=dev)
         while True:                               # every rank must run the same number of forwards: agree on when to stop
             tiled(x_dev)
-            n_pre.fill_(1.0 if time.perf_counter() - t_pre < 1.5 else 0.0)
+            n_pre.fill_(1.0 if time.perf_counter() - t_pre < (1.5 if main else 0.5) else 0.0)
             if world > 1:
-                dist.all_reduce(n_pre, op=dist.ReduceOp.MIN)
+                env.dist.all_reduce(n_pre, op=env.dist.ReduceOp.MIN)
             if float(n_pre.item()) == 0.0:
                 break
-        sampler = ClockSampler(local)
-        barrier()
-        if rank == 0:
+        sampler = ClockSampler(env.local) if main else None
+        env.barrier()
+        if main and rank == 0:
             sampler.start()
         lib.rf_reset_launch_count()
         if not args.no_graph:
             tiled.enable_cuda_graphs()            # this rank's band forward as one graph launch per frame
+            env.barrier()
         for _ in range(max(args.warmup, 8)):
             tiled(x_dev)
-        barrier()
+        env.barrier()
         per_frame = lib.rf_launch_count()         # graph mode: kernels captured once = kernel nodes replayed per frame
         lib.rf_reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -531,24 +604,24 @@ def run_rowtiled(args):
         for _ in range(args.steps):
             band = tiled(x_dev)
         e1.record()
-        barrier()
+        env.barrier()
         launches = lib.rf_launch_count() if args.no_graph else per_frame * args.steps
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop() if rank == 0 else None
+        ms_total = env.max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if (main and rank == 0) else None
         tiled.status()
         # end to end: whole frame host -> every rank, forward, this rank's band -> host, every step, one stream
         for _ in range(2):
             x_dev.copy_(x_host, non_blocking=True)
             band_host.copy_(tiled(x_dev), non_blocking=True)
-        barrier()
+        env.barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.steps):
             x_dev.copy_(x_host, non_blocking=True)
             band_host.copy_(tiled(x_dev), non_blocking=True)
         f1.record()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+        env.barrier()
+        ms_e2e = env.max_over_ranks(f0.elapsed_time(f1))
         assert float(band_host.abs().max()) > 0.0
         # per-kernel times of this rank's band (sync-point kernels include the wait for the peers)
         agg = {}
@@ -559,44 +632,187 @@ def run_rowtiled(args):
                 a = agg.setdefault(l["name"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
                 a["ms"] += l["ms"]; a["bytes"] += l["bytes"]; a["flops"] += l["flops"]; a["n"] += 1
         tiled.status()
-        barrier()
+        env.barrier()
     tiled.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del model
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     pk = peaks()
     compute = {k: v for k, v in agg.items() if not k.startswith("band_")}
-    top_name, top = max(compute.items(), key=lambda kv: kv[1]["ms"])
-    total_prof_ms = sum(a["ms"] for a in agg.values())
-    if top_name.startswith(TENSOR_KERNELS):
-        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"]}
-    else:
-        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"]}
-    roof.update(kernel=top_name, launches_per_step=top["n"] // n_prof, share_of_step=top["ms"] / total_prof_ms,
-                avg_launch_ms=top["ms"] / top["n"], peak_source=pk["src"], traffic=None, scope="rank 0's band")
-    line = {
-        "metric": METRIC, "value": args.steps * MP_FRAME / (ms_total * 1e-3), "unit": "MP/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 8), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"RawFormer-{args.size} (flca) forward, ONE SID Sony frame raw {H_RAW}x{W_RAW} per step, "
-                               f"row-tiled over {world} GPU(s) (bands of {[r // 16 for _, r in rf.plan_bands(H_RAW, world)]} x 16 rows), "
-                               "random-init weights",
-                   "precision": "bf16", "parallelism": f"row-tiled x{world}: 4-row halo exchange + all-reduce of the per-image "
-                   "reductions per Conv_Transformer, peer-mapped memory over NVLink, no NCCL on the data path",
-                   "l2": "per-step working set >> 126 MB L2, no explicit flush",
-                   "launch": "eager" if args.no_graph else "one CUDA graph per band per frame"},
+    roof, _, _ = roofline_records(compute, n_prof, pk, size, "bf16", "flca")
+    roof["scope"] = "rank 0's band"
+    rec = {
+        "value": args.steps * MP_FRAME / (ms_total * 1e-3), "unit": "MP/s", "ms_per_step": ms_total / args.steps,
+        "scaling": "strong",
+        "workload": f"RawFormer-{size} (flca) forward, ONE SID Sony frame raw {H_RAW}x{W_RAW} per step, row-tiled over "
+                    f"{world} GPU(s) (bands of {[r // 16 for _, r in rf.plan_bands(H_RAW, world)]} x 16 rows), random-init weights",
+        "parallelism": f"row-tiled x{world}: 4-row halo exchange + all-reduce of the per-image reductions per Conv_Transformer, "
+                       "peer-mapped memory over NVLink, no NCCL on the data path",
+        "launch": "eager" if args.no_graph else "one CUDA graph per band per frame",
         "e2e": {"value": args.steps * MP_FRAME / (ms_e2e * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": int(x_host.numel() * 4) * world,
                 "d2h_bytes_per_step": 3 * H_RAW * W_RAW * 4, "ms_per_step": ms_e2e / args.steps,
                 "api": "RowTiledRawFormer.forward with pinned host buffers: whole frame H2D on every rank, forward, band D2H",
-                "host_binding": numa},
+                "host_binding": env.numa},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
         "kernel_ms_per_step": {k: round(v["ms"] / n_prof, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
         "sync_ms_per_step": round(sum(v["ms"] for k, v in agg.items() if k.startswith("band_")) / n_prof, 4),
     }
+    return rec
+
+
+def run_ours(args):
+    import torch
+
+    env = Env()
+    if args.row_tiled:
+        rec = leg_rowtiled(env, args, args.size, main=True)
+        env.close()
+        if rec is None:
+            return
+        line = {"metric": METRIC, "value": rec.pop("value"), "unit": "MP/s", "n_gpus": env.world, "steps": args.steps,
+                "warmup": max(args.warmup, 8), "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": rec.pop("workload"), "precision": "bf16", "parallelism": rec.pop("parallelism"),
+                           "l2": "per-step working set >> 126 MB L2, no explicit flush", "launch": rec.pop("launch")}}
+        rec.pop("unit", None); rec.pop("scaling", None)
+        line.update(rec)
+        print(json.dumps(line), flush=True)
+        return
+
+    rec = leg_image_parallel(env, args, args.size, args.variant, main=True)
+    agg, out_gpu, x_host, model = rec.pop("_agg"), rec.pop("_out"), rec.pop("_x_host"), rec.pop("_model")
+    extra = {}
+    if not args.no_extra:
+        with torch.no_grad():
+            if env.world == 1:
+                # the other BASELINE model sizes / the multi-level variant on the same frame (device-resident ms per frame)
+                sizes = {}
+                del model
+                torch.cuda.empty_cache()
+                x_dev = x_host.to(env.dev)
+                for name, (sz, var) in (("B", ("B", "flca")), ("L", ("L", "flca")), ("ml_S", ("S", "ml"))):
+                    if (sz, var) == (args.size, args.variant):
+                        continue
+                    m = build_model(env, sz, var, args.precision, graphs=not args.no_graph)
+                    ms, _, _, _ = time_resident(env, m, x_dev, max(3, args.steps // 2), 3, prewarm_s=0.3, load_s=0.2)
+                    n = max(3, args.steps // 2)
+                    sizes[name] = {"ms_per_frame": round(ms / n, 4), "value": round(MP_FRAME / (ms / n * 1e-3), 1), "unit": "MP/s",
+                                   "model": f"RawFormer-{sz} ({var})"}
+                    del m
+                    torch.cuda.empty_cache()
+                extra["sizes"] = sizes
+            else:
+                del model
+                torch.cuda.empty_cache()
+                if args.size != "B":
+                    extra["config3"] = leg_image_parallel(env, args, "B", "flca", main=False)
+                torch.cuda.empty_cache()
+                try:
+                    extra["config4"] = leg_rowtiled(env, args, "L", main=False)
+                except Exception as e:  # noqa: BLE001  (the default S line must survive a failure of the extra legs)
+                    extra["config4"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if env.rank != 0:
+        env.close()
+        return
+
+    pk = peaks()
+    n_prof = 3
+    roof, logical, by_symbol = roofline_records(agg, n_prof, pk, args.size, args.precision, args.variant)
+    breakdown = sorted(((k, v["ms"] / n_prof) for k, v in agg.items()), key=lambda kv: -kv[1])
+    frames_total = args.steps * args.frames * env.world
+    cpu = parity = None
+    if env.world == 1 and not args.no_cpu:
+        cpu, ref = time_cpu_port(args.size, args.variant, x_host)
+        p = psnr_db(out_gpu.cpu(), ref)
+        parity = {"psnr_vs_reference_cpu_forward_db": round(p, 2),
+                  "max_abs": float((out_gpu.cpu() - ref).abs().max()), "ref_range": float(ref.max() - ref.min()),
+                  "what": "output of the timed frame (bf16 engine) against the reference's fp32 CPU forward of the same frame and weights"}
+    eager = None
+    if env.world == 1 and args.torch_eager:
+        torch.cuda.empty_cache()
+        eager = time_torch_eager_b200(args.size, args.variant, env.dev)
+    flops = model_flops(args.size, args.variant)
+    bytes_per_frame = sum(v["bytes"] for v in agg.values()) / n_prof
+    line = {
+        "metric": METRIC, "value": rec["value"], "unit": "MP/s", "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, env.world), "precision": args.precision,
+                   "parallelism": f"image-parallel x{env.world}" if env.world > 1 else "single GPU",
+                   "input": "synthetic uint16 sensor frames (black level 512) normalised like WFB/load_dataset.py:88-89 at ratio 100",
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush",
+                   "launch": "eager" if args.no_graph else "one CUDA graph per frame (model.enable_cuda_graphs)"},
+        "e2e": rec["e2e"], "e2e_fp32_wires": rec["e2e_fp32_wires"],
+        "gpu_launches": rec["gpu_launches"], "host_enqueue_ms_per_step": rec["host_enqueue_ms_per_step"],
+        "clocks": rec["clocks"], "roofline": roof, "roofline_logical": logical,
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in breakdown}, "symbol_ms_per_step": by_symbol,
+        "model_roofline": {"flops_per_frame": flops, "achieved_tflops": flops * frames_total / (rec["ms_per_step"] * args.steps * 1e-3) / 1e12,
+                           "algorithmic_bytes_per_frame_sum_of_launches": bytes_per_frame},
+    }
+    if parity is not None:
+        line["parity_db"] = parity["psnr_vs_reference_cpu_forward_db"]
+        line["parity"] = parity
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if eager is not None:
+        line["eager_b200_baseline"] = eager
+    line.update(extra)
     print(json.dumps(line), flush=True)
+    env.close()
+
+
+def run_ops(args):
+    """--op dwt: north-star subsystem (1), the wavelet / shuffle operators as stand-alone HBM streaming kernels at the shape the
+    README quotes ([1,32,1424,2128] fp32 <-> [1,128,712,1064]): achieved GB/s = algorithmic bytes (read once + write once)
+    / CUDA-event time, against the measured copy bandwidth.  388 MB per tensor >> 126 MB L2: no flush needed."""
+    import torch
+
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    env = Env()
+    dev = env.dev
+    pk = peaks()
+    x = torch.randn(1, 32, 1424, 2128, device=dev)
+    sub = torch.randn(1, 128, 712, 1064, device=dev)
+    raw = torch.rand(1, 1, 2848, 4256, device=dev)
+    kh = [[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1]]
+    dwt, idwt = rf.CustomDWT().to(dev), rf.CustomIDWT().to(dev)
+    dwt_h, idwt_h = rf.CustomDWT(kernel=kh).to(dev), rf.CustomIDWT(kernel=kh).to(dev)
+    haar, ps = rf.HaarDWT().to(dev), rf.PixelShuffle(2)
+    ops = [
+        ("CustomDWT  [1,32,1424,2128] -> [1,128,712,1064] (README.md:111-117)", lambda: dwt(x), 2 * x.numel() * 4),
+        ("CustomIDWT [1,128,712,1064] -> [1,32,1424,2128] (README.md:139-144)", lambda: idwt(sub), 2 * sub.numel() * 4),
+        ("CustomDWT, Haar matrix", lambda: dwt_h(x), 2 * x.numel() * 4),
+        ("CustomIDWT, Haar matrix", lambda: idwt_h(sub), 2 * sub.numel() * 4),
+        ("dwt_init   [1,32,1424,2128] -> [4,32,712,1064] (WFB/blocks.py:102-115)", lambda: rf.dwt_init(x), 2 * x.numel() * 4),
+        ("iwt_init   [4,32,712,1064] -> [1,32,1424,2128] (WFB/blocks.py:119-136)",
+         lambda: rf.iwt_init(sub.view(4, 32, 712, 1064)), 2 * sub.numel() * 4),
+        ("HaarDWT    [1,32,1424,2128] -> 4 x [1,32,712,1064] (FLCA_RF.py:56-73)", lambda: haar(x), 2 * x.numel() * 4),
+        ("downshuffle r=2 [1,32,1424,2128] (FLCA_RF.py:18-33)", lambda: rf.downshuffle(x, 2), 2 * x.numel() * 4),
+        ("PixelShuffle(2) [1,128,712,1064] (FLCA_RF.py:328)", lambda: ps(sub), 2 * sub.numel() * 4),
+        ("downshuffle r=2, raw frame [1,1,2848,4256]", lambda: rf.downshuffle(raw, 2), 2 * raw.numel() * 4),
+    ]
+    out = []
+    with torch.no_grad():
+        for name, fn, nbytes in ops:
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out.append({"op": name, "ms": round(ms, 4), "bytes": nbytes, "achieved_gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 3)})
+    line = {"metric": "HBM GB/s of the wavelet / shuffle operators (algorithmic bytes / CUDA-event time, includes the torch.empty of "
+                      "the output tensor)", "unit": "GB/s", "peak": pk["hbm_gbs"], "peak_source": pk["src"], "steps": args.steps,
+            "ops": out}
+    print(json.dumps(line), flush=True)
+    env.close()
 
 
 def main():
@@ -609,18 +825,22 @@ def main():
     ap.add_argument("--variant", default="flca", choices=["flca", "ml"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra legs (N = 1: other model sizes; N > 1: BASELINE configs 3 and 4 sub-records)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of one CUDA graph per frame")
     ap.add_argument("--torch-eager", action="store_true",
                     help="also time the reference's operator sequence run eagerly by PyTorch on this B200 (baseline leg)")
     ap.add_argument("--row-tiled", action="store_true",
                     help="BASELINE config 4: one frame per step cut into row bands over the ranks (strong scaling)")
+    ap.add_argument("--op", default=None, choices=["dwt"],
+                    help="time the stand-alone wavelet / shuffle operators instead of the model (north-star subsystem 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    elif args.row_tiled:
-        run_rowtiled(args)
+    elif args.op == "dwt":
+        run_ops(args)
     else:
         run_ours(args)
 

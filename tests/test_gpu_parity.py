@@ -503,7 +503,10 @@ def test_frame_pipeline_u16_in_rgb_u8_out(rf, precision, graphs):
     frames = [torch.from_numpy(rng.integers(400, 2200, size=(1, 96, 160)).astype(np.uint16)).pin_memory() for _ in range(5)]
     ratios = [100.0, 300.0, 100.0, 250.0, 300.0]
     outs = [torch.empty(1, 96, 160, 3, dtype=torch.uint8).pin_memory() for _ in frames]
-    pipe = rf.FramePipeline(m, depth=2, graphs=graphs, preprocess={"black": 512, "white": 16383, "clamp": False},
+    # clamp: the normalised frame stays in [0,1] (ratio 300 saturates a part of it).  The unclamped form -- inputs up to 32 at
+    # ratio 300 -- is covered bit-exactly in test_postprocess_preprocess; through the network such inputs amplify the
+    # forward's run-to-run float-atomics noise to several uint8 steps, which says nothing about the pipeline.
+    pipe = rf.FramePipeline(m, depth=2, graphs=graphs, preprocess={"black": 512, "white": 16383, "clamp": True},
                             postprocess={"pattern": "GRBG", "auto_rb": True})
     assert pipe.wire_bytes(1, 96, 160) == (96 * 160 * 2, 96 * 160 * 3)
     for x, o, r in zip(frames, outs, ratios):
@@ -512,7 +515,7 @@ def test_frame_pipeline_u16_in_rgb_u8_out(rf, precision, graphs):
     m.enable_cuda_graphs(False)
     swapped = 0
     for i, (x, o, r) in enumerate(zip(frames, outs, ratios)):
-        xin = O.preprocess_u16(x.numpy(), 512.0, 16383.0, r, clamp=False)[:, None]
+        xin = O.preprocess_u16(x.numpy(), 512.0, 16383.0, r, clamp=True)[:, None]
         with torch.no_grad():
             pred = npy(m(cu(xin)))
         u8 = O.postprocess_u8(pred)
