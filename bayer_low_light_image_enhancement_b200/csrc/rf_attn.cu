@@ -447,6 +447,51 @@ k_attn_finalize(const float* __restrict__ stats, const float* __restrict__ tempe
   }
 }
 
+// Ordered second stage of the attention statistics (bit-reproducible: fixed summation order and association):
+//   stats[row*C + h*c + j] = sum_z gram_part[(z*C + row)*c + j]     (per-head diagonal blocks of q^T k, h = row / c)
+//   norms[ch]              = sum_slot sq_part[slot*2C + ch]          (squared norms of q | k)
+__global__ void __launch_bounds__(256)
+k_attn_reduce(const float* __restrict__ gram_part, int nsplit, const float* __restrict__ sq_part, int nslots,
+              float* __restrict__ stats, float* __restrict__ norms, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ng = gram_part != nullptr ? C * c : 0;
+  const float* src;
+  i64 step;
+  int n;
+  float* dst;
+  if (i < ng) {
+    const int row = i / c, j = i - row * c;
+    src = gram_part + i; step = (i64)C * c; n = nsplit;
+    dst = stats + (i64)row * C + (row / c) * c + j;
+  } else if (sq_part != nullptr && i - ng < 2 * C) {
+    src = sq_part + (i - ng); step = 2 * C; n = nslots;
+    dst = norms + (i - ng);
+  } else {
+    return;
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= n; k += 4) {
+    a0 += src[(i64)k * step]; a1 += src[(i64)(k + 1) * step]; a2 += src[(i64)(k + 2) * step]; a3 += src[(i64)(k + 3) * step];
+  }
+  for (; k < n; ++k) a0 += src[(i64)k * step];
+  *dst = (a0 + a1) + (a2 + a3);
+}
+
+void launch_attn_reduce(Ctx& ctx, const float* gram_part, int nsplit, const float* sq_part, int nslots, float* stats, float* norms,
+                        int C) {
+  if (ctx.dry) return;
+  if (nsplit <= 0) gram_part = nullptr;
+  if (nslots <= 0) sq_part = nullptr;
+  if (!gram_part && !sq_part) return;
+  const int n = (gram_part ? C * (C / 8) : 0) + (sq_part ? 2 * C : 0);
+  ScopedLaunch sl(RF_K_ATTN_FINALIZE, 4.0 * ((double)nsplit * C * (C / 8) + (double)nslots * 2 * C));
+  launch_pdl(k_attn_reduce, dim3(cdiv(n, 256)), dim3(256), 0, ctx.stream, gram_part, nsplit, sq_part, nslots, stats, norms, C);
+}
+
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,
                           int C, const float* norms) {
   if (ctx.dry) return;

@@ -143,18 +143,21 @@ void launch_dwconv(Ctx& ctx, const void* in, const float* dw_w, const float* dw_
   else run_dw_strip<float, 0>(ctx, in, dw_w, dw_b, out, nullptr, nullptr, gelu, B, H, W, Cn, 0, 0);
 }
 
-void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
-                       int B, int H, int W, int C) {
-  if (ctx.dry) return;
+int launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
+                      int B, int H, int W, int C, float* sq_part) {
+  if (ctx.dry) return 0;
   double px = (double)B * H * W;
   ScopedLaunch sl(RF_K_DW_QKV_GRAM, 6.0 * px * C * esize(ctx.dtype), 54.0 * px * C);
-  if (ctx.dtype == RF_BF16 && launch_dwqkv_tma(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, C)) return;
+  int nslots = 0;
+  if (ctx.dtype == RF_BF16 && launch_dwqkv_tma(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, C, sq_part, &nslots))
+    return sq_part ? nslots : 0;
   if (ctx.band != nullptr) {   // only the TMA kernel restricts the norms to the band's interior rows
     recorder().last_cuda_error = (int)cudaErrorNotSupported;
-    return;
+    return 0;
   }
   if (ctx.dtype == RF_BF16) run_dw_strip<bf16, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
   else run_dw_strip<float, 1>(ctx, qkv_pre, dw_w, dw_b, qk, v, sumsq, 0, B, H, W, 3 * C, C, 0);
+  return 0;
 }
 
 }  // namespace rf

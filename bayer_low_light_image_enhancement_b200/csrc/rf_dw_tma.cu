@@ -26,7 +26,9 @@ struct DwTmaParams {
   const float* bias;   // [Cn]
   bf16* out;           // [B,H,W,Cn]; MODE 1: q|k [B,H,W,C2]
   bf16* vout;          // MODE 1: v [B,H,W,Cn-C2]
-  float* sumsq;        // MODE 1: [B][C2]
+  float* sumsq;        // MODE 1: [B][C2] (atomic accumulation; used only when sq_part is null)
+  float* sq_part;      // MODE 1: [B][lanes][C2] per-CTA partial squared norms (plain stores: every CTA owns a slot; the
+                       // caller sums the slots in a fixed order -> bit-reproducible), pre-zeroed
   int ylo, yhi;        // MODE 1: rows that contribute to sumsq (row-tiled forward: the band's interior; else 0, H)
   int H, W, Cn, C2;
   int CC, nvec, TW;    // channel chunk, 4-channel vectors per pixel of a chunk, tile width
@@ -46,6 +48,7 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
   uint8_t* tail = smem_raw + (bars + 16 - smem_u32(smem_raw));
   int4* s_tile = reinterpret_cast<int4*>(tail);                  // [2] decoded tile (tx, ty, chunk, b) of each stage
   float* s_sum = reinterpret_cast<float*>(tail + 32);            // [CC] flush scratch (MODE 1)
+  float4* s_sq = reinterpret_cast<float4*>(tail + 32 + ((sizeof(float) * p.CC + 15) & ~15));   // [DT_THREADS] (MODE 1)
   const int tid = threadIdx.x;
   const int x = tid / p.nvec, cv = tid - x * p.nvec;
   const bool active = x < p.TW;
@@ -107,16 +110,37 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
 
   // MODE 1: add this thread's squared-norm partials of image b to sumsq (block-uniform call)
   auto flush = [&](int b) {
-    for (int i = tid; i < p.CC; i += DT_THREADS) s_sum[i] = 0.f;
-    __syncthreads();
-    if (active) {
+    if (p.sq_part != nullptr) {
+      // fixed-order combine: thread (x, cv) parks its 4 partials, channel c then adds the TW columns in column order
+      s_sq[tid] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+      __syncthreads();
+      for (int i = tid; i < p.CC; i += DT_THREADS) {
+        const int c = chunk * p.CC + i;
+        if (c < p.C2) {
+          const float* col = reinterpret_cast<const float*>(s_sq) + (i >> 2) * 4 + (i & 3);
+          float a0 = 0.f, a1 = 0.f;
+          int x2 = 0;
+          for (; x2 + 2 <= p.TW; x2 += 2) {
+            a0 += col[(x2 * p.nvec) * 4];
+            a1 += col[((x2 + 1) * p.nvec) * 4];
+          }
+          if (x2 < p.TW) a0 += col[(x2 * p.nvec) * 4];
+          p.sq_part[((i64)b * p.lanes + lane_id) * p.C2 + c] = a0 + a1;
+        }
+      }
+      __syncthreads();
+    } else {
+      for (int i = tid; i < p.CC; i += DT_THREADS) s_sum[i] = 0.f;
+      __syncthreads();
+      if (active) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) atomicAdd(&s_sum[cv * 4 + k], sq[k]);
-    }
-    __syncthreads();
-    for (int i = tid; i < p.CC; i += DT_THREADS) {
-      const int c = chunk * p.CC + i;
-      if (c < p.C2 && s_sum[i] != 0.f) atomicAdd(p.sumsq + (i64)b * p.C2 + c, s_sum[i]);
+        for (int k = 0; k < 4; ++k) atomicAdd(&s_sum[cv * 4 + k], sq[k]);
+      }
+      __syncthreads();
+      for (int i = tid; i < p.CC; i += DT_THREADS) {
+        const int c = chunk * p.CC + i;
+        if (c < p.C2 && s_sum[i] != 0.f) atomicAdd(p.sumsq + (i64)b * p.C2 + c, s_sum[i]);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) sq[k] = 0.f;
@@ -200,7 +224,7 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
 
 // false when the shape is not supported by the TMA path (caller falls back to the register-strip kernel)
 static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const float* bias, void* out, void* vout,
-                       float* sumsq, int B, int H, int W, int Cn, int C2) {
+                       float* sumsq, int B, int H, int W, int Cn, int C2, float* sq_part = nullptr, int* nslots = nullptr) {
   if (Cn % 8 || !tcgen05_enabled()) return false;
   static const int kCC[] = {64, 96, 48, 128, 32, 80, 112, 72, 56, 40, 24, 16, 8};
   const int div = mode == 1 ? C2 / 2 : Cn;   // MODE 1: a chunk must not straddle the q|k / v boundary
@@ -209,7 +233,7 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
     if (div % c == 0) { CC = c; break; }
   if (CC == 0) return false;
   DwTmaParams p;
-  p.w = w; p.bias = bias; p.out = (bf16*)out; p.vout = (bf16*)vout; p.sumsq = sumsq;
+  p.w = w; p.bias = bias; p.out = (bf16*)out; p.vout = (bf16*)vout; p.sumsq = sumsq; p.sq_part = sq_part;
   p.H = H; p.W = W; p.Cn = Cn; p.C2 = C2; p.B = B;
   p.ylo = 0; p.yhi = H;
   if (ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
@@ -224,7 +248,8 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
   if (p.lanes > p.sp_tiles) p.lanes = p.sp_tiles;
   p.tile_bytes = (uint32_t)((DT_TH + 2) * (p.TW + 2) * CC * 2);
   p.buf_stride = (p.tile_bytes + 127u) & ~127u;
-  const size_t smem = 128 + 2 * (size_t)p.buf_stride + 16 + 32 + sizeof(float) * CC;
+  const size_t smem = 128 + 2 * (size_t)p.buf_stride + 16 + 32 + sizeof(float) * CC + 16 + (mode == 1 ? sizeof(float4) * DT_THREADS : 0);
+  if (nslots) *nslots = p.lanes;
   if (smem > 227 * 1024) return false;
   CUtensorMap m;
   const i64 d[4] = {Cn, W, H, B};
@@ -252,8 +277,8 @@ bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float*
 }
 
 bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
-                      int B, int H, int W, int C) {
-  return run_dw_tma(ctx, 1, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, 3 * C, 2 * C);
+                      int B, int H, int W, int C, float* sq_part, int* nslots) {
+  return run_dw_tma(ctx, 1, qkv_pre, dw_w, dw_b, qk, v, sumsq, B, H, W, 3 * C, 2 * C, sq_part, nslots);
 }
 
 }  // namespace rf

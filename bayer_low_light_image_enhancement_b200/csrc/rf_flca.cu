@@ -9,7 +9,8 @@
 
 namespace rf {
 
-constexpr int FLCA_SLOTS = 32;   // partial-sum slots per image (atomically accumulated, then summed by se_finalize)
+constexpr int FLCA_SLOTS = 160;  // partial-sum slots per image (== IT_SLOTS of the tensor-core kernel, which owns one slot per
+                                 // CTA; this CUDA-core kernel accumulates atomically), summed in order by k_se_fold / se_finalize
 constexpr int FLCA_LS = 32;      // pixels per warp strip
 
 int flca_num_partials(int C, int B, i64 P) {

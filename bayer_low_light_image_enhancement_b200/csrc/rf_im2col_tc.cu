@@ -25,7 +25,9 @@
 namespace rf {
 
 constexpr int IT_THREADS = 512;
-constexpr int IT_SLOTS = 32;          // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image
+constexpr int IT_SLOTS = 160;         // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image; slot = CTA index within its
+                                      // channel chunk (< num_sms <= 160): every CTA owns its slot -> plain stores, and the
+                                      // ordered sum over the slots (k_se_fold) makes the channel sums bit-reproducible
 constexpr int IT_NF = 5;              // feature/output ring depth: loads run 3 tiles ahead, stores drain 1 tile behind
 constexpr int IT_NGS = 4;             // guidance patch ring depth
 constexpr int IT_TW = 8, IT_TH = 16;  // tile = 8 x 16 pixels (patch rows = the 8-row core-matrix groups)
@@ -41,7 +43,7 @@ struct Im2colTcParams {
   int wmap_of[4];        // weight map of slot m
   float scale_of[4];     // 0.5 for sigmoid inputs (sigmoid(a) = 0.5*tanh(a/2) + 0.5), else 1
   int coef_off;          // ML: index of the first gate used inside gates[b][6]
-  float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums (atomicAdd)
+  float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums, slot = CTA index within the chunk (pre-zeroed; plain stores)
   int ylo, yhi;          // FLCA: rows that contribute to the channel sums (row-tiled forward: the band's interior)
   int H, W, C, Cc, nchunks, B;
   int tiles_x, tiles_y, tiles_per_img, total_tiles, lanes;
@@ -100,6 +102,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   auto f_bar = [&](int q) { return bars + 8u * (2 + IT_NGS + q); };
   const uint32_t tmem_slot = bars + 8u * (2 + IT_NGS + IT_NF);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* s_red = reinterpret_cast<float*>(smem_raw + (tmem_slot + 64 - smem_u32(smem_raw)));   // [16 warps][16] flush scratch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x % p.nchunks, lane_id = blockIdx.x / p.nchunks;
   const int N = SEG * p.Cc;
@@ -206,16 +209,26 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
 #pragma unroll
   for (int e = 0; e < 8 * UPT; ++e) csum[e] = 0.f;
   int cur_b = -1;
-  auto flush = [&](int b) {                          // warp-reduce the 32 rows of this thread's channels
+  auto flush = [&](int b) {                          // block-uniform call: channel sums of image b -> this CTA's slot
+    // warp-reduce the 32 rows of this thread's channels (fixed shuffle tree), park the warp's values, then ONE thread per
+    // channel adds the four lane-quadrant warps in quadrant order and stores to the CTA's own slot: no atomics
     if (epi) {
 #pragma unroll
       for (int e = 0; e < 8 * UPT; ++e) {
-        float v = warp_sum(csum[e]);
-        if (lane == 0 && v != 0.f)
-          atomicAdd(p.partial + ((i64)b * IT_SLOTS + (lane_id % IT_SLOTS)) * p.C + chunk * p.Cc + part * UPT * 8 + e, v);
+        const float v = warp_sum(csum[e]);
+        if (lane == 0) s_red[warp * 16 + e] = v;
         csum[e] = 0.f;
       }
     }
+    __syncthreads();
+    if (tid < p.parts * 8 * UPT) {
+      const int pt = tid / (8 * UPT), e = tid - pt * (8 * UPT);
+      float v = 0.f;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) v += s_red[(pt * 4 + qd) * 16 + e];
+      p.partial[((i64)b * IT_SLOTS + lane_id) * p.C + chunk * p.Cc + pt * UPT * 8 + e] = v;
+    }
+    __syncthreads();
   };
 
   fence_proxy_async();                               // W (generic stores) -> tensor-core (async proxy) reads
@@ -377,7 +390,7 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   } else {
     mIn = mOut;
   }
-  const size_t smem = 1024 + IT_NF * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + IT_NF) + 64;
+  const size_t smem = 1024 + IT_NF * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + IT_NF) + 64 + 16 * 16 * 4 + 64;
 #define RF_IT_LAUNCH(M, U)                                                                                                  \
   do {                                                                                                                       \
     static bool attr = false;                                                                                                \
@@ -397,7 +410,7 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   return true;
 }
 
-// xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][32][C] += channel sums
+// xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][IT_SLOTS][C] = channel sums per CTA
 bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
                         float* partial, int B, int Hf, int Wf, int C) {
   return run_im2col_tc(ctx, 0, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C);

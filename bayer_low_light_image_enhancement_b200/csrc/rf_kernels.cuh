@@ -179,15 +179,23 @@ void launch_dwqkv_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const f
 inline i64 attn_stats_floats(int C) { return (i64)C * C + 2 * C; }
 // variant for the tensor-core Gram: dw(qkv_pre) split into qk [.,2C] (q | k) and v [.,C], both dense NHWC;
 // sumsq[b][2C] = squared norms of q,k (must be zeroed)
-void launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
-                       int B, int H, int W, int C);
+// sq_part (optional): [B][num_sms][2C] pre-zeroed per-CTA partial squared norms; when the kernel used them (return value =
+// number of slots per image > 0) sumsq is left untouched and the caller sums the slots in order (launch_attn_reduce)
+int launch_dwqkv_nhwc(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
+                      int B, int H, int W, int C, float* sq_part = nullptr);
 // TMA-staged bf16 depthwise kernels (rf_dw_tma.cu); false when the shape is not supported
 bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H, int W,
                        int Cn);
 bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
-                      int B, int H, int W, int C);
-// G[C][C] += q^T k over the P pixels of one image (bf16 NHWC qk [P][2C]); false if the tcgen05 path is unavailable
-bool launch_gram_tcgen05(Ctx& ctx, const void* qk, float* G, int C, i64 P);
+                      int B, int H, int W, int C, float* sq_part = nullptr, int* nslots = nullptr);
+// Gram of one image (bf16 NHWC qk [P][2C]) as per-split partials: part[z][C][C/8] = the per-head diagonal blocks of
+// q^T k over pixel slice z (plain stores, z < returned split count <= gram_max_splits()); 0 if the tcgen05 path is unavailable.
+// The caller sums the slices in order (launch_attn_reduce) -> bit-reproducible, unlike atomic accumulation.
+int launch_gram_tcgen05(Ctx& ctx, const void* qk, float* part, int C, i64 P);
+int gram_max_splits();
+// stats[C*C (diagonal blocks)] = sum_z gram_part[z]; norms[2C] = sum_slot sq_part[slot]  (fixed order); one image
+void launch_attn_reduce(Ctx& ctx, const float* gram_part, int nsplit, const float* sq_part, int nslots, float* stats, float* norms,
+                        int C);
 bool tcgen05_enabled();
 // Mw[b] = proj_w * blockdiag(softmax(gram / (|q||k|) * temperature))   (T [B][C][C])
 // norms (optional): [B][2C] squared norms of q,k kept outside `stats` (else they are read from stats[b][C*C ..])

@@ -276,15 +276,25 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     // split-K tcgen05 kernel with MN-major operands reading q,k straight from that tensor.
     void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
-    float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);
-    launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C);
+    // squared norms and Gram: per-CTA / per-split partial slots (plain stores) + ONE ordered reduction per image, so two
+    // runs of the forward are bit-identical (no float atomics)
+    float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);      // (zeroed for the atomically accumulating fallback kernel)
+    const int sq_cap = num_sms();
+    float* sq_part = zeroed_f32(ctx, (size_t)B * sq_cap * 2 * C);
+    const int gsplit_cap = gram_max_splits();
+    float* gram_part = A.get<float>((size_t)gsplit_cap * C * (C / 8));
+    const int nslots = launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C, sq_part);
     // row-tiled forward: the Gram and the norms run over the band's interior rows only, then are summed over the ranks
     const i64 row0 = ctx.band != nullptr ? (i64)ctx.band->ht * W : 0;
     const i64 Pg = ctx.band != nullptr ? (i64)ctx.band->rows_in * W : P;
     if (!ctx.dry) {
-      for (int b = 0; b < B; ++b)
-        if (!launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, stats + b * nst, C, Pg))
-          recorder().last_cuda_error = (int)cudaErrorNotSupported;
+      for (int b = 0; b < B; ++b) {
+        const int nsplit = launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, gram_part, C, Pg);
+        if (nsplit <= 0 || nsplit > gsplit_cap) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+        // (the depthwise kernel lays the slots out as [b][slot < nslots][2C])
+        launch_attn_reduce(ctx, gram_part, nsplit, sq_part + (size_t)b * nslots * 2 * C, nslots, stats + b * nst,
+                           sumsq + (size_t)b * 2 * C, C);
+      }
     }
     if (ctx.band != nullptr) band_allreduce(ctx, stats, C, ctx.band->se_partial, ctx.band->se_slots, sumsq);
     norms = sumsq;     // the squared norms stay where the depthwise kernel left them
@@ -475,7 +485,8 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
     size_t zb = 0;
     for (int i = 0; i < 7; ++i) {
       const size_t C = (size_t)d << kBlockStage[i];
-      zb += align_up(B * (C * C + 2 * C) * 4, 256) + align_up(B * 2 * C * 4, 256) + align_up(B * 32 * C * 4, 256);
+      zb += align_up(B * (C * C + 2 * C) * 4, 256) + align_up((size_t)B * num_sms() * 2 * C * 4, 256) +
+            align_up((size_t)B * flca_num_partials((int)C, B, 0) * C * 4, 256);
     }
     ctx.zero_cap = zb;
     ctx.zero_off = 0;
@@ -597,7 +608,8 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw,
     size_t zb = 0;
     for (int i = 0; i < 7; ++i) {
       const size_t C = (size_t)d << kBlockStage[i];
-      zb += align_up((C * C + 2 * C) * 4, 256) + align_up(2 * C * 4, 256) + align_up(32 * C * 4, 256);
+      zb += align_up((C * C + 2 * C) * 4, 256) + align_up((size_t)num_sms() * 2 * C * 4, 256) +
+            align_up((size_t)flca_num_partials((int)C, 1, 0) * C * 4, 256);
     }
     ctx.zero_cap = zb;
     ctx.zero_off = 0;

@@ -840,7 +840,8 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = packed ? cc + j - C : n0 + cc + j;   // k channel (packed: accumulator column = C + k channel)
-        if (col >= 0 && col < C && col / c == h) atomicAdd(G + (i64)row * C + col, __uint_as_float(v[j]));
+        if (col >= 0 && col < C && col / c == h)          // this split's slot: part[z][row][col - h*c] (plain store)
+          G[((i64)blockIdx.z * C + row) * c + (col - h * c)] = __uint_as_float(v[j]);
       }
     }
     tc_fence_before();
@@ -1114,14 +1115,16 @@ int launch_gemm_tcgen05(Ctx& ctx, const GemmP& g) {
   return -1;
 }
 
-// qk: bf16 NHWC [P][2C] (q | k) of ONE image; G: fp32 [C][C], zero-initialised by the caller
-bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
-  if (!tcgen05_enabled() || ctx.dtype != RF_BF16 || C % 8) return false;
+int gram_max_splits() { return 4 * num_sms(); }
+
+// qk: bf16 NHWC [P][2C] (q | k) of ONE image; G: per-split partials [ksplit][C][C/8] (see rf_kernels.cuh)
+int launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
+  if (!tcgen05_enabled() || ctx.dtype != RF_BF16 || C % 8) return 0;
   CUtensorMap m;
   const i64 d[3] = {2 * (i64)C, P, 1};
   const i64 st[3] = {1, 2 * (i64)C, 2 * (i64)C * P};
   const int bx[3] = {64, GR_PIX, 1};
-  if (!make_map(&m, qkv, 3, d, st, bx)) return false;
+  if (!make_map(&m, qkv, 3, d, st, bx)) return 0;
   const int packed = 2 * C <= 64 ? 1 : (2 * C <= 128 ? 2 : 0);
   const int mt = packed ? 1 : cdiv(C, 128);
   const int nkb = (int)((P + GR_PIX - 1) / GR_PIX);
@@ -1136,12 +1139,12 @@ bool launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
   const size_t smem = 1024 + (size_t)nst * (packed ? packed : 4) * GR_CHUNK + (packed == 1 ? GR_CHUNK : 0) + 8 * (2 * GR_STAGES + 2);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
     attr_set = true;
   }
   ScopedLaunch sl(RF_K_GEMM_GRAM, 4.0 * C * P, 2.0 * P * C * (C / 8.0));
   launch_pdl(k_tc_gram, dim3(mt, mt, ksplit), dim3(GR_THREADS), smem, ctx.stream, m, G, C, P, ksplit, packed, nst);
-  return true;
+  return ksplit;
 }
 
 }  // namespace rf

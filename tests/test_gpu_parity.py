@@ -534,6 +534,26 @@ def test_frame_pipeline_u16_in_rgb_u8_out(rf, precision, graphs):
     assert swapped > 0
 
 
+@pytest.mark.parametrize("dim,h,w,b", [(32, 480, 736, 1), (48, 160, 224, 2), (64, 96, 160, 1)])
+def test_bf16_forward_is_bit_reproducible(rf, dim, h, w, b):
+    """The reference's CPU forward is bit-reproducible run to run; so is the bf16 engine: the per-image reductions (Gram,
+    squared norms of q and k, squeeze-excite channel sums) go through per-CTA partial slots and an ordered second stage, not
+    through float atomics.  Eager launches and CUDA-graph replays must agree bit for bit as well."""
+    m = rf.RawFormer(dim=dim, precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=9, scale=1.5))
+    m = m.to(dev()).eval()
+    x = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(3)).to(dev())
+    with torch.no_grad():
+        o1 = m(x).clone()
+        o2 = m(x).clone()
+        m.enable_cuda_graphs()
+        o3 = m(x).clone()
+        o4 = m(x).clone()
+        m.enable_cuda_graphs(False)
+    assert torch.equal(o1, o2), f"two eager runs differ: max abs {(o1 - o2).abs().max().item():.3e}"
+    assert torch.equal(o1, o3) and torch.equal(o3, o4), "graph replay differs from the eager forward"
+
+
 def test_cuda_graph_replay(rf):
     """enable_cuda_graphs(): the captured forward reproduces the eager forward, replays follow new input data in the
     captured buffer, and a second input buffer gets its own graph."""
