@@ -455,8 +455,10 @@ k_attn_reduce(const float* __restrict__ gram_part, int nsplit, const float* __re
               float* __restrict__ stats, float* __restrict__ norms, int C) {
   pdl_trigger();
   pdl_wait();
-  const int c = C >> 3;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per output: lane l adds slots l, l + 32, ... (in that order), then a fixed xor-shuffle tree -- the same
+  // association every run, whatever the slot count
+  const int c = C >> 3, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int ng = gram_part != nullptr ? C * c : 0;
   const float* src;
   i64 step;
@@ -472,13 +474,15 @@ k_attn_reduce(const float* __restrict__ gram_part, int nsplit, const float* __re
   } else {
     return;
   }
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= n; k += 4) {
-    a0 += src[(i64)k * step]; a1 += src[(i64)(k + 1) * step]; a2 += src[(i64)(k + 2) * step]; a3 += src[(i64)(k + 3) * step];
+  float a0 = 0.f, a1 = 0.f;
+  int k = lane;
+  for (; k + 32 < n; k += 64) {
+    a0 += src[(i64)k * step];
+    a1 += src[(i64)(k + 32) * step];
   }
-  for (; k < n; ++k) a0 += src[(i64)k * step];
-  *dst = (a0 + a1) + (a2 + a3);
+  if (k < n) a0 += src[(i64)k * step];
+  const float v = warp_sum(a0 + a1);
+  if (lane == 0) *dst = v;
 }
 
 void launch_attn_reduce(Ctx& ctx, const float* gram_part, int nsplit, const float* sq_part, int nslots, float* stats, float* norms,
@@ -489,7 +493,7 @@ void launch_attn_reduce(Ctx& ctx, const float* gram_part, int nsplit, const floa
   if (!gram_part && !sq_part) return;
   const int n = (gram_part ? C * (C / 8) : 0) + (sq_part ? 2 * C : 0);
   ScopedLaunch sl(RF_K_ATTN_FINALIZE, 4.0 * ((double)nsplit * C * (C / 8) + (double)nslots * 2 * C));
-  launch_pdl(k_attn_reduce, dim3(cdiv(n, 256)), dim3(256), 0, ctx.stream, gram_part, nsplit, sq_part, nslots, stats, norms, C);
+  launch_pdl(k_attn_reduce, dim3(cdiv(n, 8)), dim3(256), 0, ctx.stream, gram_part, nsplit, sq_part, nslots, stats, norms, C);
 }
 
 void launch_attn_finalize(Ctx& ctx, const float* stats, const float* temperature, const float* proj_w, void* Mw, int B,

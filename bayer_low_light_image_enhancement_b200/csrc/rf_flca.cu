@@ -160,25 +160,27 @@ static void run_flca_mod(Ctx& ctx, const void* feat, const float* G, const float
                                                                                  Hf, Wf, C, level, tasks);
 }
 
-void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
-                     void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C) {
-  if (ctx.dry) return;
+int launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
+                    void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C) {
+  if (ctx.dry) return nblk;
   // (partial comes zero-initialised from zeroed_f32)
   if (G16 != nullptr && im2col_tc_supported(ctx, C)) {
     const double px = (double)B * Hf * Wf;
     ScopedLaunch sl(RF_K_FLCA_MOD, px * C * 4.0 + px * 16.0, px * C * 72.0);
-    if (!launch_flca_mod_tc(ctx, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C))
+    int used = nblk;
+    if (!launch_flca_mod_tc(ctx, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C, &used) || used > nblk)
       recorder().last_cuda_error = (int)cudaErrorNotSupported;
-    return;
+    return used;
   }
   if (ctx.band != nullptr) {   // only the tensor-core kernel restricts the channel sums to the band's interior rows
     recorder().last_cuda_error = (int)cudaErrorNotSupported;
-    return;
+    return nblk;
   }
   if (ctx.dtype == RF_BF16)
     run_flca_mod<bf16, 0>(ctx, feat, G, w36, abg, xmod, partial, nblk, B, Hf, Wf, C, 0, RF_K_FLCA_MOD);
   else
     run_flca_mod<float, 0>(ctx, feat, G, w36, abg, xmod, partial, nblk, B, Hf, Wf, C, 0, RF_K_FLCA_MOD);
+  return nblk;
 }
 
 void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,
@@ -310,15 +312,27 @@ k_se_fold(const float* __restrict__ partial, int nblk, float invP, const float* 
   float* hbuf = smem + C;        // [hid]
   float* sc = hbuf + hid;        // [C]
   const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  // channel sums over the nblk partial slots in a fixed order: 8 interleaved slot groups per channel in parallel (group
+  // g adds slots g, g + 8, ...), then the 8 group sums in group order
+  float* grp = sc + C;            // [8][C] scratch behind sc
+  for (int idx = threadIdx.x; idx < 8 * C; idx += blockDim.x) {
+    const int g = idx / C, c = idx - g * C;
     const float* pp = partial + (i64)b * nblk * C + c;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // independent chains: the loads of a channel overlap
-    int k = 0;
-    for (; k + 4 <= nblk; k += 4) {
-      s0 += pp[(i64)k * C]; s1 += pp[(i64)(k + 1) * C]; s2 += pp[(i64)(k + 2) * C]; s3 += pp[(i64)(k + 3) * C];
+    float s0 = 0.f, s1 = 0.f;
+    int k = g;
+    for (; k + 8 < nblk; k += 16) {
+      s0 += pp[(i64)k * C];
+      s1 += pp[(i64)(k + 8) * C];
     }
-    for (; k < nblk; ++k) s0 += pp[(i64)k * C];
-    mean[c] = ((s0 + s1) + (s2 + s3)) * invP;
+    if (k < nblk) s0 += pp[(i64)k * C];
+    grp[idx] = s0 + s1;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s0 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s0 += grp[g * C + c];
+    mean[c] = s0 * invP;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -362,7 +376,7 @@ void launch_se_fold(Ctx& ctx, const float* partial, int nblk, i64 P, const float
   const i64 n2 = (i64)C * 2 * C;
   unsigned gx = (unsigned)cdivl(n2, 2048);
   if (gx > (unsigned)num_sms()) gx = num_sms();
-  const size_t smem = sizeof(float) * (2 * C + hid);
+  const size_t smem = sizeof(float) * (2 * C + hid + 8 * C);
   ScopedLaunch sl(RF_K_SE_FINALIZE, 4.0 * B * nblk * C + (4.0 + esize(ctx.dtype)) * B * n2);
   if (ctx.dtype == RF_BF16)
     launch_pdl(k_se_fold<bf16>, dim3(gx, B), dim3(256), smem, ctx.stream, partial, nblk, 1.0f / (float)P, w1, b1, w2, b2, scale,

@@ -43,7 +43,7 @@ struct Im2colTcParams {
   int wmap_of[4];        // weight map of slot m
   float scale_of[4];     // 0.5 for sigmoid inputs (sigmoid(a) = 0.5*tanh(a/2) + 0.5), else 1
   int coef_off;          // ML: index of the first gate used inside gates[b][6]
-  float* partial;        // FLCA: [B][IT_SLOTS][C] channel sums, slot = CTA index within the chunk (pre-zeroed; plain stores)
+  float* partial;        // FLCA: [B][lanes][C] channel sums, slot = CTA index within the chunk (pre-zeroed; plain stores)
   int ylo, yhi;          // FLCA: rows that contribute to the channel sums (row-tiled forward: the band's interior)
   int H, W, C, Cc, nchunks, B;
   int tiles_x, tiles_y, tiles_per_img, total_tiles, lanes;
@@ -226,7 +226,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
       float v = 0.f;
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) v += s_red[(pt * 4 + qd) * 16 + e];
-      p.partial[((i64)b * IT_SLOTS + lane_id) * p.C + chunk * p.Cc + pt * UPT * 8 + e] = v;
+      p.partial[((i64)b * p.lanes + lane_id) * p.C + chunk * p.Cc + pt * UPT * 8 + e] = v;
     }
     __syncthreads();
   };
@@ -412,7 +412,14 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
 
 // xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][IT_SLOTS][C] = channel sums per CTA
 bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
-                        float* partial, int B, int Hf, int Wf, int C) {
+                        float* partial, int B, int Hf, int Wf, int C, int* used_slots) {
+  if (used_slots) {              // == p.lanes of run_im2col_tc: the slots (per image) the kernel writes
+    const int Cc = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 48);
+    const i64 total = (i64)cdiv(Wf, IT_TW) * cdiv(Hf, IT_TH) * B;
+    int lanes = num_sms() / (C / Cc);
+    if (lanes > total) lanes = (int)total;
+    *used_slots = lanes;
+  }
   return run_im2col_tc(ctx, 0, feat, G16, w36, abg, xmod, partial, B, Hf, Wf, C);
 }
 

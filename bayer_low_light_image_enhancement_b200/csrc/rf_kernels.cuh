@@ -140,8 +140,9 @@ void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1,
 int flca_num_partials(int C, int B, i64 P);
 // xmod = feat * (1 + a*sig(conv(LL)) + b*tanh(conv(yh)) + g*sig(conv(cr,cb))); partial [B][nblk][C] channel sums
 // G16 (optional): the bf16 [hi|lo] form of G for the tensor-core path (see launch_split_bf16x8)
-void launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
-                     void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C);
+// returns the number of partial slots per image the kernel used (stride of `partial` = that number; <= nblk)
+int launch_flca_mod(Ctx& ctx, const void* feat, const float* G, const void* G16, const float* w36, const float* abg,
+                    void* xmod, float* partial, int nblk, int B, int Hf, int Wf, int C);
 // tensor-core im2col forms (rf_im2col_tc.cu, bf16 only); false when the shape is not supported
 bool im2col_tc_supported(const Ctx& ctx, int C);
 // G16 / x16: the 4 fp32 maps of every pixel as [hi x4 | lo x4] bf16 (16 bytes per pixel), made by launch_split_bf16x8
@@ -150,7 +151,7 @@ void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix, int s
 bool launch_pyr_spatial_tc(Ctx& ctx, const void* x, const void* G16, const float* w54, const float* gates, void* xs, int mode,
                            int level, int B, int Hf, int Wf, int C);
 bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float* w36, const float* abg, void* xmod,
-                        float* partial, int B, int Hf, int Wf, int C);
+                        float* partial, int B, int Hf, int Wf, int C, int* used_slots = nullptr);
 bool launch_embed_tc(Ctx& ctx, const void* x16, const float* w, const float* b, void* out, int B, int h, int w_, int d);
 // ML: xs = x * (ga * sig(conv(mapA)) + gb * tanh(conv(mapB)))  [mode 0, level l] or xs = x * gc*sig(conv(cr,cb)) [mode 1]
 void launch_pyr_spatial(Ctx& ctx, const void* x, const float* G8, const float* w54, const float* gates, void* xs, int mode,

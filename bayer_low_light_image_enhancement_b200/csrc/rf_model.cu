@@ -185,13 +185,13 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
   const int C = pb.C, H = sg.H, W = sg.W;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
-  const int nblk = flca_num_partials(C, B, P);
+  int nblk = flca_num_partials(C, B, P);            // capacity; the modulation kernel reports the slots it used
   float* partial = zeroed_f32(ctx, (size_t)B * nblk * C);
   float* scale = A.get<float>((size_t)B * C);
   void* xmod = nullptr;
   if (variant == RF_VARIANT_FLCA) {
     xmod = A.elems((size_t)B * P * C, ctx.dtype);
-    launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
+    nblk = launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
   } else {
     float* gates = A.get<float>((size_t)B * 6);
     launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);

@@ -1,21 +1,29 @@
-"""Top-N SASS instructions by stall samples from an `ncu --page source --csv` export (one table per kernel)."""
-import csv, sys
-lines = open(sys.argv[1]).read().splitlines()
-topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-secs = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')] + [len(lines)]
-for a, b in zip(secs[:-1], secs[1:]):
-    rows = list(csv.reader(lines[a + 1:b]))
-    hdr, data = rows[0], rows[1:]
-    si, ii, xi = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
-    tot = sum(int(d[si]) for d in data)
-    tot_inst = sum(int(d[xi]) for d in data)
-    print("=====", lines[a][:100], "samples", tot, "warp-instr", tot_inst)
-    # opcode histogram weighted by executed count
-    hist = {}
-    for d in data:
-        op = d[ii].split()[0] if not d[ii].strip().startswith("@") else d[ii].split()[1]
-        op = op.split(".")[0]
-        hist[op] = hist.get(op, 0) + int(d[xi])
-    print("  executed mix:", ", ".join(f"{k}:{100*v/tot_inst:.1f}%" for k, v in sorted(hist.items(), key=lambda kv: -kv[1])[:14]))
-    for n, d in sorted(enumerate(data), key=lambda nd: -int(nd[1][si]))[:topn]:
-        print(f"  {n:5d} {100*int(d[si])/tot:5.1f}%  exec {int(d[xi]):9d}  {d[ii].strip()[:80]}")
+"""Hottest SASS instructions of one kernel of an ncu report (warp-stall samples per instruction, with the dominant stall
+reasons) -- `ncu -i rep --page source --csv --kernel-id ::regex:<name>:<n>` condensed.
+
+    python tools/ncu_hot.py gpurun_out/x.ncu-rep 'regex:k_tc_gemm' 3 [top]
+"""
+import csv, subprocess, sys
+
+
+def main(rep, kernel, nth, top=30):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f"::{kernel}:{nth}"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+    hdr = rows[hi]
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    si, src, ie = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
+    stalls = [(h, hdr.index(h)) for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    num = lambda v: int(v) if v.isdigit() else 0
+    tot = sum(num(r[si]) for r in data) or 1
+    print("#", rows[0][1][:100] if rows[0] else "", "| samples", tot, "| instructions", len(data))
+    agg = {h: sum(num(r[i]) for r in data) for h, i in stalls}
+    print("# stall reasons:", ", ".join(f"{h[6:]} {100 * v / tot:.0f}%" for h, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
+    for idx, r in sorted(enumerate(data), key=lambda t: -num(t[1][si]))[:top]:
+        st = sorted(((h[6:], num(r[i])) for h, i in stalls if num(r[i]) > 0), key=lambda kv: -kv[1])[:3]
+        print(f"{idx:5d} {100 * num(r[si]) / tot:5.1f}%  exec {r[ie]:>8s}  {r[src].strip()[:64]:64s} {st}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 30)
