@@ -19,6 +19,7 @@ from .modules_ml import FLCA_Pyramid
 from .modules_ml import RawFormer as RawFormerMultiLevel
 from .extras import (BiasFree_LayerNorm, FeedForward, WFBLayerNorm, WithBias_LayerNorm, correct_rgb_u8, postprocess_rgb_u8, postprocess_u8, preprocess_u16, psnr_u8,
                      ssim_u8)
+from . import truecolor
 from .pipeline import FramePipeline
 from .rowtiled import LocalBands, RowTiledRawFormer, plan_bands
 from .wavelets import DWT, IWT, CustomDWT, CustomIDWT, dwt_init, iwt_init
@@ -27,5 +28,5 @@ __all__ = [
     "RawFormer", "RawFormerMultiLevel", "Conv_Transformer", "WaveTransformBlock", "FLCA", "FLCA_Pyramid", "HaarDWT",
     "BayerLumaChroma", "Attention", "conv_ffn", "TransformerBlock", "LayerNorm", "Downsample", "PixelShuffle",
     "downshuffle", "bayer_downshuffle", "CustomDWT", "CustomIDWT", "DWT", "IWT", "dwt_init", "iwt_init", "multilevel", "MODEL_SIZES",
-    "FeedForward", "WithBias_LayerNorm", "BiasFree_LayerNorm", "WFBLayerNorm", "postprocess_u8", "postprocess_rgb_u8", "correct_rgb_u8", "psnr_u8", "ssim_u8", "preprocess_u16", "FramePipeline", "RowTiledRawFormer", "LocalBands", "plan_bands", "set_default_precision", "get_default_precision", "LIB_PATH", "exported_symbols",
+    "FeedForward", "WithBias_LayerNorm", "BiasFree_LayerNorm", "WFBLayerNorm", "postprocess_u8", "postprocess_rgb_u8", "correct_rgb_u8", "psnr_u8", "ssim_u8", "preprocess_u16", "truecolor", "FramePipeline", "RowTiledRawFormer", "LocalBands", "plan_bands", "set_default_precision", "get_default_precision", "LIB_PATH", "exported_symbols",
 ]

@@ -118,6 +118,9 @@ _SIGS = {
         _i, [_fp, _i, _i, _i, _fp, _fp, _i, _i, _BDp, _fp, _sz, _fp, C.POINTER(_f), C.POINTER(_i), _i, C.POINTER(_i)]),
     "rf_kernel_name": (C.c_char_p, [_i]),
     "rf_profiled_launch_info": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rf_conv3x3_small": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _fp]),
+    "rf_truecolor_mix": (_i, [_fp, C.POINTER(_f), _i, C.POINTER(_f), C.POINTER(_f), _f, _fp, _fp, _fp, _fp, _i, _i, _i, _fp]),
+    "rf_color_correction": (_i, [_fp, _f, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp]),
     "rf_postprocess_u8": (_i, [_fp, _fp, _i, _i, _i, _fp]),
     "rf_preprocess_u16": (_i, [_fp, _fp, _f, _f, _f, _i, _i, _i, _i, _fp]),
     "rf_postprocess_rgb_u8": (_i, [_fp, _fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),

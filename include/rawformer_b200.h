@@ -212,6 +212,31 @@ int rf_preprocess_u16(const unsigned short* raw, float* out, float black, float 
                       int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * TrueColor head / tail -- TrueColorRawFormer.py ("variant 0") and BayerTORGBColorMultiLvl.py
+ * ("variant 1") put a learned colour front end and a tone-mapping tail around the same U-Net body.  fp32 NCHW.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.Conv2d(Cin, Cout, 3, padding=1) for a handful of channels (the demosaic_refine / chroma_extractor stacks of
+ * EnhancedBayerProcessor, TrueColorRawFormer.py:90-103): out = act(conv(in * in_scale) + bias) + resid.
+ * in [B,Cin,H,W], weight [Cout,Cin,3,3] (PyTorch layout), in_scale [Cin] / bias [Cout] / resid [B,Cout,H,W] may be NULL.
+ * Cin <= 64, Cout in {2,3,4,16,32}; act: 0 none, 1 ReLU, 2 Softplus(beta 1, threshold 20), 3 tanh, 4 GELU(erf). */
+int rf_conv3x3_small(const float* in, const float* in_scale, const float* weight, const float* bias, const float* resid,
+                     float* out, int Cin, int Cout, int act, int B, int H, int W, void* stream);
+/* The per-pixel part of EnhancedBayerProcessor.forward (TrueColorRawFormer.py:120-137; BayerTORGBColorMultiLvl.py:107-127):
+ * planes [B,4,H,W] = (R,G1,G2,B) [times gains_host[4] if apply_gains] -> r, g = (G1+G2)/2, b -> rgb_linear = M rgb + bias
+ * (color_matrix_host [3][4]) -> y = <rgb_linear, y_weights_host> / max(amax_hw, eps).  Writes rgb_linear [B,3,H,W],
+ * chroma_in [B,4,H,W] = (r, g, b, y) (the chroma_extractor's input) and y [B,1,H,W].  ymax_ws: B floats of scratch. */
+int rf_truecolor_mix(const float* planes, const float* gains_host, int apply_gains, const float* color_matrix_host,
+                     const float* y_weights_host, float eps, float* rgb_linear, float* chroma_in, float* y, float* ymax_ws,
+                     int B, int H, int W, void* stream);
+/* CameraAwareColorCorrection.forward -- TrueColorRawFormer.py:170-185 (variant 0: gamma = the parameter; tone curve output
+ * IS the pixel), BayerTORGBColorMultiLvl.py:164-181 (variant 1: gamma = softplus(gamma_param) + 1e-6, computed by the caller;
+ * tone curve modulates by 0.8 + 0.4 * sigmoid).  x, out [B,3,H,W]; w1 [64,3], b1 [64], w2 [3,64], b2 [3] (color_transform),
+ * w3 [32], b3 [32], w4 [32], b4 [1] (tone_curve), all device fp32. */
+int rf_color_correction(const float* x, float gamma, int variant, const float* w1, const float* b1, const float* w2,
+                        const float* b2, const float* w3, const float* b3, const float* w4, const float* b4, float* out, int B,
+                        int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole model — RawFormer.forward, FLCA_RF.py:330-370 (variant ML: ML_RF.py:356-416)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rf_model_weights {

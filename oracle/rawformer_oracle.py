@@ -477,6 +477,69 @@ def layernorm_biasfree(x, w):
 
 
 # ----------------------------------------------------------------------------------------------
+# TrueColor head / tail.  variant 0 = TrueColorRawFormer.py, 1 = BayerTORGBColorMultiLvl.py
+# ----------------------------------------------------------------------------------------------
+def softplus(x):
+    """F.softplus / nn.Softplus defaults (beta 1, threshold 20)."""
+    x = np.asarray(x)
+    return np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20)))).astype(x.dtype)
+
+
+def enhanced_bayer_processor(sd, x, variant=0, eps=1e-6):
+    """EnhancedBayerProcessor.forward: TrueColorRawFormer.py:109-142 (variant 0), BayerTORGBColorMultiLvl.py:103-136
+    (variant 1).  x [B,4,H,W] -> (y, cr, cb, rgb) with rgb = rgb_linear (variant 0) or the residually refined linear RGB."""
+    dt = x.dtype
+    M = sd["color_matrix"].astype(dt)
+    yw = sd["y_weights"].astype(dt)
+
+    def chroma(r, g, b, y):
+        c = conv3x3(np.concatenate([r, g, b, y], 1), sd["chroma_extractor.0.weight"], sd["chroma_extractor.0.bias"])
+        c = np.tanh(conv3x3(np.maximum(c, 0), sd["chroma_extractor.2.weight"], sd["chroma_extractor.2.bias"]))
+        return c[:, 0:1], c[:, 1:2]
+
+    def linear(r, g, b):
+        rgb = np.concatenate([r, g, b], 1)
+        lin = np.einsum("ij,bjhw->bihw", M[:, :3], rgb) + M[:, 3][None, :, None, None]
+        y = (lin * yw[None, :, None, None]).sum(1, keepdims=True)
+        y = y / np.maximum(y.max(axis=(2, 3), keepdims=True), dt.type(eps))
+        return lin.astype(dt), y.astype(dt)
+
+    if variant == 0:
+        wb = x * sd["wb_gains"].astype(dt)[None, :, None, None]
+        h = np.maximum(conv3x3(wb, sd["demosaic_refine.0.weight"], sd["demosaic_refine.0.bias"]), 0)
+        refined = softplus(conv3x3(h, sd["demosaic_refine.2.weight"], sd["demosaic_refine.2.bias"]))
+        r, g, b = refined[:, 0:1], dt.type(0.5) * (refined[:, 1:2] + refined[:, 2:3]), refined[:, 3:4]
+        lin, y = linear(r, g, b)
+        cr, cb = chroma(r, g, b, y)
+        return y, cr, cb, lin
+    gains = softplus(sd["wb_gains"].astype(dt)) + dt.type(1e-6)
+    wb = x * gains[None, :, None, None]
+    r, g, b = wb[:, 0:1], dt.type(0.5) * (wb[:, 1:2] + wb[:, 2:3]), wb[:, 3:4]
+    lin, y = linear(r, g, b)
+    cr, cb = chroma(r, g, b, y)
+    h = gelu_erf(conv3x3(lin, sd["demosaic_refine.0.weight"], sd["demosaic_refine.0.bias"]))
+    refined = lin + conv3x3(h, sd["demosaic_refine.2.weight"], sd["demosaic_refine.2.bias"])
+    return y, cr, cb, refined.astype(dt)
+
+
+def camera_aware_color_correction(sd, x, variant=0):
+    """CameraAwareColorCorrection.forward: TrueColorRawFormer.py:170-185 (variant 0), BayerTORGBColorMultiLvl.py:164-181
+    (variant 1).  x [B,3,H,W] -> [B,3,H,W] in [0,1]."""
+    dt = x.dtype
+    gamma = sd["gamma"].astype(dt) if variant == 0 else softplus(sd["gamma_param"].astype(dt)) + dt.type(1e-6)
+    v = np.power(np.clip(x, 0, 1), dt.type(1.0) / gamma).astype(dt)
+    t = conv1x1(np.maximum(conv1x1(v, sd["color_transform.0.weight"], sd["color_transform.0.bias"]), 0),
+                sd["color_transform.2.weight"], sd["color_transform.2.bias"])
+    out = []
+    for i in range(t.shape[1]):
+        ch = t[:, i:i + 1]
+        m = sigmoid(conv1x1(np.maximum(conv1x1(ch, sd["tone_curve.0.weight"], sd["tone_curve.0.bias"]), 0),
+                            sd["tone_curve.2.weight"], sd["tone_curve.2.bias"]))
+        out.append(m if variant == 0 else np.clip(ch * (dt.type(0.8) + dt.type(0.4) * m), 0, 1))
+    return np.clip(np.concatenate(out, 1), 0, 1).astype(dt)
+
+
+# ----------------------------------------------------------------------------------------------
 # caller side of the forward: uint8 conversion, Bayer channel order, R/B auto-correction, PSNR  (SURVEY 8f row 1)
 # ----------------------------------------------------------------------------------------------
 # Pinned: ``tests/golden/make_golden_post.py`` executes the reference's own ``correct_bayer_channels`` /

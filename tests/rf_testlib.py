@@ -150,3 +150,47 @@ def block_inputs(case):
     feat = gen_input("randn", (b, C, hf, wf), seed)
     x_ds = gen_input("rand", (b, 4, hy, wy), seed + 100)
     return feat, x_ds
+
+
+# ---------------------------------------------------------------------------------------------------
+# TrueColor head / tail: name, variant (0 TrueColorRawFormer.py, 1 BayerTORGBColorMultiLvl.py), kind,
+# input shape, seed, weight scale
+# ---------------------------------------------------------------------------------------------------
+TRUECOLOR_CASES = [
+    ("tc_head_v0", 0, "head", (2, 4, 18, 26), 40, 1.5),
+    ("tc_head_v1", 1, "head", (2, 4, 18, 26), 41, 1.5),
+    ("tc_tail_v0", 0, "tail", (2, 3, 20, 28), 42, 2.0),
+    ("tc_tail_v1", 1, "tail", (2, 3, 20, 28), 43, 2.0),
+    ("tc_head_v0_zeros", 0, "head0", (1, 4, 8, 8), 44, 1.0),
+]
+
+
+def build_truecolor(kind, variant):
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    ns = rf.truecolor if variant == 0 else rf.truecolor.multilevel
+    return ns.EnhancedBayerProcessor() if kind.startswith("head") else ns.CameraAwareColorCorrection()
+
+
+def make_truecolor_state_dict(module, seed, scale):
+    """make_state_dict plus non-neutral white balance / colour matrix / gamma."""
+    sd = make_state_dict(module, seed=seed, scale=scale)
+    rng = np.random.default_rng([seed, 99])
+    for k in sd:
+        if k == "wb_gains":
+            sd[k] = torch.from_numpy(rng.uniform(0.7, 2.0, 4).astype(np.float32))
+        elif k == "color_matrix":
+            m = np.eye(3, 4, dtype=np.float32) + rng.uniform(-0.2, 0.2, (3, 4)).astype(np.float32)
+            sd[k] = torch.from_numpy(m)
+        elif k in ("gamma", "gamma_param"):
+            sd[k] = torch.tensor(float(rng.uniform(1.6, 2.6)), dtype=torch.float32)
+    return sd
+
+
+def truecolor_input(kind, shape, seed):
+    if kind == "head0":
+        return np.zeros(shape, np.float32)
+    x = gen_input("rand", shape, seed)
+    if kind == "tail":                      # exercise both clamps of the tail: values below 0 and above 1
+        x = x * 1.4 - 0.2
+    return x.astype(np.float32)
