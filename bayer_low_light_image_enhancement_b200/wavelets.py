@@ -29,8 +29,13 @@ class _CustomWavelet(_Op):
         self.register_buffer("weight", k)
 
     def _k16(self):
-        vals = self.weight.detach().float().cpu().reshape(16).tolist()
-        return (C.c_float * 16)(*vals)
+        # the 4x4 matrix travels as a kernel argument: read it back from the device ONCE per weight version (a .cpu() per
+        # call would synchronise the stream on every forward)
+        key = (self.weight.data_ptr(), self.weight._version)
+        if getattr(self, "_k16_key", None) != key:
+            vals = self.weight.detach().float().cpu().reshape(16).tolist()
+            self._k16_val, self._k16_key = (C.c_float * 16)(*vals), key
+        return self._k16_val
 
 
 class CustomDWT(_CustomWavelet):
