@@ -31,6 +31,7 @@ struct DwTmaParams {
                        // caller sums the slots in a fixed order -> bit-reproducible), pre-zeroed
   int ylo, yhi;        // MODE 1: rows that contribute to sumsq (row-tiled forward: the band's interior; else 0, H)
   int H, W, Cn, C2;
+  int wpitch;          // channels per tap row of w (== Cn unless the kernel runs on a channel sub-range of a wider tensor)
   int CC, nvec, TW;    // channel chunk, 4-channel vectors per pixel of a chunk, tile width
   int tiles_x, tiles_y, nchunks, B;
   int sp_tiles;        // spatial tiles per chunk = B * tiles_y * tiles_x
@@ -90,7 +91,7 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
   if (active) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float4 w4 = *reinterpret_cast<const float4*>(p.w + (i64)k * p.Cn + c0);
+      const float4 w4 = *reinterpret_cast<const float4*>(p.w + (i64)k * p.wpitch + c0);
       wv[k][0] = make_float2(w4.x, w4.y);
       wv[k][1] = make_float2(w4.z, w4.w);
     }
@@ -224,7 +225,10 @@ k_dw_tma(const __grid_constant__ CUtensorMap mapIn, const DwTmaParams p) {
 
 // false when the shape is not supported by the TMA path (caller falls back to the register-strip kernel)
 static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const float* bias, void* out, void* vout,
-                       float* sumsq, int B, int H, int W, int Cn, int C2, float* sq_part = nullptr, int* nslots = nullptr) {
+                       float* sumsq, int B, int H, int W, int Cn, int C2, float* sq_part = nullptr, int* nslots = nullptr,
+                       int in_pitch = 0, int wpitch = 0) {
+  if (in_pitch == 0) in_pitch = Cn;
+  if (wpitch == 0) wpitch = Cn;
   if (Cn % 8 || !tcgen05_enabled()) return false;
   static const int kCC[] = {64, 96, 48, 128, 32, 80, 112, 72, 56, 40, 24, 16, 8};
   const int div = mode == 1 ? C2 / 2 : Cn;   // MODE 1: a chunk must not straddle the q|k / v boundary
@@ -234,7 +238,7 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
   if (CC == 0) return false;
   DwTmaParams p;
   p.w = w; p.bias = bias; p.out = (bf16*)out; p.vout = (bf16*)vout; p.sumsq = sumsq; p.sq_part = sq_part;
-  p.H = H; p.W = W; p.Cn = Cn; p.C2 = C2; p.B = B;
+  p.H = H; p.W = W; p.Cn = Cn; p.C2 = C2; p.B = B; p.wpitch = wpitch;
   p.ylo = 0; p.yhi = H;
   if (ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
   p.CC = CC; p.nvec = CC / 4;
@@ -253,7 +257,7 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
   if (smem > 227 * 1024) return false;
   CUtensorMap m;
   const i64 d[4] = {Cn, W, H, B};
-  const i64 st[4] = {1, Cn, (i64)Cn * W, (i64)Cn * W * H};
+  const i64 st[4] = {1, in_pitch, (i64)in_pitch * W, (i64)in_pitch * W * H};
   const int bx[4] = {CC, p.TW + 2, DT_TH + 2, 1};
   if (!make_map_ex(&m, in, 4, d, st, bx, 2, 0)) return false;
   static bool attr_set = false;
@@ -274,6 +278,13 @@ static bool run_dw_tma(Ctx& ctx, int mode, const void* in, const float* w, const
 bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float* dw_b, void* out, int gelu, int B, int H, int W,
                        int Cn) {
   return run_dw_tma(ctx, gelu ? 2 : 0, in, dw_w, dw_b, out, nullptr, nullptr, B, H, W, Cn, 0);
+}
+
+// depthwise 3x3 (+bias) of Cn channels that are a sub-range of a wider NHWC tensor (row pitch in_pitch elements, tap rows of
+// wpitch channels): `in`, `dw_w`, `dw_b` point at the first channel of the range; out is dense [B,H,W,Cn]
+bool launch_dwconv_tma_sub(Ctx& ctx, const void* in, int in_pitch, const float* dw_w, int wpitch, const float* dw_b, void* out,
+                           int B, int H, int W, int Cn) {
+  return run_dw_tma(ctx, 0, in, dw_w, dw_b, out, nullptr, nullptr, B, H, W, Cn, 0, nullptr, nullptr, in_pitch, wpitch);
 }
 
 bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,

@@ -189,6 +189,13 @@ bool launch_dwconv_tma(Ctx& ctx, const void* in, const float* dw_w, const float*
                        int Cn);
 bool launch_dwqkv_tma(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, void* qk, void* v, float* sumsq,
                       int B, int H, int W, int C, float* sq_part = nullptr, int* nslots = nullptr);
+bool launch_dwconv_tma_sub(Ctx& ctx, const void* in, int in_pitch, const float* dw_w, int wpitch, const float* dw_b, void* out,
+                           int B, int H, int W, int Cn);
+// q|k depthwise + Gram + squared norms of ONE image in one kernel (rf_qk_gram.cu): q|k never reach HBM.  Writes per-CTA
+// partial slots gram_part [slot][C][C/8] and sq_part [slot][2C] (slot < the returned count <= slot_cap); 0 = unsupported.
+bool qk_gram_supported(const Ctx& ctx, int C);
+int launch_dwqk_gram(Ctx& ctx, const void* qkv_pre, const float* dw_w, const float* dw_b, float* gram_part, float* sq_part,
+                     int H, int W, int C, int slot_cap);
 // Gram of one image (bf16 NHWC qk [P][2C]) as per-split partials: part[z][C][C/8] = the per-head diagonal blocks of
 // q^T k over pixel slice z (plain stores, z < returned split count <= gram_max_splits()); 0 if the tcgen05 path is unavailable.
 // The caller sums the slices in order (launch_attn_reduce) -> bit-reproducible, unlike atomic accumulation.

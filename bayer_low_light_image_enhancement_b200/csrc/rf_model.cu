@@ -274,26 +274,44 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
     // depthwise pass writes q|k [P][2C] and v [P][C] (dense NHWC, coalesced) and reduces |q|^2,|k|^2; the Gram is a
     // split-K tcgen05 kernel with MN-major operands reading q,k straight from that tensor.
-    void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
     void* vbuf = A.elems((size_t)B * P * C, ctx.dtype);
     // squared norms and Gram: per-CTA / per-split partial slots (plain stores) + ONE ordered reduction per image, so two
     // runs of the forward are bit-identical (no float atomics)
     float* sumsq = zeroed_f32(ctx, (size_t)B * 2 * C);      // (zeroed for the atomically accumulating fallback kernel)
     const int sq_cap = num_sms();
-    float* sq_part = zeroed_f32(ctx, (size_t)B * sq_cap * 2 * C);
     const int gsplit_cap = gram_max_splits();
     float* gram_part = A.get<float>((size_t)gsplit_cap * C * (C / 8));
-    const int nslots = launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C, sq_part);
     // row-tiled forward: the Gram and the norms run over the band's interior rows only, then are summed over the ranks
     const i64 row0 = ctx.band != nullptr ? (i64)ctx.band->ht * W : 0;
     const i64 Pg = ctx.band != nullptr ? (i64)ctx.band->rows_in * W : P;
-    if (!ctx.dry) {
-      for (int b = 0; b < B; ++b) {
-        const int nsplit = launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, gram_part, C, Pg);
-        if (nsplit <= 0 || nsplit > gsplit_cap) recorder().last_cuda_error = (int)cudaErrorNotSupported;
-        // (the depthwise kernel lays the slots out as [b][slot < nslots][2C])
-        launch_attn_reduce(ctx, gram_part, nsplit, sq_part + (size_t)b * nslots * 2 * C, nslots, stats + b * nst,
-                           sumsq + (size_t)b * 2 * C, C);
+    if (qk_gram_supported(ctx, C)) {
+      // q|k depthwise + Gram + norms in one kernel per image (q|k never reach HBM); v by the plain depthwise kernel
+      float* sq_part = A.get<float>((size_t)sq_cap * 2 * C);
+      if (!ctx.dry) {
+        for (int b = 0; b < B; ++b) {
+          const int ns = launch_dwqk_gram(ctx, (const char*)qkv + (size_t)b * P * 3 * C * 2, pb.qkv_dw_w, pb.qkv_dw_b, gram_part,
+                                          sq_part, H, W, C, sq_cap);
+          if (ns <= 0) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+          launch_attn_reduce(ctx, gram_part, ns, sq_part, ns, stats + b * nst, sumsq + (size_t)b * 2 * C, C);
+        }
+        const double px = (double)B * P;
+        ScopedLaunch sl(RF_K_DW_QKV_GRAM, px * C * 2.0 * 2.0, 18.0 * px * C);
+        if (!launch_dwconv_tma_sub(ctx, (const char*)qkv + (size_t)2 * C * 2, 3 * C, pb.qkv_dw_w + 2 * C, 3 * C,
+                                   pb.qkv_dw_b + 2 * C, vbuf, B, H, W, C))
+          recorder().last_cuda_error = (int)cudaErrorNotSupported;
+      }
+    } else {
+      void* qk = A.elems((size_t)B * P * 2 * C, ctx.dtype);
+      float* sq_part = zeroed_f32(ctx, (size_t)B * sq_cap * 2 * C);
+      const int nslots = launch_dwqkv_nhwc(ctx, qkv, pb.qkv_dw_w, pb.qkv_dw_b, qk, vbuf, sumsq, B, H, W, C, sq_part);
+      if (!ctx.dry) {
+        for (int b = 0; b < B; ++b) {
+          const int nsplit = launch_gram_tcgen05(ctx, (const char*)qk + ((size_t)b * P + row0) * 2 * C * 2, gram_part, C, Pg);
+          if (nsplit <= 0 || nsplit > gsplit_cap) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+          // (the depthwise kernel lays the slots out as [b][slot < nslots][2C])
+          launch_attn_reduce(ctx, gram_part, nsplit, sq_part + (size_t)b * nslots * 2 * C, nslots, stats + b * nst,
+                             sumsq + (size_t)b * 2 * C, C);
+        }
       }
     }
     if (ctx.band != nullptr) band_allreduce(ctx, stats, C, ctx.band->se_partial, ctx.band->se_slots, sumsq);
