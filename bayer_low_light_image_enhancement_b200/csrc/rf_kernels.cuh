@@ -40,6 +40,11 @@ struct PackedBlock {
   float* red_b = nullptr;
   void* convout_w = nullptr;   // T [C][9][C]  (k = tap*C + ci)
   float* convout_b = nullptr;
+  // norm -> 1x1 -> depthwise 3x3 as one dense 3x3 conv (rf_lnconv.cu; bf16 mode, C <= 64 only, else null)
+  void* ffn_cw = nullptr;      // T [2C][9][C] = ffn_dw[n][tap] * pw1[n][c] * ln2_g[c]
+  float* ffn_bt = nullptr;     // [9][2C] bias by border state
+  void* qkv_cw = nullptr;      // T [3C][9][C]
+  float* qkv_bt = nullptr;     // [9][3C]
   // ML extras
   float* gate_w = nullptr;     // [2 levels][2][2]
   float* gate_b = nullptr;     // [2][2]
@@ -218,6 +223,17 @@ bool ffn_fused_supported(const Ctx& ctx, int C, int W);
 bool launch_ffn_fused(Ctx& ctx, const void* x, const void* W1f, const float* cs, const float* b1, const float* stats, int npart,
                       const float* dw_w, const float* dw_b, const void* W2, const float* b2, void* out, int B, int H, int W,
                       int C);
+// norm -> 1x1 conv -> depthwise 3x3 as ONE dense 3x3 convolution on the tensor cores (rf_lnconv.cu, bf16, C = 32):
+// pack-time weights Weff [N][9][K] and the border-state bias table [9][N] from the PyTorch-layout fp32 parameters
+void launch_pack_lnconv(Ctx& ctx, const float* W, const float* gamma, const float* beta, const float* bias, const float* dw,
+                        const float* dwb, void* cw, float* btab, int N, int K);
+bool lnconv_supported(const Ctx& ctx, int C, int H, int W);
+// out = x + conv_ffn(norm2(x)); stats = [rows] (sum, sumsq) of x's rows
+bool launch_lnconv_ffn(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const void* W2,
+                       const float* b2, void* out, int B, int H, int W, int C);
+// ONE image: v [H,W,C] + per-CTA partial slots of the Gram / squared norms of q, k (as launch_dwqk_gram); returns the slots
+int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, void* v, float* gram_part,
+                      float* sq_part, int H, int W, int C, int slot_cap);
 // embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
 void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
                   int w_, int d);

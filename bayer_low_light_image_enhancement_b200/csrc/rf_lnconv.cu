@@ -1,0 +1,730 @@
+// LayerNorm -> 1x1 conv -> depthwise 3x3 of the transformer branch as ONE dense 3x3 convolution on the tensor cores
+// (bf16 mode, C = 32: the full-resolution stage of RawFormer-S).
+//
+//   conv_ffn   (FLCA_RF.py:204-209, :253):  out = x + pointwise2( gelu( depthwise( pointwise1( norm2(x) ) ) ) )
+//   Attention  (FLCA_RF.py:223)          :  q|k|v = qkv_dwconv( qkv( norm1(x) ) )
+//
+// A 1x1 conv followed by a depthwise 3x3 is linear, so it IS a dense 3x3 conv with the weights
+//     Weff[n][tap][c] = dw[n][tap] * W[n][c] * gamma[c]                    (made once at pack time, k_pack_lnconv)
+// applied to xhat = (x - mean) * rstd.  The depthwise convolution zero-pads the HIDDEN tensor (bias included), so the bias
+// term of an output pixel is dw_b + sum over the taps that fall inside the image of dw[tap] * (b + W beta): a table of 9
+// vectors indexed by the pixel's border state (3 row states x 3 column states).
+//
+// Why: on the CUDA cores the depthwise 3x3 (+ GELU) costs 17-20 cycles per pixel per 64 channels per SM whether its
+// input comes from HBM or from shared memory (k_dw_tma, k_ffn_fused, k_dwqk_gram are all bound by
+// that loop); as part of the contraction it costs 9x the tensor FLOPs of the 1x1 conv, which the tensor pipe has to
+// spare: 18 tcgen05.mma per 128-pixel tile, ~60 issue cycles each whatever N <= 96 is.
+//
+// One persistent CTA per SM, 576 threads:
+//   warp 0      TMA producer: per tile ONE 4-d box = the (16+2) x (8+2) halo patch of x (pixel-major) and ONE box of the
+//               per-pixel LayerNorm statistics (sum, sumsq) of the same pixels; zero fill outside the image
+//   warp 1      MMA issuer: 9 taps x C/16 k-steps out of the re-laid-out patch (no-swizzle K-major operand, rows =
+//               pixels: the taps are nine start addresses into the same buffer, see rf_tc_gemm.cu), then the second
+//               contraction of the tile before (pointwise2, or the self-Gram of [q|k])
+//   warps 2-17  compute: (a) normalise + re-lay patch i+2 ([pixel][C] -> [C/8][pixel][16 B]); (b) FFN: acc3 of tile
+//               i-1 + bias + residual (the patch's own centre pixels) -> bf16 -> global; (c) acc1 of tile i + bias table
+//               -> FFN: GELU -> bf16 -> g tile (SWIZZLE_128B K-major operand of pointwise2); QKV: q|k -> bf16 -> g tile
+//               (the same bytes are the MN-major operand of the Gram), v -> bf16 -> global.
+// q and k never reach HBM, nor does the 2C-wide hidden tensor of the FFN; the Gram and the squared norms of the CTA's
+// pixels stay in tensor memory until the CTA's last tile and go to its own partial slot (k_attn_reduce sums the slots in
+// order: bit-reproducible).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rf_kernels.cuh"
+#include "rf_tma.cuh"
+#include "rf_dw_math.cuh"
+
+namespace rf {
+
+constexpr int LC_CW = 16;                   // compute warps
+constexpr int LC_CT = LC_CW * 32;           // compute threads
+constexpr int LC_THREADS = LC_CT + 64;      // + producer warp + MMA warp
+constexpr int LC_NPIX = 180;                // (16 + 2) x (8 + 2) patch pixels, row pitch 10
+constexpr int LC_NT = 3;                    // re-laid-out patch buffers
+constexpr int LC_MAXR = 5;                  // raw patch buffers (FFN: a patch lives until its tile's residual add)
+constexpr uint32_t LC_ST_BYTES = 18 * 12 * 8, LC_ST_STRIDE = 1792;
+enum { LC_FFN = 0, LC_QKV = 1 };
+
+struct LcP {
+  const float* btab;     // [9][N] bias by border state (3 * row state + column state; state 0 = first, 1 = inner, 2 = last)
+  const float* b2;       // FFN: [C] pointwise2 bias
+  bf16* out;             // FFN: out [B,H,W,C]; QKV: v [B,H,W,C]
+  float* gram_part;      // QKV: [slot][C][C/8] per-head diagonal blocks of q^T k of the CTA's pixels
+  float* sq_part;        // QKV: [slot][2C]
+  float invC, eps;
+  int H, W, B;
+  int ylo, yhi;          // QKV: rows that count for the statistics (row-tiled forward: the band's interior)
+  int tiles_x, tiles_y, total_tiles;
+  int nr;                // raw patch buffers in use
+  int sched;             // 0: the first contraction of tile i+1 runs under tile i's accumulator loads; 1: after them
+  unsigned long long* dbg;   // debugging aid (RAWFORMER_B200_LNCONV_DBG=1): cycles per phase of compute thread 0, per CTA
+};
+
+template <int MODE, int C>
+struct LcCfg {
+  static constexpr int N = MODE == LC_FFN ? 2 * C : 3 * C;
+  static constexpr int NCH = C / 8;                              // 16-byte units per pixel
+  static constexpr int LBO_PX = 184;                             // chunk pitch in pixels (a multiple of 128 bytes)
+  static constexpr uint32_t LBO = LBO_PX * 16;
+  static constexpr uint32_t RAW_BYTES = LC_NPIX * C * 2;
+  static constexpr uint32_t RAW_STRIDE = (RAW_BYTES + 1023) & ~1023u;   // (the patch lands 64 / 128-byte swizzled)
+  static constexpr uint32_t T_STRIDE = (NCH * LBO + 1023) & ~1023u;
+  static constexpr uint32_t WTAP = N * C * 2;                    // bytes of one tap's [N][C] weights
+  static constexpr uint32_t W_BYTES = 9 * WTAP;
+  static constexpr uint32_t W2_BYTES = MODE == LC_FFN ? C * 128 : 0;
+  static constexpr uint32_t G_BYTES = 16384;                     // 128 pixels x 128 B
+  static constexpr int ACC1_STRIDE = N <= 64 ? 64 : 128;         // two accumulators of the first contraction
+  static constexpr int ACC3_COL = 2 * ACC1_STRIDE;               // FFN: the [128 x C] pointwise2 accumulator; QKV: the Gram
+  static constexpr int TMEM_COLS = MODE == LC_FFN ? 256 : 512;
+  static constexpr int UPW = N / 8 / 4;                          // 8-column units per compute warp in the first epilogue
+  static constexpr uint32_t BT_BYTES = 9 * N * 4;
+  static constexpr size_t smem(int nr) {
+    return 1024 + W_BYTES + W2_BYTES + G_BYTES + 2048 + LC_NT * T_STRIDE + (size_t)nr * (RAW_STRIDE + LC_ST_STRIDE) +
+           BT_BYTES + C * 4 + 256 + 64;
+  }
+};
+
+__device__ __forceinline__ void lc_warp_wait(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ float4 lc_lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lc_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lc_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lc_pack(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// MN-major SWIZZLE_128B operand (the Gram reads the g tile with pixels as the contraction axis), see rf_qk_gram.cu
+__device__ __forceinline__ uint64_t lc_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ bool lc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with the two 64-bit shared-memory descriptors given as 32-bit halves (the high halves are constants, the low
+// halves base + compile-time offset: one 32-bit add per operand instead of a 64-bit carry chain)
+__device__ __forceinline__ void lc_umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int MODE, int C, bool DBG>
+__global__ void __launch_bounds__(LC_THREADS, 1)
+k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapS,
+         const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapW2, const LcP p) {
+  using K = LcCfg<MODE, C>;
+  constexpr int N = K::N;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;
+  const uint32_t sW2 = sW + K::W_BYTES;
+  const uint32_t sG = sW2 + K::W2_BYTES;
+  const uint32_t sZ = sG + K::G_BYTES;                          // 2 KB of zeros: rows 64..127 of the Gram operand
+  const uint32_t sT = sZ + 2048;
+  const uint32_t sRaw = sT + LC_NT * K::T_STRIDE;
+  const uint32_t sSt = sRaw + (uint32_t)p.nr * K::RAW_STRIDE;
+  const uint32_t sBT = sSt + (uint32_t)p.nr * LC_ST_STRIDE;
+  const uint32_t sB2 = sBT + K::BT_BYTES;
+  const uint32_t bars = (sB2 + C * 4 + 7u) & ~7u;
+  auto raw_full = [&](int i) { return bars + 8u * i; };
+  auto raw_free = [&](int i) { return bars + 8u * (LC_MAXR + i); };
+  auto t_full = [&](int i) { return bars + 8u * (2 * LC_MAXR + i); };
+  const uint32_t mma1_done0 = bars + 8u * (2 * LC_MAXR + LC_NT), mma2_done = mma1_done0 + 16, drained0 = mma1_done0 + 24,
+                 g_full = mma1_done0 + 40, w_full = mma1_done0 + 48, tmem_slot = mma1_done0 + 56;
+  auto mma1_done = [&](int i) { return mma1_done0 + 8u * i; };
+  auto drained = [&](int i) { return drained0 + 8u * i; };
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapS);
+    tma_prefetch_desc(&mapW);
+    if (MODE == LC_FFN) tma_prefetch_desc(&mapW2);
+    // barriers the compute warps arrive on count one arrival per warp: no CTA-wide barrier in the tile loop, the warps
+    // drift apart by as much as the buffer depths allow
+    for (int i = 0; i < LC_MAXR; ++i) {
+      mbar_init(raw_full(i), 1);
+      mbar_init(raw_free(i), LC_CW);
+    }
+    for (int i = 0; i < LC_NT; ++i) mbar_init(t_full(i), LC_CW);
+    mbar_init(mma1_done(0), 1);
+    mbar_init(mma1_done(1), 1);
+    mbar_init(mma2_done, 1);
+    mbar_init(drained(0), LC_CW);
+    mbar_init(drained(1), LC_CW);
+    mbar_init(g_full, LC_CW);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (MODE == LC_QKV) {
+    for (uint32_t o = (uint32_t)tid * 16u; o < 2048u; o += LC_THREADS * 16u) lc_sts128(sZ + o, 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)K::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+  {
+    float* bt = reinterpret_cast<float*>(smem_raw + (sBT - smem_u32(smem_raw)));
+    for (int i = tid; i < 9 * N; i += LC_THREADS) bt[i] = __ldg(p.btab + i);
+    if (MODE == LC_FFN) {
+      float* b2 = reinterpret_cast<float*>(smem_raw + (sB2 - smem_u32(smem_raw)));
+      for (int i = tid; i < C; i += LC_THREADS) b2[i] = __ldg(p.b2 + i);
+    }
+  }
+  __syncthreads();
+
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n = first < p.total_tiles ? (p.total_tiles - first + stride - 1) / stride : 0;
+  // tile coordinates of this CTA's tiles without per-tile divisions: the walk advances by `stride` tiles
+  struct TileIter {
+    int tx, ty, b;
+  };
+  const int step_x = stride % p.tiles_x, step_y = stride / p.tiles_x;
+  auto tile_first = [&]() {
+    TileIter t;
+    t.tx = first % p.tiles_x;
+    const int r = first / p.tiles_x;
+    t.ty = r % p.tiles_y;
+    t.b = r / p.tiles_y;
+    return t;
+  };
+  auto tile_next = [&](TileIter& t) {
+    t.tx += step_x;
+    if (t.tx >= p.tiles_x) { t.tx -= p.tiles_x; ++t.ty; }
+    t.ty += step_y;
+    while (t.ty >= p.tiles_y) { t.ty -= p.tiles_y; ++t.b; }
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0 && n > 0) {
+      mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, 0);
+      if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, 0, 0, 0);
+      int rb = 0;
+      uint32_t rph = 0;
+      TileIter tl = tile_first();
+      for (int i = 0; i < n; ++i) {
+        if (i >= p.nr) mbar_wait(raw_free(rb), rph ^ 1u);
+        const int px0 = tl.tx * 8, py0 = tl.ty * 16, b = tl.b;
+        tile_next(tl);
+        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + LC_ST_BYTES);
+        tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE, &mapX, raw_full(rb), 0, px0 - 1, py0 - 1, b);
+        tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
+        if (++rb == p.nr) { rb = 0; rph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // A tcgen05.ld queues behind the MMAs in flight (measured: ~900 cycles behind an 18-MMA batch), so the accumulators
+    // are read only while the tensor pipe is empty: the first contraction of tile i+1 is issued when every compute warp
+    // has drained tile i's accumulators into registers (`drained`), the second contraction of tile i when its g tile is
+    // complete; the compute warps wait for both before the next tile's loads.  One accumulator of each kind suffices.
+    // The whole warp walks the loop and ONE elected lane issues (elect.sync): under a plain `lane == 0` branch the
+    // compiler wraps every tcgen05.mma in a loop over the active lanes (vector -> uniform register moves), ~20 instructions
+    // per MMA on a thread that shares its scheduler with four busy compute warps: the issue loop alone took 1700-2400
+    // cycles per 18-MMA tile.
+    if (n > 0) {
+      const bool leader = lc_elect_one();
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t idesc1 = make_idesc_m128(N);
+      // A: no-swizzle K-major, LBO = chunk pitch, SBO = patch row pitch (10 pixels x 16 B); B: the resident weights
+      const uint32_t a_hi = (160u >> 4) | (1u << 14), a_lo0 = (K::LBO >> 4) << 16;
+      const uint64_t wdesc0 = make_kmajor_desc(sW, C);
+      const uint32_t b_hi = (uint32_t)(wdesc0 >> 32), b_lo0 = (uint32_t)wdesc0;
+      int tb = 0;
+      uint32_t tph = 0;
+      long long t_issue = 0;
+      auto mma1 = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(t_full(tb), tph);
+        if (i >= 2) mbar_wait(drained(s), (uint32_t)(((i >> 1) + 1) & 1));   // tile i-2's accumulator is in registers
+        if (p.sched == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
+        tc_fence_after();
+        if (DBG) t_issue = clock64();
+        if (leader) {
+          const uint32_t a_lo = a_lo0 | (((sT + (uint32_t)tb * K::T_STRIDE) & 0x3FFFF) >> 4);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * K::ACC1_STRIDE);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk)
+              lc_umma(d_tmem, a_lo + (uint32_t)(((tap / 3) * 10 + (tap % 3)) + 2 * kk * K::LBO_PX), a_hi,
+                      b_lo0 + (uint32_t)tap * (K::WTAP >> 4) + 2u * (uint32_t)kk, b_hi, idesc1, (tap | kk) ? 1u : 0u);
+          }
+          umma_commit(mma1_done(s));
+        }
+        __syncwarp();
+        if (++tb == LC_NT) { tb = 0; tph ^= 1u; }
+      };
+      if (DBG) {
+        mma1(0);
+        const long long t1 = clock64();
+        mbar_wait(mma1_done(0), 0);
+        if (leader) {
+          p.dbg[(gridDim.x + blockIdx.x) * 8 + 0] = (unsigned long long)(clock64() - t_issue);
+          p.dbg[(gridDim.x + blockIdx.x) * 8 + 2] = (unsigned long long)(t1 - t_issue);
+        }
+      } else {
+        mma1(0);
+      }
+      if (p.sched == 0 && n > 1) mma1(1);
+      const uint32_t idesc3 = make_idesc_m128(C);
+      // Gram: kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (rows 2C.. are zeros), N = 2C
+      const uint32_t idescg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(2 * C >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t gdesc = make_sw128_desc(sG), w2desc = make_sw128_desc(sW2);
+      for (int i = 0; i < n; ++i) {
+        if (p.sched == 1 && i + 1 < n) {
+          if (DBG && i == 8) {
+            mma1(i + 1);
+            mbar_wait(mma1_done((i + 1) & 1), (uint32_t)(((i + 1) >> 1) & 1));
+            if (leader) p.dbg[(gridDim.x + blockIdx.x) * 8 + 1] = (unsigned long long)(clock64() - t_issue);
+          } else {
+            mma1(i + 1);
+          }
+        }
+        mbar_wait(g_full, (uint32_t)(i & 1));
+        tc_fence_after();
+        if (leader) {
+          if (MODE == LC_FFN) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              lc_umma(tmem_base + (uint32_t)K::ACC3_COL, (uint32_t)gdesc + 2u * k, (uint32_t)(gdesc >> 32), (uint32_t)w2desc + 2u * k,
+                      (uint32_t)(w2desc >> 32), idesc3, k ? 1u : 0u);
+          } else {
+            // MN-major SWIZZLE_128B operand, 16 pixels (16 rows of 128 B) per k-step; LBO = distance to the zero block
+            const uint32_t g_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a0 = sG + (uint32_t)k * 2048u;
+              const uint32_t lo = ((a0 & 0x3FFFF) >> 4) | (((sZ - a0) >> 4) << 16);
+              lc_umma(tmem_base + (uint32_t)K::ACC3_COL, lo, g_hi, lo, g_hi, idescg, (i | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(mma2_done);
+        }
+        __syncwarp();
+        if (p.sched == 0 && i + 2 < n) mma1(i + 2);
+      }
+    }
+  } else {
+    // ================= compute warps =================
+    const int ctid = tid - 64;
+    const int q = warp & 3, wi = (warp - 2) >> 2;        // TMEM lane quadrant; index among the quadrant's four warps
+    const int r = q * 32 + lane;                         // accumulator row = tile pixel
+    const int ty = r >> 3, tx = r & 7;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int UB = MODE == LC_FFN ? C / 8 / 4 : 1;   // 8-column units of acc3 per warp (FFN)
+    long long tph[DBG ? 8 : 1] = {0}, tlast = DBG ? clock64() : 0;
+    auto mark = [&](int k) {
+      if (DBG && ctid == 0) {
+        const long long now = clock64();
+        tph[DBG ? k : 0] += now - tlast;
+        tlast = now;
+      }
+    };
+    auto warp_arrive = [&](uint32_t bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+
+    // ---- normalise + re-lay patch j: [pixel][C] -> [C/8][pixel][16 B] ----
+    // (its buffer was last read by the MMAs of tile j-3, whose completion this warp observed before that tile's loads)
+    // One thread per patch pixel (statistics, rsqrt and index arithmetic once per pixel instead of once per 16 bytes: the
+    // tile loop is bound by instruction issue); the 180 pixels go to a window of the 512 compute threads that rotates from
+    // tile to tile so that every warp does the same work on average.  TMA delivers the patch 64-byte swizzled (16-byte unit
+    // u of patch pixel q sits at unit u ^ ((q >> 1) & 3)), which makes these 64-byte-strided loads -- and the residual
+    // loads of the second epilogue -- conflict-free.
+    int rl_rb = 0, rl_tb = 0, rl_rot = 0;
+    uint32_t rl_rph = 0;
+    auto relayout = [&]() {
+      lc_warp_wait(raw_full(rl_rb), rl_rph, lane);
+      mark(5);
+      const int px = (ctid - rl_rot) & (LC_CT - 1);
+      if (px < LC_NPIX) {
+        const uint32_t src = sRaw + (uint32_t)rl_rb * K::RAW_STRIDE + (uint32_t)px * (C * 2);
+        const uint32_t dst = sT + (uint32_t)rl_tb * K::T_STRIDE + (uint32_t)px * 16u;
+        const int py = px / 10, pxx = px - py * 10;
+        float sum, ssq;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sum), "=f"(ssq)
+                     : "r"(sSt + (uint32_t)rl_rb * LC_ST_STRIDE + (uint32_t)(py * 12 + pxx + 1) * 8u));
+        const float mu = sum * p.invC;
+        const float rs = rsqrtf(fmaxf(ssq * p.invC - mu * mu, 0.f) + p.eps);
+        const float nm = -mu * rs;
+        const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
+        uint4 v[K::NCH];
+#pragma unroll
+        for (int k = 0; k < K::NCH; ++k) v[k] = lc_lds128(src + (uint32_t)((k ^ ((px >> 1) & 3)) * 16));
+#pragma unroll
+        for (int k = 0; k < K::NCH; ++k) {
+          const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+            const float2 f = __ffma2_rn(a, r2, n2);
+            o[e] = lc_pack(f.x, f.y);
+          }
+          lc_sts128(dst + (uint32_t)k * K::LBO, o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async();                                 // generic stores -> tensor-core (async proxy) reads
+      warp_arrive(t_full(rl_tb));
+      if (MODE == LC_QKV && lane == 0) mbar_arrive(raw_free(rl_rb));   // (FFN: the patch stays for the residual add)
+      if (++rl_rb == p.nr) { rl_rb = 0; rl_rph ^= 1u; }
+      if (++rl_tb == LC_NT) rl_tb = 0;
+      rl_rot = (rl_rot + 192) & (LC_CT - 1);
+      mark(6);
+    };
+
+    // ---- FFN: second epilogue of the tile before: acc3 (in v3) + bias + residual -> bf16 -> global ----
+    TileIter ta = tile_first(), tb2 = ta;
+    int eb_rb = 0;
+    auto epi_b = [&](uint32_t (&v3)[UB][8]) {
+      const int y = tb2.ty * 16 + ty, x = tb2.tx * 8 + tx, b = tb2.b;
+      tile_next(tb2);
+#pragma unroll
+      for (int t = 0; t < UB; ++t) {
+        const int u = wi * UB + t;
+        const int pr = (ty + 1) * 10 + tx + 1;
+        const uint4 res = lc_lds128(sRaw + (uint32_t)eb_rb * K::RAW_STRIDE + (uint32_t)(pr * C * 2 + ((u ^ ((pr >> 1) & 3)) << 4)));
+        const float4 b0 = lc_lds128f(sB2 + (uint32_t)u * 32u), b1 = lc_lds128f(sB2 + (uint32_t)u * 32u + 16u);
+        const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = __uint_as_float(v3[t][2 * e]) + bias[2 * e] + __uint_as_float(rw[e] << 16);
+          const float f1 = __uint_as_float(v3[t][2 * e + 1]) + bias[2 * e + 1] + __uint_as_float(rw[e] & 0xffff0000u);
+          o[e] = lc_pack(f0, f1);
+        }
+        if (y < p.H && x < p.W) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ((((i64)b * p.H + y) * p.W + x) * C + u * 8));
+          *dst = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      warp_arrive(raw_free(eb_rb));
+      if (++eb_rb == p.nr) eb_rb = 0;
+    };
+
+    if (n > 0) relayout();
+    if (n > 1) relayout();
+    for (int i = 0; i < n; ++i) {
+      // ---- A: both contractions that feed this step are complete -> accumulators into registers ----
+      mark(0);
+      lc_warp_wait(mma1_done(i & 1), (uint32_t)((i >> 1) & 1), lane);
+      mark(1);
+      if (i >= 1) lc_warp_wait(mma2_done, (uint32_t)((i - 1) & 1), lane);
+      tc_fence_after();
+      mark(2);
+      uint32_t v[K::UPW][8], v3[UB][8];
+#pragma unroll
+      for (int t = 0; t < K::UPW; ++t) tmem_ld8(tq + (uint32_t)((i & 1) * K::ACC1_STRIDE + (wi * K::UPW + t) * 8), v[t]);
+      if (MODE == LC_FFN && i >= 1) {
+#pragma unroll
+        for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      warp_arrive(drained(i & 1));
+      mark(3);
+      // ---- B: epilogues on registers ----
+      if (MODE == LC_FFN && i >= 1) epi_b(v3);
+      const int y = ta.ty * 16 + ty, x = ta.tx * 8 + tx, b = ta.b;
+      tile_next(ta);
+      const int rs_ = y == 0 ? 0 : (y == p.H - 1 ? 2 : 1), cs_ = x == 0 ? 0 : (x == p.W - 1 ? 2 : 1);
+      const uint32_t bt = sBT + (uint32_t)((rs_ * 3 + cs_) * N) * 4u;
+      const bool inside = y < p.H && x < p.W;
+      const bool counts = inside && y >= p.ylo && y < p.yhi;
+      const uint32_t grow = sG + (uint32_t)r * 128u;
+#pragma unroll
+      for (int t = 0; t < K::UPW; ++t) {
+        const int u = wi * K::UPW + t;
+        const float4 b0 = lc_lds128f(bt + (uint32_t)u * 32u), b1 = lc_lds128f(bt + (uint32_t)u * 32u + 16u);
+        const float2 h[4] = {__fadd2_rn(make_float2(__uint_as_float(v[t][0]), __uint_as_float(v[t][1])), make_float2(b0.x, b0.y)),
+                             __fadd2_rn(make_float2(__uint_as_float(v[t][2]), __uint_as_float(v[t][3])), make_float2(b0.z, b0.w)),
+                             __fadd2_rn(make_float2(__uint_as_float(v[t][4]), __uint_as_float(v[t][5])), make_float2(b1.x, b1.y)),
+                             __fadd2_rn(make_float2(__uint_as_float(v[t][6]), __uint_as_float(v[t][7])), make_float2(b1.z, b1.w))};
+        uint32_t o[4];
+        if (MODE == LC_FFN) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 g = gelu_tanh2(h[e]);
+            o[e] = lc_pack(g.x, g.y);
+          }
+          lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = lc_pack(h[e].x, h[e].y);
+          if (u < 2 * C / 8) {                              // q|k: pixels that do not count contribute exact zeros
+            if (!counts) o[0] = o[1] = o[2] = o[3] = 0u;
+            lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
+          } else if (inside) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + ((((i64)b * p.H + y) * p.W + x) * C + (u - 2 * C / 8) * 8));
+            *dst = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      warp_arrive(g_full);
+      mark(4);
+      // ---- C: the patch two tiles ahead ----
+      if (i + 2 < n) relayout();
+    }
+    if (n > 0) {
+      lc_warp_wait(mma2_done, (uint32_t)((n - 1) & 1), lane);
+      tc_fence_after();
+    }
+    if (MODE == LC_FFN && n > 0) {
+      uint32_t v3[UB][8];
+#pragma unroll
+      for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
+      tmem_ld_wait();
+      epi_b(v3);
+    }
+    if (DBG && ctid == 0)
+      for (int k = 0; k < 8; ++k) p.dbg[blockIdx.x * 8 + k] = (unsigned long long)tph[DBG ? k : 0];
+
+    // ---- QKV read-out: per-head diagonal blocks of q^T k and the squared norms -> this CTA's slot ----
+    if (MODE == LC_QKV && wi == 0) {
+      constexpr int c = C >> 3;
+      const int row = r;                               // accumulator row = channel of [q|k]
+      float* gp = p.gram_part + (i64)blockIdx.x * C * c;
+      float* sp = p.sq_part + (i64)blockIdx.x * 2 * C;
+      const int h = row < C ? row / c : -1;
+      for (int cc = 0; cc < 2 * C; cc += 16) {
+        uint32_t v[16];
+        if (n > 0) {
+          tmem_ld16(tq + (uint32_t)(K::ACC3_COL + cc), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (row < 2 * C) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cc + j;
+            if (col == row) sp[row] = __uint_as_float(v[j]);
+            const int kc = col - C;                    // k channel of this accumulator column
+            if (h >= 0 && kc >= h * c && kc < (h + 1) * c) gp[(i64)row * c + (kc - h * c)] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)K::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack time: Weff [N][9][K] (T) and the border-state bias table [9][N]; one warp per output channel n
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_lnconv(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ bias, const float* __restrict__ dw, const float* __restrict__ dwb,
+              bf16* __restrict__ cw, float* __restrict__ btab, int N, int Kc) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float bb = 0.f;
+  for (int k = lane; k < Kc; k += 32) {
+    const float w = W[(i64)n * Kc + k];
+    bb = fmaf(w, beta[k], bb);
+    const float wg = w * gamma[k];
+    for (int tap = 0; tap < 9; ++tap) cw[((i64)n * 9 + tap) * Kc + k] = __float2bfloat16_rn(wg * dw[n * 9 + tap]);
+  }
+  bb = warp_sum(bb) + (bias ? bias[n] : 0.f);
+  if (lane < 9) {
+    const int rs = lane / 3, cs = lane % 3;
+    float s = dwb ? dwb[n] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const bool valid = !(rs == 0 && ky == 0) && !(rs == 2 && ky == 2) && !(cs == 0 && kx == 0) && !(cs == 2 && kx == 2);
+      if (valid) s = fmaf(dw[n * 9 + tap], bb, s);
+    }
+    btab[lane * N + n] = s;
+  }
+}
+
+void launch_pack_lnconv(Ctx& ctx, const float* W, const float* gamma, const float* beta, const float* bias, const float* dw,
+                        const float* dwb, void* cw, float* btab, int N, int K) {
+  if (ctx.dry || !W || !gamma || !beta || !dw || !cw || ctx.dtype != RF_BF16) return;
+  ScopedLaunch sl(RF_K_WEIGHT_PACK);
+  k_pack_lnconv<<<cdiv(N, 8), 256, 0, ctx.stream>>>(W, gamma, beta, bias, dw, dwb, (bf16*)cw, btab, N, K);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool lnconv_enabled() {
+  static int enabled = -1;                // debugging aid: RAWFORMER_B200_NO_LNCONV=1 keeps the separate kernels
+  if (enabled < 0) {
+    const char* e = getenv("RAWFORMER_B200_NO_LNCONV");
+    enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  return enabled != 0;
+}
+
+bool lnconv_supported(const Ctx& ctx, int C, int H, int W) {
+  return lnconv_enabled() && tcgen05_enabled() && ctx.dtype == RF_BF16 && C == 32 && (W & 1) == 0 && H >= 2 && W >= 2;
+}
+
+template <int MODE, int C>
+static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const void* W2,
+                         const float* b2, void* out, float* gram_part, float* sq_part, int B, int H, int W, int slot_cap) {
+  using K = LcCfg<MODE, C>;
+  LcP p;
+  memset(&p, 0, sizeof(p));
+  p.btab = btab; p.b2 = b2; p.out = (bf16*)out; p.gram_part = gram_part; p.sq_part = sq_part;
+  p.invC = 1.0f / (float)C; p.eps = 1e-5f;
+  p.H = H; p.W = W; p.B = B;
+  p.ylo = 0; p.yhi = H;
+  if (MODE == LC_QKV && ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
+  p.tiles_x = cdiv(W, 8); p.tiles_y = cdiv(H, 16);
+  const i64 total = (i64)p.tiles_x * p.tiles_y * B;
+  if (total <= 0 || total > 0x7fffffff) return 0;
+  p.total_tiles = (int)total;
+  p.nr = MODE == LC_FFN ? LC_MAXR : 3;
+  {
+    // measured (RawFormer-S stage 0): FFN 236 us with schedule 1 / 262 us with 0; QKV 273 / 238 us
+    static int sched = -1;
+    if (sched < 0) {
+      const char* e = getenv("RAWFORMER_B200_LNCONV_SCHED");
+      sched = e ? atoi(e) : 2;
+    }
+    p.sched = sched == 2 ? (MODE == LC_FFN ? 1 : 0) : sched;
+  }
+  const size_t smem = K::smem(p.nr);
+  if (smem > 232448) return 0;
+  if (((uintptr_t)stats & 15) || ((uintptr_t)x & 15)) return 0;
+  CUtensorMap mX, mS, mW, mW2;
+  {
+    const i64 d[4] = {C, W, H, B};
+    const i64 s[4] = {1, C, (i64)C * W, (i64)C * W * H};
+    const int bx[4] = {C, 10, 18, 1};
+    if (!make_map_ex(&mX, x, 4, d, s, bx, 2, C * 2)) return 0;
+  }
+  {
+    // statistics as a [B, H, 2W] fp32 tensor: the box of a tile is its patch pixels' (sum, sumsq) pairs; it starts one
+    // pixel left of the patch so that its global start address is 16-byte aligned; zero fill outside the image
+    const i64 d[3] = {2 * (i64)W, H, B};
+    const i64 s[3] = {1, 2 * (i64)W, (i64)2 * W * H};
+    const int bx[3] = {24, 18, 1};
+    if (!make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
+  }
+  {
+    const i64 d[3] = {C, 9, K::N};
+    const i64 s[3] = {1, C, (i64)9 * C};
+    const int bx[3] = {C, 1, K::N};
+    if (!make_map_ex(&mW, cw, 3, d, s, bx, 2, C * 2)) return 0;
+  }
+  if (MODE == LC_FFN) {
+    const i64 d[3] = {2 * C, C, 1};
+    const i64 s[3] = {1, 2 * C, (i64)2 * C * C};
+    const int bx[3] = {64, C, 1};
+    if (!make_map_ex(&mW2, W2, 3, d, s, bx, 2, 128)) return 0;
+  } else {
+    mW2 = mW;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_lnconv<MODE, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lnconv<MODE, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return 0;
+    attr_set = true;
+  }
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (MODE == LC_QKV && grid > slot_cap) grid = slot_cap;
+  static int dbg_on = -1;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on < 0) {
+    const char* e = getenv("RAWFORMER_B200_LNCONV_DBG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on && cudaMalloc(&dbg_buf, 8 * 8 * 2048) != cudaSuccess) dbg_on = 0;
+  }
+  p.dbg = dbg_on ? dbg_buf : nullptr;
+  if (dbg_on) {
+    launch_pdl(k_lnconv<MODE, C, true>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, p);
+    static unsigned long long h[8 * 2048];
+    cudaStreamSynchronize(ctx.stream);
+    cudaMemcpy(h, dbg_buf, sizeof(unsigned long long) * 8 * 2 * grid, cudaMemcpyDeviceToHost);
+    {
+      double m0 = 0, m1 = 0, m2 = 0;
+      for (int i = 0; i < grid; ++i) { m0 += (double)h[(grid + i) * 8] / grid; m1 += (double)h[(grid + i) * 8 + 1] / grid; m2 += (double)h[(grid + i) * 8 + 2] / grid; }
+      fprintf(stderr, "[lnconv] 18-MMA batch first issue->complete: first tile %.0f cycles (issue loop alone %.0f), tile 9 (steady state, schedule 1) %.0f cycles\n", m0, m2, m1);
+    }
+    double a[8] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid;
+    const double tiles = (double)cdiv(p.total_tiles, grid);
+    fprintf(stderr, "[lnconv mode %d C=%d %dx%d tiles/CTA %.0f] cycles/tile (warp 2): loop %.0f wait_mma1 %.0f wait_mma2 %.0f tmem_ld %.0f "
+            "epilogues %.0f | relayout: wait_raw %.0f work %.0f\n",
+            MODE, C, H, W, tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles);
+  } else {
+    launch_pdl(k_lnconv<MODE, C, false>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, p);
+  }
+  return grid;
+}
+
+// out = x + conv_ffn(norm2(x)); stats: [rows] (sum, sumsq) of x's rows; cw / btab from launch_pack_lnconv
+bool launch_lnconv_ffn(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const void* W2,
+                       const float* b2, void* out, int B, int H, int W, int C) {
+  if (!lnconv_supported(ctx, C, H, W)) return false;
+  const double rows = (double)B * H * W;
+  ScopedLaunch sl(RF_K_FFN_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 2 * C + 2.0 * 2 * C * C));
+  return lnconv_launch<LC_FFN, 32>(ctx, x, stats, cw, btab, W2, b2, out, nullptr, nullptr, B, H, W, 0) > 0;
+}
+
+// ONE image: v = third part of qkv_dwconv(qkv(norm1(x))); Gram / squared norms of q, k into per-CTA partial slots.
+// Returns the number of slots written (= CTAs), 0 if unsupported.
+int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, void* v, float* gram_part,
+                      float* sq_part, int H, int W, int C, int slot_cap) {
+  if (!lnconv_supported(ctx, C, H, W)) return 0;
+  const double rows = (double)H * W;
+  ScopedLaunch sl(RF_K_QKV_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 3 * C + 2.0 * (2 * C) * (2 * C)));
+  return lnconv_launch<LC_QKV, 32>(ctx, x, stats, cw, btab, nullptr, nullptr, v, gram_part, sq_part, 1, H, W, slot_cap);
+}
+
+}  // namespace rf

@@ -52,6 +52,10 @@ static PackedBlock layout_block(Layout& L, int C, int dtype, int variant) {
   pb.pw2_w = L.elems(2 * c * c, dtype); pb.pw2_b = L.f32(c);
   pb.red_w = L.f32(2 * c * c); pb.red_b = L.f32(c);
   pb.convout_w = L.elems(9 * c * c, dtype); pb.convout_b = L.f32(c);
+  if (dtype == RF_BF16 && C <= 64) {
+    pb.ffn_cw = L.elems(2 * c * 9 * c, dtype); pb.ffn_bt = L.f32(9 * 2 * c);
+    pb.qkv_cw = L.elems(3 * c * 9 * c, dtype); pb.qkv_bt = L.f32(9 * 3 * c);
+  }
   if (variant == RF_VARIANT_ML) {
     pb.gate_w = L.f32(8); pb.gate_b = L.f32(4); pb.cgate = L.f32(2);
     pb.res_w0 = L.elems(c * c, dtype); pb.res_b0 = L.f32(c);
@@ -155,6 +159,10 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
   copy_f32(ctx, w.reduce_b, pb.red_b, C);
   pack_conv3(ctx, w.convout_w, pb.convout_w, C, C);
   copy_f32(ctx, w.convout_b, pb.convout_b, C);
+  if (pb.ffn_cw != nullptr) {
+    launch_pack_lnconv(ctx, w.pw1_w, w.norm2_w, w.norm2_b, w.pw1_b, w.ffn_dw_w, w.ffn_dw_b, pb.ffn_cw, pb.ffn_bt, 2 * C, C);
+    launch_pack_lnconv(ctx, w.qkv_w, w.norm1_w, w.norm1_b, w.qkv_b, w.qkv_dw_w, w.qkv_dw_b, pb.qkv_cw, pb.qkv_bt, 3 * C, C);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,8 +268,10 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
-  void* qkv = A.elems((size_t)B * P * 3 * C, ctx.dtype);
-  {
+  // norm1 -> qkv -> qkv_dwconv as one dense 3x3 conv on the tensor cores with the Gram / norms / v epilogue (rf_lnconv.cu)
+  const bool conv_qkv = ln != nullptr && ln->npart == 1 && pb.qkv_cw != nullptr && lnconv_supported(ctx, C, H, W);
+  void* qkv = conv_qkv ? nullptr : A.elems((size_t)B * P * 3 * C, ctx.dtype);
+  if (!conv_qkv) {
     GemmP gq = gemm_rows(xin, C, ln ? pb.qkv_wf : pb.qkv_w, ln ? pb.qkv_bf : pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV);
     if (ln) { gq.ln_stats = ln->stats; gq.ln_npart = ln->npart; gq.ln_cs = pb.qkv_cs; gq.ln_C = C; gq.ln_eps = 1e-5f; }
     launch_gemm(ctx, gq);
@@ -284,7 +294,17 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
     // row-tiled forward: the Gram and the norms run over the band's interior rows only, then are summed over the ranks
     const i64 row0 = ctx.band != nullptr ? (i64)ctx.band->ht * W : 0;
     const i64 Pg = ctx.band != nullptr ? (i64)ctx.band->rows_in * W : P;
-    if (qk_gram_supported(ctx, C)) {
+    if (conv_qkv) {
+      float* sq_part = A.get<float>((size_t)sq_cap * 2 * C);
+      if (!ctx.dry) {
+        for (int b = 0; b < B; ++b) {
+          const int ns = launch_lnconv_qkv(ctx, (const char*)xin + (size_t)b * P * C * 2, ln->stats + (size_t)b * P * 2, pb.qkv_cw,
+                                           pb.qkv_bt, (char*)vbuf + (size_t)b * P * C * 2, gram_part, sq_part, H, W, C, sq_cap);
+          if (ns <= 0) recorder().last_cuda_error = (int)cudaErrorNotSupported;
+          launch_attn_reduce(ctx, gram_part, ns, sq_part, ns, stats + b * nst, sumsq + (size_t)b * 2 * C, C);
+        }
+      }
+    } else if (qk_gram_supported(ctx, C)) {
       // q|k depthwise + Gram + norms in one kernel per image (q|k never reach HBM); v by the plain depthwise kernel
       float* sq_part = A.get<float>((size_t)sq_cap * 2 * C);
       if (!ctx.dry) {
@@ -342,6 +362,14 @@ static void ffn(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* re
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   // one kernel for the whole FFN (hidden tensor in shared / tensor memory) where the shape allows
+  // norm2 -> pointwise1 -> depthwise as one dense 3x3 conv on the tensor cores, GELU + pointwise2 + residual in its
+  // epilogues (rf_lnconv.cu)
+  if (ln != nullptr && xin == resid && ln->npart == 1 && pb.ffn_cw != nullptr && lnconv_supported(ctx, C, H, W)) {
+    if (ctx.dry) return;
+    if (!launch_lnconv_ffn(ctx, xin, ln->stats, pb.ffn_cw, pb.ffn_bt, pb.pw2_w, pb.pw2_b, out, B, H, W, C))
+      recorder().last_cuda_error = (int)cudaErrorNotSupported;
+    return;
+  }
   if (ln != nullptr && xin == resid && ffn_fused_supported(ctx, C, W) && ln->npart == 1) {
     if (ctx.dry) return;
     if (launch_ffn_fused(ctx, xin, pb.pw1_wf, pb.pw1_cs, pb.pw1_bf, ln->stats, ln->npart, pb.ffn_dw_w, pb.ffn_dw_b, pb.pw2_w,
