@@ -20,6 +20,8 @@ from .modules_ml import RawFormer as RawFormerMultiLevel
 from .extras import (BiasFree_LayerNorm, FeedForward, WFBLayerNorm, WithBias_LayerNorm, correct_rgb_u8, postprocess_rgb_u8, postprocess_u8, preprocess_u16, psnr_u8,
                      ssim_u8)
 from . import truecolor
+from . import wfb
+from .wfb import FEB, FFAB, WMB, Illumination_Estimator, ProcessBlock
 from .pipeline import FramePipeline
 from .rowtiled import LocalBands, RowTiledRawFormer, plan_bands
 from .wavelets import DWT, IWT, CustomDWT, CustomIDWT, dwt_init, iwt_init

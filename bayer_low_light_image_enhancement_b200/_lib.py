@@ -127,6 +127,16 @@ _SIGS = {
     "rf_correct_rgb_u8": (_i, [_fp, C.POINTER(_i), _i, _i, _i, _i, _fp, _sz, _fp]),
     "rf_sse_u8": (_i, [_fp, _fp, _fp, _i, C.c_longlong, _fp]),
     "rf_ssim_u8": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp]),
+    "rf_dft2_plan_floats": (_sz, [_i, _i]),
+    "rf_dft2_plan_init": (_i, [_fp, _i, _i, _fp]),
+    "rf_rfft2_ortho": (_i, [_fp, _fp, _fp, _fp, C.c_longlong, _i, _i, _fp]),
+    "rf_irfft2_ortho": (_i, [_fp, _fp, _fp, _fp, C.c_longlong, _i, _i, _fp]),
+    "rf_spec_abs_angle": (_i, [_fp, _fp, _fp, C.c_longlong, _i, _i, _fp]),
+    "rf_spec_polar": (_i, [_fp, _fp, _fp, C.c_longlong, _i, _i, _fp]),
+    "rf_conv1x1_nchw": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _i, _f, _f, _i, C.c_longlong, _fp]),
+    "rf_add_clamp": (_i, [_fp, _fp, _fp, _f, C.c_longlong, _fp]),
+    "rf_channel_mean": (_i, [_fp, _fp, _i, _i, C.c_longlong, _fp]),
+    "rf_dwconv5x5_nchw": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp]),
 }
 
 

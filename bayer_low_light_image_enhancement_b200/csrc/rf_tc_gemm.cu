@@ -265,7 +265,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp walks the tile / k-block loops (warp-uniform control flow and descriptor arithmetic, which the compiler
+    // keeps on the uniform datapath) and ONE elected lane issues the tcgen05 instructions.  Under a plain `lane == 0` branch
+    // every tcgen05.mma was wrapped in a loop over the active lanes with vector -> uniform register moves: ~20 instructions
+    // per MMA on a thread that shares its scheduler with busy epilogue warps (measured in rf_lnconv.cu: 95-135 cycles per MMA
+    // instead of the tensor pipe's 59).
+    {
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+      const bool leader = elected != 0;
+      auto umma_f16 = [&](uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc_, uint32_t accumulate) {
+        if (leader) rf::umma_f16(d_tmem, adesc, bdesc, idesc_, accumulate);
+      };
+      auto umma_commit = [&](uint32_t bar) {
+        if (leader) rf::umma_commit(bar);
+      };
       const uint32_t idesc = make_idesc(p.BN);
       int s = 0, wrap = 0, ti = 0;
       if (HALO) {
@@ -281,12 +295,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
           for (int kk = 0; kk < ksteps; ++kk, ++i) {
             const uint64_t ad = dbase0 | (uint64_t)(uint32_t)((dy * p.pitch + dx) + 2 * kk * p.npix);
             const uint64_t bd = wdesc0 + (uint64_t)((tap * p.kb1 + kk / kpb) * wstep + 2u * (kk % kpb));
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sDesc + (uint32_t)i * 16u), "r"((uint32_t)ad),
-                         "r"((uint32_t)(ad >> 32)), "r"((uint32_t)bd), "r"((uint32_t)(bd >> 32))
-                         : "memory");
+            if (leader)
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sDesc + (uint32_t)i * 16u), "r"((uint32_t)ad),
+                           "r"((uint32_t)(ad >> 32)), "r"((uint32_t)bd), "r"((uint32_t)(bd >> 32))
+                           : "memory");
           }
         }
       }
+      __syncwarp();
       if (p.w_resident) {
         mbar_wait(wres_bar, 0);
         tc_fence_after();

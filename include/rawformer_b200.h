@@ -237,6 +237,37 @@ int rf_color_correction(const float* x, float gamma, int variant, const float* w
                         int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * WFB "WMB" block pieces -- RawFomer_WFB_FFAB/blocks.py:11-92 (FEB / ProcessBlock / FFAB: rFFT amplitude /
+ * phase blocks) and RawFomer_WFB_FFAB/model.py:174-200 (Illumination_Estimator).  fp32 NCHW; the module mirrors in wfb.py
+ * compose these calls exactly as the reference's forward does.  (WM = mamba_ssm.Mamba is third-party and not built.)
+ * ---------------------------------------------------------------------------------------------- */
+/* torch.fft.rfft2 / irfft2 (norm='ortho') of [BC,H,W] real planes, any H, W, as dense DFT matrix products in fp32.
+ * plan: rf_dft2_plan_floats(H, W) floats, filled once per (H, W) by rf_dft2_plan_init (twiddles made in double precision
+ * on the device).  spec / tmp: [BC][2][H][W/2+1] floats (real plane, imaginary plane); tmp is scratch of the same size. */
+size_t rf_dft2_plan_floats(int H, int W);
+int rf_dft2_plan_init(float* plan, int H, int W, void* stream);
+int rf_rfft2_ortho(const float* x, const float* plan, float* spec, float* tmp, long long BC, int H, int W, void* stream);
+/* ignores the imaginary parts of the DC / Nyquist bins like torch.fft.irfft2(s=(H, W)) (blocks.py:35) */
+int rf_irfft2_ortho(const float* spec, const float* plan, float* out, float* tmp, long long BC, int H, int W, void* stream);
+/* blocks.py:28-29: mag = |z| + 1e-6, pha = angle(z), both [BC][H*(W/2+1)]; the four self-conjugate bins take imag = +0 */
+int rf_spec_abs_angle(const float* spec, float* mag, float* pha, long long BC, int H, int W, void* stream);
+/* blocks.py:32-34: spec = (mag cos pha, mag sin pha) */
+int rf_spec_polar(const float* mag, const float* pha, float* spec, long long BC, int H, int W, void* stream);
+/* nn.Conv2d(Cin + Cin2, Cout, 1) on [B,C,P] planes (weight [Cout][Cin + Cin2]; in2 = the second half of a torch.cat, may
+ * be NULL with Cin2 = 0): out = clamp(act(W clamp(in, +-in_clamp) + bias), out_lo, out_hi) + resid.  in_clamp <= 0: no
+ * input clamp; act: 0 none, 1 LeakyReLU(0.1); out_lo >= out_hi: no output clamp; bias / resid may be NULL. */
+int rf_conv1x1_nchw(const float* in, const float* in2, const float* weight, const float* bias, const float* resid, float* out,
+                    int Cin, int Cin2, int Cout, float in_clamp, int act, float out_lo, float out_hi, int B, long long P,
+                    void* stream);
+/* blocks.py:24,36-37: out = clamp(a + clamp(b, -lim, lim), -lim, lim), n elements */
+int rf_add_clamp(const float* a, const float* b, float* out, float lim, long long n, void* stream);
+/* model.py:192: mean over the channels, in [B,C,P] -> out [B,1,P] */
+int rf_channel_mean(const float* in, float* out, int B, int C, long long P, void* stream);
+/* model.py:181-182: nn.Conv2d(C, C, 5, padding=2, groups=C), weight [C,1,5,5] */
+int rf_dwconv5x5_nchw(const float* in, const float* weight, const float* bias, float* out, int B, int C, int H, int W,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole model — RawFormer.forward, FLCA_RF.py:330-370 (variant ML: ML_RF.py:356-416)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rf_model_weights {

@@ -608,3 +608,83 @@ def ssim_u8(a, b, win_size=7, K1=0.01, K2=0.03):
         S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
         vals.append(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
     return float(np.mean(vals))
+
+
+# ----------------------------------------------------------------------------------------------
+# WFB "WMB" block pieces: FEB / ProcessBlock / FFAB (WFB/blocks.py:11-92),
+# Illumination_Estimator (WFB/model.py:174-200).  Pinned to tests/golden/wfb.npz (reference classes executed on CPU).
+# ----------------------------------------------------------------------------------------------
+def feb(sd, x):
+    """FEB.forward, WFB/blocks.py:23-39."""
+    dt = x.dtype
+    H, W = x.shape[-2:]
+    x = np.clip(x, -10, 10).astype(dt)                                              # :25
+    pre = conv1x1(x, sd["fpre.weight"], sd["fpre.bias"])
+    x_freq = np.fft.rfft2(pre, norm="ortho")                                        # :27
+    # The four self-conjugate bins of a real input (k in {0, H/2}, f in {0, W/2}) are real.  torch's CPU FFT (MKL) returns
+    # imag = +0 there (checked against the goldens); pocketfft leaves a rounding residue of either sign, which would flip the
+    # phase of a negative real bin between +pi and -pi.
+    ks = [0] + ([H // 2] if H % 2 == 0 else [])
+    fs = [0] + ([W // 2] if W % 2 == 0 else [])
+    for k in ks:
+        for f in fs:
+            x_freq[..., k, f] = x_freq[..., k, f].real
+    mag = (np.abs(x_freq) + 1e-6).astype(dt)                                        # :28
+    pha = np.angle(x_freq).astype(dt)                                               # :29
+
+    def process(t, p):
+        t = conv1x1(t, sd[p + ".0.weight"], sd[p + ".0.bias"])
+        t = leaky_relu(t, 0.1)
+        return conv1x1(t, sd[p + ".2.weight"], sd[p + ".2.bias"])
+
+    mag = np.clip(process(mag, "process1"), 0, 1e4).astype(dt)                      # :30
+    pha = process(pha, "process2")                                                  # :31
+    z = (mag * np.cos(pha)) + 1j * (mag * np.sin(pha))                              # :32-34
+    y = np.fft.irfft2(z, s=(H, W), norm="ortho").astype(dt)                         # :35
+    return np.clip(y + x, -10, 10).astype(dt)                                       # :36-37
+
+
+def process_block(sd, x):
+    """ProcessBlock.forward, WFB/blocks.py:48-56."""
+    xf = feb(_sd(sd, "frequency_process."), x)
+    return conv1x1(xf, sd["cat.weight"], sd["cat.bias"]) + x
+
+
+def ffab(sd, x):
+    """FFAB.forward, WFB/blocks.py:83-92."""
+    def tail(p, a, b):
+        t = process_block(_sd(sd, p + ".0."), np.concatenate((a, b), 1))
+        return conv1x1(t, sd[p + ".1.weight"], sd[p + ".1.bias"])
+
+    x = process_block(_sd(sd, "conv0.1."), conv1x1(x, sd["conv0.0.weight"], sd["conv0.0.bias"]))
+    x1 = process_block(_sd(sd, "conv1."), x)
+    x2 = process_block(_sd(sd, "conv2."), x1)
+    x3 = process_block(_sd(sd, "conv3."), x2)
+    x4 = tail("conv4", x2, x3)
+    x5 = tail("conv5", x1, x4)
+    return tail("convout", x, x5)
+
+
+def dwconv5x5(x, w, b=None):
+    """nn.Conv2d(C, C, 5, padding=2, groups=C).  w [C,1,5,5]."""
+    B, C, H, W = x.shape
+    xp = np.zeros((B, C, H + 4, W + 4), x.dtype)
+    xp[:, :, 2:-2, 2:-2] = x
+    y = np.zeros_like(x)
+    w = w.astype(x.dtype)
+    for dy in range(5):
+        for dx in range(5):
+            y += xp[:, :, dy:dy + H, dx:dx + W] * w[None, :, 0, dy, dx, None, None]
+    if b is not None:
+        y = y + b.astype(x.dtype)[None, :, None, None]
+    return y
+
+
+def illumination_estimator(sd, img):
+    """Illumination_Estimator.forward, WFB/model.py:185-200 -> (illu_fea, illu_map)."""
+    mean_c = img.mean(axis=1, keepdims=True).astype(img.dtype)
+    inp = np.concatenate((img, mean_c), 1)
+    x1 = conv1x1(inp, sd["conv1.weight"], sd["conv1.bias"])
+    illu_fea = dwconv5x5(x1, sd["depth_conv.weight"], sd["depth_conv.bias"])
+    illu_map = conv1x1(illu_fea, sd["conv2.weight"], sd["conv2.bias"])
+    return illu_fea, illu_map

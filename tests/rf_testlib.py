@@ -194,3 +194,35 @@ def truecolor_input(kind, shape, seed):
     if kind == "tail":                      # exercise both clamps of the tail: values below 0 and above 1
         x = x * 1.4 - 0.2
     return x.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# WFB "WMB" block pieces: name, kind, channels, input shape, seed, weight scale
+# ---------------------------------------------------------------------------------------------------
+WFB_CASES = [
+    ("wfb_feb_c8_even", "feb", 8, (2, 8, 12, 20), 50, 1.5),
+    ("wfb_feb_c4_odd", "feb", 4, (1, 4, 9, 15), 51, 1.5),
+    ("wfb_pb_c8", "pb", 8, (1, 8, 10, 14), 52, 1.5),
+    ("wfb_ffab_c8", "ffab", 8, (2, 8, 12, 18), 53, 1.0),
+    ("wfb_ffab_c32", "ffab", 32, (1, 32, 16, 24), 54, 1.0),
+    ("wfb_illu_c16", "illu", 16, (2, 16, 11, 13), 55, 1.5),
+]
+
+
+def build_wfb(kind, c):
+    import bayer_low_light_image_enhancement_b200 as rf
+
+    if kind == "feb":
+        return rf.FEB(c)
+    if kind == "pb":
+        return rf.ProcessBlock(c)
+    if kind == "ffab":
+        return rf.FFAB(c)
+    return rf.Illumination_Estimator(c, n_fea_in=c + 1, n_fea_out=c)
+
+
+def wfb_input(kind, shape, seed):
+    x = gen_input("randn", shape, seed)
+    if kind == "feb":
+        x = x * 4.0            # a few values beyond the +-10 input clamp
+    return x.astype(np.float32)
