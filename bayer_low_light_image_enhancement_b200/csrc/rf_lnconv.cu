@@ -45,12 +45,19 @@ constexpr int LC_NPIX = 180;                // (16 + 2) x (8 + 2) patch pixels, 
 constexpr int LC_NT = 3;                    // re-laid-out patch buffers
 constexpr int LC_MAXR = 5;                  // raw patch buffers (FFN: a patch lives until its tile's residual add)
 constexpr uint32_t LC_ST_BYTES = 18 * 12 * 8, LC_ST_STRIDE = 1792;
-enum { LC_FFN = 0, LC_QKV = 1 };
+// FFN: GELU + pointwise2 + residual epilogues (C = 64: one half of the 2C hidden channels per launch); QKV (C = 32): q|k -> Gram,
+// v -> global; QK / V (C = 64): the same split over three launches (q|k of heads 0-3, of heads 4-7, v): 9 taps of 64 output
+// channels are all the weights that fit next to the patches in shared memory
+enum { LC_FFN = 0, LC_QKV = 1, LC_QK = 2, LC_V = 3 };
 
 struct LcP {
-  const float* btab;     // [9][N] bias by border state (3 * row state + column state; state 0 = first, 1 = inner, 2 = last)
-  const float* b2;       // FFN: [C] pointwise2 bias
-  bf16* out;             // FFN: out [B,H,W,C]; QKV: v [B,H,W,C]
+  const float* btab;     // [9][n_tab] bias by border state (3 * row state + column state; state 0 = first, 1 = inner, 2 = last)
+  const float* b2;       // FFN: [C] pointwise2 bias (NULL: none -- second half of the hidden channels)
+  const bf16* resid;     // FFN, C = 64: residual [B,H,W,C] read from global memory (C = 32: the patch's own centre pixels)
+  bf16* out;             // FFN: out [B,H,W,C]; QKV / V: v [B,H,W,C]
+  int n_tab;             // channels of the whole conv (pitch of btab)
+  int t0, t1, tn;        // this launch computes conv channels [t0, t0 + tn) and, if tn < N, [t1, t1 + tn)
+  int ch0;               // QKV / QK: first q (= k) channel of this launch
   float* gram_part;      // QKV: [slot][C][C/8] per-head diagonal blocks of q^T k of the CTA's pixels
   float* sq_part;        // QKV: [slot][2C]
   float invC, eps;
@@ -64,7 +71,10 @@ struct LcP {
 
 template <int MODE, int C>
 struct LcCfg {
-  static constexpr int N = MODE == LC_FFN ? 2 * C : 3 * C;
+  static constexpr int N = MODE == LC_QKV ? 3 * C : 64;          // conv output channels per launch
+  static constexpr int GU = MODE == LC_V ? 0 : (MODE == LC_QKV ? 2 * C / 8 : N / 8);   // 8-channel units that go to the g tile
+  static constexpr bool SECOND = MODE != LC_V;                   // a second contraction follows (pointwise2 / Gram)
+  static constexpr bool RES_RAW = C == 32;                       // FFN residual from the patch (else from global memory)
   static constexpr int NCH = C / 8;                              // 16-byte units per pixel
   static constexpr int LBO_PX = 184;                             // chunk pitch in pixels (a multiple of 128 bytes)
   static constexpr uint32_t LBO = LBO_PX * 16;
@@ -77,7 +87,7 @@ struct LcCfg {
   static constexpr uint32_t G_BYTES = 16384;                     // 128 pixels x 128 B
   static constexpr int ACC1_STRIDE = N <= 64 ? 64 : 128;         // two accumulators of the first contraction
   static constexpr int ACC3_COL = 2 * ACC1_STRIDE;               // FFN: the [128 x C] pointwise2 accumulator; QKV: the Gram
-  static constexpr int TMEM_COLS = MODE == LC_FFN ? 256 : 512;
+  static constexpr int TMEM_COLS = N <= 64 ? 256 : 512;
   static constexpr int UPW = N / 8 / 4;                          // 8-column units per compute warp in the first epilogue
   static constexpr uint32_t BT_BYTES = 9 * N * 4;
   static constexpr size_t smem(int nr) {
@@ -106,6 +116,18 @@ __device__ __forceinline__ void lc_sts128(uint32_t addr, uint32_t a, uint32_t b,
 __device__ __forceinline__ uint32_t lc_pack(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// 32-byte global accesses (sm_100: 256-bit vector ld / st): a thread's two adjacent 16-byte units of a pixel as ONE full
+// 32-byte sector per lane instead of two half-sector instructions
+__device__ __forceinline__ void lc_ldg256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
+__device__ __forceinline__ void lc_stg256(void* ptr, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
+               "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+               : "memory");
 }
 // MN-major SWIZZLE_128B operand (the Gram reads the g tile with pixels as the contraction axis), see rf_qk_gram.cu
 __device__ __forceinline__ uint64_t lc_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -189,7 +211,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (MODE == LC_QKV) {
+  if (MODE == LC_QKV || MODE == LC_QK) {
     for (uint32_t o = (uint32_t)tid * 16u; o < 2048u; o += LC_THREADS * 16u) lc_sts128(sZ + o, 0u, 0u, 0u, 0u);
     fence_proxy_async();
   }
@@ -202,10 +224,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   pdl_wait();
   {
     float* bt = reinterpret_cast<float*>(smem_raw + (sBT - smem_u32(smem_raw)));
-    for (int i = tid; i < 9 * N; i += LC_THREADS) bt[i] = __ldg(p.btab + i);
+    for (int i = tid; i < 9 * N; i += LC_THREADS) {
+      const int idx = i / N, j = i - idx * N;
+      bt[i] = __ldg(p.btab + idx * p.n_tab + (j < p.tn ? p.t0 + j : p.t1 + j - p.tn));
+    }
     if (MODE == LC_FFN) {
       float* b2 = reinterpret_cast<float*>(smem_raw + (sB2 - smem_u32(smem_raw)));
-      for (int i = tid; i < C; i += LC_THREADS) b2[i] = __ldg(p.b2 + i);
+      for (int i = tid; i < C; i += LC_THREADS) b2[i] = p.b2 ? __ldg(p.b2 + i) : 0.f;
     }
   }
   __syncthreads();
@@ -236,8 +261,11 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     // ================= TMA producer =================
     if (lane == 0 && n > 0) {
       mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES);
-      for (int tap = 0; tap < 9; ++tap) tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, 0);
-      if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, 0, 0, 0);
+      for (int tap = 0; tap < 9; ++tap) {
+        tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, p.t0);
+        if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * C * 2, &mapW, w_full, 0, tap, p.t1);
+      }
+      if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, p.t0, 0, 0);     // pointwise2 columns of these hidden channels
       int rb = 0;
       uint32_t rph = 0;
       TileIter tl = tile_first();
@@ -277,7 +305,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const int s = i & 1;
         mbar_wait(t_full(tb), tph);
         if (i >= 2) mbar_wait(drained(s), (uint32_t)(((i >> 1) + 1) & 1));   // tile i-2's accumulator is in registers
-        if (p.sched == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
+        if ((p.sched & 7) == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
         tc_fence_after();
         if (DBG) t_issue = clock64();
         if (leader) {
@@ -306,13 +334,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       } else {
         mma1(0);
       }
-      if (p.sched == 0 && n > 1) mma1(1);
+      if ((p.sched & 7) == 0 && n > 1) mma1(1);
       const uint32_t idesc3 = make_idesc_m128(C);
-      // Gram: kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (rows 2C.. are zeros), N = 2C
-      const uint32_t idescg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(2 * C >> 3) << 17) | ((128u >> 4) << 24);
+      // Gram: kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (rows 64.. are zeros), N = 64 (32 q | 32 k)
+      const uint32_t idescg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t gdesc = make_sw128_desc(sG), w2desc = make_sw128_desc(sW2);
       for (int i = 0; i < n; ++i) {
-        if (p.sched == 1 && i + 1 < n) {
+        if ((p.sched & 7) == 1 && i + 1 < n) {
           if (DBG && i == 8) {
             mma1(i + 1);
             mbar_wait(mma1_done((i + 1) & 1), (uint32_t)(((i + 1) >> 1) & 1));
@@ -321,9 +349,11 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             mma1(i + 1);
           }
         }
-        mbar_wait(g_full, (uint32_t)(i & 1));
-        tc_fence_after();
-        if (leader) {
+        if (K::SECOND) {
+          mbar_wait(g_full, (uint32_t)(i & 1));
+          tc_fence_after();
+        }
+        if (K::SECOND && leader) {
           if (MODE == LC_FFN) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -342,7 +372,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           umma_commit(mma2_done);
         }
         __syncwarp();
-        if (p.sched == 0 && i + 2 < n) mma1(i + 2);
+        if ((p.sched & 7) == 0 && i + 2 < n) mma1(i + 2);
       }
     }
   } else {
@@ -352,7 +382,10 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     const int r = q * 32 + lane;                         // accumulator row = tile pixel
     const int ty = r >> 3, tx = r & 7;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int UB = MODE == LC_FFN ? C / 8 / 4 : 1;   // 8-column units of acc3 per warp (FFN)
+    // second epilogue (FFN): C/32 adjacent 8-column units of acc3 per warp; at C = 64 a pixel's piece is one full 32-byte
+    // sector (256-bit global accesses).  (C = 32 with two units on two of a quadrant's four warps: slower, 252 vs 230 us.)
+    constexpr int UB = C / 32;
+    constexpr bool eb_on = true;
     long long tph[DBG ? 8 : 1] = {0}, tlast = DBG ? clock64() : 0;
     auto mark = [&](int k) {
       if (DBG && ctid == 0) {
@@ -392,7 +425,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
         uint4 v[K::NCH];
 #pragma unroll
-        for (int k = 0; k < K::NCH; ++k) v[k] = lc_lds128(src + (uint32_t)((k ^ ((px >> 1) & 3)) * 16));
+        for (int k = 0; k < K::NCH; ++k) v[k] = lc_lds128(src + (uint32_t)((k ^ (C == 32 ? (px >> 1) & 3 : px & 7)) * 16));
 #pragma unroll
         for (int k = 0; k < K::NCH; ++k) {
           const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
@@ -408,7 +441,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       }
       fence_proxy_async();                                 // generic stores -> tensor-core (async proxy) reads
       warp_arrive(t_full(rl_tb));
-      if (MODE == LC_QKV && lane == 0) mbar_arrive(raw_free(rl_rb));   // (FFN: the patch stays for the residual add)
+      if (!(MODE == LC_FFN && K::RES_RAW) && lane == 0) mbar_arrive(raw_free(rl_rb));   // (else it stays for the residual add)
       if (++rl_rb == p.nr) { rl_rb = 0; rl_rph ^= 1u; }
       if (++rl_tb == LC_NT) rl_tb = 0;
       rl_rot = (rl_rot + 192) & (LC_CT - 1);
@@ -418,31 +451,49 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     // ---- FFN: second epilogue of the tile before: acc3 (in v3) + bias + residual -> bf16 -> global ----
     TileIter ta = tile_first(), tb2 = ta;
     int eb_rb = 0;
+    // (C = 64) the residual of the tile tb2 points at, from global memory: requested one tile before its use (a load issued
+    // in the same step would expose its full latency in every warp)
+    uint4 rres[UB];
+    auto res_prefetch = [&]() {
+      const int y = tb2.ty * 16 + ty, x = tb2.tx * 8 + tx, b = tb2.b;
+#pragma unroll
+      for (int t = 0; t < UB; ++t) rres[t] = make_uint4(0u, 0u, 0u, 0u);
+      if (y < p.H && x < p.W) {
+        const bf16* src = p.resid + ((((i64)b * p.H + y) * p.W + x) * C + wi * UB * 8);
+        if (UB == 2) lc_ldg256(src, rres[0], rres[UB - 1]);
+        else rres[0] = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+    };
     auto epi_b = [&](uint32_t (&v3)[UB][8]) {
       const int y = tb2.ty * 16 + ty, x = tb2.tx * 8 + tx, b = tb2.b;
       tile_next(tb2);
+      uint32_t ob[UB][4];
 #pragma unroll
       for (int t = 0; t < UB; ++t) {
+        if (!eb_on) break;
         const int u = wi * UB + t;
         const int pr = (ty + 1) * 10 + tx + 1;
-        const uint4 res = lc_lds128(sRaw + (uint32_t)eb_rb * K::RAW_STRIDE + (uint32_t)(pr * C * 2 + ((u ^ ((pr >> 1) & 3)) << 4)));
+        uint4 res = rres[t];
+        if (K::RES_RAW) res = lc_lds128(sRaw + (uint32_t)eb_rb * K::RAW_STRIDE + (uint32_t)(pr * C * 2 + ((u ^ ((pr >> 1) & 3)) << 4)));
         const float4 b0 = lc_lds128f(sB2 + (uint32_t)u * 32u), b1 = lc_lds128f(sB2 + (uint32_t)u * 32u + 16u);
         const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
-        uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float f0 = __uint_as_float(v3[t][2 * e]) + bias[2 * e] + __uint_as_float(rw[e] << 16);
           const float f1 = __uint_as_float(v3[t][2 * e + 1]) + bias[2 * e + 1] + __uint_as_float(rw[e] & 0xffff0000u);
-          o[e] = lc_pack(f0, f1);
-        }
-        if (y < p.H && x < p.W) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + ((((i64)b * p.H + y) * p.W + x) * C + u * 8));
-          *dst = make_uint4(o[0], o[1], o[2], o[3]);
+          ob[t][e] = lc_pack(f0, f1);
         }
       }
-      warp_arrive(raw_free(eb_rb));
-      if (++eb_rb == p.nr) eb_rb = 0;
+      if (y < p.H && x < p.W) {
+        bf16* dst = p.out + ((((i64)b * p.H + y) * p.W + x) * C + wi * UB * 8);
+        if (UB == 2) lc_stg256(dst, ob[0], ob[UB - 1]);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(ob[0][0], ob[0][1], ob[0][2], ob[0][3]);
+      }
+      if (K::RES_RAW) {
+        warp_arrive(raw_free(eb_rb));
+        if (++eb_rb == p.nr) eb_rb = 0;
+      }
     };
 
     if (n > 0) relayout();
@@ -452,13 +503,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       mark(0);
       lc_warp_wait(mma1_done(i & 1), (uint32_t)((i >> 1) & 1), lane);
       mark(1);
-      if (i >= 1) lc_warp_wait(mma2_done, (uint32_t)((i - 1) & 1), lane);
+      if (K::SECOND && i >= 1) lc_warp_wait(mma2_done, (uint32_t)((i - 1) & 1), lane);
       tc_fence_after();
       mark(2);
       uint32_t v[K::UPW][8], v3[UB][8];
 #pragma unroll
       for (int t = 0; t < K::UPW; ++t) tmem_ld8(tq + (uint32_t)((i & 1) * K::ACC1_STRIDE + (wi * K::UPW + t) * 8), v[t]);
-      if (MODE == LC_FFN && i >= 1) {
+      if (MODE == LC_FFN && i >= 1 && eb_on) {
 #pragma unroll
         for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
       }
@@ -468,6 +519,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       mark(3);
       // ---- B: epilogues on registers ----
       if (MODE == LC_FFN && i >= 1) epi_b(v3);
+      if (MODE == LC_FFN && !K::RES_RAW) res_prefetch();     // tile i's residual: a whole tile ahead of its use
       const int y = ta.ty * 16 + ty, x = ta.tx * 8 + tx, b = ta.b;
       tile_next(ta);
       const int rs_ = y == 0 ? 0 : (y == p.H - 1 ? 2 : 1), cs_ = x == 0 ? 0 : (x == p.W - 1 ? 2 : 1);
@@ -475,6 +527,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       const bool inside = y < p.H && x < p.W;
       const bool counts = inside && y >= p.ylo && y < p.yhi;
       const uint32_t grow = sG + (uint32_t)r * 128u;
+      uint32_t ov[K::UPW][4];
 #pragma unroll
       for (int t = 0; t < K::UPW; ++t) {
         const int u = wi * K::UPW + t;
@@ -494,43 +547,54 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[e] = lc_pack(h[e].x, h[e].y);
-          if (u < 2 * C / 8) {                              // q|k: pixels that do not count contribute exact zeros
+          if (u < K::GU) {                                  // q|k: pixels that do not count contribute exact zeros
             if (!counts) o[0] = o[1] = o[2] = o[3] = 0u;
             lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
+          } else if (MODE == LC_V) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ov[t][e] = o[e];
           } else if (inside) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + ((((i64)b * p.H + y) * p.W + x) * C + (u - 2 * C / 8) * 8));
+            uint4* dst = reinterpret_cast<uint4*>(p.out + ((((i64)b * p.H + y) * p.W + x) * C + (u - K::GU) * 8));
             *dst = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
-      fence_proxy_async();
-      warp_arrive(g_full);
+      if (MODE == LC_V && inside)                           // this warp's two adjacent units of v: one 32-byte store per pixel
+        lc_stg256(p.out + ((((i64)b * p.H + y) * p.W + x) * C + wi * K::UPW * 8), ov[0], ov[K::UPW - 1]);
+      if (K::SECOND) {
+        fence_proxy_async();
+        warp_arrive(g_full);
+      }
       mark(4);
       // ---- C: the patch two tiles ahead ----
       if (i + 2 < n) relayout();
     }
-    if (n > 0) {
+    if (K::SECOND && n > 0) {
       lc_warp_wait(mma2_done, (uint32_t)((n - 1) & 1), lane);
       tc_fence_after();
     }
     if (MODE == LC_FFN && n > 0) {
       uint32_t v3[UB][8];
 #pragma unroll
-      for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
+      if (eb_on) {
+#pragma unroll
+        for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
+      }
       tmem_ld_wait();
       epi_b(v3);
     }
     if (DBG && ctid == 0)
       for (int k = 0; k < 8; ++k) p.dbg[blockIdx.x * 8 + k] = (unsigned long long)tph[DBG ? k : 0];
 
-    // ---- QKV read-out: per-head diagonal blocks of q^T k and the squared norms -> this CTA's slot ----
-    if (MODE == LC_QKV && wi == 0) {
-      constexpr int c = C >> 3;
-      const int row = r;                               // accumulator row = channel of [q|k]
+    // ---- QKV / QK read-out: per-head diagonal blocks of q^T k and the squared norms -> this CTA's slot ----
+    // accumulator rows / columns 0..31 = q channels ch0.., 32..63 = k channels ch0..; a head has c = C/8 channels
+    if ((MODE == LC_QKV || MODE == LC_QK) && wi == 0) {
+      constexpr int c = C >> 3, NQ = 32;
+      const int row = r;
       float* gp = p.gram_part + (i64)blockIdx.x * C * c;
       float* sp = p.sq_part + (i64)blockIdx.x * 2 * C;
-      const int h = row < C ? row / c : -1;
-      for (int cc = 0; cc < 2 * C; cc += 16) {
+      const int h = row < NQ ? row / c : -1;           // head of this q row (local to the launch)
+      for (int cc = 0; cc < 2 * NQ; cc += 16) {
         uint32_t v[16];
         if (n > 0) {
           tmem_ld16(tq + (uint32_t)(K::ACC3_COL + cc), v);
@@ -539,13 +603,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
-        if (row < 2 * C) {
+        if (row < 2 * NQ) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = cc + j;
-            if (col == row) sp[row] = __uint_as_float(v[j]);
-            const int kc = col - C;                    // k channel of this accumulator column
-            if (h >= 0 && kc >= h * c && kc < (h + 1) * c) gp[(i64)row * c + (kc - h * c)] = __uint_as_float(v[j]);
+            if (col == row) sp[row < NQ ? p.ch0 + row : C + p.ch0 + row - NQ] = __uint_as_float(v[j]);
+            const int kc = col - NQ;                   // k channel (local) of this accumulator column
+            if (h >= 0 && kc >= h * c && kc < (h + 1) * c) gp[(i64)(p.ch0 + row) * c + (kc - h * c)] = __uint_as_float(v[j]);
           }
         }
       }
@@ -608,25 +672,37 @@ static bool lnconv_enabled() {
 }
 
 bool lnconv_supported(const Ctx& ctx, int C, int H, int W) {
-  return lnconv_enabled() && tcgen05_enabled() && ctx.dtype == RF_BF16 && C == 32 && (W & 1) == 0 && H >= 2 && W >= 2;
+  static int c64 = -1;                  // debugging aid: RAWFORMER_B200_LNCONV_C64=0 keeps C = 64 on the separate kernels
+  if (c64 < 0) {
+    const char* e = getenv("RAWFORMER_B200_LNCONV_C64");
+    c64 = (e && e[0] == '0') ? 0 : 1;
+  }
+  return lnconv_enabled() && tcgen05_enabled() && ctx.dtype == RF_BF16 && (C == 32 || (C == 64 && c64)) && (W & 1) == 0 && H >= 2 &&
+         W >= 2;
 }
 
+// one launch: conv channels [t0, t0 + tn) (and [t1, t1 + tn) when tn < N) of the n_tab-channel dense conv cw / btab
+struct LcSel {
+  int n_tab, t0, t1, tn, ch0;
+};
 template <int MODE, int C>
-static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const void* W2,
-                         const float* b2, void* out, float* gram_part, float* sq_part, int B, int H, int W, int slot_cap) {
+static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const LcSel& sel,
+                         const void* W2, const float* b2, const void* resid, void* out, float* gram_part, float* sq_part, int B,
+                         int H, int W, int slot_cap) {
   using K = LcCfg<MODE, C>;
   LcP p;
   memset(&p, 0, sizeof(p));
-  p.btab = btab; p.b2 = b2; p.out = (bf16*)out; p.gram_part = gram_part; p.sq_part = sq_part;
+  p.btab = btab; p.b2 = b2; p.resid = (const bf16*)resid; p.out = (bf16*)out; p.gram_part = gram_part; p.sq_part = sq_part;
+  p.n_tab = sel.n_tab; p.t0 = sel.t0; p.t1 = sel.t1; p.tn = sel.tn; p.ch0 = sel.ch0;
   p.invC = 1.0f / (float)C; p.eps = 1e-5f;
   p.H = H; p.W = W; p.B = B;
   p.ylo = 0; p.yhi = H;
-  if (MODE == LC_QKV && ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
+  if ((MODE == LC_QKV || MODE == LC_QK) && ctx.band != nullptr) { p.ylo = ctx.band->ht; p.yhi = ctx.band->ht + ctx.band->rows_in; }
   p.tiles_x = cdiv(W, 8); p.tiles_y = cdiv(H, 16);
   const i64 total = (i64)p.tiles_x * p.tiles_y * B;
   if (total <= 0 || total > 0x7fffffff) return 0;
   p.total_tiles = (int)total;
-  p.nr = MODE == LC_FFN ? LC_MAXR : 3;
+  p.nr = C == 32 ? (MODE == LC_FFN ? LC_MAXR : 3) : 2;
   {
     // measured (RawFormer-S stage 0): FFN 236 us with schedule 1 / 262 us with 0; QKV 273 / 238 us
     static int sched = -1;
@@ -634,7 +710,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
       const char* e = getenv("RAWFORMER_B200_LNCONV_SCHED");
       sched = e ? atoi(e) : 2;
     }
-    p.sched = sched == 2 ? (MODE == LC_FFN ? 1 : 0) : sched;
+    p.sched = (sched & 7) == 2 ? (MODE == LC_FFN ? 1 : 0) | (sched & ~7) : sched;
   }
   const size_t smem = K::smem(p.nr);
   if (smem > 232448) return 0;
@@ -655,9 +731,9 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     if (!make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
   }
   {
-    const i64 d[3] = {C, 9, K::N};
+    const i64 d[3] = {C, 9, sel.n_tab};
     const i64 s[3] = {1, C, (i64)9 * C};
-    const int bx[3] = {C, 1, K::N};
+    const int bx[3] = {C, 1, sel.tn};
     if (!make_map_ex(&mW, cw, 3, d, s, bx, 2, C * 2)) return 0;
   }
   if (MODE == LC_FFN) {
@@ -676,7 +752,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     attr_set = true;
   }
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (MODE == LC_QKV && grid > slot_cap) grid = slot_cap;
+  if ((MODE == LC_QKV || MODE == LC_QK) && grid > slot_cap) grid = slot_cap;
   static int dbg_on = -1;
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_on < 0) {
@@ -713,8 +789,20 @@ bool launch_lnconv_ffn(Ctx& ctx, const void* x, const float* stats, const void* 
                        const float* b2, void* out, int B, int H, int W, int C) {
   if (!lnconv_supported(ctx, C, H, W)) return false;
   const double rows = (double)B * H * W;
-  ScopedLaunch sl(RF_K_FFN_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 2 * C + 2.0 * 2 * C * C));
-  return lnconv_launch<LC_FFN, 32>(ctx, x, stats, cw, btab, W2, b2, out, nullptr, nullptr, B, H, W, 0) > 0;
+  if (C == 32) {
+    ScopedLaunch sl(RF_K_FFN_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 2 * C + 2.0 * 2 * C * C));
+    const LcSel sel{2 * C, 0, 0, 2 * C, 0};
+    return lnconv_launch<LC_FFN, 32>(ctx, x, stats, cw, btab, sel, W2, b2, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
+  }
+  // C = 64: hidden channels 0..63, then 64..127 on top of the first launch's output (its own residual, in place)
+  for (int half = 0; half < 2; ++half) {
+    ScopedLaunch sl(RF_K_FFN_FUSED, rows * C * 2.0 * (half ? 3.0 : 2.0) + rows * 8.0, rows * (2.0 * 9 * C * C + 2.0 * C * C));
+    const LcSel sel{2 * C, 64 * half, 0, 64, 0};
+    if (lnconv_launch<LC_FFN, 64>(ctx, x, stats, cw, btab, sel, W2, half ? nullptr : b2, half ? out : x, out, nullptr, nullptr, B, H,
+                                  W, 0) <= 0)
+      return false;
+  }
+  return true;
 }
 
 // ONE image: v = third part of qkv_dwconv(qkv(norm1(x))); Gram / squared norms of q, k into per-CTA partial slots.
@@ -723,8 +811,28 @@ int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* c
                       float* sq_part, int H, int W, int C, int slot_cap) {
   if (!lnconv_supported(ctx, C, H, W)) return 0;
   const double rows = (double)H * W;
-  ScopedLaunch sl(RF_K_QKV_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 3 * C + 2.0 * (2 * C) * (2 * C)));
-  return lnconv_launch<LC_QKV, 32>(ctx, x, stats, cw, btab, nullptr, nullptr, v, gram_part, sq_part, 1, H, W, slot_cap);
+  if (C == 32) {
+    ScopedLaunch sl(RF_K_QKV_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 3 * C + 2.0 * (2 * C) * (2 * C)));
+    const LcSel sel{3 * C, 0, 0, 3 * C, 0};
+    return lnconv_launch<LC_QKV, 32>(ctx, x, stats, cw, btab, sel, nullptr, nullptr, nullptr, v, gram_part, sq_part, 1, H, W,
+                                     slot_cap);
+  }
+  // C = 64: q|k of heads 0-3, q|k of heads 4-7 (the Gram is block-diagonal over the heads), then v
+  int ns = 0;
+  for (int half = 0; half < 2; ++half) {
+    ScopedLaunch sl(RF_K_QKV_FUSED, rows * C * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 64 + 2.0 * 64 * 64));
+    const LcSel sel{3 * C, 32 * half, C + 32 * half, 32, 32 * half};
+    const int g = lnconv_launch<LC_QK, 64>(ctx, x, stats, cw, btab, sel, nullptr, nullptr, nullptr, nullptr, gram_part, sq_part, 1, H,
+                                           W, slot_cap);
+    if (g <= 0 || (half && g != ns)) return 0;
+    ns = g;
+  }
+  {
+    ScopedLaunch sl(RF_K_QKV_FUSED, rows * C * 2.0 * 2.0 + rows * 8.0, rows * (2.0 * 9 * C * 64));
+    const LcSel sel{3 * C, 2 * C, 0, 64, 0};
+    if (lnconv_launch<LC_V, 64>(ctx, x, stats, cw, btab, sel, nullptr, nullptr, nullptr, v, nullptr, nullptr, 1, H, W, 0) <= 0) return 0;
+  }
+  return ns;
 }
 
 }  // namespace rf
