@@ -234,6 +234,8 @@ bool launch_lnconv_ffn(Ctx& ctx, const void* x, const float* stats, const void* 
 // ONE image: v [H,W,C] + per-CTA partial slots of the Gram / squared norms of q, k (as launch_dwqk_gram); returns the slots
 int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, void* v, float* gram_part,
                       float* sq_part, int H, int W, int C, int slot_cap);
+// Conv_out (C -> C 3x3 + bias + LeakyReLU 0.2) through the same pipeline; w = T [C][9][C]
+bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C);
 // embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
 void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
                   int w_, int d);

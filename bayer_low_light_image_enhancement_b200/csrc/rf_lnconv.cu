@@ -48,14 +48,17 @@ constexpr uint32_t LC_ST_BYTES = 18 * 12 * 8, LC_ST_STRIDE = 1792;
 // FFN: GELU + pointwise2 + residual epilogues (C = 64: one half of the 2C hidden channels per launch); QKV (C = 32): q|k -> Gram,
 // v -> global; QK / V (C = 64): the same split over three launches (q|k of heads 0-3, of heads 4-7, v): 9 taps of 64 output
 // channels are all the weights that fit next to the patches in shared memory
-enum { LC_FFN = 0, LC_QKV = 1, LC_QK = 2, LC_V = 3 };
+// CONV: the block's plain Conv_out 3x3 (C -> C, + bias, LeakyReLU(0.2), FLCA_RF.py:276) through the same pipeline: no
+// LayerNorm in the re-layout, no statistics box, one bias row for all border states
+enum { LC_FFN = 0, LC_QKV = 1, LC_QK = 2, LC_V = 3, LC_CONV = 4 };
 
 struct LcP {
   const float* btab;     // [9][n_tab] bias by border state (3 * row state + column state; state 0 = first, 1 = inner, 2 = last)
   const float* b2;       // FFN: [C] pointwise2 bias (NULL: none -- second half of the hidden channels)
   const bf16* resid;     // FFN, C = 64: residual [B,H,W,C] read from global memory (C = 32: the patch's own centre pixels)
   bf16* out;             // FFN: out [B,H,W,C]; QKV / V: v [B,H,W,C]
-  int n_tab;             // channels of the whole conv (pitch of btab)
+  int n_tab;             // channels of the whole conv
+  int tab_stride;        // pitch of btab (0: one bias row for every border state)
   int t0, t1, tn;        // this launch computes conv channels [t0, t0 + tn) and, if tn < N, [t1, t1 + tn)
   int ch0;               // QKV / QK: first q (= k) channel of this launch
   float* gram_part;      // QKV: [slot][C][C/8] per-head diagonal blocks of q^T k of the CTA's pixels
@@ -71,9 +74,10 @@ struct LcP {
 
 template <int MODE, int C>
 struct LcCfg {
-  static constexpr int N = MODE == LC_QKV ? 3 * C : 64;          // conv output channels per launch
-  static constexpr int GU = MODE == LC_V ? 0 : (MODE == LC_QKV ? 2 * C / 8 : N / 8);   // 8-channel units that go to the g tile
-  static constexpr bool SECOND = MODE != LC_V;                   // a second contraction follows (pointwise2 / Gram)
+  static constexpr int N = MODE == LC_QKV ? 3 * C : (MODE == LC_CONV ? C : 64);   // conv output channels per launch
+  static constexpr bool LN = MODE != LC_CONV;                    // normalise the patch while re-laying it
+  static constexpr int GU = (MODE == LC_V || MODE == LC_CONV) ? 0 : (MODE == LC_QKV ? 2 * C / 8 : N / 8);   // 8-channel units that go to the g tile
+  static constexpr bool SECOND = MODE != LC_V && MODE != LC_CONV;                   // a second contraction follows (pointwise2 / Gram)
   static constexpr bool RES_RAW = C == 32;                       // FFN residual from the patch (else from global memory)
   static constexpr int NCH = C / 8;                              // 16-byte units per pixel
   static constexpr int LBO_PX = 184;                             // chunk pitch in pixels (a multiple of 128 bytes)
@@ -96,8 +100,21 @@ struct LcCfg {
   }
 };
 
+__device__ __forceinline__ bool lc_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void lc_warp_wait(uint32_t bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
+  if (lane == 0 && !lc_test_wait(bar, parity)) mbar_wait(bar, parity);
   __syncwarp();
 }
 __device__ __forceinline__ float4 lc_lds128f(uint32_t addr) {
@@ -226,7 +243,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     float* bt = reinterpret_cast<float*>(smem_raw + (sBT - smem_u32(smem_raw)));
     for (int i = tid; i < 9 * N; i += LC_THREADS) {
       const int idx = i / N, j = i - idx * N;
-      bt[i] = __ldg(p.btab + idx * p.n_tab + (j < p.tn ? p.t0 + j : p.t1 + j - p.tn));
+      bt[i] = __ldg(p.btab + idx * p.tab_stride + (j < p.tn ? p.t0 + j : p.t1 + j - p.tn));
     }
     if (MODE == LC_FFN) {
       float* b2 = reinterpret_cast<float*>(smem_raw + (sB2 - smem_u32(smem_raw)));
@@ -273,9 +290,9 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         if (i >= p.nr) mbar_wait(raw_free(rb), rph ^ 1u);
         const int px0 = tl.tx * 8, py0 = tl.ty * 16, b = tl.b;
         tile_next(tl);
-        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + LC_ST_BYTES);
+        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + (K::LN ? LC_ST_BYTES : 0u));
         tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE, &mapX, raw_full(rb), 0, px0 - 1, py0 - 1, b);
-        tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
+        if (K::LN) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
         if (++rb == p.nr) { rb = 0; rph ^= 1u; }
       }
     }
@@ -416,9 +433,10 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const uint32_t src = sRaw + (uint32_t)rl_rb * K::RAW_STRIDE + (uint32_t)px * (C * 2);
         const uint32_t dst = sT + (uint32_t)rl_tb * K::T_STRIDE + (uint32_t)px * 16u;
         const int py = px / 10, pxx = px - py * 10;
-        float sum, ssq;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sum), "=f"(ssq)
-                     : "r"(sSt + (uint32_t)rl_rb * LC_ST_STRIDE + (uint32_t)(py * 12 + pxx + 1) * 8u));
+        float sum = 0.f, ssq = 0.f;
+        if (K::LN)
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sum), "=f"(ssq)
+                       : "r"(sSt + (uint32_t)rl_rb * LC_ST_STRIDE + (uint32_t)(py * 12 + pxx + 1) * 8u));
         const float mu = sum * p.invC;
         const float rs = rsqrtf(fmaxf(ssq * p.invC - mu * mu, 0.f) + p.eps);
         const float nm = -mu * rs;
@@ -432,9 +450,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 a = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
-            const float2 f = __ffma2_rn(a, r2, n2);
-            o[e] = lc_pack(f.x, f.y);
+            if (K::LN) {
+              const float2 a = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+              const float2 f = __ffma2_rn(a, r2, n2);
+              o[e] = lc_pack(f.x, f.y);
+            } else {
+              o[e] = w[e];
+            }
           }
           lc_sts128(dst + (uint32_t)k * K::LBO, o[0], o[1], o[2], o[3]);
         }
@@ -546,11 +568,14 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = lc_pack(h[e].x, h[e].y);
+          for (int e = 0; e < 4; ++e) {
+            if (MODE == LC_CONV) o[e] = lc_pack(lrelu_f(h[e].x), lrelu_f(h[e].y));
+            else o[e] = lc_pack(h[e].x, h[e].y);
+          }
           if (u < K::GU) {                                  // q|k: pixels that do not count contribute exact zeros
             if (!counts) o[0] = o[1] = o[2] = o[3] = 0u;
             lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
-          } else if (MODE == LC_V) {
+          } else if ((MODE == LC_V || MODE == LC_CONV) && K::UPW == 2) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) ov[t][e] = o[e];
           } else if (inside) {
@@ -559,7 +584,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           }
         }
       }
-      if (MODE == LC_V && inside)                           // this warp's two adjacent units of v: one 32-byte store per pixel
+      if ((MODE == LC_V || MODE == LC_CONV) && K::UPW == 2 && inside)   // this warp's two adjacent units: one 32-byte store per pixel
         lc_stg256(p.out + ((((i64)b * p.H + y) * p.W + x) * C + wi * K::UPW * 8), ov[0], ov[K::UPW - 1]);
       if (K::SECOND) {
         fence_proxy_async();
@@ -693,7 +718,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   LcP p;
   memset(&p, 0, sizeof(p));
   p.btab = btab; p.b2 = b2; p.resid = (const bf16*)resid; p.out = (bf16*)out; p.gram_part = gram_part; p.sq_part = sq_part;
-  p.n_tab = sel.n_tab; p.t0 = sel.t0; p.t1 = sel.t1; p.tn = sel.tn; p.ch0 = sel.ch0;
+  p.n_tab = sel.n_tab; p.tab_stride = MODE == LC_CONV ? 0 : sel.n_tab; p.t0 = sel.t0; p.t1 = sel.t1; p.tn = sel.tn; p.ch0 = sel.ch0;
   p.invC = 1.0f / (float)C; p.eps = 1e-5f;
   p.H = H; p.W = W; p.B = B;
   p.ylo = 0; p.yhi = H;
@@ -714,7 +739,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   }
   const size_t smem = K::smem(p.nr);
   if (smem > 232448) return 0;
-  if (((uintptr_t)stats & 15) || ((uintptr_t)x & 15)) return 0;
+  if ((K::LN && ((uintptr_t)stats & 15)) || ((uintptr_t)x & 15)) return 0;
   CUtensorMap mX, mS, mW, mW2;
   {
     const i64 d[4] = {C, W, H, B};
@@ -728,7 +753,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     const i64 d[3] = {2 * (i64)W, H, B};
     const i64 s[3] = {1, 2 * (i64)W, (i64)2 * W * H};
     const int bx[3] = {24, 18, 1};
-    if (!make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
+    if (K::LN && !make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
   }
   {
     const i64 d[3] = {C, 9, sel.n_tab};
@@ -833,6 +858,22 @@ int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* c
     if (lnconv_launch<LC_V, 64>(ctx, x, stats, cw, btab, sel, nullptr, nullptr, nullptr, v, nullptr, nullptr, 1, H, W, 0) <= 0) return 0;
   }
   return ns;
+}
+
+// Conv_out of a Conv_Transformer: out = LeakyReLU_0.2(conv3x3(x) + bias), C -> C (FLCA_RF.py:276); w = T [C][9][C]
+bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C) {
+  if (!lnconv_supported(ctx, C, H, W)) return false;
+  static int on = -1;                     // debugging aid: RAWFORMER_B200_LNCONV_CONV=0 keeps Conv_out on k_tc_gemm
+  if (on < 0) {
+    const char* e = getenv("RAWFORMER_B200_LNCONV_CONV");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on) return false;
+  const double rows = (double)B * H * W;
+  ScopedLaunch sl(RF_K_CONV3X3_OUT, rows * C * 2.0 * 2.0, rows * 2.0 * 9 * C * C);
+  const LcSel sel{C, 0, 0, C, 0};
+  if (C == 32) return lnconv_launch<LC_CONV, 32>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
+  return lnconv_launch<LC_CONV, 64>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
 }
 
 }  // namespace rf

@@ -463,7 +463,9 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   g.A2 = x2; g.K2 = C; g.lda2 = C;
   g.w_img = (i64)C * 2 * C;
   launch_gemm(ctx, g);
-  conv3x3(ctx, xr, pb.convout_w, pb.convout_b, out, C, C, ACT_LRELU, OMODE_ROWS, B, H, W, RF_K_CONV3X3_OUT);
+  if (!(ctx.dtype == RF_BF16 && pb.convout_b != nullptr && lnconv_supported(ctx, C, H, W) &&
+        (ctx.dry || launch_lnconv_conv3(ctx, xr, pb.convout_w, pb.convout_b, out, B, H, W, C))))
+    conv3x3(ctx, xr, pb.convout_w, pb.convout_b, out, C, C, ACT_LRELU, OMODE_ROWS, B, H, W, RF_K_CONV3X3_OUT);
   A.release(mk);
 }
 
