@@ -1,8 +1,9 @@
 // LayerNorm -> 1x1 conv -> depthwise 3x3 of the transformer branch as ONE dense 3x3 convolution on the tensor cores
-// (bf16 mode, C = 32: the full-resolution stage of RawFormer-S).
+// (bf16 mode, C = 32 and C = 64: the two full-resolution stages of RawFormer-S, the first stage of RawFormer-L).
 //
 //   conv_ffn   (FLCA_RF.py:204-209, :253):  out = x + pointwise2( gelu( depthwise( pointwise1( norm2(x) ) ) ) )
 //   Attention  (FLCA_RF.py:223)          :  q|k|v = qkv_dwconv( qkv( norm1(x) ) )
+//   Conv_out   (FLCA_RF.py:276)          :  out = lrelu( conv3x3(x) )                 (the same pipeline without the norm)
 //
 // A 1x1 conv followed by a depthwise 3x3 is linear, so it IS a dense 3x3 conv with the weights
 //     Weff[n][tap][c] = dw[n][tap] * W[n][c] * gamma[c]                    (made once at pack time, k_pack_lnconv)
@@ -13,21 +14,28 @@
 // Why: on the CUDA cores the depthwise 3x3 (+ GELU) costs 17-20 cycles per pixel per 64 channels per SM whether its
 // input comes from HBM or from shared memory (k_dw_tma, k_ffn_fused, k_dwqk_gram are all bound by
 // that loop); as part of the contraction it costs 9x the tensor FLOPs of the 1x1 conv, which the tensor pipe has to
-// spare: 18 tcgen05.mma per 128-pixel tile, ~60 issue cycles each whatever N <= 96 is.
+// spare: 18 (C = 32) / 36 (C = 64) tcgen05.mma per 128-pixel tile, ~60 cycles each whatever N <= 96 is.
 //
-// One persistent CTA per SM, 576 threads:
-//   warp 0      TMA producer: per tile ONE 4-d box = the (16+2) x (8+2) halo patch of x (pixel-major) and ONE box of the
-//               per-pixel LayerNorm statistics (sum, sumsq) of the same pixels; zero fill outside the image
-//   warp 1      MMA issuer: 9 taps x C/16 k-steps out of the re-laid-out patch (no-swizzle K-major operand, rows =
-//               pixels: the taps are nine start addresses into the same buffer, see rf_tc_gemm.cu), then the second
-//               contraction of the tile before (pointwise2, or the self-Gram of [q|k])
-//   warps 2-17  compute: (a) normalise + re-lay patch i+2 ([pixel][C] -> [C/8][pixel][16 B]); (b) FFN: acc3 of tile
-//               i-1 + bias + residual (the patch's own centre pixels) -> bf16 -> global; (c) acc1 of tile i + bias table
-//               -> FFN: GELU -> bf16 -> g tile (SWIZZLE_128B K-major operand of pointwise2); QKV: q|k -> bf16 -> g tile
-//               (the same bytes are the MN-major operand of the Gram), v -> bf16 -> global.
+// One persistent CTA per SM, 576 threads, NO CTA-wide barrier in the tile loop (the mbarriers count one arrival per warp,
+// the warps drift apart by as much as the buffer depths allow):
+//   warp 0      TMA producer: per tile ONE 4-d box = the (16+2) x (8+2) halo patch of x (pixel-major, 64 / 128-byte
+//               swizzled) and ONE box of the per-pixel LayerNorm statistics (sum, sumsq); zero fill outside the image
+//   warp 1      MMA issuer, one elected lane: 9 taps x C/16 k-steps out of the re-laid-out patch (no-swizzle K-major
+//               operand, rows = pixels: the taps are nine start addresses into the same buffer, see rf_tc_gemm.cu), then
+//               the second contraction of the tile (pointwise2, or the self-Gram of [q|k])
+//   warps 2-17  compute, per tile: (A) both accumulators into registers, (B) FFN: acc3 of the tile before + bias + residual
+//               -> bf16 -> global; acc1 + bias table -> FFN: GELU -> bf16 -> g tile (SWIZZLE_128B K-major operand of
+//               pointwise2); QKV: q|k -> bf16 -> g tile (the same bytes are the MN-major operand of the Gram), v -> global;
+//               (C) normalise + re-lay the patch two tiles ahead ([pixel][C] -> [C/8][pixel][16 B], one thread per pixel).
 // q and k never reach HBM, nor does the 2C-wide hidden tensor of the FFN; the Gram and the squared norms of the CTA's
 // pixels stay in tensor memory until the CTA's last tile and go to its own partial slot (k_attn_reduce sums the slots in
-// order: bit-reproducible).
+// order: bit-reproducible).  At C = 64 nine taps of 64 output channels are all the weights that fit: the FFN runs as two
+// launches (hidden channels 0-63, then 64-127 on top of the first launch's output), q|k|v as three (q|k of heads 0-3, of
+// heads 4-7 -- the Gram is block-diagonal over the heads -- and v).
+//
+// Measured (RawFormer-S full frame, B200): FFN 486 -> 228 us and qkv (1x1 + depthwise + Gram) 469 -> 218 us per stage-0
+// block, 249 -> 206 and 251 -> 212 us per stage-1 block; Conv_out 88 -> 67 us at stage 1.  RAWFORMER_B200_LNCONV_DBG=1
+// prints the per-phase cycle counters of compute warp 0.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -322,7 +330,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const int s = i & 1;
         mbar_wait(t_full(tb), tph);
         if (i >= 2) mbar_wait(drained(s), (uint32_t)(((i >> 1) + 1) & 1));   // tile i-2's accumulator is in registers
-        if ((p.sched & 7) == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
+        if (p.sched == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
         tc_fence_after();
         if (DBG) t_issue = clock64();
         if (leader) {
@@ -351,13 +359,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       } else {
         mma1(0);
       }
-      if ((p.sched & 7) == 0 && n > 1) mma1(1);
+      if (p.sched == 0 && n > 1) mma1(1);
       const uint32_t idesc3 = make_idesc_m128(C);
       // Gram: kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (rows 64.. are zeros), N = 64 (32 q | 32 k)
       const uint32_t idescg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t gdesc = make_sw128_desc(sG), w2desc = make_sw128_desc(sW2);
       for (int i = 0; i < n; ++i) {
-        if ((p.sched & 7) == 1 && i + 1 < n) {
+        if (p.sched == 1 && i + 1 < n) {
           if (DBG && i == 8) {
             mma1(i + 1);
             mbar_wait(mma1_done((i + 1) & 1), (uint32_t)(((i + 1) >> 1) & 1));
@@ -389,7 +397,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           umma_commit(mma2_done);
         }
         __syncwarp();
-        if ((p.sched & 7) == 0 && i + 2 < n) mma1(i + 2);
+        if (p.sched == 0 && i + 2 < n) mma1(i + 2);
       }
     }
   } else {
@@ -542,6 +550,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       // ---- B: epilogues on registers ----
       if (MODE == LC_FFN && i >= 1) epi_b(v3);
       if (MODE == LC_FFN && !K::RES_RAW) res_prefetch();     // tile i's residual: a whole tile ahead of its use
+      mark(7);
       const int y = ta.ty * 16 + ty, x = ta.tx * 8 + tx, b = ta.b;
       tile_next(ta);
       const int rs_ = y == 0 ? 0 : (y == p.H - 1 ? 2 : 1), cs_ = x == 0 ? 0 : (x == p.W - 1 ? 2 : 1);
@@ -735,7 +744,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
       const char* e = getenv("RAWFORMER_B200_LNCONV_SCHED");
       sched = e ? atoi(e) : 2;
     }
-    p.sched = (sched & 7) == 2 ? (MODE == LC_FFN ? 1 : 0) | (sched & ~7) : sched;
+    p.sched = sched == 2 ? (MODE == LC_FFN ? 1 : 0) : (sched & 1);
   }
   const size_t smem = K::smem(p.nr);
   if (smem > 232448) return 0;
@@ -801,8 +810,9 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
       for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid;
     const double tiles = (double)cdiv(p.total_tiles, grid);
     fprintf(stderr, "[lnconv mode %d C=%d %dx%d tiles/CTA %.0f] cycles/tile (warp 2): loop %.0f wait_mma1 %.0f wait_mma2 %.0f tmem_ld %.0f "
-            "epilogues %.0f | relayout: wait_raw %.0f work %.0f\n",
-            MODE, C, H, W, tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles);
+            "epilogue 2 (+ residual prefetch) %.0f epilogue 1 %.0f | relayout: wait_raw %.0f work %.0f\n",
+            MODE, C, H, W, tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[7] / tiles, a[4] / tiles, a[5] / tiles,
+            a[6] / tiles);
   } else {
     launch_pdl(k_lnconv<MODE, C, false>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, p);
   }
