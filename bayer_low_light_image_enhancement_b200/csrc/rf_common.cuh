@@ -193,6 +193,10 @@ struct Ctx {
   size_t zero_cap = 0, zero_off = 0;
   bool fits() const { return dry || arena.peak <= arena.cap; }
 };
+// fork / join of the per-thread side stream (rf_runtime.cu): false = no fork (dry run, profiling, disabled, or no side stream
+// could be made because the stream is being captured and none exists yet)
+bool side_fork(Ctx& ctx, cudaStream_t* side);
+void side_join(Ctx& ctx, cudaStream_t side);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -451,10 +451,19 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
   // squeeze-excite MLP + fold of its scale into channel_reduce: one launch.  Row-tiled forward: after the transformer
   // branch, whose all-reduce brings the channel sums of the whole frame (into row 0 of the partial sums)
-  if (ctx.band == nullptr)
+  // (whole-frame forward: on the side stream, next to the transformer branch -- only channel_reduce needs its result)
+  cudaStream_t side = nullptr;
+  bool forked = false;
+  if (ctx.band == nullptr) {
+    forked = side_fork(ctx, &side);
+    cudaStream_t main_stream = ctx.stream;
+    if (forked) ctx.stream = side;
     launch_se_fold(ctx, se.partial, se.nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C, pb.hid);
+    ctx.stream = main_stream;
+  }
   void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
   transformer(ctx, pb, feat, x2, B, H, W, pre);
+  if (forked) side_join(ctx, side);
   if (ctx.band != nullptr)
     launch_se_fold(ctx, se.partial, 1, ctx.band->P_full, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C,
                    pb.hid);

@@ -13,6 +13,69 @@ bool tcgen05_enabled();
 static thread_local LaunchRecorder g_rec;
 LaunchRecorder& recorder() { return g_rec; }
 
+// ---------------------------------------------------------------------------------------------
+// side stream (per host thread and device): small per-image kernels that only the END of a block needs (the squeeze-excite
+// MLP + channel_reduce fold) run next to the block's transformer branch instead of in front of it.  fork: the side stream
+// waits for everything enqueued on the forward's stream so far; join: the forward's stream waits for the side stream.  Inside
+// a stream capture the two become a fork / join of the CUDA graph.  Never created inside a capture (a forward captured
+// before any eager forward of this thread simply does not fork).
+// ---------------------------------------------------------------------------------------------
+struct SideStream {
+  int dev = -1;
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+};
+static thread_local SideStream g_side[8];
+
+static bool side_enabled() {
+  static int on = -1;                     // debugging aid: RAWFORMER_B200_SIDE_STREAM=0 keeps everything on one stream
+  if (on < 0) {
+    const char* e = getenv("RAWFORMER_B200_SIDE_STREAM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+bool side_fork(Ctx& ctx, cudaStream_t* side) {
+  if (ctx.dry || !side_enabled() || recorder().profiling) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  SideStream* ss = nullptr;
+  for (auto& c : g_side)
+    if (c.dev == dev) { ss = &c; break; }
+  if (ss == nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx.stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return false;
+    for (auto& c : g_side)
+      if (c.dev < 0) { ss = &c; break; }
+    if (ss == nullptr) return false;
+    SideStream n;
+    if (cudaStreamCreateWithFlags(&n.s, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&n.fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n.join_ev, cudaEventDisableTiming) != cudaSuccess)
+      return false;
+    n.dev = dev;
+    *ss = n;
+  }
+  if (cudaEventRecord(ss->fork_ev, ctx.stream) != cudaSuccess || cudaStreamWaitEvent(ss->s, ss->fork_ev, 0) != cudaSuccess) {
+    recorder().last_cuda_error = (int)cudaGetLastError();
+    return false;
+  }
+  *side = ss->s;
+  return true;
+}
+
+void side_join(Ctx& ctx, cudaStream_t side) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& c : g_side)
+    if (c.dev == dev && c.s == side) {
+      if (cudaEventRecord(c.join_ev, side) != cudaSuccess || cudaStreamWaitEvent(ctx.stream, c.join_ev, 0) != cudaSuccess)
+        recorder().last_cuda_error = (int)cudaGetLastError();
+      return;
+    }
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms <= 0) {
