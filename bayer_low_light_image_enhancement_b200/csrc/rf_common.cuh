@@ -59,6 +59,7 @@ enum KernelId {
   RF_K_BAND_ALLREDUCE,
   RF_K_FFN_FUSED,
   RF_K_QKV_FUSED,
+  RF_K_CONV3X3_LC,     // Conv_out through the k_lnconv pipeline (C = 32 / 64)
   RF_K_COUNT
 };
 

@@ -880,7 +880,7 @@ bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bi
   }
   if (!on) return false;
   const double rows = (double)B * H * W;
-  ScopedLaunch sl(RF_K_CONV3X3_OUT, rows * C * 2.0 * 2.0, rows * 2.0 * 9 * C * C);
+  ScopedLaunch sl(RF_K_CONV3X3_LC, rows * C * 2.0 * 2.0, rows * 2.0 * 9 * C * C);
   const LcSel sel{C, 0, 0, C, 0};
   if (C == 32) return lnconv_launch<LC_CONV, 32>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
   return lnconv_launch<LC_CONV, 64>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;

@@ -144,7 +144,7 @@ static const char* const kKernelNames[RF_K_COUNT] = {
     "gemm_qkv", "dw_qkv_gram", "attn_finalize", "gemm_proj_resid", "gemm_pw1", "dw_gelu", "gemm_pw2_resid",
     "gemm_cat_reduce", "conv3x3_out", "down_conv3x3", "up_convT", "skip_reduce", "embed", "head", "layout",
     "weight_pack", "misc", "pyr_spatial", "gemm_pyr_res1", "gemm_pyr_res2", "channel_sums", "tail_stats",
-    "tail_apply", "index_op", "gemm_gram", "band_halo", "band_allreduce", "ffn_fused", "qkv_fused"};
+    "tail_apply", "index_op", "gemm_gram", "band_halo", "band_allreduce", "ffn_fused", "qkv_fused", "conv3x3_lc"};
 
 const char* kernel_name_of(int id) { return (id >= 0 && id < RF_K_COUNT) ? kKernelNames[id] : "?"; }
 

@@ -39,7 +39,7 @@ H_RAW, W_RAW = 2848, 4256  # SID Sony frame
 MP_FRAME = H_RAW * W_RAW / 1e6
 METRIC = "megapixels/sec of RAW input (SID Sony full frame)"
 SIZES = {"S": 32, "B": 48, "L": 64}
-TENSOR_KERNELS = ("gemm_", "conv3x3_out", "down_conv3x3", "up_convT", "skip_reduce")
+TENSOR_KERNELS = ("gemm_", "conv3x3_out", "conv3x3_lc", "down_conv3x3", "up_convT", "skip_reduce")
 # logical launch name -> CUDA symbol family (template instantiation) it runs as, and which roofline bounds that family at
 # the benchmarked sizes: the LayerNorm-folded GEMM is ONE symbol although it appears under two logical names
 SYMBOL_OF = {
@@ -53,7 +53,8 @@ SYMBOL_OF = {
     # norm -> 1x1 -> depthwise 3x3 as ONE dense 3x3 conv on the tensor cores (rf_lnconv.cu; C = 32 / 64): bound by the tensor
     # pipe BY DESIGN -- it executes 9x the FLOPs of the 1x1 + depthwise it replaces so that the hidden / q|k tensors never
     # reach HBM; `achieved` counts the EXECUTED dense-conv FLOPs, `algorithmic_hbm` in the record is the compulsory-byte view
-    "ffn_fused": ("k_lnconv<FFN>", "tensor"), "qkv_fused": ("k_lnconv<QKV | QK | V>", "tensor"), "flca_mod": ("k_im2col_tc<0>", "hbm"), "embed": ("k_im2col_tc<1>", "hbm"),
+    "ffn_fused": ("k_lnconv<FFN>", "tensor"), "qkv_fused": ("k_lnconv<QKV | QK | V>", "tensor"),
+    "conv3x3_lc": ("k_lnconv<CONV>", "tensor"), "flca_mod": ("k_im2col_tc<0>", "hbm"), "embed": ("k_im2col_tc<1>", "hbm"),
     "pyr_spatial": ("k_im2col_tc<2|3>", "hbm"), "gemm_gram": ("k_tc_gram", "hbm"),
 }
 
@@ -428,7 +429,7 @@ def roofline_records(agg, n_prof, pk, size, precision, variant):
             r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
         r.update(kernel=name, launches_per_step=n // n_prof, share_of_step=ms / total_ms, avg_launch_ms=ms / n,
                  peak_source=pk["src"], algorithmic_per_launch=(fl if bound == "tensor" else by) / n)
-        if name.startswith("k_lnconv"):
+        if name.startswith("k_lnconv") and "CONV" not in name:
             gbs = by / (ms * 1e-3) / 1e9
             r["flops_counted"] = "executed (dense 3x3 form = 9x the FLOPs of the 1x1 conv + depthwise 3x3 it replaces)"
             r["algorithmic_hbm"] = {"bytes_per_launch": by / n, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
