@@ -45,6 +45,8 @@ struct PackedBlock {
   float* ffn_bt = nullptr;     // [9][2C] bias by border state
   void* qkv_cw = nullptr;      // T [3C][9][C]
   float* qkv_bt = nullptr;     // [9][3C]
+  float* cat_p2 = nullptr;     // fp32 [C][9][2C] = Conv_out o channel_reduce (C = 32 only)
+  float* cat_bt = nullptr;     // [9][C]
   // ML extras
   float* gate_w = nullptr;     // [2 levels][2][2]
   float* gate_b = nullptr;     // [2][2]
@@ -236,6 +238,13 @@ int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* c
                       float* sq_part, int H, int W, int C, int slot_cap);
 // Conv_out (C -> C 3x3 + bias + LeakyReLU 0.2) through the same pipeline; w = T [C][9][C]
 bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C);
+// channel_reduce folded into Conv_out (C = 32): one dense 3x3 conv of the pair (xmod | x2) with per-image weights
+void launch_pack_cat(Ctx& ctx, const float* wout, const float* bout, const float* wred, const float* bred, float* p2, float* bt,
+                     int C);
+void launch_cat_scale(Ctx& ctx, const float* p2, const float* scale, void* weff, int B, int C);
+bool lnconv_cat_supported(const Ctx& ctx, int C, int H, int W);
+bool launch_lnconv_cat(Ctx& ctx, const void* xmod, const void* x2, const void* weff, const float* btab, void* out, int H, int W,
+                       int C);
 // embedding 3x3 4->d from x_ds (fp32 [B,h,w,4]) ; head 3x3 d->12 + lrelu + pixel-shuffle to fp32 NCHW [B,3,2h,2w]
 void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, const float* b, void* out, int B, int h,
                   int w_, int d);

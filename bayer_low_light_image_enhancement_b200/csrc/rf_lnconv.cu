@@ -58,7 +58,10 @@ constexpr uint32_t LC_ST_BYTES = 18 * 12 * 8, LC_ST_STRIDE = 1792;
 // channels are all the weights that fit next to the patches in shared memory
 // CONV: the block's plain Conv_out 3x3 (C -> C, + bias, LeakyReLU(0.2), FLCA_RF.py:276) through the same pipeline: no
 // LayerNorm in the re-layout, no statistics box, one bias row for all border states
-enum { LC_FFN = 0, LC_QKV = 1, LC_QK = 2, LC_V = 3, LC_CONV = 4 };
+// CAT (C = 32): Conv_out(channel_reduce(cat(xmod * s, x2))) (FLCA_RF.py:274-276) is linear before the LeakyReLU, so it is ONE
+// dense 3x3 conv of the 2C-channel pair (xmod | x2) with the per-image weights sum_m Wout[n][tap][m] * Wred[m][k] * s[k]: two
+// patches per tile, K = 2C per tap, N = C; the channel_reduce GEMM and its output tensor disappear
+enum { LC_FFN = 0, LC_QKV = 1, LC_QK = 2, LC_V = 3, LC_CONV = 4, LC_CAT = 5 };
 
 struct LcP {
   const float* btab;     // [9][n_tab] bias by border state (3 * row state + column state; state 0 = first, 1 = inner, 2 = last)
@@ -82,18 +85,20 @@ struct LcP {
 
 template <int MODE, int C>
 struct LcCfg {
-  static constexpr int N = MODE == LC_QKV ? 3 * C : (MODE == LC_CONV ? C : 64);   // conv output channels per launch
-  static constexpr bool LN = MODE != LC_CONV;                    // normalise the patch while re-laying it
-  static constexpr int GU = (MODE == LC_V || MODE == LC_CONV) ? 0 : (MODE == LC_QKV ? 2 * C / 8 : N / 8);   // 8-channel units that go to the g tile
-  static constexpr bool SECOND = MODE != LC_V && MODE != LC_CONV;                   // a second contraction follows (pointwise2 / Gram)
+  static constexpr int N = MODE == LC_QKV ? 3 * C : ((MODE == LC_CONV || MODE == LC_CAT) ? C : 64);   // conv output channels per launch
+  static constexpr int CIN = MODE == LC_CAT ? 2 * C : C;         // conv input channels (CAT: two C-channel patches)
+  static constexpr bool LN = MODE != LC_CONV && MODE != LC_CAT;                    // normalise the patch while re-laying it
+  static constexpr int GU = (MODE == LC_V || MODE == LC_CONV || MODE == LC_CAT) ? 0 : (MODE == LC_QKV ? 2 * C / 8 : N / 8);   // 8-channel units that go to the g tile
+  static constexpr bool SECOND = MODE != LC_V && MODE != LC_CONV && MODE != LC_CAT;                   // a second contraction follows (pointwise2 / Gram)
   static constexpr bool RES_RAW = C == 32;                       // FFN residual from the patch (else from global memory)
-  static constexpr int NCH = C / 8;                              // 16-byte units per pixel
+  static constexpr int NCH = CIN / 8;                            // 16-byte units per patch pixel
   static constexpr int LBO_PX = 184;                             // chunk pitch in pixels (a multiple of 128 bytes)
   static constexpr uint32_t LBO = LBO_PX * 16;
-  static constexpr uint32_t RAW_BYTES = LC_NPIX * C * 2;
-  static constexpr uint32_t RAW_STRIDE = (RAW_BYTES + 1023) & ~1023u;   // (the patch lands 64 / 128-byte swizzled)
+  static constexpr uint32_t RAW_SRC = (LC_NPIX * C * 2 + 1023) & ~1023u;   // one source's patch
+  static constexpr uint32_t RAW_BYTES = LC_NPIX * CIN * 2;
+  static constexpr uint32_t RAW_STRIDE = MODE == LC_CAT ? 2 * RAW_SRC : RAW_SRC;   // (the patches land 64 / 128-byte swizzled)
   static constexpr uint32_t T_STRIDE = (NCH * LBO + 1023) & ~1023u;
-  static constexpr uint32_t WTAP = N * C * 2;                    // bytes of one tap's [N][C] weights
+  static constexpr uint32_t WTAP = N * CIN * 2;                  // bytes of one tap's [N][CIN] weights
   static constexpr uint32_t W_BYTES = 9 * WTAP;
   static constexpr uint32_t W2_BYTES = MODE == LC_FFN ? C * 128 : 0;
   static constexpr uint32_t G_BYTES = 16384;                     // 128 pixels x 128 B
@@ -219,7 +224,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapS);
     tma_prefetch_desc(&mapW);
-    if (MODE == LC_FFN) tma_prefetch_desc(&mapW2);
+    if (MODE == LC_FFN || MODE == LC_CAT) tma_prefetch_desc(&mapW2);
     // barriers the compute warps arrive on count one arrival per warp: no CTA-wide barrier in the tile loop, the warps
     // drift apart by as much as the buffer depths allow
     for (int i = 0; i < LC_MAXR; ++i) {
@@ -288,7 +293,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES);
       for (int tap = 0; tap < 9; ++tap) {
         tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, p.t0);
-        if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * C * 2, &mapW, w_full, 0, tap, p.t1);
+        if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * K::CIN * 2, &mapW, w_full, 0, tap, p.t1);
       }
       if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, p.t0, 0, 0);     // pointwise2 columns of these hidden channels
       int rb = 0;
@@ -300,6 +305,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         tile_next(tl);
         mbar_expect_tx(raw_full(rb), K::RAW_BYTES + (K::LN ? LC_ST_BYTES : 0u));
         tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE, &mapX, raw_full(rb), 0, px0 - 1, py0 - 1, b);
+        if (MODE == LC_CAT) tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE + K::RAW_SRC, &mapW2, raw_full(rb), 0, px0 - 1, py0 - 1, b);
         if (K::LN) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
         if (++rb == p.nr) { rb = 0; rph ^= 1u; }
       }
@@ -321,7 +327,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       const uint32_t idesc1 = make_idesc_m128(N);
       // A: no-swizzle K-major, LBO = chunk pitch, SBO = patch row pitch (10 pixels x 16 B); B: the resident weights
       const uint32_t a_hi = (160u >> 4) | (1u << 14), a_lo0 = (K::LBO >> 4) << 16;
-      const uint64_t wdesc0 = make_kmajor_desc(sW, C);
+      const uint64_t wdesc0 = make_kmajor_desc(sW, K::CIN);
       const uint32_t b_hi = (uint32_t)(wdesc0 >> 32), b_lo0 = (uint32_t)wdesc0;
       int tb = 0;
       uint32_t tph = 0;
@@ -339,7 +345,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-            for (int kk = 0; kk < C / 16; ++kk)
+            for (int kk = 0; kk < K::CIN / 16; ++kk)
               lc_umma(d_tmem, a_lo + (uint32_t)(((tap / 3) * 10 + (tap % 3)) + 2 * kk * K::LBO_PX), a_hi,
                       b_lo0 + (uint32_t)tap * (K::WTAP >> 4) + 2u * (uint32_t)kk, b_hi, idesc1, (tap | kk) ? 1u : 0u);
           }
@@ -451,7 +457,8 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
         uint4 v[K::NCH];
 #pragma unroll
-        for (int k = 0; k < K::NCH; ++k) v[k] = lc_lds128(src + (uint32_t)((k ^ (C == 32 ? (px >> 1) & 3 : px & 7)) * 16));
+        for (int k = 0; k < K::NCH; ++k)     // (CAT: units C/8.. come from the second source's patch)
+          v[k] = lc_lds128(src + (k >= C / 8 ? K::RAW_SRC : 0u) + (uint32_t)(((k % (C / 8)) ^ (C == 32 ? (px >> 1) & 3 : px & 7)) * 16));
 #pragma unroll
         for (int k = 0; k < K::NCH; ++k) {
           const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
@@ -578,13 +585,13 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (MODE == LC_CONV) o[e] = lc_pack(lrelu_f(h[e].x), lrelu_f(h[e].y));
+            if (MODE == LC_CONV || MODE == LC_CAT) o[e] = lc_pack(lrelu_f(h[e].x), lrelu_f(h[e].y));
             else o[e] = lc_pack(h[e].x, h[e].y);
           }
           if (u < K::GU) {                                  // q|k: pixels that do not count contribute exact zeros
             if (!counts) o[0] = o[1] = o[2] = o[3] = 0u;
             lc_sts128(grow + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4), o[0], o[1], o[2], o[3]);
-          } else if ((MODE == LC_V || MODE == LC_CONV) && K::UPW == 2) {
+          } else if ((MODE == LC_V || MODE == LC_CONV || MODE == LC_CAT) && K::UPW == 2) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) ov[t][e] = o[e];
           } else if (inside) {
@@ -593,7 +600,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           }
         }
       }
-      if ((MODE == LC_V || MODE == LC_CONV) && K::UPW == 2 && inside)   // this warp's two adjacent units: one 32-byte store per pixel
+      if ((MODE == LC_V || MODE == LC_CONV || MODE == LC_CAT) && K::UPW == 2 && inside)   // this warp's two adjacent units: one 32-byte store per pixel
         lc_stg256(p.out + ((((i64)b * p.H + y) * p.W + x) * C + wi * K::UPW * 8), ov[0], ov[K::UPW - 1]);
       if (K::SECOND) {
         fence_proxy_async();
@@ -765,16 +772,21 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     if (K::LN && !make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
   }
   {
-    const i64 d[3] = {C, 9, sel.n_tab};
-    const i64 s[3] = {1, C, (i64)9 * C};
-    const int bx[3] = {C, 1, sel.tn};
-    if (!make_map_ex(&mW, cw, 3, d, s, bx, 2, C * 2)) return 0;
+    const i64 d[3] = {K::CIN, 9, sel.n_tab};
+    const i64 s[3] = {1, K::CIN, (i64)9 * K::CIN};
+    const int bx[3] = {K::CIN, 1, sel.tn};
+    if (!make_map_ex(&mW, cw, 3, d, s, bx, 2, K::CIN * 2)) return 0;
   }
   if (MODE == LC_FFN) {
     const i64 d[3] = {2 * C, C, 1};
     const i64 s[3] = {1, 2 * C, (i64)2 * C * C};
     const int bx[3] = {64, C, 1};
     if (!make_map_ex(&mW2, W2, 3, d, s, bx, 2, 128)) return 0;
+  } else if (MODE == LC_CAT) {           // the second source's patch (W2 = x2 here)
+    const i64 d[4] = {C, W, H, B};
+    const i64 s[4] = {1, C, (i64)C * W, (i64)C * W * H};
+    const int bx[4] = {C, 10, 18, 1};
+    if (((uintptr_t)W2 & 15) || !make_map_ex(&mW2, W2, 4, d, s, bx, 2, C * 2)) return 0;
   } else {
     mW2 = mW;
   }
@@ -884,6 +896,80 @@ bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bi
   const LcSel sel{C, 0, 0, C, 0};
   if (C == 32) return lnconv_launch<LC_CONV, 32>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
   return lnconv_launch<LC_CONV, 64>(ctx, x, nullptr, w, bias, sel, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, H, W, 0) > 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel_reduce folded into Conv_out (C = 32): pack-time product P2[n][tap][k] = sum_m Wout[n][m][tap] * Wred[m][k] (fp32) and
+// the border-state bias table bt[idx][n] = bout[n] + sum_{valid taps} sum_m Wout[n][m][tap] * bred[m]; per image the first C
+// input channels are scaled by the squeeze-excite vector and the result is rounded to bf16 (k_cat_scale)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_cat(const float* __restrict__ wout, const float* __restrict__ bout, const float* __restrict__ wred,
+           const float* __restrict__ bred, float* __restrict__ p2, float* __restrict__ bt, int C) {
+  // wout [C][C][3][3] (PyTorch), wred [C][2C]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = C * 9 * 2 * C;
+  if (i < total) {
+    const int k = i % (2 * C), tap = (i / (2 * C)) % 9, n = i / (18 * C);
+    float acc = 0.f;
+    for (int m = 0; m < C; ++m) acc = fmaf(wout[((i64)n * C + m) * 9 + tap], wred[(i64)m * 2 * C + k], acc);
+    p2[i] = acc;
+  }
+  if (i < 9 * C) {
+    const int n = i % C, idx = i / C, rs = idx / 3, cs = idx % 3;
+    float acc = bout ? bout[n] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const bool valid = !(rs == 0 && ky == 0) && !(rs == 2 && ky == 2) && !(cs == 0 && kx == 0) && !(cs == 2 && kx == 2);
+      if (!valid || !bred) continue;
+      for (int m = 0; m < C; ++m) acc = fmaf(wout[((i64)n * C + m) * 9 + tap], bred[m], acc);
+    }
+    bt[i] = acc;
+  }
+}
+void launch_pack_cat(Ctx& ctx, const float* wout, const float* bout, const float* wred, const float* bred, float* p2, float* bt,
+                     int C) {
+  if (ctx.dry || !wout || !wred || !p2 || !bt) return;
+  ScopedLaunch sl(RF_K_WEIGHT_PACK);
+  k_pack_cat<<<cdiv(C * 9 * 2 * C, 256), 256, 0, ctx.stream>>>(wout, bout, wred, bred, p2, bt, C);
+}
+
+__global__ void __launch_bounds__(256)
+k_cat_scale(const float* __restrict__ p2, const float* __restrict__ scale, bf16* __restrict__ weff, int C, int n_per_image) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_per_image) return;
+  const int k = i % (2 * C);
+  const float s = k < C ? scale[b * C + k] : 1.f;
+  weff[(i64)b * n_per_image + i] = __float2bfloat16_rn(p2[i] * s);
+}
+// weff [B][C][9][2C] (T) = P2 with the first C input channels scaled by scale[b]
+void launch_cat_scale(Ctx& ctx, const float* p2, const float* scale, void* weff, int B, int C) {
+  if (ctx.dry) return;
+  const int n = C * 9 * 2 * C;
+  ScopedLaunch sl(RF_K_SE_FINALIZE, 6.0 * B * n);
+  launch_pdl(k_cat_scale, dim3(cdiv(n, 256), B), dim3(256), 0, ctx.stream, p2, scale, (bf16*)weff, C, n);
+}
+
+bool lnconv_cat_supported(const Ctx& ctx, int C, int H, int W) {
+  static int on = -1;                     // debugging aid: RAWFORMER_B200_LNCONV_CAT=0 keeps channel_reduce as its own GEMM
+  if (on < 0) {
+    const char* e = getenv("RAWFORMER_B200_LNCONV_CAT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && C == 32 && lnconv_supported(ctx, C, H, W);
+}
+
+// ONE image: out = LeakyReLU_0.2(Conv_out(channel_reduce(cat(xmod * s, x2)))); weff = this image's [C][9][2C] weights
+bool launch_lnconv_cat(Ctx& ctx, const void* xmod, const void* x2, const void* weff, const float* btab, void* out, int H, int W,
+                       int C) {
+  if (!lnconv_cat_supported(ctx, C, H, W)) return false;
+  const double rows = (double)H * W;
+  ScopedLaunch sl(RF_K_CONV3X3_LC, rows * C * 2.0 * 3.0, rows * 2.0 * 9 * 2 * C * C);
+  const LcSel sel{C, 0, 0, C, 0};
+  return lnconv_launch<LC_CAT, 32>(ctx, xmod, nullptr, weff, btab, sel, x2, nullptr, nullptr, out, nullptr, nullptr, 1, H, W, 0) > 0;
 }
 
 }  // namespace rf

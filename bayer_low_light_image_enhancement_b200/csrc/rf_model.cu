@@ -55,6 +55,7 @@ static PackedBlock layout_block(Layout& L, int C, int dtype, int variant) {
   if (dtype == RF_BF16 && C <= 64) {
     pb.ffn_cw = L.elems(2 * c * 9 * c, dtype); pb.ffn_bt = L.f32(9 * 2 * c);
     pb.qkv_cw = L.elems(3 * c * 9 * c, dtype); pb.qkv_bt = L.f32(9 * 3 * c);
+    if (C == 32) { pb.cat_p2 = L.f32(c * 9 * 2 * c); pb.cat_bt = L.f32(9 * c); }
   }
   if (variant == RF_VARIANT_ML) {
     pb.gate_w = L.f32(8); pb.gate_b = L.f32(4); pb.cgate = L.f32(2);
@@ -162,6 +163,7 @@ static void pack_block(Ctx& ctx, const rf_block_weights& w, const PackedBlock& p
   if (pb.ffn_cw != nullptr) {
     launch_pack_lnconv(ctx, w.pw1_w, w.norm2_w, w.norm2_b, w.pw1_b, w.ffn_dw_w, w.ffn_dw_b, pb.ffn_cw, pb.ffn_bt, 2 * C, C);
     launch_pack_lnconv(ctx, w.qkv_w, w.norm1_w, w.norm1_b, w.qkv_b, w.qkv_dw_w, w.qkv_dw_b, pb.qkv_cw, pb.qkv_bt, 3 * C, C);
+    if (pb.cat_p2 != nullptr) launch_pack_cat(ctx, w.convout_w, w.convout_b, w.reduce_w, w.reduce_b, pb.cat_p2, pb.cat_bt, C);
   }
 }
 
@@ -449,6 +451,9 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
   SePartial se;
   flca_branch(ctx, pb, variant, feat, sg, B, &xmod, &scale, &se);
   void* wred = A.elems((size_t)B * C * 2 * C, ctx.dtype);
+  // channel_reduce folded into Conv_out (C = 32, rf_lnconv.cu): the squeeze-excite scale goes into per-image 3x3 weights
+  const bool cat_conv = ctx.dtype == RF_BF16 && pb.cat_p2 != nullptr && lnconv_cat_supported(ctx, C, H, W);
+  void* weff = cat_conv ? A.elems((size_t)B * C * 9 * 2 * C, ctx.dtype) : nullptr;
   // squeeze-excite MLP + fold of its scale into channel_reduce: one launch.  Row-tiled forward: after the transformer
   // branch, whose all-reduce brings the channel sums of the whole frame (into row 0 of the partial sums)
   // (whole-frame forward: on the side stream, next to the transformer branch -- only channel_reduce needs its result)
@@ -459,14 +464,29 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
     cudaStream_t main_stream = ctx.stream;
     if (forked) ctx.stream = side;
     launch_se_fold(ctx, se.partial, se.nblk, P, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C, pb.hid);
+    if (cat_conv) launch_cat_scale(ctx, pb.cat_p2, scale, weff, B, C);
     ctx.stream = main_stream;
   }
   void* x2 = A.elems((size_t)B * P * C, ctx.dtype);
   transformer(ctx, pb, feat, x2, B, H, W, pre);
   if (forked) side_join(ctx, side);
-  if (ctx.band != nullptr)
+  if (ctx.band != nullptr) {
     launch_se_fold(ctx, se.partial, 1, ctx.band->P_full, pb.se_w1, pb.se_b1, pb.se_w2, pb.se_b2, scale, pb.red_w, wred, B, C,
                    pb.hid);
+    if (cat_conv) launch_cat_scale(ctx, pb.cat_p2, scale, weff, B, C);
+  }
+  if (cat_conv) {
+    if (!ctx.dry) {
+      for (int b = 0; b < B; ++b) {
+        const size_t img = (size_t)b * P * C * 2;
+        if (!launch_lnconv_cat(ctx, (const char*)xmod + img, (const char*)x2 + img, (const char*)weff + (size_t)b * C * 9 * 2 * C * 2,
+                               pb.cat_bt, (char*)out + img, H, W, C))
+          recorder().last_cuda_error = (int)cudaErrorNotSupported;
+      }
+    }
+    A.release(mk);
+    return;
+  }
   void* xr = A.elems((size_t)B * P * C, ctx.dtype);
   GemmP g = gemm_rows(xmod, C, wred, pb.red_b, xr, C, B, P, RF_K_GEMM_CAT_REDUCE);
   g.A2 = x2; g.K2 = C; g.lda2 = C;

@@ -315,6 +315,27 @@ def test_full_frame_launch_accounting(rf):
     assert torch.isfinite(o16).all()
 
 
+def test_dense_conv_forms_are_on_the_path(rf):
+    """RawFormer-S in bf16: the transformer branches of the two full-resolution stages (C = 32 / 64) run as dense 3x3 convolutions
+    on the tensor cores (rf_lnconv.cu) -- 2 + 2*2 FFN launches, 2 + 2*3 q|k|v launches and 4 Conv_out launches per frame -- and
+    none of the kernels they replace is launched at those stages.  (Their numerics are covered by every bf16 test of this file
+    and by tests/test_fullframe.py.)"""
+    m = rf.RawFormer(model_size="S", precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=5))
+    m = m.to(dev()).eval()
+    x = torch.rand(2, 1, 96, 160, device=dev())
+    with torch.no_grad():
+        out, launches = m.forward_profiled(x)
+    names = [l["name"] for l in launches]
+    assert names.count("ffn_fused") == 6
+    assert names.count("qkv_fused") == 2 * 8                      # (the attention statistics are per image: batch 2)
+    # Conv_out: stage 0 with channel_reduce folded in (per-image weights: one launch per image), stage 1 plain
+    assert names.count("conv3x3_lc") == 2 * 2 + 2 and names.count("gemm_cat_reduce") == 5
+    assert names.count("gemm_pw1") == 3 and names.count("dw_gelu") == 3 and names.count("gemm_qkv") == 3   # stages 2, 3, 2 only
+    with torch.no_grad():
+        assert torch.equal(out, m(x))                             # profiled (eager, one stream) == plain forward (side stream)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # callers either side of the forward and the WFB gated FFN
 # ---------------------------------------------------------------------------------------------------------
