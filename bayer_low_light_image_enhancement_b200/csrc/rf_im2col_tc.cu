@@ -163,7 +163,16 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            ((uint64_t)1 << 46);
   };
-  auto issue_mma = [&](int j, uint32_t tmem_base) {          // thread 0: the 5 k-steps of my j-th tile
+  // warp 0, all lanes (warp-uniform descriptor arithmetic stays on the uniform datapath), ONE elected lane issues: under a
+  // `tid == 0` branch every tcgen05.mma cost ~20 instructions, and warp 0 -- an epilogue warp like the others -- reached the
+  // tile's barrier that much later than everybody else
+  bool mma_leader = false;
+  if (warp == 0) {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(e));
+    mma_leader = e != 0;
+  }
+  auto issue_mma = [&](int j, uint32_t tmem_base) {          // warp 0: the 5 k-steps of my j-th tile
     mbar_wait(g_bar(j % IT_NGS), (j / IT_NGS) & 1);
     tc_fence_after();
     const uint32_t Gp = sG + (j % IT_NGS) * IT_PATCH_STRIDE;
@@ -176,9 +185,10 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
       const uint32_t oa = (uint32_t)((ta[s5] / 3) * IT_PITCH + ta[s5] % 3), ob = (uint32_t)((tb[s5] / 3) * IT_PITCH + tb[s5] % 3);
       const uint64_t adesc = nosw_desc(Gp + oa * 16u, (ob - oa) * 16u, IT_PITCH * 16u);
       const uint64_t bdesc = nosw_desc(sW + (uint32_t)(2 * s5 * N) * 16u, (uint32_t)N * 16u, 128u);
-      umma_f16(d, adesc, bdesc, idesc, s5 ? 1u : 0u);
+      if (mma_leader) umma_f16(d, adesc, bdesc, idesc, s5 ? 1u : 0u);
     }
-    umma_commit(acc_bar(j & 1));
+    if (mma_leader) umma_commit(acc_bar(j & 1));
+    __syncwarp();
   };
 
   // ---- epilogue role of this thread -------------------------------------------------------------------------------
@@ -241,7 +251,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   if (tid == 32) {
     for (int j = 0; j < 3 && j < n_my; ++j) issue_loads(j);
   }
-  if (tid == 0 && n_my > 0) issue_mma(0, tmem_base);
+  if (warp == 0 && n_my > 0) issue_mma(0, tmem_base);
 
   for (int i = 0; i < n_my; ++i) {
     const int a = i & 1;                             // TMEM buffer of tile i
@@ -253,7 +263,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
       tma_store_wait_read<1>();
       if (i + 3 < n_my) issue_loads(i + 3);
     }
-    if (tid == 0 && i + 1 < n_my) issue_mma(i + 1, tmem_base);   // TMEM buffer a^1 was drained by epilogue(i-1)
+    if (warp == 0 && i + 1 < n_my) issue_mma(i + 1, tmem_base);   // TMEM buffer a^1 was drained by epilogue(i-1)
     if (MODULATE) {
       const int b = (t0 + i * tstep) / p.tiles_per_img;
       if (b != cur_b) {

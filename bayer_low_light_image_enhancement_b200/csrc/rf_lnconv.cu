@@ -79,6 +79,7 @@ struct LcP {
   int ylo, yhi;          // QKV: rows that count for the statistics (row-tiled forward: the band's interior)
   int tiles_x, tiles_y, total_tiles;
   int nr;                // raw patch buffers in use
+  int own_stats;         // C = 32: no statistics tensor, the re-layout thread computes (sum, sumsq) of its pixel itself
   int sched;             // 0: the first contraction of tile i+1 runs under tile i's accumulator loads; 1: after them
   unsigned long long* dbg;   // debugging aid (RAWFORMER_B200_LNCONV_DBG=1): cycles per phase of compute thread 0, per CTA
 };
@@ -303,10 +304,10 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         if (i >= p.nr) mbar_wait(raw_free(rb), rph ^ 1u);
         const int px0 = tl.tx * 8, py0 = tl.ty * 16, b = tl.b;
         tile_next(tl);
-        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + (K::LN ? LC_ST_BYTES : 0u));
+        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + ((K::LN && !p.own_stats) ? LC_ST_BYTES : 0u));
         tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE, &mapX, raw_full(rb), 0, px0 - 1, py0 - 1, b);
         if (MODE == LC_CAT) tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE + K::RAW_SRC, &mapW2, raw_full(rb), 0, px0 - 1, py0 - 1, b);
-        if (K::LN) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
+        if (K::LN && !p.own_stats) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
         if (++rb == p.nr) { rb = 0; rph ^= 1u; }
       }
     }
@@ -447,18 +448,34 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         const uint32_t src = sRaw + (uint32_t)rl_rb * K::RAW_STRIDE + (uint32_t)px * (C * 2);
         const uint32_t dst = sT + (uint32_t)rl_tb * K::T_STRIDE + (uint32_t)px * 16u;
         const int py = px / 10, pxx = px - py * 10;
-        float sum = 0.f, ssq = 0.f;
-        if (K::LN)
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sum), "=f"(ssq)
-                       : "r"(sSt + (uint32_t)rl_rb * LC_ST_STRIDE + (uint32_t)(py * 12 + pxx + 1) * 8u));
-        const float mu = sum * p.invC;
-        const float rs = rsqrtf(fmaxf(ssq * p.invC - mu * mu, 0.f) + p.eps);
-        const float nm = -mu * rs;
-        const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
         uint4 v[K::NCH];
 #pragma unroll
         for (int k = 0; k < K::NCH; ++k)     // (CAT: units C/8.. come from the second source's patch)
           v[k] = lc_lds128(src + (k >= C / 8 ? K::RAW_SRC : 0u) + (uint32_t)(((k % (C / 8)) ^ (C == 32 ? (px >> 1) & 3 : px & 7)) * 16));
+        float sum = 0.f, ssq = 0.f;
+        if (K::LN && C == 32 && p.own_stats) {
+          // no statistics tensor (an encoder block's input: nobody's epilogue produced them): from the pixel's own values
+          float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < K::NCH; ++k) {
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+              s2 = __fadd2_rn(s2, a);
+              q2 = __ffma2_rn(a, a, q2);
+            }
+          }
+          sum = s2.x + s2.y;
+          ssq = q2.x + q2.y;
+        } else if (K::LN) {
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sum), "=f"(ssq)
+                       : "r"(sSt + (uint32_t)rl_rb * LC_ST_STRIDE + (uint32_t)(py * 12 + pxx + 1) * 8u));
+        }
+        const float mu = sum * p.invC;
+        const float rs = rsqrtf(fmaxf(ssq * p.invC - mu * mu, 0.f) + p.eps);
+        const float nm = -mu * rs;
+        const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
 #pragma unroll
         for (int k = 0; k < K::NCH; ++k) {
           const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
@@ -755,6 +772,8 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   }
   const size_t smem = K::smem(p.nr);
   if (smem > 232448) return 0;
+  p.own_stats = (K::LN && stats == nullptr) ? 1 : 0;
+  if (p.own_stats && C != 32) return 0;
   if ((K::LN && ((uintptr_t)stats & 15)) || ((uintptr_t)x & 15)) return 0;
   CUtensorMap mX, mS, mW, mW2;
   {
@@ -769,7 +788,8 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     const i64 d[3] = {2 * (i64)W, H, B};
     const i64 s[3] = {1, 2 * (i64)W, (i64)2 * W * H};
     const int bx[3] = {24, 18, 1};
-    if (K::LN && !make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
+    if (K::LN && !p.own_stats && !make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
+    if (!K::LN || p.own_stats) mS = mX;
   }
   {
     const i64 d[3] = {K::CIN, 9, sel.n_tab};

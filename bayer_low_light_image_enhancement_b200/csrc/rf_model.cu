@@ -271,7 +271,8 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
   // norm1 -> qkv -> qkv_dwconv as one dense 3x3 conv on the tensor cores with the Gram / norms / v epilogue (rf_lnconv.cu)
-  const bool conv_qkv = ln != nullptr && ln->npart == 1 && pb.qkv_cw != nullptr && lnconv_supported(ctx, C, H, W);
+  const bool conv_qkv = ln != nullptr && ln->npart == 1 && pb.qkv_cw != nullptr && lnconv_supported(ctx, C, H, W) &&
+                        (ln->stats != nullptr || C == 32 || ctx.dry);
   void* qkv = conv_qkv ? nullptr : A.elems((size_t)B * P * 3 * C, ctx.dtype);
   if (!conv_qkv) {
     GemmP gq = gemm_rows(xin, C, ln ? pb.qkv_wf : pb.qkv_w, ln ? pb.qkv_bf : pb.qkv_b, qkv, 3 * C, B, P, RF_K_GEMM_QKV);
@@ -300,7 +301,8 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
       float* sq_part = A.get<float>((size_t)sq_cap * 2 * C);
       if (!ctx.dry) {
         for (int b = 0; b < B; ++b) {
-          const int ns = launch_lnconv_qkv(ctx, (const char*)xin + (size_t)b * P * C * 2, ln->stats + (size_t)b * P * 2, pb.qkv_cw,
+          const int ns = launch_lnconv_qkv(ctx, (const char*)xin + (size_t)b * P * C * 2,
+                                           ln->stats ? ln->stats + (size_t)b * P * 2 : nullptr, pb.qkv_cw,
                                            pb.qkv_bt, (char*)vbuf + (size_t)b * P * C * 2, gram_part, sq_part, H, W, C, sq_cap);
           if (ns <= 0) recorder().last_cuda_error = (int)cudaErrorNotSupported;
           launch_attn_reduce(ctx, gram_part, ns, sq_part, ns, stats + b * nst, sumsq + (size_t)b * 2 * C, C);
@@ -411,6 +413,8 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
     LnFold l1;
     if (pre != nullptr && pre->stats != nullptr && pre->npart > 0) {
       l1 = *pre;
+    } else if (C == 32 && pb.qkv_cw != nullptr && lnconv_supported(ctx, C, H, W)) {
+      l1.stats = nullptr; l1.npart = 1;       // the dense-conv qkv kernel computes norm1's statistics itself (no pass over feat)
     } else {
       float* st1 = A.get<float>((size_t)B * P * 2);
       launch_row_stats(ctx, feat, st1, B * P, C);

@@ -823,7 +823,11 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // the whole warp walks the loop, ONE elected lane issues (see the MMA issuer of k_tc_gemm)
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+      const bool leader = elected != 0;
       // kind::f16, D=f32, A=B=bf16, both MN-major (bits 15, 16), M = N = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       int s = 0, wrap = 0;
@@ -833,13 +837,16 @@ k_tc_gram(const __grid_constant__ CUtensorMap mapQK, float* __restrict__ G, int 
         const uint32_t a0 = base + s * stage_bytes, b0 = packed ? a0 : a0 + 2 * GR_CHUNK;
         const uint32_t lbo = packed == 1 ? zero_chunk - a0 : GR_CHUNK;
         const uint64_t adesc = make_sw128_mn_desc(a0, lbo), bdesc = make_sw128_mn_desc(b0, lbo);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < GR_PIX / 16; ++k)   // 16 pixels = 16 rows of 128 B = 2048 B per MMA
-          umma_f16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (il | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));
+          for (int k = 0; k < GR_PIX / 16; ++k)   // 16 pixels = 16 rows of 128 B = 2048 B per MMA
+            umma_f16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc, (il | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        __syncwarp();
         if (++s == nst) { s = 0; ++wrap; }
       }
-      umma_commit(tmem_full);
+      if (leader) umma_commit(tmem_full);
     }
   } else {
     const int quad = warp & 3;
