@@ -238,6 +238,10 @@ int launch_lnconv_qkv(Ctx& ctx, const void* x, const float* stats, const void* c
                       float* sq_part, int H, int W, int C, int slot_cap);
 // Conv_out (C -> C 3x3 + bias + LeakyReLU 0.2) through the same pipeline; w = T [C][9][C]
 bool launch_lnconv_conv3(Ctx& ctx, const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C);
+// project_out fused in front of the FFN (C = 32, one image): out = x1 + conv_ffn(norm2(x1)), x1 = x + Mw v + proj_b
+bool lnconv_proj_supported(const Ctx& ctx, int C, int H, int W);
+bool launch_lnconv_ffn_proj(Ctx& ctx, const void* x, const void* v, const void* Mw, const float* proj_b, const void* cw,
+                            const float* btab, const void* W2, const float* b2, void* out, int H, int W, int C);
 // channel_reduce folded into Conv_out (C = 32): one dense 3x3 conv of the pair (xmod | x2) with per-image weights
 void launch_pack_cat(Ctx& ctx, const float* wout, const float* bout, const float* wred, const float* bred, float* p2, float* bt,
                      int C);

@@ -51,7 +51,7 @@ constexpr int LC_CT = LC_CW * 32;           // compute threads
 constexpr int LC_THREADS = LC_CT + 64;      // + producer warp + MMA warp
 constexpr int LC_NPIX = 180;                // (16 + 2) x (8 + 2) patch pixels, row pitch 10
 constexpr int LC_NT = 3;                    // re-laid-out patch buffers
-constexpr int LC_MAXR = 5;                  // raw patch buffers (FFN: a patch lives until its tile's residual add)
+constexpr int LC_MAXR = 6;                  // raw patch buffers (FFN: a patch lives until its tile's residual add)
 constexpr uint32_t LC_ST_BYTES = 18 * 12 * 8, LC_ST_STRIDE = 1792;
 // FFN: GELU + pointwise2 + residual epilogues (C = 64: one half of the 2C hidden channels per launch); QKV (C = 32): q|k -> Gram,
 // v -> global; QK / V (C = 64): the same split over three launches (q|k of heads 0-3, of heads 4-7, v): 9 taps of 64 output
@@ -79,6 +79,8 @@ struct LcP {
   int ylo, yhi;          // QKV: rows that count for the statistics (row-tiled forward: the band's interior)
   int tiles_x, tiles_y, total_tiles;
   int nr;                // raw patch buffers in use
+  int proj;              // FFN, C = 32: project_out fused in front (x1 = x + Mw v + proj_b never reaches HBM), see below
+  const float* proj_b;   // [C]
   int own_stats;         // C = 32: no statistics tensor, the re-layout thread computes (sum, sumsq) of its pixel itself
   int sched;             // 0: the first contraction of tile i+1 runs under tile i's accumulator loads; 1: after them
   unsigned long long* dbg;   // debugging aid (RAWFORMER_B200_LNCONV_DBG=1): cycles per phase of compute thread 0, per CTA
@@ -196,7 +198,8 @@ __device__ __forceinline__ void lc_umma(uint32_t d_tmem, uint32_t a_lo, uint32_t
 template <int MODE, int C, bool DBG>
 __global__ void __launch_bounds__(LC_THREADS, 1)
 k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapS,
-         const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapW2, const LcP p) {
+         const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapW2,
+         const __grid_constant__ CUtensorMap mapM, const LcP p) {
   using K = LcCfg<MODE, C>;
   constexpr int N = K::N;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -220,6 +223,22 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   auto drained = [&](int i) { return drained0 + 8u * i; };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- project_out fused in front of the FFN (p.proj; C = 32): per tile the v patch (its own ring) times the image's folded
+  //      attention / project_out weights Mw on the tensor cores -> x1acc (tensor memory, two 128-row groups over the 180 patch
+  //      pixels).  Part 1 (all compute warps, three patches ahead): x1acc is read with the tile's other accumulators while the
+  //      tensor pipe is empty; x1 = x + x1acc + bias, rounded to bf16, goes over x (the block input) in the raw ring -- it is
+  //      the residual of the second epilogue.  Part 2 (two patches ahead) is the ordinary re-layout with norm2's statistics
+  //      computed from the pixel's own bf16 values.  Measured: 363 us against 224 (FFN) + 127 (project_out GEMM) per stage-0
+  //      block launch by launch, 5.65 against 5.71 ms per RawFormer-S frame in the graph (two launches and 3 C-passes less).
+  constexpr bool PJ = MODE == LC_FFN && C == 32;
+  constexpr int NV = 3, X1_COL = 192;
+  const uint32_t pj_bars = (tmem_slot + 16u + 7u) & ~7u;            // v_full[3], v_free[3], mma0_done, x1_free, x1_ready[2]
+  auto v_full = [&](int i) { return pj_bars + 8u * i; };
+  auto v_free = [&](int i) { return pj_bars + 8u * (NV + i); };
+  const uint32_t mma0_done = pj_bars + 8u * (2 * NV), x1_free = mma0_done + 8, x1_ready = x1_free + 8;
+  const uint32_t sPB = (x1_ready + 16u + 15u) & ~15u;                // (x1_ready: two barriers) proj bias [C] floats
+  const uint32_t sMw = (sPB + C * 4 + 1023u) & ~1023u;               // [C rows][C] bf16, K-major 64-byte swizzled
+  const uint32_t sV = sMw + 2048u;                                   // NV v patches (+ 4 KB: the second row group reads 256 rows)
 
   if (tid == 0) {
     tma_prefetch_desc(&mapX);
@@ -240,6 +259,16 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     mbar_init(drained(1), LC_CW);
     mbar_init(g_full, LC_CW);
     mbar_init(w_full, 1);
+    if (PJ && p.proj) {
+      for (int i = 0; i < NV; ++i) {
+        mbar_init(v_full(i), 1);
+        mbar_init(v_free(i), 1);
+      }
+      mbar_init(mma0_done, 1);
+      mbar_init(x1_free, LC_CW);
+      mbar_init(x1_ready, LC_CW);
+      mbar_init(x1_ready + 8, LC_CW);
+    }
     fence_barrier_init();
   }
   if (MODE == LC_QKV || MODE == LC_QK) {
@@ -262,6 +291,10 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     if (MODE == LC_FFN) {
       float* b2 = reinterpret_cast<float*>(smem_raw + (sB2 - smem_u32(smem_raw)));
       for (int i = tid; i < C; i += LC_THREADS) b2[i] = p.b2 ? __ldg(p.b2 + i) : 0.f;
+      if (PJ && p.proj) {
+        float* pb = reinterpret_cast<float*>(smem_raw + (sPB - smem_u32(smem_raw)));
+        for (int i = tid; i < C; i += LC_THREADS) pb[i] = p.proj_b ? __ldg(p.proj_b + i) : 0.f;
+      }
     }
   }
   __syncthreads();
@@ -291,14 +324,15 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0 && n > 0) {
-      mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES);
+      mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES + ((PJ && p.proj) ? (uint32_t)(C * C * 2) : 0u));
       for (int tap = 0; tap < 9; ++tap) {
         tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, p.t0);
         if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * K::CIN * 2, &mapW, w_full, 0, tap, p.t1);
       }
       if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, p.t0, 0, 0);     // pointwise2 columns of these hidden channels
-      int rb = 0;
-      uint32_t rph = 0;
+      if (PJ && p.proj) tma_load_3d(sMw, &mapM, w_full, 0, 0, 0);
+      int rb = 0, vb = 0;
+      uint32_t rph = 0, vph = 0;
       TileIter tl = tile_first();
       for (int i = 0; i < n; ++i) {
         if (i >= p.nr) mbar_wait(raw_free(rb), rph ^ 1u);
@@ -309,6 +343,12 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         if (MODE == LC_CAT) tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE + K::RAW_SRC, &mapW2, raw_full(rb), 0, px0 - 1, py0 - 1, b);
         if (K::LN && !p.own_stats) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
         if (++rb == p.nr) { rb = 0; rph ^= 1u; }
+        if (PJ && p.proj) {                  // (mapS is the v tensor's patch map here)
+          if (i >= NV) mbar_wait(v_free(vb), vph ^ 1u);
+          mbar_expect_tx(v_full(vb), K::RAW_BYTES);
+          tma_load_4d(sV + (uint32_t)vb * K::RAW_SRC, &mapS, v_full(vb), 0, px0 - 1, py0 - 1, b);
+          if (++vb == NV) { vb = 0; vph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -330,6 +370,31 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       const uint32_t a_hi = (160u >> 4) | (1u << 14), a_lo0 = (K::LBO >> 4) << 16;
       const uint64_t wdesc0 = make_kmajor_desc(sW, K::CIN);
       const uint32_t b_hi = (uint32_t)(wdesc0 >> 32), b_lo0 = (uint32_t)wdesc0;
+      // project_out of patch j (p.proj): rows = patch pixels 0..255 of the v patch as it landed (64-byte swizzled K-major),
+      // two row groups, N = C, K = C -> x1acc
+      int v_b = 0;
+      uint32_t v_ph = 0;
+      auto mma0 = [&](int j) {
+        if (!(PJ && p.proj)) return;
+        mbar_wait(v_full(v_b), v_ph);
+        if (j >= 1) mbar_wait(x1_free, (uint32_t)((j - 1) & 1));          // the re-layout of patch j-1 has read x1acc
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = make_kmajor_desc(sV + (uint32_t)v_b * K::RAW_SRC, C), bd = make_kmajor_desc(sMw, C);
+          const uint32_t idesc0 = make_idesc_m128(C);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk)
+              lc_umma(tmem_base + (uint32_t)(X1_COL + g * C), (uint32_t)ad + (uint32_t)(g * ((128 * C * 2) >> 4)) + 2u * kk,
+                      (uint32_t)(ad >> 32), (uint32_t)bd + 2u * kk, (uint32_t)(bd >> 32), idesc0, kk ? 1u : 0u);
+          }
+          umma_commit(mma0_done);
+          umma_commit(v_free(v_b));
+        }
+        __syncwarp();
+        if (++v_b == NV) { v_b = 0; v_ph ^= 1u; }
+      };
       int tb = 0;
       uint32_t tph = 0;
       long long t_issue = 0;
@@ -355,6 +420,9 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         __syncwarp();
         if (++tb == LC_NT) { tb = 0; tph ^= 1u; }
       };
+      mma0(0);
+      if (n > 1) mma0(1);
+      if (n > 2) mma0(2);
       if (DBG) {
         mma1(0);
         const long long t1 = clock64();
@@ -366,6 +434,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       } else {
         mma1(0);
       }
+      if (n > 3) mma0(3);
       if (p.sched == 0 && n > 1) mma1(1);
       const uint32_t idesc3 = make_idesc_m128(C);
       // Gram: kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (rows 64.. are zeros), N = 64 (32 q | 32 k)
@@ -381,6 +450,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             mma1(i + 1);
           }
         }
+        if (i + 4 < n) mma0(i + 4);          // (under the compute warps' first epilogue; x1acc was read in their phase A)
         if (K::SECOND) {
           mbar_wait(g_full, (uint32_t)(i & 1));
           tc_fence_after();
@@ -440,8 +510,54 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     // loads of the second epilogue -- conflict-free.
     int rl_rb = 0, rl_tb = 0, rl_rot = 0;
     uint32_t rl_rph = 0;
+    // ---- project_out in front (p.proj), part 1: x1acc is loaded in phase A of the tile loop (a tcgen05.ld queues behind the
+    //      MMAs in flight: 387 us with the load in phase C), the arithmetic runs in phase C.  ALL compute warps take part (on six
+    //      warps per patch, a whole pixel per thread: 463 us): warp (q, wi) owns channels 8 wi .. 8 wi + 7 of the patch pixels
+    //      32 q + lane (row group 0) and, q < 2, 128 + 32 q + lane (row group 1)
+    TileIter trl = tile_first();
+    int rl_j = 0, p1_rb = 0, p1_j = 0;
+    uint32_t p1_rph = 0;
+    auto proj_load = [&](uint32_t (&a)[2][8]) {
+      tmem_ld8(tq + (uint32_t)(X1_COL + wi * 8), a[0]);
+      if (q < 2) tmem_ld8(tq + (uint32_t)(X1_COL + C + wi * 8), a[1]);
+    };
+    auto proj_part1 = [&](const uint32_t (&a)[2][8]) {
+      const float4 b0 = lc_lds128f(sPB + (uint32_t)wi * 32u), b1 = lc_lds128f(sPB + (uint32_t)wi * 32u + 16u);
+      const float pb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int px = g * 128 + q * 32 + lane;
+        if ((g == 0 || q < 2) && px < LC_NPIX) {
+          const uint32_t ua = sRaw + (uint32_t)p1_rb * K::RAW_STRIDE + (uint32_t)px * (C * 2) + (uint32_t)((wi ^ ((px >> 1) & 3)) * 16);
+          const uint4 xv = lc_lds128(ua);
+          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float f0 = __uint_as_float(a[g][2 * e]) + pb[2 * e] + __uint_as_float(xw[e] << 16);
+            const float f1 = __uint_as_float(a[g][2 * e + 1]) + pb[2 * e + 1] + __uint_as_float(xw[e] & 0xffff0000u);
+            o[e] = lc_pack(f0, f1);                   // x1 as the project_out GEMM would have stored it
+          }
+          lc_sts128(ua, o[0], o[1], o[2], o[3]);
+        }
+      }
+      // (two barriers by patch parity: part 1 runs a step ahead of the re-layout that waits for it; with one barrier a warp
+      // still waiting for patch j could see the barrier already in the phase of patch j + 2)
+      warp_arrive(x1_ready + 8u * (uint32_t)(p1_j & 1));
+      ++p1_j;
+      if (++p1_rb == p.nr) { p1_rb = 0; p1_rph ^= 1u; }
+    };
+    // (p.proj: the patch is x1, complete once every warp's part 1 has arrived; norm2's statistics from its bf16 values)
     auto relayout = [&]() {
-      lc_warp_wait(raw_full(rl_rb), rl_rph, lane);
+      int py0 = 0, px0 = 0;
+      if (PJ && p.proj) {
+        lc_warp_wait(x1_ready + 8u * (uint32_t)(rl_j & 1), (uint32_t)((rl_j >> 1) & 1), lane);
+        ++rl_j;
+        py0 = trl.ty * 16 - 1; px0 = trl.tx * 8 - 1;
+        tile_next(trl);
+      } else {
+        lc_warp_wait(raw_full(rl_rb), rl_rph, lane);
+      }
       mark(5);
       const int px = (ctid - rl_rot) & (LC_CT - 1);
       if (px < LC_NPIX) {
@@ -486,6 +602,10 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
               const float2 a = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
               const float2 f = __ffma2_rn(a, r2, n2);
               o[e] = lc_pack(f.x, f.y);
+              if (PJ && p.proj) {                     // outside the image the conv sees zeros (x1 there is the bias)
+                const int y = py0 + py, x = px0 + pxx;
+                if (!(y >= 0 && y < p.H && x >= 0 && x < p.W)) o[e] = 0u;
+              }
             } else {
               o[e] = w[e];
             }
@@ -550,26 +670,52 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       }
     };
 
-    if (n > 0) relayout();
-    if (n > 1) relayout();
+    // (p.proj) part 1 runs THREE patches ahead and the re-layout two: a warp's re-layout never waits for the other warps'
+    // part 1 of the same step (that would take away the slack that lets the warps drift apart)
+    for (int j = 0; j < 3 && j < n; ++j) {
+      if (PJ && p.proj) {
+        lc_warp_wait(raw_full(p1_rb), p1_rph, lane);
+        lc_warp_wait(mma0_done, (uint32_t)(j & 1), lane);
+        tc_fence_after();
+        uint32_t a[2][8];
+        proj_load(a);
+        tmem_ld_wait();
+        tc_fence_before();
+        warp_arrive(x1_free);
+        proj_part1(a);
+      }
+      if (j < 2) relayout();
+    }
     for (int i = 0; i < n; ++i) {
       // ---- A: both contractions that feed this step are complete -> accumulators into registers ----
       mark(0);
       lc_warp_wait(mma1_done(i & 1), (uint32_t)((i >> 1) & 1), lane);
       mark(1);
       if (K::SECOND && i >= 1) lc_warp_wait(mma2_done, (uint32_t)((i - 1) & 1), lane);
+      // (p.proj) x1acc of the patch two tiles ahead is read here too, with the tensor pipe empty
+      const bool pj_on = PJ && p.proj && i + 3 < n;
+      if (pj_on) {
+        lc_warp_wait(raw_full(p1_rb), p1_rph, lane);
+        lc_warp_wait(mma0_done, (uint32_t)((i + 1) & 1), lane);
+      }
       tc_fence_after();
       mark(2);
-      uint32_t v[K::UPW][8], v3[UB][8];
+      uint32_t v[K::UPW][8], v3[UB][8], xa[2][8];
 #pragma unroll
       for (int t = 0; t < K::UPW; ++t) tmem_ld8(tq + (uint32_t)((i & 1) * K::ACC1_STRIDE + (wi * K::UPW + t) * 8), v[t]);
       if (MODE == LC_FFN && i >= 1 && eb_on) {
 #pragma unroll
         for (int t = 0; t < UB; ++t) tmem_ld8(tq + (uint32_t)(K::ACC3_COL + (wi * UB + t) * 8), v3[t]);
       }
+      if (PJ) {
+        if (pj_on) proj_load(xa);
+      }
       tmem_ld_wait();
       tc_fence_before();
       warp_arrive(drained(i & 1));
+      if (PJ) {
+        if (pj_on) warp_arrive(x1_free);
+      }
       mark(3);
       // ---- B: epilogues on registers ----
       if (MODE == LC_FFN && i >= 1) epi_b(v3);
@@ -624,7 +770,11 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         warp_arrive(g_full);
       }
       mark(4);
-      // ---- C: the patch two tiles ahead ----
+      // ---- C: the patch two tiles ahead (p.proj: first part 1 of the patch three tiles ahead, off the A -> B -> pointwise2
+      //      chain that bounds the tile loop) ----
+      if (PJ) {
+        if (pj_on) proj_part1(xa);
+      }
       if (i + 2 < n) relayout();
     }
     if (K::SECOND && n > 0) {
@@ -743,10 +893,16 @@ bool lnconv_supported(const Ctx& ctx, int C, int H, int W) {
 struct LcSel {
   int n_tab, t0, t1, tn, ch0;
 };
+// FFN with project_out fused in front (C = 32, one image): x1 = x + Mw v + pb
+struct LcProj {
+  const void* v = nullptr;     // [H,W,C]
+  const void* Mw = nullptr;    // T [C][C] (this image's softmax(attention) folded into project_out)
+  const float* pb = nullptr;   // [C]
+};
 template <int MODE, int C>
 static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void* cw, const float* btab, const LcSel& sel,
                          const void* W2, const float* b2, const void* resid, void* out, float* gram_part, float* sq_part, int B,
-                         int H, int W, int slot_cap) {
+                         int H, int W, int slot_cap, const LcProj* pj = nullptr) {
   using K = LcCfg<MODE, C>;
   LcP p;
   memset(&p, 0, sizeof(p));
@@ -760,7 +916,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   const i64 total = (i64)p.tiles_x * p.tiles_y * B;
   if (total <= 0 || total > 0x7fffffff) return 0;
   p.total_tiles = (int)total;
-  p.nr = C == 32 ? (MODE == LC_FFN ? LC_MAXR : 3) : 2;
+  p.nr = C == 32 ? (MODE == LC_FFN ? (pj != nullptr ? 6 : 5) : 3) : 2;     // (project_out in front: part 1 runs a patch further ahead)
   {
     // measured (RawFormer-S stage 0): FFN 236 us with schedule 1 / 262 us with 0; QKV 273 / 238 us
     static int sched = -1;
@@ -770,12 +926,15 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     }
     p.sched = sched == 2 ? (MODE == LC_FFN ? 1 : 0) : (sched & 1);
   }
-  const size_t smem = K::smem(p.nr);
+  // (p.proj: + its barriers and bias, the 1 KB-aligned Mw tile, three v patches and the 4 KB the second row group reads past them)
+  p.proj = (pj != nullptr && MODE == LC_FFN && C == 32) ? 1 : 0;
+  p.proj_b = p.proj ? pj->pb : nullptr;
+  const size_t smem = K::smem(p.nr) + (p.proj ? 1024 + 2048 + 3 * (size_t)K::RAW_SRC + 4096 + 256 : 0);
   if (smem > 232448) return 0;
   p.own_stats = (K::LN && stats == nullptr) ? 1 : 0;
   if (p.own_stats && C != 32) return 0;
   if ((K::LN && ((uintptr_t)stats & 15)) || ((uintptr_t)x & 15)) return 0;
-  CUtensorMap mX, mS, mW, mW2;
+  CUtensorMap mX, mS, mW, mW2, mM;
   {
     const i64 d[4] = {C, W, H, B};
     const i64 s[4] = {1, C, (i64)C * W, (i64)C * W * H};
@@ -790,6 +949,16 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
     const int bx[3] = {24, 18, 1};
     if (K::LN && !p.own_stats && !make_map_ex(&mS, stats, 3, d, s, bx, 4, 0)) return 0;
     if (!K::LN || p.own_stats) mS = mX;
+    if (p.proj) {                          // mapS = the v tensor's patch map, mapM = Mw [C][C]
+      const i64 dv[4] = {C, W, H, B};
+      const i64 sv[4] = {1, C, (i64)C * W, (i64)C * W * H};
+      const int bv[4] = {C, 10, 18, 1};
+      if (((uintptr_t)pj->v & 15) || !make_map_ex(&mS, pj->v, 4, dv, sv, bv, 2, C * 2)) return 0;
+      const i64 dm[3] = {C, C, 1};
+      const i64 sm[3] = {1, C, (i64)C * C};
+      const int bm[3] = {C, C, 1};
+      if (((uintptr_t)pj->Mw & 15) || !make_map_ex(&mM, pj->Mw, 3, dm, sm, bm, 2, C * 2)) return 0;
+    }
   }
   {
     const i64 d[3] = {K::CIN, 9, sel.n_tab};
@@ -810,6 +979,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   } else {
     mW2 = mW;
   }
+  if (!p.proj) mM = mX;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_lnconv<MODE, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -828,7 +998,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
   if (dbg_on) {
-    launch_pdl(k_lnconv<MODE, C, true>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, p);
+    launch_pdl(k_lnconv<MODE, C, true>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, mM, p);
     static unsigned long long h[8 * 2048];
     cudaStreamSynchronize(ctx.stream);
     cudaMemcpy(h, dbg_buf, sizeof(unsigned long long) * 8 * 2 * grid, cudaMemcpyDeviceToHost);
@@ -846,7 +1016,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
             MODE, C, H, W, tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[7] / tiles, a[4] / tiles, a[5] / tiles,
             a[6] / tiles);
   } else {
-    launch_pdl(k_lnconv<MODE, C, false>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, p);
+    launch_pdl(k_lnconv<MODE, C, false>, dim3(grid), dim3(LC_THREADS), smem, ctx.stream, mX, mS, mW, mW2, mM, p);
   }
   return grid;
 }
@@ -990,6 +1160,27 @@ bool launch_lnconv_cat(Ctx& ctx, const void* xmod, const void* x2, const void* w
   ScopedLaunch sl(RF_K_CONV3X3_LC, rows * C * 2.0 * 3.0, rows * 2.0 * 9 * 2 * C * C);
   const LcSel sel{C, 0, 0, C, 0};
   return lnconv_launch<LC_CAT, 32>(ctx, xmod, nullptr, weff, btab, sel, x2, nullptr, nullptr, out, nullptr, nullptr, 1, H, W, 0) > 0;
+}
+
+// ONE image, C = 32: out = x1 + conv_ffn(norm2(x1)) with x1 = x + Mw v + proj_b computed per halo patch inside the kernel
+// (project_out fused in front: x1 never reaches HBM)
+bool lnconv_proj_supported(const Ctx& ctx, int C, int H, int W) {
+  static int on = -1;                     // debugging aid: RAWFORMER_B200_LNCONV_PROJ=0 keeps project_out as its own GEMM
+  if (on < 0) {
+    const char* e = getenv("RAWFORMER_B200_LNCONV_PROJ");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && C == 32 && lnconv_supported(ctx, C, H, W);
+}
+bool launch_lnconv_ffn_proj(Ctx& ctx, const void* x, const void* v, const void* Mw, const float* proj_b, const void* cw,
+                            const float* btab, const void* W2, const float* b2, void* out, int H, int W, int C) {
+  if (!lnconv_proj_supported(ctx, C, H, W)) return false;
+  const double rows = (double)H * W;
+  ScopedLaunch sl(RF_K_FFN_FUSED, rows * C * 2.0 * 3.0, rows * (2.0 * 9 * C * 2 * C + 2.0 * 2 * C * C + 2.0 * C * C * 1.4));
+  const LcSel sel{2 * C, 0, 0, 2 * C, 0};
+  LcProj pj;
+  pj.v = v; pj.Mw = Mw; pj.pb = proj_b;
+  return lnconv_launch<LC_FFN, 32>(ctx, x, nullptr, cw, btab, sel, W2, b2, nullptr, out, nullptr, nullptr, 1, H, W, 0, &pj) > 0;
 }
 
 }  // namespace rf

@@ -264,8 +264,14 @@ struct LnFold {
 
 // out = (resid ? resid : 0) + Attention(xin).  xin is the normalised input, or -- with `ln` -- the raw block input
 // whose LayerNorm (norm1) is folded into the qkv projection.  stats_out (optional): row statistics of `out`.
+// keep (optional): project_out is left to the caller (fused in front of the FFN, rf_lnconv.cu): the v tensor and the per-image
+// weights Mw stay allocated in the arena (the caller releases them) and no GEMM is launched
+struct AttnKeep {
+  const void* v = nullptr;
+  void* Mw = nullptr;
+};
 static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const void* resid, void* out, int B, int H, int W,
-                     const LnFold* ln = nullptr, float* stats_out = nullptr) {
+                     const LnFold* ln = nullptr, float* stats_out = nullptr, AttnKeep* keep = nullptr) {
   const int C = pb.C;
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
@@ -349,6 +355,11 @@ static int attention(Ctx& ctx, const PackedBlock& pb, const void* xin, const voi
   }
   void* Mw = A.elems((size_t)B * C * C, ctx.dtype);
   launch_attn_finalize(ctx, stats, pb.temperature, pb.proj_w, Mw, B, C, norms);
+  if (keep != nullptr) {
+    keep->v = v;
+    keep->Mw = Mw;
+    return 0;
+  }
   GemmP g = gemm_rows(v, C, Mw, pb.proj_b, out, C, B, P, RF_K_GEMM_PROJ);
   g.lda1 = ldv;
   g.w_img = (i64)C * C;
@@ -422,6 +433,22 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
     }
     LnFold l2;
     l2.stats = st2;
+    // project_out fused in front of the FFN (C = 32): x1 = feat + Mw v + b exists per halo patch inside the kernel only
+    const bool fuse_proj = ctx.dtype == RF_BF16 && pb.ffn_cw != nullptr && pb.qkv_cw != nullptr && lnconv_proj_supported(ctx, C, H, W);
+    if (fuse_proj) {
+      AttnKeep keep;
+      attention(ctx, pb, feat, feat, nullptr, B, H, W, &l1, nullptr, &keep);
+      if (!ctx.dry) {
+        for (int b = 0; b < B; ++b) {
+          const size_t img = (size_t)b * P * C * 2;
+          if (!launch_lnconv_ffn_proj(ctx, (const char*)feat + img, (const char*)keep.v + img, (const char*)keep.Mw + (size_t)b * C * C * 2,
+                                      pb.proj_b, pb.ffn_cw, pb.ffn_bt, pb.pw2_w, pb.pw2_b, (char*)out + img, H, W, C))
+            recorder().last_cuda_error = (int)cudaErrorNotSupported;
+        }
+      }
+      A.release(mk);
+      return;
+    }
     l2.npart = attention(ctx, pb, feat, feat, x1, B, H, W, &l1, st2);
     ffn(ctx, pb, x1, x1, out, B, H, W, &l2);
   } else {

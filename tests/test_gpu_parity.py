@@ -327,7 +327,9 @@ def test_dense_conv_forms_are_on_the_path(rf):
     with torch.no_grad():
         out, launches = m.forward_profiled(x)
     names = [l["name"] for l in launches]
-    assert names.count("ffn_fused") == 6
+    # stage 0: project_out fused in front of the FFN (per-image weights: one launch per image, no project_out GEMM); stage 1:
+    # two launches (halves of the hidden channels)
+    assert names.count("ffn_fused") == 2 * 2 + 2 * 2 and names.count("gemm_proj_resid") == 5
     assert names.count("qkv_fused") == 2 * 8                      # (the attention statistics are per image: batch 2)
     # Conv_out: stage 0 with channel_reduce folded in (per-image weights: one launch per image), stage 1 plain
     assert names.count("conv3x3_lc") == 2 * 2 + 2 and names.count("gemm_cat_reduce") == 5
