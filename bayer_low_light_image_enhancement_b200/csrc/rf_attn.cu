@@ -664,36 +664,58 @@ k_tail_stats(const float* __restrict__ out, const float4* __restrict__ x_ds, flo
     acc[1] += w00 * (0.5f * (q00.y + q00.z)) + w01 * (0.5f * (q01.y + q01.z)) + w10 * (0.5f * (q10.y + q10.z)) +
               w11 * (0.5f * (q11.y + q11.z));
     acc[2] += w00 * q00.w + w01 * q01.w + w10 * q10.w + w11 * q11.w;
+    if (out != nullptr) {
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) acc[3 + ch] += out[(b * 3 + ch) * total + i];
+      for (int ch = 0; ch < 3; ++ch) acc[3 + ch] += out[(b * 3 + ch) * total + i];
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < (out != nullptr ? 6 : 3); ++k) {
     float s = warp_sum(acc[k]);
     if ((threadIdx.x & 31) == 0) atomicAdd(sums + b * 8 + k, s);
   }
+}
+__global__ void __launch_bounds__(256)
+k_out_sums(const float* __restrict__ out, i64 ch_stride, i64 first, i64 count, float* sums3) {
+  float acc[3] = {0, 0, 0};
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) acc[ch] += out[ch * ch_stride + first + i];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float s = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sums3 + k, s);
+  }
+}
+void launch_out_sums(Ctx& ctx, const float* out, int rows_total, int row0, int rows, int Wo, float* sums3) {
+  if (ctx.dry) return;
+  const i64 count = (i64)rows * Wo;
+  unsigned gx = (unsigned)(cdivl(count, 256) < 8 * num_sms() ? cdivl(count, 256) : 8 * num_sms());
+  ScopedLaunch sl(RF_K_TAIL_STATS, 12.0 * count);
+  k_out_sums<<<gx, 256, 0, ctx.stream>>>(out, (i64)rows_total * Wo, (i64)row0 * Wo, count, sums3);
 }
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_) {
   if (ctx.dry) return;
   i64 total = 4 * (i64)h * w_;
   unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
-  ScopedLaunch sl(RF_K_TAIL_STATS, 12.0 * B * total + 16.0 * B * h * w_);
+  ScopedLaunch sl(RF_K_TAIL_STATS, (out ? 12.0 : 0.0) * B * total + 16.0 * B * h * w_);
   k_tail_stats<<<dim3(gx, B), 256, 0, ctx.stream>>>(out, (const float4*)x_ds, sums, h, w_);
 }
 
 __global__ void __launch_bounds__(256)
 k_tail_apply(float* __restrict__ out, const float* __restrict__ sums, const float* __restrict__ LL2, int H2, int W2, int h,
-             int wd) {
+             int wd, int y_off, int rows) {
   const i64 b = blockIdx.y;
   const int Ho = 2 * h, Wo = 2 * wd;
-  const i64 total = (i64)Ho * Wo;
-  const float inv = 1.0f / (float)total;
+  const i64 total = (i64)rows * Wo;                      // elements per channel of `out` (rows [y_off, y_off + rows) of the frame)
+  const float inv = 1.0f / (float)((i64)Ho * Wo);        // the means are the whole frame's
   float corr[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) corr[ch] = 0.12f * (sums[b * 8 + ch] * inv - sums[b * 8 + 3 + ch] * inv);
   const float* ll = LL2 + b * (i64)H2 * W2;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
-    const int x = (int)(i % Wo), y = (int)(i / Wo);
+    const int x = (int)(i % Wo), y = (int)(i / Wo) + y_off;
     int ya, yb, xa, xb;
     float ly, lx;
     bilinear_taps(y, H2, Ho, ya, yb, ly);
@@ -710,12 +732,14 @@ k_tail_apply(float* __restrict__ out, const float* __restrict__ sums, const floa
     out[(b * 3 + 2) * total + i] = bl + yres;
   }
 }
-void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_) {
+void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_,
+                       int y_off, int rows) {
   if (ctx.dry) return;
-  i64 total = 4 * (i64)h * w_;
+  if (rows < 0) { y_off = 0; rows = 2 * h; }
+  i64 total = 2 * (i64)rows * w_;
   unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
   ScopedLaunch sl(RF_K_TAIL_APPLY, 24.0 * B * total);
-  k_tail_apply<<<dim3(gx, B), 256, 0, ctx.stream>>>(out, sums, LL2, H2, W2, h, w_);
+  k_tail_apply<<<dim3(gx, B), 256, 0, ctx.stream>>>(out, sums, LL2, H2, W2, h, w_, y_off, rows);
 }
 
 }  // namespace rf

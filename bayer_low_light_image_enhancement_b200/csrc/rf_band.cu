@@ -236,6 +236,50 @@ void band_allreduce(Ctx& ctx, float* stats, int C, float* se, int se_slots, floa
   launch_pdl(k_band_allreduce, dim3(grid), dim3(256), 0, ctx.stream, p);
 }
 
+// ---- all-reduce (sum) of a few floats (multi-level variant: the three output-channel sums of the colour anchor,
+//      ML_RF.py:284-285); every rank adds the ranks' contributions in rank order
+struct BandSmallP {
+  BandSyncP s;
+  float* v;
+  int n, n_pad;
+  float* mail_local;              // [nranks][n_pad]
+  float* mail_peer[BAND_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(64)
+k_band_allreduce_small(BandSmallP p) {
+  pdl_wait();
+  band_load_target(p.s);
+  for (int e = threadIdx.x; e < p.n; e += blockDim.x) {
+    const float v = p.v[e];
+    for (int r = 0; r < p.s.nranks; ++r) p.mail_peer[r][(i64)p.s.rank * p.n_pad + e] = v;
+  }
+  const unsigned mask = (1u << p.s.nranks) - 1u;
+  band_signal(p.s, mask);
+  band_wait(p.s, mask);
+  if (p.s.target == 0u) return;                       // rehearsal: nothing was exchanged
+  for (int e = threadIdx.x; e < p.n; e += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < p.s.nranks; ++r) sum += __ldcg(p.mail_local + (i64)r * p.n_pad + e);
+    p.v[e] = sum;
+  }
+}
+
+void band_allreduce_small(Ctx& ctx, float* v, int n) {
+  Band& b = *ctx.band;
+  const int n_pad = (int)align_up((size_t)n, 64);
+  const size_t off = b.mail_off;
+  b.mail_off += (size_t)b.nranks * n_pad * sizeof(float);
+  BandSmallP p;
+  if (!band_sync_params(ctx, p.s, 1) || ctx.dry) return;
+  if (b.nranks == 1) return;
+  p.v = v; p.n = n; p.n_pad = n_pad;
+  for (int r = 0; r < b.nranks; ++r) p.mail_peer[r] = reinterpret_cast<float*>(b.comm[r] + off);
+  p.mail_local = p.mail_peer[b.rank];
+  ScopedLaunch sl(RF_K_BAND_ALLREDUCE, 4.0 * n * (2.0 * b.nranks));
+  launch_pdl(k_band_allreduce_small, dim3(1), dim3(64), 0, ctx.stream, p);
+}
+
 }  // namespace rf
 
 using namespace rf;

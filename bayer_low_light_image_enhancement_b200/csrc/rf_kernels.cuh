@@ -254,12 +254,19 @@ void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, 
                   int w_, int d);
 void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float* out, int B, int h, int w_, int d);
 // ML tail: out += 0.12*(mean(up(in_rgb)) - mean(out)); out += 0.03*(up8(LL2) - Y(out))
+// (out == nullptr: the input sums only)
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_);
-void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_);
+// sums3[ch] += sum over rows [row0, row0 + rows) of out [3][rows_total][Wo]  (row-tiled forward: the band's interior rows)
+void launch_out_sums(Ctx& ctx, const float* out, int rows_total, int row0, int rows, int Wo, float* sums3);
+// y_off / rows (row-tiled forward): out holds rows [y_off, y_off + rows) of the 2h x 2w_ frame; rows < 0: the whole frame
+void launch_tail_apply(Ctx& ctx, float* out, const float* sums, const float* LL2, int H2, int W2, int B, int h, int w_,
+                       int y_off = 0, int rows = -1);
 
 // ---- row-tiled forward: cross-GPU steps over peer-mapped comm regions (rf_band.cu); ctx.band must be set -------------
 // fetch the BAND_HALO halo rows of the band image x [ht + rows_in + hb][W][C] from the band neighbours' interiors
 void band_halo_exchange(Ctx& ctx, void* x, int W, int C);
+// v[0..n) summed over the ranks, in place (one sync point)
+void band_allreduce_small(Ctx& ctx, float* v, int n);
 // advance the frame counter of the local comm region (first launch of a real forward)
 void band_begin(Ctx& ctx);
 // one all-reduce (sum over ranks) per Conv_Transformer: the attention statistics of C channels (diagonal Gram blocks +

@@ -204,7 +204,8 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     nblk = launch_flca_mod(ctx, feat, sg.G, sg.G16, pb.flca_w, pb.abg, xmod, partial, nblk, B, H, W, C);
   } else {
     float* gates = A.get<float>((size_t)B * 6);
-    launch_pyr_gates(ctx, sg.sums, P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
+    // (row-tiled forward: the guidance maps and their sums are the whole frame's, replicated on every rank)
+    launch_pyr_gates(ctx, sg.sums, ctx.band != nullptr ? ctx.band->P_full : P, pb.gate_w, pb.gate_b, pb.cgate, gates, B);
     void* xa = A.elems((size_t)B * P * C, ctx.dtype);
     void* xb = A.elems((size_t)B * P * C, ctx.dtype);
     const size_t mk = A.mark();
@@ -238,7 +239,11 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
     }
     A.release(mk);
     xmod = const_cast<void*>(cur);  // == xa after three steps
-    launch_channel_sums(ctx, xmod, partial, nblk, B, P, C);
+    if (ctx.band != nullptr)        // row-tiled forward (B = 1): the band's interior rows only, summed over the ranks later
+      launch_channel_sums(ctx, (const char*)xmod + (size_t)ctx.band->ht * W * C * esize(ctx.dtype), partial, nblk, B,
+                          (i64)ctx.band->rows_in * W, C);
+    else
+      launch_channel_sums(ctx, xmod, partial, nblk, B, P, C);
   }
   if (ctx.band != nullptr) {
     // row-tiled forward: the channel sums of the whole frame arrive with the block's attention statistics (ONE exchange
@@ -695,10 +700,10 @@ static int check_model_args(int dim, int dtype, int variant, int B, int H, int W
 //   qkv 1x1 (4) -> dw3x3 (3) -> x1 (3) -> pointwise1 (3) -> dw3x3+GELU (2) -> x2 (2) -> channel_reduce (2) -> Conv_out (1)
 // and Downsample's / conv_out's 3x3 consumes the last one.  The 1-channel guidance (y, cr, cb, Haar pyramid: FLCA_RF.py:
 // 87-97,140-148) is computed for the WHOLE frame on every rank (replicate, 12 MB), so FLCA needs no halo.
-static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw, float* out, int H, int W,
+static int model_forward_band(Ctx& ctx, const PackedModel& pm, int variant, const float* raw, float* out, int H, int W,
                               const rf_band& rb) {
   Band& bd = *ctx.band;
-  const int d = pm.dim, variant = RF_VARIANT_FLCA, B = 1;
+  const int d = pm.dim, B = 1;
   const int h = H / 2, w = W / 2;
   Arena& A = ctx.arena;
   const int u0 = rb.row0 / 16, nu = rb.rows / 16;
@@ -744,13 +749,16 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw,
   GuidanceMaps gm = make_pyramid(ctx, variant, y, pm.haar, B, h, w);
   Stage st[4];
   for (int s = 0; s < 4; ++s) {
-    // (the maps are laid out for the whole frame, but only the band's rows are produced)
+    // (the maps are laid out for the whole frame, but only the band's rows are produced -- except for the multi-level
+    // variant, whose gates need the maps' whole-frame sums, ML_RF.py:151-156: every rank makes the whole maps)
+    const bool ml = variant == RF_VARIANT_ML;
     make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w, B,
-               first_row(s), rows_img(s));
+               ml ? 0 : first_row(s), ml ? -1 : rows_img(s));
     // the band's view of the stage guidance: rows [first_row, first_row + rows_img)
     const size_t px0 = (size_t)first_row(s) * (w >> s);
-    if (st[s].G) st[s].G += px0 * 4;
+    if (st[s].G) st[s].G += px0 * (ml ? 8 : 4);
     if (st[s].G16) st[s].G16 = (char*)st[s].G16 + px0 * 16;
+    if (st[s].G16b) st[s].G16b = (char*)st[s].G16b + px0 * 16;
     st[s].H = rows_img(s);
   }
   auto feat_buf = [&](int s) { return A.elems((size_t)rows_img(s) * (w >> s) * ((size_t)d << s), ctx.dtype); };
@@ -811,13 +819,23 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, const float* raw,
   hp.Wt = pm.head_wt; hp.bias = pm.head_b16; hp.Y = out; hp.ldy = 0;
   hp.M = rows_img(0) * w; hp.N = 16; hp.B = B; hp.H = rows_img(0); hp.W = w; hp.omode = OMODE_HEAD; hp.kernel_id = RF_K_HEAD;
   if (!ctx.dry && launch_gemm_tcgen05(ctx, hp) < 0) return RF_ERR_UNSUPPORTED;
+  if (variant == RF_VARIANT_ML) {
+    // colour anchor + LL nudge (ML_RF.py:270-288): the input means are the whole frame's (every rank has the packed frame), the
+    // three output-channel sums run over the band's interior rows and are summed over the ranks (one more sync point)
+    float* sums = A.get<float>(8);
+    launch_fill_f32(ctx, sums, 0.f, 8);
+    launch_tail_stats(ctx, nullptr, x_ds, sums, 1, h, w);
+    launch_out_sums(ctx, out, 2 * rows_img(0), 2 * ht, 2 * rows_in(0), 2 * w, sums + 3);
+    band_allreduce_small(ctx, sums + 3, 3);
+    launch_tail_apply(ctx, out, sums, gm.LL2, gm.H2, gm.W2, 1, h, w, 2 * first_row(0), 2 * rows_img(0));
+  }
   return RF_OK;
 }
 
 static int check_band_args(int dim, int dtype, int variant, int H, int W, const rf_band* band) {
   if (!band) return RF_ERR_BAD_ARG;
   RF_TRY(check_model_args(dim, dtype, variant, 1, H, W));
-  if (dtype != RF_BF16 || variant != RF_VARIANT_FLCA) return RF_ERR_UNSUPPORTED;
+  if (dtype != RF_BF16) return RF_ERR_UNSUPPORTED;                // (the fp32 parity engine has no band mode)
   if (dim % 32 && dim % 48) return RF_ERR_UNSUPPORTED;            // tensor-core FLCA / embed kernels (dim 32/48/64)
   if (band->nranks < 1 || band->nranks > RF_BAND_MAX_RANKS || band->rank < 0 || band->rank >= band->nranks)
     return RF_ERR_BAD_ARG;
@@ -1111,7 +1129,7 @@ static int band_dry_run(int dim, int dtype, int variant, int H, int W, const rf_
   ctx.band = &bd;
   Layout L(nullptr);
   PackedModel pm = layout_model(L, dim, dtype, variant);
-  RF_TRY(model_forward_band(ctx, pm, nullptr, nullptr, H, W, rb));
+  RF_TRY(model_forward_band(ctx, pm, variant, nullptr, nullptr, H, W, rb));
   if (ws) *ws = ctx.arena.peak + 4096;
   if (comm) *comm = bd.mail_off + 256;
   return RF_OK;
@@ -1152,7 +1170,7 @@ int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int varian
   ctx.band = &bd;
   Layout L(const_cast<void*>(packed));
   PackedModel pm = layout_model(L, dim, dtype, variant);
-  RF_TRY(model_forward_band(ctx, pm, raw, out, H, W, *band));
+  RF_TRY(model_forward_band(ctx, pm, variant, raw, out, H, W, *band));
   return finish(ctx);
 }
 

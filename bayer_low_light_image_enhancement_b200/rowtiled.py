@@ -74,8 +74,8 @@ class RowTiledRawFormer:
 
     def __init__(self, model, H: int, W: int, rank: int, nranks: int, comm_ptrs, own_region=None, group=None,
                  opened=()):
-        if getattr(model, "variant", None) != _lib.RF_VARIANT_FLCA:
-            raise NotImplementedError("row tiling implements FLCA_RF.py::RawFormer (config 4)")
+        if getattr(model, "variant", None) not in (_lib.RF_VARIANT_FLCA, _lib.RF_VARIANT_ML):
+            raise NotImplementedError("row tiling implements FLCA_RF.py::RawFormer (config 4) and ML_RF.py::RawFormer")
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("RowTiledRawFormer needs a model on a CUDA device (there is no CPU path)")

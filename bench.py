@@ -558,7 +558,8 @@ def leg_rowtiled(env, args, size, main):
 
     world, rank, dev = env.world, env.rank, env.dev
     lib = _lib.load()
-    model = build_model(env, size, "flca", "bf16", graphs=False)
+    variant = args.variant if main else "flca"    # (--row-tiled --variant ml: the multi-level variant row-tiled)
+    model = build_model(env, size, variant, "bf16", graphs=False)
     u16_host = synthetic_u16_frames(1, 0).pin_memory()              # the same frame on all ranks
     x_dev = rf.preprocess_u16(u16_host.to(dev), **PRE)
     x_host = x_dev.cpu().pin_memory()
@@ -648,12 +649,12 @@ def leg_rowtiled(env, args, size, main):
         return None
     pk = peaks()
     compute = {k: v for k, v in agg.items() if not k.startswith("band_")}
-    roof, _, _ = roofline_records(compute, n_prof, pk, size, "bf16", "flca")
+    roof, _, _ = roofline_records(compute, n_prof, pk, size, "bf16", variant)
     roof["scope"] = "rank 0's band"
     rec = {
         "value": args.steps * MP_FRAME / (ms_total * 1e-3), "unit": "MP/s", "ms_per_step": ms_total / args.steps,
         "scaling": "strong",
-        "workload": f"RawFormer-{size} (flca) forward, ONE SID Sony frame raw {H_RAW}x{W_RAW} per step, row-tiled over "
+        "workload": f"RawFormer-{size} ({variant}) forward, ONE SID Sony frame raw {H_RAW}x{W_RAW} per step, row-tiled over "
                     f"{world} GPU(s) (bands of {[r // 16 for _, r in rf.plan_bands(H_RAW, world)]} x 16 rows), random-init weights",
         "parallelism": f"row-tiled x{world}: 4-row halo exchange + all-reduce of the per-image reductions per Conv_Transformer, "
                        "peer-mapped memory over NVLink, no NCCL on the data path",

@@ -343,7 +343,8 @@ int rf_band_comm_reset(void* comm_own, void* stream);
 int rf_band_out_rows(const rf_band* band, int* out_rows_host, int* interior_row0_host);
 size_t rf_rawformer_band_workspace_bytes(int dim, int dtype, int variant, int H, int W, const rf_band* band);
 /* raw [1,1,H,W] float32 = the WHOLE frame (replicated on every rank: the 1-channel guidance is computed locally);
- * out = this rank's band image of the result (see rf_band_out_rows). */
+ * out = this rank's band image of the result (see rf_band_out_rows).  dtype RF_BF16 only (RF_ERR_UNSUPPORTED otherwise);
+ * variant RF_VARIANT_FLCA (FLCA_RF.py) or RF_VARIANT_ML (ML_RF.py: its colour anchor adds one sync point). */
 int rf_rawformer_forward_band(const void* packed, int dim, int dtype, int variant, const float* raw, float* out, int H,
                               int W, const rf_band* band, void* workspace, size_t workspace_bytes, void* stream);
 /* Same with a cudaEvent pair around every launch (see rf_rawformer_forward_profiled); the times of the band_halo /

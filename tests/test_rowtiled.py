@@ -63,9 +63,10 @@ def test_band_sizing_through_the_abi():
             assert lib.rf_band_out_rows(C.byref(b), C.byref(orows), C.byref(r0)) == 0
             assert r0.value == (8 if r > 0 else 0)
             assert orows.value == rows + r0.value + (8 if r < n - 1 else 0)
-    # unsupported: fp32 engine, multi-level variant, bands that do not tile the frame
+    # the multi-level variant has one more sync point (the colour anchor's output sums) -> a slightly larger region
+    assert lib.rf_band_comm_bytes(64, _lib.RF_BF16, 1, H, W, 2) > lib.rf_band_comm_bytes(64, _lib.RF_BF16, 0, H, W, 2)
+    # unsupported: fp32 engine, bands that do not tile the frame
     assert lib.rf_band_comm_bytes(64, _lib.RF_F32, 0, H, W, 2) == 0
-    assert lib.rf_band_comm_bytes(64, _lib.RF_BF16, 1, H, W, 2) == 0
     assert lib.rf_band_comm_bytes(32, _lib.RF_BF16, 0, 256, 256, 5) == 0
     b = _lib.Band()
     b.rank, b.nranks, b.row0, b.rows = 0, 2, 16, 1424          # rank 0 must start at row 0
@@ -75,12 +76,12 @@ def test_band_sizing_through_the_abi():
 
 
 def test_row_tiled_rejects_what_it_does_not_implement():
-    """No silent fallback: CPU models, the fp32 engine and the multi-level variant are refused before any device work."""
+    """No silent fallback: CPU models and the fp32 engine are refused before any device work."""
     import bayer_low_light_image_enhancement_b200 as rf
 
     with pytest.raises(RuntimeError):                                   # model on the CPU
         rf.RowTiledRawFormer(rf.RawFormer(dim=32, precision="bf16"), 128, 128, 0, 2, [0, 0])
-    with pytest.raises(NotImplementedError):                            # ML_RF variant
+    with pytest.raises(RuntimeError):                                   # ML_RF variant: supported, but not on the CPU either
         rf.RowTiledRawFormer(rf.multilevel.RawFormer(dim=32, precision="bf16"), 128, 128, 0, 2, [0, 0])
     with pytest.raises(ValueError):
         rf.plan_bands(100, 2)
@@ -177,6 +178,50 @@ def test_row_tiled_matches_whole_frame_and_oracle(case):
         bands.close()
     with torch.no_grad():
         ref = oracle.rawformer_forward({k: v.float() for k, v in sd.items()}, x.cpu(), "flca").numpy()
+    rng = max(float(ref.max() - ref.min()), 1e-6)
+    p_t, p_w = _psnr(tiled, ref, rng), _psnr(whole, ref, rng)
+    assert p_t >= 35.0, f"PSNR(row-tiled, oracle) = {p_t:.1f} dB"
+    assert abs(p_t - p_w) <= 0.5, f"row-tiled {p_t:.2f} dB vs whole-frame {p_w:.2f} dB against the oracle"
+
+
+ML_CASES = [
+    # dim, H, W, bands, input, weight scale
+    (32, 128, 128, 2, "rand", 1.5),
+    (32, 256, 192, 3, "dark", 1.5),      # uneven bands, a band with two halos
+    (64, 192, 128, 2, "rand", 1.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ML_CASES, ids=[f"ml_d{c[0]}_{c[1]}x{c[2]}_n{c[3]}" for c in ML_CASES])
+def test_row_tiled_multilevel_matches_whole_frame_and_oracle(case):
+    """ML_RF.py::RawFormer row-tiled (config 4 x config 5): FLCA_Pyramid gates from the whole-frame guidance sums (replicated),
+    channel sums over the band's interior, colour anchor (ML_RF.py:284-285) with the output-channel sums all-reduced over the
+    bands, LL nudge at the band's frame rows."""
+    import bayer_low_light_image_enhancement_b200 as rf
+    from oracle import rawformer_torch as oracle
+
+    dim, H, W, n, kind, scale = case
+    dev = torch.device("cuda", 0)
+    m = rf.multilevel.RawFormer(dim=dim, precision="bf16")
+    sd = T.make_state_dict(m, seed=977 + dim, scale=scale)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    x = torch.from_numpy(T.gen_input(kind, (1, 1, H, W), 5)).to(dev)
+    with torch.no_grad():
+        whole = m(x).float().cpu().numpy()
+    bands = rf.LocalBands(m, H, W, n)
+    try:
+        for it in range(2):
+            tiled = bands(x).float().cpu().numpy()
+            assert tiled.shape == whole.shape and np.isfinite(tiled).all()
+            rng = max(float(whole.max() - whole.min()), 1e-6)
+            p = _psnr(tiled, whole, rng)
+            assert p >= 50.0, f"frame {it}: PSNR(row-tiled, whole-frame) = {p:.1f} dB"
+    finally:
+        bands.close()
+    with torch.no_grad():
+        ref = oracle.rawformer_forward({k: v.float() for k, v in sd.items()}, x.cpu(), "ml").numpy()
     rng = max(float(ref.max() - ref.min()), 1e-6)
     p_t, p_w = _psnr(tiled, ref, rng), _psnr(whole, ref, rng)
     assert p_t >= 35.0, f"PSNR(row-tiled, oracle) = {p_t:.1f} dB"
