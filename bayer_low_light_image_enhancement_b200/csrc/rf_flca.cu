@@ -9,7 +9,7 @@
 
 namespace rf {
 
-constexpr int FLCA_SLOTS = 160;  // partial-sum slots per image (== IT_SLOTS of the tensor-core kernel, which owns one slot per
+constexpr int FLCA_SLOTS = 320;  // partial-sum slots per image (== IT_SLOTS of the tensor-core kernel, which owns one slot per
                                  // CTA; this CUDA-core kernel accumulates atomically), summed in order by k_se_fold / se_finalize
 constexpr int FLCA_LS = 32;      // pixels per warp strip
 

@@ -19,16 +19,17 @@
 //   thread 32: TMA loads (guidance patch + feature tile) 3 tiles ahead, TMA store of the finished tile
 //   thread 0 : tcgen05.mma of tile i+1 into the other TMEM buffer while
 //   all warps: epilogue of tile i (tcgen05.ld, feature tile from smem, result in place)
+#include <stdlib.h>
+
 #include "rf_kernels.cuh"
 #include "rf_tma.cuh"
 
 namespace rf {
 
 constexpr int IT_THREADS = 512;
-constexpr int IT_SLOTS = 160;         // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image; slot = CTA index within its
+constexpr int IT_SLOTS = 320;         // == FLCA_SLOTS (rf_flca.cu): partial-sum slots per image; slot = CTA index within its
                                       // channel chunk (< num_sms <= 160): every CTA owns its slot -> plain stores, and the
                                       // ordered sum over the slots (k_se_fold) makes the channel sums bit-reproducible
-constexpr int IT_NF = 5;              // feature/output ring depth: loads run 3 tiles ahead, stores drain 1 tile behind
 constexpr int IT_NGS = 4;             // guidance patch ring depth
 constexpr int IT_TW = 8, IT_TH = 16;  // tile = 8 x 16 pixels (patch rows = the 8-row core-matrix groups)
 constexpr int IT_PITCH = IT_TW + 2, IT_NPIX = (IT_TW + 2) * (IT_TH + 2);
@@ -85,12 +86,16 @@ void launch_split_bf16x8(Ctx& ctx, const float* g4, void* out16, i64 npix, int s
   launch_pdl(k_split_bf16x8, dim3(gx), dim3(256), 0, ctx.stream, (const float4*)g4, (uint4*)out16, npix, stride_floats / 4);
 }
 
-template <int MODE, int UPT>
-__global__ void __launch_bounds__(IT_THREADS, 1)
+// TWO: two CTAs per SM (ring depth 4 instead of 5, <= 64 registers): the tile loop is a latency chain (accumulator ready ->
+// tcgen05.ld -> MUFU -> store -> CTA barrier -> TMA store) with 8 elements per thread per tile; a second resident CTA fills it
+template <int MODE, int UPT, bool TWO>
+__global__ void __launch_bounds__(IT_THREADS, TWO ? 2 : 1)
 k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapIn,
             const __grid_constant__ CUtensorMap mapOut, const Im2colTcParams p) {
   constexpr int SEG = MODE == 0 ? 3 : (MODE == 2 ? 2 : 1);
   constexpr bool MODULATE = MODE != 1;               // multiply the feature tile (vs. bias epilogue)
+  constexpr int IT_NF = TWO ? 4 : 5;                 // feature/output ring depth: loads run IT_NF - 2 tiles ahead, stores drain 1 behind
+  constexpr int AHEAD = IT_NF - 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sF = base;                                   // IT_NF x 16 KB feature / output tiles (ring, in place)
@@ -249,7 +254,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   pdl_trigger();                                     // (after the TMEM allocation, see launch_pdl)
 
   if (tid == 32) {
-    for (int j = 0; j < 3 && j < n_my; ++j) issue_loads(j);
+    for (int j = 0; j < AHEAD && j < n_my; ++j) issue_loads(j);
   }
   if (warp == 0 && n_my > 0) issue_mma(0, tmem_base);
 
@@ -261,7 +266,7 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
       // stage (i+3) % IT_NF, so the load that runs 3 tiles ahead may overwrite it; the guidance slot (i+3) % IT_NGS was
       // consumed by the MMAs of tile i-1, complete before the epilogue of tile i-1 started
       tma_store_wait_read<1>();
-      if (i + 3 < n_my) issue_loads(i + 3);
+      if (i + AHEAD < n_my) issue_loads(i + AHEAD);
     }
     if (warp == 0 && i + 1 < n_my) issue_mma(i + 1, tmem_base);   // TMEM buffer a^1 was drained by epilogue(i-1)
     if (MODULATE) {
@@ -335,6 +340,15 @@ k_im2col_tc(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CU
   }
 }
 
+static bool im2col_two_enabled() {
+  static int on = -1;                     // debugging aid: RAWFORMER_B200_IM2COL_TWO=0 keeps one CTA per SM
+  if (on < 0) {
+    const char* e = getenv("RAWFORMER_B200_IM2COL_TWO");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 bool im2col_tc_supported(const Ctx& ctx, int C) {
   if (!tcgen05_enabled() || ctx.dtype != RF_BF16) return false;
   if (C % 32 && C % 48) return false;
@@ -377,15 +391,18 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   const i64 total = (i64)p.tiles_per_img * B;
   if (total > 0x7fffffff || p.nchunks > num_sms()) return false;
   p.total_tiles = (int)total;
-  p.lanes = num_sms() / p.nchunks;
-  if (p.lanes > p.total_tiles) p.lanes = p.total_tiles;
-  p.parts = parts;
-  p.row_bytes = (uint32_t)Cc * 2;
-  p.swz = p.row_bytes == 128 ? 128 : (p.row_bytes == 64 ? 64 : 0);
   const int N = (mode == 0 ? 3 : (mode == 2 ? 2 : 1)) * Cc;
   int cols = 32;
   while (cols < N) cols *= 2;
   p.tmem_cols = cols;
+  // two CTAs per SM where two double-buffered accumulators fit in tensor memory (FLCA modulation at C = 32)
+  const bool two = im2col_two_enabled() && mode == 0 && upt == 1 && 4 * cols <= 512;
+  p.lanes = (two ? 2 : 1) * num_sms() / p.nchunks;
+  if (p.lanes > IT_SLOTS) p.lanes = IT_SLOTS;
+  if (p.lanes > p.total_tiles) p.lanes = p.total_tiles;
+  p.parts = parts;
+  p.row_bytes = (uint32_t)Cc * 2;
+  p.swz = p.row_bytes == 128 ? 128 : (p.row_bytes == 64 ? 64 : 0);
   CUtensorMap mG, mIn, mOut;
   const i64 dg[3] = {(i64)8 * W, H, B};
   const i64 sg[3] = {1, (i64)8 * W, (i64)8 * W * H};
@@ -400,22 +417,23 @@ static bool run_im2col_tc(Ctx& ctx, int mode, const void* feat, const void* G16,
   } else {
     mIn = mOut;
   }
-  const size_t smem = 1024 + IT_NF * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + IT_NF) + 64 + 16 * 16 * 4 + 64;
-#define RF_IT_LAUNCH(M, U)                                                                                                  \
+  const int nf = two ? 4 : 5;
+  const size_t smem = 1024 + nf * 16384 + 30720 + IT_NGS * IT_PATCH_STRIDE + 8 * (2 + IT_NGS + nf) + 64 + 16 * 16 * 4 + 64;
+#define RF_IT_LAUNCH(M, U, T)                                                                                               \
   do {                                                                                                                       \
     static bool attr = false;                                                                                                \
     if (!attr) {                                                                                                             \
-      if (cudaFuncSetAttribute(k_im2col_tc<M, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)   \
+      if (cudaFuncSetAttribute(k_im2col_tc<M, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
         return false;                                                                                                        \
       attr = true;                                                                                                           \
     }                                                                                                                        \
-    launch_pdl(k_im2col_tc<M, U>, dim3(grid), dim3(IT_THREADS), smem, ctx.stream, mG, mIn, mOut, p);                         \
+    launch_pdl(k_im2col_tc<M, U, T>, dim3(grid), dim3(IT_THREADS), smem, ctx.stream, mG, mIn, mOut, p);                      \
   } while (0)
   const int grid = p.lanes * p.nchunks;
-  if (mode == 0) { if (upt == 1) RF_IT_LAUNCH(0, 1); else RF_IT_LAUNCH(0, 2); }
-  else if (mode == 1) { if (upt == 1) RF_IT_LAUNCH(1, 1); else RF_IT_LAUNCH(1, 2); }
-  else if (mode == 2) { if (upt == 1) RF_IT_LAUNCH(2, 1); else RF_IT_LAUNCH(2, 2); }
-  else { if (upt == 1) RF_IT_LAUNCH(3, 1); else RF_IT_LAUNCH(3, 2); }
+  if (mode == 0) { if (two) RF_IT_LAUNCH(0, 1, true); else if (upt == 1) RF_IT_LAUNCH(0, 1, false); else RF_IT_LAUNCH(0, 2, false); }
+  else if (mode == 1) { if (upt == 1) RF_IT_LAUNCH(1, 1, false); else RF_IT_LAUNCH(1, 2, false); }
+  else if (mode == 2) { if (upt == 1) RF_IT_LAUNCH(2, 1, false); else RF_IT_LAUNCH(2, 2, false); }
+  else { if (upt == 1) RF_IT_LAUNCH(3, 1, false); else RF_IT_LAUNCH(3, 2, false); }
 #undef RF_IT_LAUNCH
   return true;
 }
@@ -426,7 +444,9 @@ bool launch_flca_mod_tc(Ctx& ctx, const void* feat, const void* G16, const float
   if (used_slots) {              // == p.lanes of run_im2col_tc: the slots (per image) the kernel writes
     const int Cc = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 48);
     const i64 total = (i64)cdiv(Wf, IT_TW) * cdiv(Hf, IT_TH) * B;
-    int lanes = num_sms() / (C / Cc);
+    const bool two = im2col_two_enabled() && Cc == 32;     // (== run_im2col_tc: mode 0, one unit per thread, N = 96)
+    int lanes = (two ? 2 : 1) * num_sms() / (C / Cc);
+    if (lanes > IT_SLOTS) lanes = IT_SLOTS;
     if (lanes > total) lanes = (int)total;
     *used_slots = lanes;
   }
