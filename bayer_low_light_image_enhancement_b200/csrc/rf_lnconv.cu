@@ -81,6 +81,7 @@ struct LcP {
   int nr;                // raw patch buffers in use
   int proj;              // FFN, C = 32: project_out fused in front (x1 = x + Mw v + proj_b never reaches HBM), see below
   const float* proj_b;   // [C]
+  int wpre;              // static weights are fetched before the dependency wait (debugging aid: RAWFORMER_B200_LNCONV_WPRE=0)
   int own_stats;         // C = 32: no statistics tensor, the re-layout thread computes (sum, sumsq) of its pixel itself
   int sched;             // 0: the first contraction of tile i+1 runs under tile i's accumulator loads; 1: after them
   unsigned long long* dbg;   // debugging aid (RAWFORMER_B200_LNCONV_DBG=1): cycles per phase of compute thread 0, per CTA
@@ -281,7 +282,17 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_trigger();
-  pdl_wait();
+  // What does not depend on the kernel before -- the packed weights (not CAT's per-image ones, nor Mw) and the bias tables -- is
+  // fetched BEFORE the dependency wait: under the previous kernel's tail (programmatic dependent launch)
+  auto load_weights = [&]() {
+    mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES + ((PJ && p.proj) ? (uint32_t)(C * C * 2) : 0u));
+    for (int tap = 0; tap < 9; ++tap) {
+      tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, p.t0);
+      if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * K::CIN * 2, &mapW, w_full, 0, tap, p.t1);
+    }
+    if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, p.t0, 0, 0);     // pointwise2 columns of these hidden channels
+  };
+  if (MODE != LC_CAT && p.wpre && tid == 0 && (int)blockIdx.x < p.total_tiles) load_weights();
   {
     float* bt = reinterpret_cast<float*>(smem_raw + (sBT - smem_u32(smem_raw)));
     for (int i = tid; i < 9 * N; i += LC_THREADS) {
@@ -297,6 +308,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       }
     }
   }
+  pdl_wait();
   __syncthreads();
 
   const int first = blockIdx.x, stride = gridDim.x;
@@ -324,12 +336,7 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0 && n > 0) {
-      mbar_expect_tx(w_full, K::W_BYTES + K::W2_BYTES + ((PJ && p.proj) ? (uint32_t)(C * C * 2) : 0u));
-      for (int tap = 0; tap < 9; ++tap) {
-        tma_load_3d(sW + (uint32_t)tap * K::WTAP, &mapW, w_full, 0, tap, p.t0);
-        if (p.tn < N) tma_load_3d(sW + (uint32_t)tap * K::WTAP + (uint32_t)p.tn * K::CIN * 2, &mapW, w_full, 0, tap, p.t1);
-      }
-      if (MODE == LC_FFN) tma_load_3d(sW2, &mapW2, w_full, p.t0, 0, 0);     // pointwise2 columns of these hidden channels
+      if (MODE == LC_CAT || !p.wpre) load_weights();
       if (PJ && p.proj) tma_load_3d(sMw, &mapM, w_full, 0, 0, 0);
       int rb = 0, vb = 0;
       uint32_t rph = 0, vph = 0;
@@ -931,6 +938,14 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   p.proj_b = p.proj ? pj->pb : nullptr;
   const size_t smem = K::smem(p.nr) + (p.proj ? 1024 + 2048 + 3 * (size_t)K::RAW_SRC + 4096 + 256 : 0);
   if (smem > 232448) return 0;
+  {
+    static int wpre = -1;
+    if (wpre < 0) {
+      const char* e = getenv("RAWFORMER_B200_LNCONV_WPRE");
+      wpre = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.wpre = wpre;
+  }
   p.own_stats = (K::LN && stats == nullptr) ? 1 : 0;
   if (p.own_stats && C != 32) return 0;
   if ((K::LN && ((uintptr_t)stats & 15)) || ((uintptr_t)x & 15)) return 0;

@@ -185,12 +185,23 @@ class _BlockPart(_Op):
     def _weights(self, bw, keep):
         raise NotImplementedError
 
+    def __getstate__(self):                       # (copy / pickle: the cached ctypes record holds raw pointers)
+        d = self.__dict__.copy()
+        d.pop("_bw_cache", None)
+        return d
+
     def _run(self, fn_name, C_, x, extra_in=(), hy_wy=None, variant=None):
         lib = _lib.load()
         b, _, h, w = x.shape
         hy, wy = hy_wy if hy_wy is not None else (h, w)
-        bw, keep = BlockWeights(), []
-        self._weights(bw, keep)
+        # the marshalled weight record is kept until a parameter / buffer changes (pointer or in-place version)
+        sig = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        cached = self.__dict__.get("_bw_cache")
+        if cached is None or cached[0] != sig:
+            bw, keep = BlockWeights(), []
+            self._weights(bw, keep)
+            self.__dict__["_bw_cache"] = cached = (sig, bw, keep)
+        bw = cached[1]
         dt = self._dtype()
         nbytes = lib.rf_block_workspace_bytes(C_, dt, b, h, w, hy, wy)
         ws = _lib.shared_workspace(nbytes, x.device)

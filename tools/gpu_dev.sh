@@ -1,6 +1,8 @@
 #!/bin/bash
-# full -m gpu suite + smoke + compute-sanitizer memcheck of the dense-conv forms on small frames
-tag=${1:-s27}
-timeout 700 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/${tag}_tests.log; cat gpurun_out/${tag}_tests.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 500 compute-sanitizer --tool memcheck --print-limit 10 python tools/dev_lnconv.py > gpurun_out/${tag}_memcheck.log 2>&1; echo memcheck rc=$?; tail -6 gpurun_out/${tag}_memcheck.log
+# dev: A/B (alternating) of a debugging-aid environment variable on the default bench
+tag=${1:-s28}; var=${2:-RAWFORMER_B200_LNCONV_WPRE}
+timeout 60 python tools/dev_lnconv.py > gpurun_out/${tag}_dev.log 2>&1; echo dev rc=$?; tail -3 gpurun_out/${tag}_dev.log
+for k in 1 2 3; do for v in 0 1; do
+env $var=$v timeout 100 python bench.py --no-cpu --no-extra --steps 30 > gpurun_out/${tag}_bench_$v$k.json 2> gpurun_out/${tag}_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/${tag}_bench_$v$k.json')); print('$var=$v', d['ms_per_step'], d['value'], d['clocks']['sm_mhz'])"
+done; done
