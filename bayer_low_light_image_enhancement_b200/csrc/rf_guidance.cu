@@ -152,14 +152,16 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
     bilinear_taps(x, Wy, Wf, xa, xb, lx);
     v[o] = bilerp(cr + b * (i64)Hy * Wy, Hy, Wy, ya, yb, ly, xa, xb, lx);
     v[o + 1] = bilerp(cb + b * (i64)Hy * Wy, Hy, Wy, ya, yb, ly, xa, xb, lx);
-    float* g = G + (b * total + idx) * NG;
+    float* g = G + (b * total + idx) * NG;                // (G == nullptr: only the bf16 [hi | lo] pixels are wanted)
     if (G16a != nullptr) G16a[b * total + idx] = split4(v[0], v[1], v[2], v[3]);
     if (NG == 4) {
-      *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
+      if (G != nullptr) *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
       v[6] = sqrtf(v[4] * v[4] + v[5] * v[5] + 1e-8f);  // chr_mag, ML_RF.py:172
-      *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], 0.f);
+      if (G != nullptr) {
+        *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], 0.f);
+      }
       if (G16b != nullptr) G16b[b * total + idx] = split4(v[4], v[5], v[6], 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
@@ -181,7 +183,8 @@ void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1,
   if (y_rows < 0) { y_begin = 0; y_rows = Hf; }
   i64 total = (i64)y_rows * Wf;
   unsigned gx = (unsigned)(cdivl(total, 256) < 4 * num_sms() ? cdivl(total, 256) : 4 * num_sms());
-  ScopedLaunch sl(RF_K_GUIDANCE, 4.0 * NG * B * total + 4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
+  ScopedLaunch sl(RF_K_GUIDANCE, (G ? 4.0 * NG : 0.0) * B * total + (G16a ? 16.0 : 0.0) * B * total * (G16b ? 2 : 1) +
+                                     4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
   if (NG == 4)
     k_guidance_stage<4><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
                                                           Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);

@@ -5,6 +5,8 @@
 // workspace.  The same code runs in "dry" mode to answer the *_workspace_bytes queries.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "rf_kernels.cuh"
 
 namespace rf {
@@ -226,7 +228,7 @@ static void flca_branch(Ctx& ctx, const PackedBlock& pb, int variant, const void
           if (!done) recorder().last_cuda_error = (int)cudaErrorNotSupported;
         }
       }
-      if (!done) launch_pyr_spatial(ctx, cur, sg.G, pb.flca_w, gates, xs, smode, slevel, B, H, W, C);
+      if (!done && sg.G != nullptr) launch_pyr_spatial(ctx, cur, sg.G, pb.flca_w, gates, xs, smode, slevel, B, H, W, C);
       GemmP g1 = gemm_rows(xs, C, pb.res_w0, pb.res_b0, t1, C, B, P, RF_K_GEMM_PYR_RES1);
       g1.act = ACT_RELU;
       launch_gemm(ctx, g1);
@@ -537,10 +539,13 @@ static void conv_transformer(Ctx& ctx, const PackedBlock& pb, int variant, const
 // guidance of one stage from planar y-derived maps
 static void make_stage(Ctx& ctx, int variant, Stage& sg, int Hf, int Wf, const float* LL1, const float* yh1, int H1, int W1,
                        const float* LL2, const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy,
-                       int B, int y_begin = 0, int y_rows = -1) {
+                       int B, int y_begin = 0, int y_rows = -1, int C_stage = 0) {
   const int NG = variant == RF_VARIANT_ML ? 8 : 4;
   sg.H = Hf; sg.W = Wf;
-  sg.G = ctx.arena.get<float>((size_t)B * Hf * Wf * NG);
+  // the fp32 maps are read by the CUDA-core kernels only: where the stage's FLCA kernels run on the tensor cores (they read
+  // the [hi | lo] bf16 pixels) the maps are neither allocated nor written (half of this pass's stores)
+  const bool tc_only = C_stage > 0 && ctx.dtype == RF_BF16 && tcgen05_enabled() && im2col_tc_supported(ctx, C_stage);
+  sg.G = tc_only ? nullptr : ctx.arena.get<float>((size_t)B * Hf * Wf * NG);
   sg.sums = nullptr;
   if (variant == RF_VARIANT_ML) {
     sg.sums = ctx.arena.get<float>((size_t)B * 8);
@@ -621,9 +626,10 @@ static int model_forward(Ctx& ctx, const PackedModel& pm, int variant, const flo
   launch_luma_finalize(ctx, x_ds, y_raw, ymax, 1e-6f, y, cr, cb, B, h, w);
   GuidanceMaps gm = make_pyramid(ctx, variant, y, pm.haar, B, h, w);
   Stage st[4];
+  // (the guidance of stages 1-3 on a side stream next to the embedding and block 0: measured, no gain -- 5.451 vs 5.435 ms)
   for (int s = 0; s < 4; ++s)
     make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w,
-               B);
+               B, 0, -1, d << s);
   auto feat_buf = [&](int s) { return A.elems((size_t)B * (P0 >> (2 * s)) * ((size_t)d << s), ctx.dtype); };
   void* x0 = feat_buf(0);
   void* x16 = nullptr;
@@ -753,7 +759,7 @@ static int model_forward_band(Ctx& ctx, const PackedModel& pm, int variant, cons
     // variant, whose gates need the maps' whole-frame sums, ML_RF.py:151-156: every rank makes the whole maps)
     const bool ml = variant == RF_VARIANT_ML;
     make_stage(ctx, variant, st[s], h >> s, w >> s, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, h, w, B,
-               ml ? 0 : first_row(s), ml ? -1 : rows_img(s));
+               ml ? 0 : first_row(s), ml ? -1 : rows_img(s), d << s);
     // the band's view of the stage guidance: rows [first_row, first_row + rows_img)
     const size_t px0 = (size_t)first_row(s) * (w >> s);
     if (st[s].G) st[s].G += px0 * (ml ? 8 : 4);
@@ -924,7 +930,8 @@ static int run_block_entry(const rf_block_weights* w, int C, int dtype, int vari
   if (y != nullptr || dry) {
     if (Hy > 0 && Wy > 0) {
       GuidanceMaps gm = make_pyramid(ctx, variant, y, w ? w->flca_filt : nullptr, B, Hy, Wy);
-      make_stage(ctx, variant, env.sg, Hf, Wf, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, Hy, Wy, B);
+      make_stage(ctx, variant, env.sg, Hf, Wf, gm.LL1, gm.yh1, gm.H1, gm.W1, gm.LL2, gm.yh2, gm.H2, gm.W2, cr, cb, Hy, Wy, B, 0, -1,
+                 C);
     }
   }
   env.sg.H = Hf; env.sg.W = Wf;
