@@ -422,12 +422,10 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
   const i64 P = (i64)H * W;
   Arena& A = ctx.arena;
   const size_t mk = A.mark();
-  void* x1 = A.elems((size_t)B * P * C, ctx.dtype);
   if (ctx.dtype == RF_BF16 && tcgen05_enabled()) {
     // bf16 mode: both LayerNorms are folded into the 1x1 conv that follows them (W*diag(g), per-row mean/rstd applied in
     // the GEMM epilogue), so the normalised tensors never exist.  norm1 statistics: one read pass over the block input;
     // norm2 statistics: emitted by the project_out GEMM epilogue that produces x1.
-    float* st2 = A.get<float>((size_t)B * P * 2 * 2);     // up to two N tiles of partials
     LnFold l1;
     if (pre != nullptr && pre->stats != nullptr && pre->npart > 0) {
       l1 = *pre;
@@ -438,9 +436,8 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
       launch_row_stats(ctx, feat, st1, B * P, C);
       l1.stats = st1; l1.npart = 1;
     }
-    LnFold l2;
-    l2.stats = st2;
-    // project_out fused in front of the FFN (C = 32): x1 = feat + Mw v + b exists per halo patch inside the kernel only
+    // project_out fused in front of the FFN (C = 32): x1 = feat + Mw v + b exists per halo patch inside the kernel only (neither
+    // x1 nor its statistics tensor is allocated)
     const bool fuse_proj = ctx.dtype == RF_BF16 && pb.ffn_cw != nullptr && pb.qkv_cw != nullptr && lnconv_proj_supported(ctx, C, H, W);
     if (fuse_proj) {
       AttnKeep keep;
@@ -456,9 +453,14 @@ static void transformer(Ctx& ctx, const PackedBlock& pb, const void* feat, void*
       A.release(mk);
       return;
     }
+    void* x1 = A.elems((size_t)B * P * C, ctx.dtype);
+    float* st2 = A.get<float>((size_t)B * P * 2 * 2);     // up to two N tiles of partials
+    LnFold l2;
+    l2.stats = st2;
     l2.npart = attention(ctx, pb, feat, feat, x1, B, H, W, &l1, st2);
     ffn(ctx, pb, x1, x1, out, B, H, W, &l2);
   } else {
+    void* x1 = A.elems((size_t)B * P * C, ctx.dtype);
     void* ln = A.elems((size_t)B * P * C, ctx.dtype);
     launch_layernorm(ctx, feat, pb.ln1_g, pb.ln1_b, ln, 1e-5f, 0, B * P, C);
     attention(ctx, pb, ln, feat, x1, B, H, W);
