@@ -345,15 +345,15 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         if (i >= p.nr) mbar_wait(raw_free(rb), rph ^ 1u);
         const int px0 = tl.tx * 8, py0 = tl.ty * 16, b = tl.b;
         tile_next(tl);
-        mbar_expect_tx(raw_full(rb), K::RAW_BYTES + ((K::LN && !p.own_stats) ? LC_ST_BYTES : 0u));
+        const uint32_t rfull = raw_full(rb);      // (p.proj: the v patch of the tile lands on the same barrier)
+        mbar_expect_tx(rfull, K::RAW_BYTES + ((K::LN && !p.own_stats) ? LC_ST_BYTES : 0u) + ((PJ && p.proj) ? K::RAW_BYTES : 0u));
         tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE, &mapX, raw_full(rb), 0, px0 - 1, py0 - 1, b);
         if (MODE == LC_CAT) tma_load_4d(sRaw + (uint32_t)rb * K::RAW_STRIDE + K::RAW_SRC, &mapW2, raw_full(rb), 0, px0 - 1, py0 - 1, b);
         if (K::LN && !p.own_stats) tma_load_3d(sSt + (uint32_t)rb * LC_ST_STRIDE, &mapS, raw_full(rb), 2 * (px0 - 2), py0 - 1, b);
         if (++rb == p.nr) { rb = 0; rph ^= 1u; }
         if (PJ && p.proj) {                  // (mapS is the v tensor's patch map here)
           if (i >= NV) mbar_wait(v_free(vb), vph ^ 1u);
-          mbar_expect_tx(v_full(vb), K::RAW_BYTES);
-          tma_load_4d(sV + (uint32_t)vb * K::RAW_SRC, &mapS, v_full(vb), 0, px0 - 1, py0 - 1, b);
+          tma_load_4d(sV + (uint32_t)vb * K::RAW_SRC, &mapS, rfull, 0, px0 - 1, py0 - 1, b);
           if (++vb == NV) { vb = 0; vph ^= 1u; }
         }
       }
@@ -379,12 +379,16 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       const uint32_t b_hi = (uint32_t)(wdesc0 >> 32), b_lo0 = (uint32_t)wdesc0;
       // project_out of patch j (p.proj): rows = patch pixels 0..255 of the v patch as it landed (64-byte swizzled K-major),
       // two row groups, N = C, K = C -> x1acc
-      int v_b = 0;
-      uint32_t v_ph = 0;
+      // Waits are what the tile loop pays for (150-200 cycles each, on the chain): the patches of tile j (x and v) land on ONE
+      // barrier; x1acc is free once the compute warps have arrived on `drained` of the tile whose phase A read it -- which the
+      // first contraction issued just before has waited for (schedule 1) -- so only the first patches wait for x1_free
+      int v_b = 0, m0_rb = 0;
+      uint32_t m0_rph = 0;
       auto mma0 = [&](int j) {
         if (!(PJ && p.proj)) return;
-        mbar_wait(v_full(v_b), v_ph);
-        if (j >= 1) mbar_wait(x1_free, (uint32_t)((j - 1) & 1));          // the re-layout of patch j-1 has read x1acc
+        mbar_wait(raw_full(m0_rb), m0_rph);
+        if (++m0_rb == p.nr) { m0_rb = 0; m0_rph ^= 1u; }
+        if (j >= 1 && j <= 3) mbar_wait(x1_free, (uint32_t)((j - 1) & 1));     // part 1 of patch j-1 (before the tile loop) has read x1acc
         tc_fence_after();
         if (leader) {
           const uint64_t ad = make_kmajor_desc(sV + (uint32_t)v_b * K::RAW_SRC, C), bd = make_kmajor_desc(sMw, C);
@@ -400,16 +404,18 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           umma_commit(v_free(v_b));
         }
         __syncwarp();
-        if (++v_b == NV) { v_b = 0; v_ph ^= 1u; }
+        if (++v_b == NV) v_b = 0;
       };
       int tb = 0;
       uint32_t tph = 0;
       long long t_issue = 0;
       auto mma1 = [&](int i) {
         const int s = i & 1;
-        mbar_wait(t_full(tb), tph);
-        if (i >= 2) mbar_wait(drained(s), (uint32_t)(((i >> 1) + 1) & 1));   // tile i-2's accumulator is in registers
-        if (p.sched == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));   // ... and tile i-1's
+        mbar_wait(t_full(tb), tph);          // (implied by the wait below in schedule 1; dropping it measured neutral: kept)
+        // tile i-2's accumulator (the one this batch overwrites) is in registers; schedule 1: tile i-1's too -- which implies
+        // the former (every warp arrives tile by tile), so ONE wait either way
+        if (p.sched == 1 && i >= 1) mbar_wait(drained(s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
+        else if (i >= 2) mbar_wait(drained(s), (uint32_t)(((i >> 1) + 1) & 1));
         tc_fence_after();
         if (DBG) t_issue = clock64();
         if (leader) {
@@ -696,15 +702,16 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     for (int i = 0; i < n; ++i) {
       // ---- A: both contractions that feed this step are complete -> accumulators into registers ----
       mark(0);
-      lc_warp_wait(mma1_done(i & 1), (uint32_t)((i >> 1) & 1), lane);
+      // (with a second contraction: its commit for tile i-1 came after this tile's first contraction was issued, in both
+      // schedules, and a commit covers everything issued before it: one wait instead of two)
+      if (!(K::SECOND && i >= 1)) lc_warp_wait(mma1_done(i & 1), (uint32_t)((i >> 1) & 1), lane);
       mark(1);
       if (K::SECOND && i >= 1) lc_warp_wait(mma2_done, (uint32_t)((i - 1) & 1), lane);
       // (p.proj) x1acc of the patch two tiles ahead is read here too, with the tensor pipe empty
+      // Its MMAs were issued before the second contraction of tile i-1, whose completion was just awaited (a commit covers
+      // everything issued before it); the issuer had waited for the patch's barrier: no wait of its own here, except for i = 0
       const bool pj_on = PJ && p.proj && i + 3 < n;
-      if (pj_on) {
-        lc_warp_wait(raw_full(p1_rb), p1_rph, lane);
-        lc_warp_wait(mma0_done, (uint32_t)((i + 1) & 1), lane);
-      }
+      if (pj_on && i == 0) lc_warp_wait(mma0_done, 1u, lane);
       tc_fence_after();
       mark(2);
       uint32_t v[K::UPW][8], v3[UB][8], xa[2][8];
@@ -720,9 +727,6 @@ k_lnconv(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       tmem_ld_wait();
       tc_fence_before();
       warp_arrive(drained(i & 1));
-      if (PJ) {
-        if (pj_on) warp_arrive(x1_free);
-      }
       mark(3);
       // ---- B: epilogues on registers ----
       if (MODE == LC_FFN && i >= 1) epi_b(v3);
@@ -935,6 +939,7 @@ static int lnconv_launch(Ctx& ctx, const void* x, const float* stats, const void
   }
   // (p.proj: + its barriers and bias, the 1 KB-aligned Mw tile, three v patches and the 4 KB the second row group reads past them)
   p.proj = (pj != nullptr && MODE == LC_FFN && C == 32) ? 1 : 0;
+  if (p.proj) p.sched = 1;                 // (the x1acc hand-over relies on the order of schedule 1, see the issuer)
   p.proj_b = p.proj ? pj->pb : nullptr;
   const size_t smem = K::smem(p.nr) + (p.proj ? 1024 + 2048 + 3 * (size_t)K::RAW_SRC + 4096 + 256 : 0);
   if (smem > 232448) return 0;
