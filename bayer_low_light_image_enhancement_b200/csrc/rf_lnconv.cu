@@ -34,8 +34,10 @@
 // heads 4-7 -- the Gram is block-diagonal over the heads -- and v).
 //
 // Measured (RawFormer-S full frame, B200): FFN 486 -> 228 us and qkv (1x1 + depthwise + Gram) 469 -> 218 us per stage-0
-// block, 249 -> 206 and 251 -> 212 us per stage-1 block; Conv_out 88 -> 67 us at stage 1.  RAWFORMER_B200_LNCONV_DBG=1
-// prints the per-phase cycle counters of compute warp 0.
+// block, 249 -> 206 and 251 -> 212 us per stage-1 block; Conv_out 88 -> 67 us at stage 1; with project_out in front of the
+// stage-0 FFN (p.proj below) 312 us against 224 + 127 for the pair.  RAWFORMER_B200_LNCONV_DBG=1 prints the per-phase cycle
+// counters of compute warp 0.  The tile loop is a dependency chain on which every mbarrier wait costs 50-200 cycles, even on a
+// phase that completed long ago: a completion that causally follows another one stands for it (see the comments at the waits).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
