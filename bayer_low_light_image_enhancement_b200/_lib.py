@@ -237,7 +237,9 @@ class Workspace:
         if b is None or b.numel() < nbytes:
             if b is not None:
                 b.record_stream(stream)          # work already enqueued on this stream may still use the old buffer
-            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            # zero-filled once: a scratch buffer straight from the allocator may hold any bit pattern (open issue
+            # "workspace history")
+            b = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._buf[key] = b
         return b
 

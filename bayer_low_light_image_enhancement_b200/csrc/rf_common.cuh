@@ -6,6 +6,8 @@
 //   * every launcher takes a Ctx (stream + bump arena over the caller's workspace); in `dry` mode the
 //     launchers do nothing, which is how the *_workspace_bytes queries size the arena.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -147,10 +149,14 @@ struct Arena {
   void* alloc(size_t bytes) {
     off = align_up(off, 256);
     char* p = base ? base + off : nullptr;
+    // debugging aid (RAWFORMER_B200_ARENA_LOG=1): offset and size of every allocation of a real forward, in call order
+    static const bool log = getenv("RAWFORMER_B200_ARENA_LOG") != nullptr;
+    if (log && base) fprintf(stderr, "[arena] #%d off %zu size %zu\n", nlog++, off, bytes);
     off += bytes;
     if (off > peak) peak = off;
     return p;
   }
+  int nlog = 0;
   template <typename U>
   U* get(size_t n) { return reinterpret_cast<U*>(alloc(n * sizeof(U))); }
   void* elems(size_t n, int dtype) { return alloc(n * esize(dtype)); }

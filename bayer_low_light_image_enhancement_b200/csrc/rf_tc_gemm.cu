@@ -1159,6 +1159,10 @@ int launch_gram_tcgen05(Ctx& ctx, const void* qkv, float* G, int C, i64 P) {
   if (ksplit > nkb / 24) ksplit = nkb / 24;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkb) ksplit = nkb;
+  // no EMPTY split: the kernel gives every split ceil(nkb / ksplit) k-blocks, so the last split(s) can end up without any
+  // (nkb = 1024, ksplit = 42: 41 x 25 >= 1024) -- such a CTA returns without writing its partial slot, and the ordered
+  // reduction that sums `ksplit` slots would read whatever the workspace held there
+  while (ksplit > 1 && (ksplit - 1) * cdiv(nkb, ksplit) >= nkb) --ksplit;
   const size_t smem = 1024 + (size_t)nst * (packed ? packed : 4) * GR_CHUNK + (packed == 1 ? GR_CHUNK : 0) + 8 * (2 * GR_STAGES + 2);
   static bool attr_set = false;
   if (!attr_set) {

@@ -511,7 +511,7 @@ class RawFormer(_Op):
             b, _, h, w = x.shape
             # the graph OWNS its scratch memory: the captured pointers stay valid for as long as the cache entry lives,
             # whatever other models, shapes or streams ask of the shared pool
-            ws = torch.empty(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), dtype=torch.uint8,
+            ws = torch.zeros(lib.rf_rawformer_workspace_bytes(self.dim, dt, self.variant, b, h, w), dtype=torch.uint8,
                              device=x.device)
             cur = torch.cuda.current_stream(x.device)
             side = torch.cuda.Stream(x.device)

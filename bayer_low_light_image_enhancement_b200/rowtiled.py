@@ -101,7 +101,7 @@ class RowTiledRawFormer:
                                                     C.byref(self._band))
         if nws == 0:
             raise ValueError(f"unsupported row-tiled configuration: dim {model.dim}, frame {H}x{W}, {nranks} bands")
-        self._ws = torch.empty(nws, dtype=torch.uint8, device=self.device)   # own: bands of one GPU run concurrently
+        self._ws = torch.zeros(nws, dtype=torch.uint8, device=self.device)   # own: bands of one GPU run concurrently
         self.rehearse()
 
     @torch.no_grad()

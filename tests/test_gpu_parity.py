@@ -599,3 +599,64 @@ def test_cuda_graph_replay(rf):
         p = psnr(got, ref, rng)
         assert p >= 45.0, f"{name}: graph vs eager PSNR {p:.1f} dB"
     assert psnr(gab, ea, rng) < 40.0         # (the replay really used the new data)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# persistent dense-conv kernels: 1, 2, 3, ... tiles per CTA (prologues, ring wrap-arounds, tails of the pipelines)
+# ---------------------------------------------------------------------------------------------------------
+TILE_CASES = [(32, 32, 1), (64, 96, 3), (160, 176, 1), (320, 304, 1), (384, 400, 2), (512, 608, 1), (1024, 1024, 1)]
+
+
+@pytest.mark.parametrize("h,w,b", TILE_CASES, ids=[f"{c[0]}x{c[1]}_b{c[2]}" for c in TILE_CASES])
+def test_dense_conv_tiles_per_cta(rf, h, w, b):
+    """RawFormer-S bf16 on frames whose stage-0 / stage-1 tile counts give the 148 persistent CTAs of rf_lnconv.cu 1, 2, 3, 5, 14
+    tiles each (and fewer tiles than CTAs): every pipeline depth of the kernels' prologues (three patches ahead with project_out
+    in front of the FFN), the wrap-around of their rings and their tails.  Each forward must finish, repeat bit-identically eager
+    and as a CUDA graph, and stay within the bf16 bar of the fp32 parity engine."""
+    m32 = rf.RawFormer(model_size="S", precision="fp32")
+    sd = T.make_state_dict(m32, seed=77, scale=1.0)
+    m32.load_state_dict(sd)
+    m32 = m32.to(dev()).eval()
+    m16 = rf.RawFormer(model_size="S", precision="bf16")
+    m16.load_state_dict(sd)
+    m16 = m16.to(dev()).eval()
+    x = cu(T.gen_input("rand", (b, 1, h, w), h + w))
+    with torch.no_grad():
+        ref = m32(x)
+        outs = [m16(x).clone() for _ in range(3)]
+        m16.enable_cuda_graphs()
+        outs += [m16(x).clone() for _ in range(3)]
+        m16.enable_cuda_graphs(False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all()
+    assert all(torch.equal(outs[0], o) for o in outs[1:]), "runs of the same forward differ"
+    r = npy(ref)
+    p = psnr(npy(outs[0]), r, max(float(r.max() - r.min()), 1e-6))
+    assert p >= 50.0, f"PSNR(bf16, fp32 engine) = {p:.1f} dB"
+
+
+def test_forward_does_not_depend_on_workspace_history(rf):
+    """The forward must not read scratch memory it has not written itself: the same frame over a zero-filled and over a
+    0xFF-filled (NaN in every float format) workspace gives bit-identical, finite results.  2000 x 2560 makes the split-K Gram of
+    stage 2 (80 000 pixels = 625 k-blocks) pick 26 splits of 25 k-blocks -- the 26th would be empty: such a CTA used to return
+    without writing its partial slot, which the ordered reduction then read (round 2: run-to-run differences of ~1e-3 on full
+    SID frames, NaN over a poisoned workspace)."""
+    from bayer_low_light_image_enhancement_b200 import _lib
+
+    m = rf.RawFormer(model_size="S", precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=11, scale=1.0))
+    m = m.to(dev()).eval()
+    h, w = 2000, 2560
+    x = cu(T.gen_input("rand", (1, 1, h, w), 5))
+    nbytes = _lib.load().rf_rawformer_workspace_bytes(m.dim, m._dtype(), m.variant, 1, h, w)
+    outs = []
+    with torch.no_grad():
+        m(x)                                          # sizes the shared workspace, packs the weights
+        ws = _lib.shared_workspace(nbytes, dev())
+        for pattern in (0x00, 0xFF, 0x7F):
+            ws.fill_(pattern)
+            torch.cuda.synchronize()
+            outs.append(m(x).clone())
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1]).all() and torch.isfinite(outs[2]).all(), "stale workspace bytes reach the output"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "the result depends on the workspace's history"
