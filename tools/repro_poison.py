@@ -10,10 +10,11 @@ dev = torch.device("cuda", 0)
 H, W = int(sys.argv[1]), int(sys.argv[2])
 size = sys.argv[3] if len(sys.argv) > 3 else "S"
 prec = sys.argv[4] if len(sys.argv) > 4 else "bf16"
-m = rf.RawFormer(model_size=size, precision=prec)
+variant = sys.argv[5] if len(sys.argv) > 5 else "flca"
+m = (rf.RawFormer if variant == "flca" else rf.multilevel.RawFormer)(model_size=size, precision=prec)
 m.load_state_dict(T.make_state_dict(m, seed=77, scale=1.0)); m = m.to(dev).eval()
 x = torch.from_numpy(T.gen_input("rand", (1, 1, H, W), H + W)).to(dev)
-nbytes = _lib.load().rf_rawformer_workspace_bytes(m.dim, m._dtype(), 0, 1, H, W)
+nbytes = _lib.load().rf_rawformer_workspace_bytes(m.dim, m._dtype(), m.variant, 1, H, W)
 with torch.no_grad():
     m(x)                                             # sizes the shared workspace, packs the weights
     ws = _lib.shared_workspace(nbytes, dev)
