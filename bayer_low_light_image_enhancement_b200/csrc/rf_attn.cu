@@ -645,8 +645,40 @@ void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float
 // sums[b][3..5] = sum of out channels.  apply: out += 0.12*(in_mean - out_mean); then
 // out += 0.03*(up(LL2) - (.299 R + .587 G + .114 B)) on the corrected values.
 // ---------------------------------------------------------------------------------------------
+// per-CTA partial sums -> this CTA's slot (plain stores: bit-reproducible, unlike atomics); 256 threads
+template <int NK>
+__device__ __forceinline__ void cta_store_sums(const float (&acc)[NK], float* slot, int nk) {
+  __shared__ float red[8][NK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = s;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nk) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    slot[threadIdx.x] = t;
+  }
+}
+__global__ void k_sum_slots(const float* __restrict__ part, int nslots, int width, float* __restrict__ out, int ostride) {
+  const int b = blockIdx.x, i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (i >= width) return;
+  float a = 0.f;
+  for (int s = lane; s < nslots; s += 32) a += part[((i64)b * nslots + s) * width + i];
+  a = warp_sum(a);
+  if (lane == 0) out[b * ostride + i] = a;
+}
+void launch_sum_slots(Ctx& ctx, const float* part, int nslots, int width, float* out, int ostride, int B) {
+  if (ctx.dry) return;
+  ScopedLaunch sl(RF_K_MISC);
+  k_sum_slots<<<B, 32 * width, 0, ctx.stream>>>(part, nslots, width, out, ostride);
+}
+
 __global__ void __launch_bounds__(256)
-k_tail_stats(const float* __restrict__ out, const float4* __restrict__ x_ds, float* sums, int h, int wd) {
+k_tail_stats(const float* __restrict__ out, const float4* __restrict__ x_ds, float* part, int h, int wd) {
   const i64 b = blockIdx.y;
   const int Ho = 2 * h, Wo = 2 * wd;
   const i64 total = (i64)Ho * Wo;
@@ -669,38 +701,46 @@ k_tail_stats(const float* __restrict__ out, const float4* __restrict__ x_ds, flo
       for (int ch = 0; ch < 3; ++ch) acc[3 + ch] += out[(b * 3 + ch) * total + i];
     }
   }
-#pragma unroll
-  for (int k = 0; k < (out != nullptr ? 6 : 3); ++k) {
-    float s = warp_sum(acc[k]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sums + b * 8 + k, s);
-  }
+  const int nk = out != nullptr ? 6 : 3;
+  cta_store_sums<6>(acc, part + ((i64)b * gridDim.x + blockIdx.x) * nk, nk);
 }
 __global__ void __launch_bounds__(256)
-k_out_sums(const float* __restrict__ out, i64 ch_stride, i64 first, i64 count, float* sums3) {
+k_out_sums(const float* __restrict__ out, i64 ch_stride, i64 first, i64 count, float* part) {
   float acc[3] = {0, 0, 0};
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) acc[ch] += out[ch * ch_stride + first + i];
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float s = warp_sum(acc[k]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sums3 + k, s);
-  }
+  cta_store_sums<3>(acc, part + (i64)blockIdx.x * 3, 3);
 }
 void launch_out_sums(Ctx& ctx, const float* out, int rows_total, int row0, int rows, int Wo, float* sums3) {
-  if (ctx.dry) return;
   const i64 count = (i64)rows * Wo;
-  unsigned gx = (unsigned)(cdivl(count, 256) < 8 * num_sms() ? cdivl(count, 256) : 8 * num_sms());
-  ScopedLaunch sl(RF_K_TAIL_STATS, 12.0 * count);
-  k_out_sums<<<gx, 256, 0, ctx.stream>>>(out, (i64)rows_total * Wo, (i64)row0 * Wo, count, sums3);
+  const unsigned gx = (unsigned)(cdivl(count, 256) < 8 * num_sms() ? cdivl(count, 256) : 8 * num_sms());
+  const size_t mk = ctx.arena.mark();
+  float* part = ctx.arena.get<float>((size_t)gx * 3);
+  if (!ctx.dry) {
+    {
+      ScopedLaunch sl(RF_K_TAIL_STATS, 12.0 * count);
+      k_out_sums<<<gx, 256, 0, ctx.stream>>>(out, (i64)rows_total * Wo, (i64)row0 * Wo, count, part);
+    }
+    launch_sum_slots(ctx, part, (int)gx, 3, sums3, 3, 1);
+  }
+  ctx.arena.release(mk);
 }
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_) {
-  if (ctx.dry) return;
-  i64 total = 4 * (i64)h * w_;
-  unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
-  ScopedLaunch sl(RF_K_TAIL_STATS, (out ? 12.0 : 0.0) * B * total + 16.0 * B * h * w_);
-  k_tail_stats<<<dim3(gx, B), 256, 0, ctx.stream>>>(out, (const float4*)x_ds, sums, h, w_);
+  const i64 total = 4 * (i64)h * w_;
+  const unsigned gx = (unsigned)(cdivl(total, 256) < 8 * num_sms() ? cdivl(total, 256) : 8 * num_sms());
+  const int nk = (out != nullptr || ctx.dry) ? 6 : 3;
+  const size_t mk = ctx.arena.mark();
+  float* part = ctx.arena.get<float>((size_t)B * gx * 6);
+  if (!ctx.dry) {
+    {
+      ScopedLaunch sl(RF_K_TAIL_STATS, (out ? 12.0 : 0.0) * B * total + 16.0 * B * h * w_);
+      k_tail_stats<<<dim3(gx, B), 256, 0, ctx.stream>>>(out, (const float4*)x_ds, part, h, w_);
+    }
+    launch_sum_slots(ctx, part, (int)gx, nk, sums, 8, B);
+  }
+  ctx.arena.release(mk);
 }
 
 __global__ void __launch_bounds__(256)

@@ -237,7 +237,10 @@ __global__ void k_channel_sums(const T* __restrict__ x, float* __restrict__ part
   for (int c = tid; c < C; c += nthr) {
     float s = 0.f;
     for (int r = 0; r < ppb; ++r) s += smem[r * C + c];
-    atomicAdd(partial + (b * nslots + blockIdx.x % nslots) * C + c, s);   // partial is zero-initialised by the caller
+    // (the launcher keeps the grid within the slots: every CTA owns its slot -> a plain store, bit-reproducible)
+    float* dst = partial + (b * nslots + blockIdx.x % nslots) * C + c;
+    if ((int)gridDim.x <= nslots) *dst = s;
+    else atomicAdd(dst, s);                                               // partial is zero-initialised by the caller
   }
 }
 void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int B, i64 P, int C) {
@@ -248,7 +251,8 @@ void launch_channel_sums(Ctx& ctx, const void* x, float* partial, int nblk, int 
   size_t smem = sizeof(float) * (size_t)C * ppb;
   // enough CTAs to stream at HBM speed; they add into the nblk partial slots (zero-initialised by the caller)
   i64 want = cdivl(P, (i64)ppb * 64);
-  const unsigned gx = (unsigned)(want < 1 ? 1 : (want > 8 * num_sms() ? 8 * num_sms() : want));
+  unsigned gx = (unsigned)(want < 1 ? 1 : (want > 8 * num_sms() ? 8 * num_sms() : want));
+  if (nblk > 0 && gx > (unsigned)nblk) gx = (unsigned)nblk;      // one CTA per partial slot (320: still > 2 CTAs per SM)
   ScopedLaunch sl(RF_K_CHANNEL_SUMS, (double)B * P * C * esize(ctx.dtype));
   if (ctx.dtype == RF_BF16) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_channel_sums<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -168,10 +168,20 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
     }
   }
   if (NG == 8 && sums != nullptr) {
+    // (`sums` = per-CTA partial slots [B][gridDim.x][8]; launch_sum_slots adds them in order: no float atomics)
+    __shared__ float red[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      float s = warp_sum(acc[i]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(sums + b * 8 + i, s);
+    for (int i = 0; i < 8; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      sums[((i64)b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = t;
     }
   }
 }
@@ -179,18 +189,25 @@ __global__ void k_guidance_stage(const float* __restrict__ LL1, const float* __r
 void launch_guidance_stage(Ctx& ctx, const float* LL1, const float* yh1, int H1, int W1, const float* LL2,
                            const float* yh2, int H2, int W2, const float* cr, const float* cb, int Hy, int Wy, float* G,
                            int NG, float* sums, int B, int Hf, int Wf, void* G16a, void* G16b, int y_begin, int y_rows) {
-  if (ctx.dry) return;
   if (y_rows < 0) { y_begin = 0; y_rows = Hf; }
   i64 total = (i64)y_rows * Wf;
   unsigned gx = (unsigned)(cdivl(total, 256) < 4 * num_sms() ? cdivl(total, 256) : 4 * num_sms());
-  ScopedLaunch sl(RF_K_GUIDANCE, (G ? 4.0 * NG : 0.0) * B * total + (G16a ? 16.0 : 0.0) * B * total * (G16b ? 2 : 1) +
-                                     4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
-  if (NG == 4)
-    k_guidance_stage<4><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
-  else
-    k_guidance_stage<8><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
-                                                          Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
+  // multi-level variant: the maps' sums as per-CTA partial slots + an ordered second stage (bit-reproducible)
+  const size_t mk = ctx.arena.mark();
+  float* part = (NG == 8 && sums != nullptr) ? ctx.arena.get<float>((size_t)B * gx * 8) : nullptr;
+  struct Rel { Arena& a; size_t m; ~Rel() { a.release(m); } } rel{ctx.arena, mk};
+  if (ctx.dry) return;
+  {
+    ScopedLaunch sl(RF_K_GUIDANCE, (G ? 4.0 * NG : 0.0) * B * total + (G16a ? 16.0 : 0.0) * B * total * (G16b ? 2 : 1) +
+                                       4.0 * B * (2.0 * H1 * W1 + 2.0 * Hy * Wy));
+    if (NG == 4)
+      k_guidance_stage<4><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, sums,
+                                                            Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
+    else
+      k_guidance_stage<8><<<dim3(gx, B), 256, 0, ctx.stream>>>(LL1, yh1, H1, W1, LL2, yh2, H2, W2, cr, cb, Hy, Wy, G, part,
+                                                            Hf, Wf, (uint4*)G16a, (uint4*)G16b, y_begin, y_rows);
+  }
+  if (part != nullptr) launch_sum_slots(ctx, part, (int)gx, 8, sums, 8, B);
 }
 
 }  // namespace rf

@@ -254,6 +254,9 @@ void launch_embed(Ctx& ctx, const float* x_ds, const void* x16, const float* w, 
                   int w_, int d);
 void launch_head(Ctx& ctx, const void* in, const float* w, const float* b, float* out, int B, int h, int w_, int d);
 // ML tail: out += 0.12*(mean(up(in_rgb)) - mean(out)); out += 0.03*(up8(LL2) - Y(out))
+// out[b * ostride + i] = sum over the slots s (in a fixed order) of part[(b * nslots + s) * width + i], i < width <= 8: the ordered
+// second stage of the per-CTA partial sums of the multi-level variant's guidance means and colour-anchor sums
+void launch_sum_slots(Ctx& ctx, const float* part, int nslots, int width, float* out, int ostride, int B);
 // (out == nullptr: the input sums only)
 void launch_tail_stats(Ctx& ctx, const float* out, const float* x_ds, float* sums, int B, int h, int w_);
 // sums3[ch] += sum over rows [row0, row0 + rows) of out [3][rows_total][Wo]  (row-tiled forward: the band's interior rows)

@@ -577,6 +577,25 @@ def test_bf16_forward_is_bit_reproducible(rf, dim, h, w, b):
     assert torch.equal(o1, o3) and torch.equal(o3, o4), "graph replay differs from the eager forward"
 
 
+def test_multilevel_bf16_forward_is_bit_reproducible(rf):
+    """ML_RF.py variant: the guidance-map means of the FLCA_Pyramid gates, the channel sums of its modulated features and the
+    colour anchor's six sums are per-CTA partial slots with an ordered second stage as well (no float atomics left on the
+    bf16 path): two runs, eager or as a CUDA graph, are bit-identical."""
+    m = rf.multilevel.RawFormer(dim=32, precision="bf16")
+    m.load_state_dict(T.make_state_dict(m, seed=13, scale=1.5))
+    m = m.to(dev()).eval()
+    x = torch.rand(2, 1, 160, 224, generator=torch.Generator().manual_seed(4)).to(dev())
+    with torch.no_grad():
+        o1 = m(x).clone()
+        o2 = m(x).clone()
+        m.enable_cuda_graphs()
+        o3 = m(x).clone()
+        o4 = m(x).clone()
+        m.enable_cuda_graphs(False)
+    assert torch.equal(o1, o2), f"two eager runs differ: max abs {(o1 - o2).abs().max().item():.3e}"
+    assert torch.equal(o1, o3) and torch.equal(o3, o4), "graph replay differs from the eager forward"
+
+
 def test_cuda_graph_replay(rf):
     """enable_cuda_graphs(): the captured forward reproduces the eager forward, replays follow new input data in the
     captured buffer, and a second input buffer gets its own graph."""
